@@ -1,0 +1,248 @@
+"""ctypes binding of the CPU oracle (oracle/so_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+
+Prefers oracle/_ref/libso_oracle_ref.so (restatement + the reference's own octree header
+compiled verbatim) and falls back to oracle/libso_oracle.so (restatement only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_ICP_ITERS = 32
+
+STATUS_NAMES = ["SUCCESS", "NOT_ENOUGH_NEIGHBORS", "NEIGHBORS_TOO_FAR", "BAD_PCA_STRUCTURE",
+                "INVALID_NUMERICAL", "MSE_TOO_LARGE", "UNKNOWN"]
+
+
+class Opts(C.Structure):
+    _fields_ = [("plane_res", C.c_float), ("max_icp_iters", C.c_int32), ("max_surface_features", C.c_int32),
+                ("lm_max_iterations", C.c_int32), ("knn_mode", C.c_int32), ("n_threads", C.c_int32),
+                ("yaw_ratio", C.c_float), ("skip_map_checks", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("pose", C.c_double * 7), ("pose_opt", C.c_double * 7), ("status", C.c_int32), ("n_iterations", C.c_int32),
+                ("iter_n_surf", C.c_int32 * MAX_ICP_ITERS), ("iter_n_edge", C.c_int32 * MAX_ICP_ITERS),
+                ("iter_dtrans", C.c_double * MAX_ICP_ITERS), ("iter_drot", C.c_double * MAX_ICP_ITERS),
+                ("iter_lm_steps", C.c_int32 * MAX_ICP_ITERS), ("iter_lm_successful", C.c_int32 * MAX_ICP_ITERS),
+                ("iter_lm_termination", C.c_int32 * MAX_ICP_ITERS), ("iter_cost", C.c_double * MAX_ICP_ITERS),
+                ("hist_obs", C.c_int32 * 9), ("hist_reject_plane", C.c_int32 * 7), ("hist_reject_line", C.c_int32 * 7),
+                ("cov", C.c_double * 36),
+                ("pos_err", C.c_double), ("pos_dir", C.c_double * 3), ("pos_inv_cond", C.c_double),
+                ("ori_err_deg", C.c_double), ("ori_dir", C.c_double * 3), ("ori_inv_cond", C.c_double),
+                ("total_translation", C.c_double), ("total_rotation", C.c_double),
+                ("translation_from_last", C.c_double), ("rotation_from_last", C.c_double),
+                ("map_surf_5x5", C.c_int32), ("map_edge_5x5", C.c_int32), ("scan_surf_num", C.c_int32), ("scan_edge_num", C.c_int32),
+                ("pos_in_localmap", C.c_int32 * 3), ("pad_", C.c_int32),
+                ("time_ms", C.c_double), ("time_knn_ms", C.c_double)]
+
+
+CORR_DTYPE = np.dtype([("p", "<f8", 3), ("n", "<f8", 3), ("d", "<f8"), ("w", "<f8"), ("eigval", "<f8", 3),
+                       ("mean_dist", "<f8"), ("nn", "<i8", 5), ("nn_d2", "<f4", 5), ("status", "<i4"), ("obs", "<i4", 3)],
+                      align=True)
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle (plain lib always; _ref lib when /root/reference exists)."""
+    lib = os.path.join(_HERE, "libso_oracle.so")
+    src = os.path.join(_HERE, "so_oracle.cpp")
+    if force or not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "libso_oracle.so"], stdout=subprocess.DEVNULL)
+    ref = os.path.join(_HERE, "_ref", "libso_oracle_ref.so")
+    if os.path.isdir("/root/reference") and (force or not os.path.exists(ref) or os.path.getmtime(ref) < os.path.getmtime(src)):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    ref = os.path.join(_HERE, "_ref", "libso_oracle_ref.so")
+    plain = os.path.join(_HERE, "libso_oracle.so")
+    if not os.path.exists(plain) and not os.path.exists(ref):
+        build()
+    path = ref if os.path.exists(ref) else plain
+    L = C.CDLL(path)
+    L.orc_map_create.restype = C.c_void_p
+    L.orc_map_destroy.argtypes = [C.c_void_p]
+    L.orc_map_set_points.restype = C.c_int64
+    L.orc_map_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
+    L.orc_map_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_map_get_origin.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_map_counts_5x5.restype = C.c_int32
+    L.orc_map_counts_5x5.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_correspond.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_evaluate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_solve.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_covariance.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_float, C.c_void_p]
+    L.orc_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_sym_eig.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_colpiv_qr_solve.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_pose_plus.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_yaw_round_trip.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+    L.orc_lidar_uncertainty.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_sizeof_corr.restype = C.c_size_t
+    L.orc_sizeof_result.restype = C.c_size_t
+    assert L.orc_sizeof_corr() == CORR_DTYPE.itemsize, (L.orc_sizeof_corr(), CORR_DTYPE.itemsize)
+    assert L.orc_sizeof_result() == C.sizeof(Result), (L.orc_sizeof_result(), C.sizeof(Result))
+    L._path = path
+    _lib = L
+    return L
+
+
+def has_ref_octree() -> bool:
+    return bool(lib().orc_has_ref_octree())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleMap:
+    """LocalMap stand-in: block grid (21x21x11 of 50 m) + per-block surf cloud + k-NN index."""
+
+    def __init__(self, xyzi: np.ndarray | None = None, ref_octree: bool | None = None):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.orc_map_create())
+        self.xyzi = None
+        if xyzi is not None:
+            self.set_points(xyzi, ref_octree)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_map_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_points(self, xyzi: np.ndarray, ref_octree: bool | None = None) -> int:
+        xyzi = np.ascontiguousarray(xyzi, dtype=np.float32)
+        self.xyzi = xyzi
+        if ref_octree is None:
+            ref_octree = has_ref_octree()
+        return int(self.L.orc_map_set_points(self.h, _p(xyzi), xyzi.shape[0], xyzi.shape[1], int(ref_octree)))
+
+    def origin(self):
+        o = np.zeros(3, np.int32)
+        self.L.orc_map_get_origin(self.h, _p(o))
+        return o
+
+    def shift(self, t):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        out = np.zeros(3, np.int32)
+        self.L.orc_map_shift(self.h, _p(t), _p(out))
+        return out
+
+    def counts_5x5(self, ijk) -> int:
+        ijk = np.ascontiguousarray(ijk, dtype=np.int32)
+        return int(self.L.orc_map_counts_5x5(self.h, _p(ijk)))
+
+    def knn(self, q_xyz: np.ndarray, k: int = 5, mode: int = 0):
+        q = np.ascontiguousarray(q_xyz, dtype=np.float32)
+        nq = q.shape[0]
+        idx = np.empty((nq, k), np.int64)
+        d2 = np.empty((nq, k), np.float32)
+        found = np.empty(nq, np.uint8)
+        rc = self.L.orc_knn(self.h, _p(q), nq, q.shape[1], k, mode, _p(idx), _p(d2), _p(found))
+        assert rc == 0
+        return idx, d2, found.astype(bool)
+
+    def correspond(self, scan_xyzi, pose7, plane_res, max_surface_features=0, knn_mode=0, n_threads=1):
+        s = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        corr = np.zeros(s.shape[0], CORR_DTYPE)
+        ho = np.zeros(9, np.int32)
+        hr = np.zeros(7, np.int32)
+        self.L.orc_correspond(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.c_float(plane_res), max_surface_features,
+                              knn_mode, n_threads, _p(corr), _p(ho), _p(hr))
+        return corr, ho, hr
+
+    def register(self, scan_xyzi, pose7, plane_res, max_icp_iters, max_surface_features=0, knn_mode=0, n_threads=1,
+                 lm_max_iterations=4, yaw_ratio=0.0, skip_map_checks=False) -> Result:
+        s = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        o = Opts(plane_res, max_icp_iters, max_surface_features, lm_max_iterations, knn_mode, n_threads, yaw_ratio, int(skip_map_checks))
+        r = Result()
+        self.L.orc_register(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.byref(o), C.byref(r))
+        return r
+
+
+def evaluate(corr: np.ndarray, pose7, plane_res):
+    L = lib()
+    pose = np.ascontiguousarray(pose7, dtype=np.float64)
+    H = np.zeros((6, 6))
+    g = np.zeros(6)
+    cost = C.c_double()
+    nok = C.c_int64()
+    L.orc_evaluate(_p(corr), corr.shape[0], _p(pose), C.c_float(plane_res), _p(H), _p(g), C.byref(cost), C.byref(nok))
+    return H, g, cost.value, nok.value
+
+
+def solve(corr: np.ndarray, pose7, plane_res, lm_max_iterations=4):
+    L = lib()
+    pose = np.array(pose7, dtype=np.float64)
+    summ = np.zeros(4, np.int32)
+    costs = np.zeros(2)
+    L.orc_solve(_p(corr), corr.shape[0], _p(pose), C.c_float(plane_res), lm_max_iterations, _p(summ), _p(costs))
+    return pose, dict(successful=int(summ[0]), unsuccessful=int(summ[1]), iterations=int(summ[2]), termination=int(summ[3]),
+                      initial_cost=costs[0], final_cost=costs[1])
+
+
+def covariance(corr: np.ndarray, pose7, plane_res):
+    L = lib()
+    pose = np.ascontiguousarray(pose7, dtype=np.float64)
+    cov = np.zeros((6, 6))
+    rc = L.orc_covariance(_p(corr), corr.shape[0], _p(pose), C.c_float(plane_res), _p(cov))
+    return cov if rc == 0 else None
+
+
+def sym_eig(a: np.ndarray):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    w = np.zeros(n)
+    v = np.zeros((n, n))
+    lib().orc_sym_eig(n, _p(a), _p(w), _p(v))
+    return w, v
+
+
+def colpiv_qr_solve(A: np.ndarray, b: np.ndarray):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(3)
+    lib().orc_colpiv_qr_solve(A.shape[0], _p(A), _p(b), _p(x))
+    return x
+
+
+def pose_plus(x, d):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    out = np.zeros(7)
+    lib().orc_pose_plus(_p(x), _p(d), _p(out))
+    return out
+
+
+def yaw_round_trip(last, T, yaw_ratio=0.0):
+    last = np.ascontiguousarray(last, dtype=np.float64)
+    T = np.array(T, dtype=np.float64)
+    lib().orc_yaw_round_trip(_p(last), _p(T), C.c_double(yaw_ratio))
+    return T
+
+
+def lidar_uncertainty(hist9):
+    h = np.ascontiguousarray(hist9, dtype=np.int32)
+    u = np.zeros(6)
+    lib().orc_lidar_uncertainty(_p(h), _p(u))
+    return u

@@ -1,0 +1,343 @@
+"""Seeded synthetic worlds, maps and LiDAR scans.
+
+Shared by the oracle tests, the GPU parity tests and bench.py so that all of
+them see identical bytes.  Nothing here touches the GPU or the oracle.
+
+World: an analytic "warehouse" -- a closed room (ground z=-1.8 m, ceiling
+z=+6 m, four outer walls) filled with axis-aligned boxes (shelving rows and
+floor-to-ceiling pillars).  No face plane lies within 1 m of the world origin
+(the reference plane fit ``A n = -1`` is undefined for planes through the
+origin, LidarSlam.cpp:798-806).
+
+Map: every face sampled on a lattice of pitch = leaf, jittered by
+N(0, (0.02 m)^2) per axis (keeps the PCA gate lambda0 >= 1e-6 alive,
+LidarSlam.cpp:772, and removes distance ties), then passed through the
+per-block voxel-centroid filter of the reference insert path
+(LocalMap.h:591-645; semantics of pcl::VoxelGrid restated in
+``voxel_filter_blocks``).
+
+Scans: ray-cast from a ground-truth pose, range noise N(0,(0.01 m)^2), returns
+outside [0.2, 130] m dropped (featureExtraction.cpp:128-129 defaults).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import numpy as np
+
+BLOCK = 50.0          # LocalMap::voxelResulation (LocalMap.h:136)
+HALF_BLOCK = 25.0     # LocalMap::halfVoxelResulation
+GRID = (21, 21, 11)   # laserCloudWidth/Height/Depth (LocalMap.h:131-133)
+ORIGIN0 = (10, 10, 5) # LocalMap() constructor origin (LocalMap.h:141-144)
+
+
+# --------------------------------------------------------------------------
+# scene
+# --------------------------------------------------------------------------
+@dataclasses.dataclass
+class Scene:
+    room: np.ndarray    # [6] xmin,xmax,ymin,ymax,zmin,zmax
+    boxes: np.ndarray   # [nb,6] same layout
+
+    def free(self, p: np.ndarray, margin: float = 0.6) -> bool:
+        r = self.room
+        if not (r[0] + margin < p[0] < r[1] - margin and r[2] + margin < p[1] < r[3] - margin
+                and r[4] + 0.3 < p[2] < r[5] - 0.3):
+            return False
+        b = self.boxes
+        inside = ((p[0] > b[:, 0] - margin) & (p[0] < b[:, 1] + margin) &
+                  (p[1] > b[:, 2] - margin) & (p[1] < b[:, 3] + margin) &
+                  (p[2] > b[:, 4] - margin) & (p[2] < b[:, 5] + margin))
+        return not bool(inside.any())
+
+
+def make_scene(half_extent: float, seed: int = 77, aisle: float = 5.0) -> Scene:
+    """Room [-h,h]^2 x [-1.8,6] with shelving rows every `aisle` metres and pillars."""
+    h = float(half_extent)
+    rng = np.random.default_rng(seed)
+    room = np.array([-h, h, -h, h, -1.8, 6.0])
+    boxes = []
+    # shelving rows: long boxes parallel to x, broken into segments with gaps
+    y = -h + aisle
+    row = 0
+    while y < h - aisle + 1e-9:
+        if abs(y) >= 2.0:           # keep faces |y| >= 1 and the origin aisle free
+            x = -h + 2.0
+            while x < h - 2.0:
+                seg = float(rng.uniform(4.0, 9.0))
+                x1 = min(x + seg, h - 2.0)
+                if x1 - x > 1.5 and not (x < 1.0 and x1 > -1.0):
+                    top = float(rng.uniform(1.2, 4.5))      # box top z (>= 1 m from origin plane)
+                    depth = float(rng.uniform(0.6, 1.4))
+                    boxes.append([x, x1, y - depth / 2, y + depth / 2, -1.8, top])
+                x = x1 + float(rng.uniform(1.5, 3.0))
+        y += aisle
+        row += 1
+    # pillars (floor to ceiling) on a coarse lattice, jittered
+    step = max(10.0, h / 4)
+    for px in np.arange(-h + step / 2, h, step):
+        for py in np.arange(-h + step / 2 + 2.5, h, step):
+            cx = float(px + rng.uniform(-1, 1))
+            cy = float(py + rng.uniform(-1, 1))
+            if abs(cx) < 2.0 or abs(cy) < 2.0:
+                continue
+            s = float(rng.uniform(0.4, 0.8))
+            boxes.append([cx - s, cx + s, cy - s, cy + s, -1.8, 6.0])
+    boxes = np.array(boxes, dtype=np.float64).reshape(-1, 6)
+    # enforce: no face plane within 1 m of the origin on any axis
+    for ax in range(3):
+        for side in (0, 1):
+            c = boxes[:, 2 * ax + side]
+            bad = np.abs(c) < 1.0
+            c[bad] = np.where(c[bad] >= 0, 1.0 + 0.05 * ax, -1.0 - 0.05 * ax)
+    keep = (boxes[:, 1] - boxes[:, 0] > 0.2) & (boxes[:, 3] - boxes[:, 2] > 0.2) & (boxes[:, 5] - boxes[:, 4] > 0.2)
+    return Scene(room=room, boxes=boxes[keep])
+
+
+def _face_samples(lo_u, hi_u, lo_v, hi_v, pitch):
+    nu = max(1, int(math.floor((hi_u - lo_u) / pitch)))
+    nv = max(1, int(math.floor((hi_v - lo_v) / pitch)))
+    u = lo_u + (np.arange(nu) + 0.5) * pitch
+    v = lo_v + (np.arange(nv) + 0.5) * pitch
+    uu, vv = np.meshgrid(u, v, indexing="ij")
+    return uu.ravel(), vv.ravel()
+
+
+def sample_surfaces(scene: Scene, pitch: float, seed: int = 1234, noise: float = 0.02) -> np.ndarray:
+    """Raw (unfiltered) surface samples, float32 [M,3]."""
+    rng = np.random.default_rng(seed)
+    chunks = []
+
+    def add_box_faces(b, inward):
+        x0, x1, y0, y1, z0, z1 = b
+        for zc in (z0, z1):
+            u, v = _face_samples(x0, x1, y0, y1, pitch)
+            chunks.append(np.stack([u, v, np.full_like(u, zc)], 1))
+        for xc in (x0, x1):
+            u, v = _face_samples(y0, y1, z0, z1, pitch)
+            chunks.append(np.stack([np.full_like(u, xc), u, v], 1))
+        for yc in (y0, y1):
+            u, v = _face_samples(x0, x1, z0, z1, pitch)
+            chunks.append(np.stack([u, np.full_like(u, yc), v], 1))
+
+    add_box_faces(scene.room, True)
+    for b in scene.boxes:
+        add_box_faces(b, False)
+    pts = np.concatenate(chunks, 0)
+    # drop samples strictly inside another box (hidden) -- cheap chunked test
+    keep = np.ones(len(pts), dtype=bool)
+    eps = 1e-6
+    for b in scene.boxes:
+        ins = ((pts[:, 0] > b[0] + eps) & (pts[:, 0] < b[1] - eps) & (pts[:, 1] > b[2] + eps) &
+               (pts[:, 1] < b[3] - eps) & (pts[:, 2] > b[4] + eps) & (pts[:, 2] < b[5] - eps))
+        keep &= ~ins
+    pts = pts[keep]
+    pts = pts + rng.normal(0.0, noise, size=pts.shape)
+    return pts.astype(np.float32)
+
+
+# --------------------------------------------------------------------------
+# block binning + voxel-centroid filter (restates LocalMap.h:591-645 + pcl::VoxelGrid)
+# --------------------------------------------------------------------------
+def block_of(xyz: np.ndarray, origin=ORIGIN0) -> np.ndarray:
+    """LocalMap.h:594-605: int((x+25)/50)+origin, minus one when x+25<0 (double arithmetic
+    on float coordinates).  Returns int32 [n,3] grid indices (may be off-grid)."""
+    v = xyz.astype(np.float64) + HALF_BLOCK
+    c = np.trunc(v / BLOCK).astype(np.int64) + np.asarray(origin, dtype=np.int64)
+    c -= (v < 0).astype(np.int64)
+    return c.astype(np.int32)
+
+
+def block_linear(c: np.ndarray) -> np.ndarray:
+    """cubeInd = i + 21*j + 21*21*k, -1 when off-grid (LocalMap.h:607-609)."""
+    ok = ((c[:, 0] >= 0) & (c[:, 0] < GRID[0]) & (c[:, 1] >= 0) & (c[:, 1] < GRID[1]) &
+          (c[:, 2] >= 0) & (c[:, 2] < GRID[2]))
+    lin = c[:, 0].astype(np.int64) + GRID[0] * c[:, 1].astype(np.int64) + GRID[0] * GRID[1] * c[:, 2].astype(np.int64)
+    return np.where(ok, lin, -1)
+
+
+def voxel_filter_blocks(xyzi: np.ndarray, leaf: float, origin=ORIGIN0) -> np.ndarray:
+    """Per-block voxel-centroid filter.
+
+    pcl::VoxelGrid semantics (PCL 1.12 voxel_grid.hpp, third-party, not in /root/reference):
+    voxel = floor(coord * (1.0f/leaf)) per axis in float32; one output point per occupied
+    voxel = centroid of all fields, accumulated in float32 and divided by float(count);
+    output ordered by block, then by voxel index (k, j, i ascending).  PCL leaves the
+    in-voxel accumulation order unspecified (std::sort on the voxel index only); this
+    restatement fixes it to ascending input order.
+    xyzi: float32 [n,4] (x,y,z,intensity).  Returns float32 [m,4]."""
+    xyzi = np.ascontiguousarray(xyzi, dtype=np.float32)
+    lin = block_linear(block_of(xyzi[:, :3], origin))
+    keep = lin >= 0
+    xyzi = xyzi[keep]
+    lin = lin[keep]
+    inv = np.float32(1.0) / np.float32(leaf)
+    ijk = np.floor(xyzi[:, :3] * inv).astype(np.int64)
+    # sort key: block, k, j, i  (stable -> in-voxel order = input order)
+    order = np.lexsort((ijk[:, 0], ijk[:, 1], ijk[:, 2], lin))
+    xyzi = xyzi[order]
+    key = np.stack([lin[order], ijk[order, 2], ijk[order, 1], ijk[order, 0]], 1)
+    new = np.ones(len(key), dtype=bool)
+    new[1:] = (key[1:] != key[:-1]).any(1)
+    seg = np.cumsum(new) - 1
+    nseg = int(seg[-1]) + 1 if len(seg) else 0
+    start = np.flatnonzero(new)
+    rank = np.arange(len(key)) - start[seg]
+    acc = np.zeros((nseg, 4), dtype=np.float32)
+    for r in range(int(rank.max()) + 1 if len(rank) else 0):
+        m = rank == r
+        acc[seg[m]] = acc[seg[m]] + xyzi[m]           # float32 sequential accumulation
+    cnt = np.bincount(seg, minlength=nseg).astype(np.float32)
+    return (acc / cnt[:, None]).astype(np.float32)
+
+
+def make_map(half_extent: float, leaf: float, scene_seed: int = 77, map_seed: int = 1234):
+    scene = make_scene(half_extent, seed=scene_seed)
+    raw = sample_surfaces(scene, leaf, seed=map_seed)
+    xyzi = np.concatenate([raw, np.ones((len(raw), 1), np.float32)], 1)
+    return scene, voxel_filter_blocks(xyzi, leaf)
+
+
+# --------------------------------------------------------------------------
+# poses  (pose7 = tx,ty,tz,qx,qy,qz,qw  -- the reference's pose_parameters layout, LidarSlam.cpp:7-9)
+# --------------------------------------------------------------------------
+def quat_mul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx,
+                     aw * bw - ax * bx - ay * by - az * bz])
+
+
+def quat_from_rotvec(w):
+    th = float(np.linalg.norm(w))
+    if th < 1e-12:
+        return np.array([0.5 * w[0], 0.5 * w[1], 0.5 * w[2], 1.0])
+    s = math.sin(th / 2) / th
+    return np.array([w[0] * s, w[1] * s, w[2] * s, math.cos(th / 2)])
+
+
+def quat_to_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def random_sensor_pose(scene: Scene, seed: int, max_radius: float = 20.0) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    for _ in range(1000):
+        r = rng.uniform(0.0, max_radius)
+        a = rng.uniform(0, 2 * math.pi)
+        p = np.array([r * math.cos(a), r * math.sin(a), rng.uniform(-0.6, 0.6)])
+        if scene.free(p):
+            break
+    else:
+        raise RuntimeError("no free sensor position")
+    yaw = rng.uniform(-math.pi, math.pi)
+    rp = rng.uniform(-0.03, 0.03, size=2)
+    q = quat_mul(quat_from_rotvec(np.array([0, 0, yaw])), quat_from_rotvec(np.array([rp[0], rp[1], 0.0])))
+    q /= np.linalg.norm(q)
+    return np.concatenate([p, q])
+
+
+def perturb_pose(pose7: np.ndarray, seed: int, dt: float = 0.10, dth_deg: float = 1.0) -> np.ndarray:
+    """T_prior = T* [+] (dt, dtheta): dt ~ U(-dt,dt) m, dtheta ~ U(-dth,dth) deg per axis."""
+    rng = np.random.default_rng(seed)
+    d = rng.uniform(-dt, dt, size=3)
+    w = np.deg2rad(rng.uniform(-dth_deg, dth_deg, size=3))
+    q = quat_mul(pose7[3:], quat_from_rotvec(w))
+    q /= np.linalg.norm(q)
+    return np.concatenate([pose7[:3] + d, q])
+
+
+# --------------------------------------------------------------------------
+# sensors + ray casting
+# --------------------------------------------------------------------------
+def sensor_dirs(sensor: str, seed: int = 0) -> np.ndarray:
+    if sensor == "vlp16":
+        el = np.deg2rad(np.arange(-15.0, 15.1, 2.0))
+        az = np.arange(1800) * (2 * math.pi / 1800)
+    elif sensor == "os1_128":
+        el = np.deg2rad(np.linspace(-22.5, 22.5, 128))
+        az = np.arange(1024) * (2 * math.pi / 1024)
+    elif sensor == "mid360":
+        rng = np.random.default_rng(seed + 555)
+        n = 240000
+        azr = rng.uniform(0, 2 * math.pi, n)
+        elr = np.deg2rad(rng.uniform(-7.0, 52.0, n))
+        return np.stack([np.cos(elr) * np.cos(azr), np.cos(elr) * np.sin(azr), np.sin(elr)], 1)
+    else:
+        raise ValueError(sensor)
+    # azimuth-major (column firing order), rings inner
+    A, E = np.meshgrid(az, el, indexing="ij")
+    return np.stack([np.cos(E) * np.cos(A), np.cos(E) * np.sin(A), np.sin(E)], -1).reshape(-1, 3)
+
+
+def raycast(scene: Scene, o: np.ndarray, d: np.ndarray) -> np.ndarray:
+    """Range to the first surface along each ray (origin o [3], dirs d [n,3]); inf if none."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / d
+        r = scene.room
+        lo = np.array([r[0], r[2], r[4]])
+        hi = np.array([r[1], r[3], r[5]])
+        t1 = (lo - o) * inv
+        t2 = (hi - o) * inv
+        t_exit = np.min(np.maximum(t1, t2), axis=1)          # inside the room: exit distance
+        best = t_exit
+        for b in scene.boxes:
+            lo = np.array([b[0], b[2], b[4]])
+            hi = np.array([b[1], b[3], b[5]])
+            t1 = (lo - o) * inv
+            t2 = (hi - o) * inv
+            tn = np.max(np.minimum(t1, t2), axis=1)
+            tf = np.min(np.maximum(t1, t2), axis=1)
+            hit = (tn <= tf) & (tn > 0)
+            best = np.where(hit & (tn < best), tn, best)
+    return best
+
+
+def make_scan(scene: Scene, sensor: str, pose7: np.ndarray, seed: int,
+              range_noise: float = 0.01, rmin: float = 0.2, rmax: float = 130.0) -> np.ndarray:
+    """Points in the SENSOR frame, float32 [n,4] (x,y,z,intensity)."""
+    rng = np.random.default_rng(seed)
+    dirs = sensor_dirs(sensor, seed)
+    R = quat_to_R(pose7[3:])
+    rng_true = raycast(scene, pose7[:3], dirs @ R.T)
+    rn = rng_true + rng.normal(0.0, range_noise, size=rng_true.shape)
+    ok = np.isfinite(rn) & (rn > rmin) & (rn < rmax)
+    pts = dirs[ok] * rn[ok, None]
+    inten = rng.uniform(1.0, 100.0, size=(len(pts), 1))
+    return np.concatenate([pts, inten], 1).astype(np.float32)
+
+
+# --------------------------------------------------------------------------
+# BASELINE.json configs
+# --------------------------------------------------------------------------
+CONFIGS = {
+    # name: half_extent, leaf(planeRes), sensor, icp iters, max_surface_features (0 = uncapped)
+    "cfg1": dict(half_extent=17.5, plane_res=0.2, sensor="vlp16", max_iterations=5, max_surface_features=2000),
+    "cfg1_uncapped": dict(half_extent=17.5, plane_res=0.2, sensor="vlp16", max_iterations=5, max_surface_features=0),
+    "cfg2": dict(half_extent=52.0, plane_res=0.2, sensor="os1_128", max_iterations=20, max_surface_features=0),
+    "cfg3": dict(half_extent=36.5, plane_res=0.1, sensor="mid360", max_iterations=20, max_surface_features=0),
+    "tiny": dict(half_extent=9.0, plane_res=0.2, sensor="vlp16", max_iterations=5, max_surface_features=0),
+}
+
+
+def make_case(name: str, scan_index: int = 0, max_radius: float | None = None):
+    """-> dict(scene, map_xyzi [M,4] f32, scan_xyzi [N,4] f32, pose_true [7], pose_prior [7], cfg)."""
+    cfg = CONFIGS[name]
+    scene, map_xyzi = make_map(cfg["half_extent"], cfg["plane_res"])
+    return make_case_on(scene, map_xyzi, name, scan_index, max_radius)
+
+
+def make_case_on(scene, map_xyzi, name: str, scan_index: int = 0, max_radius: float | None = None):
+    cfg = CONFIGS[name]
+    if max_radius is None:
+        max_radius = min(20.0, cfg["half_extent"] * 0.6)
+    pose_true = random_sensor_pose(scene, 900 + scan_index, max_radius)
+    scan = make_scan(scene, cfg["sensor"], pose_true, 1000 + scan_index)
+    prior = perturb_pose(pose_true, 2000 + scan_index)
+    return dict(scene=scene, map_xyzi=map_xyzi, scan_xyzi=scan, pose_true=pose_true, pose_prior=prior, cfg=cfg)
