@@ -1,0 +1,204 @@
+/* =============================================================================
+ * superodom_b200.h -- C ABI of the B200-native ICP registration hot path.
+ *
+ * This is the drop-in boundary for ONE path of superxslam/SuperOdom: the per-scan
+ * registration in LidarSLAM::performLocalizationAndMapping.  The reference has no
+ * FFI layer; its seam is the C++ class surface of LidarSLAM / LocalMap as used by
+ * laserMapping.  Each entry point below names the reference
+ * interface it replaces (file:line under /root/reference/super_odometry/).  The C++
+ * shim include/superodom_b200/LidarSlam.hpp keeps the reference member names and
+ * forwards to these functions; INTEGRATION.md shows the maintainer-side binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller owns every host buffer; the context owns
+ *     all device memory, streams and CUDA graphs; no allocation crosses the ABI.
+ *   - pose7 = {tx,ty,tz,qx,qy,qz,qw}: the reference's pose_parameters layout
+ *     (src/LidarProcess/LidarSlam.cpp:7-9).
+ *   - point clouds are arrays of points with a byte stride; x,y,z are floats at byte
+ *     offsets 0,4,8 and intensity is a float at byte offset `intensity_offset`
+ *     (pcl::PointXYZI: stride 32, intensity at 16; packed float4: stride 16, at 12).
+ *   - return value: 0 = ok; >0 = reference-defined soft status (see SO_STATUS_*);
+ *     <0 = CUDA / argument error, text via so_last_error().  Nothing throws.
+ *   - one host thread per context, one context per GPU (the reference is
+ *     non-reentrant: file-scope pose globals, LidarSlam.cpp:7-9).
+ *   - there is NO CPU fallback: every entry point fails with SO_ERR_CUDA when no
+ *     sm_100 device / kernel image is available.
+ * ============================================================================= */
+#ifndef SUPERODOM_B200_H
+#define SUPERODOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO_MAX_ICP_ITERS 32
+
+/* soft statuses (>0) and errors (<0) */
+#define SO_OK 0
+#define SO_STATUS_NOT_ENOUGH_FEATURES 1 /* hasEnoughFeatures() false: pose = prior (LidarSlam.cpp:113-116,379-381) */
+#define SO_STATUS_NO_CORRESPONDENCES 2  /* every scan point was rejected; reference would CHECK-fail in ceres::Covariance */
+#define SO_ERR_ARG (-1)
+#define SO_ERR_CUDA (-2)
+#define SO_ERR_CAPACITY (-3)
+
+/* LidarSLAM::MatchingResult (include/super_odometry/LidarProcess/LidarSlam.h:85-94) */
+enum so_match_result {
+    SO_MATCH_SUCCESS = 0, SO_MATCH_NOT_ENOUGH_NEIGHBORS = 1, SO_MATCH_NEIGHBORS_TOO_FAR = 2,
+    SO_MATCH_BAD_PCA_STRUCTURE = 3, SO_MATCH_INVALID_NUMERICAL = 4, SO_MATCH_MSE_TOO_LARGE = 5,
+    SO_MATCH_UNKNOWN = 6, SO_MATCH_N = 7,
+    SO_MATCH_SKIPPED = 255 /* not in the reference: point dropped by shouldProcessPoint (LidarSlam.cpp:353-359) */
+};
+
+typedef struct so_ctx so_ctx;
+
+/* Construction-time capacities.  Zero fields take defaults. */
+typedef struct {
+    int32_t device;            /* CUDA device ordinal */
+    uint32_t max_map_points;   /* default 4,194,304 */
+    uint32_t max_scan_points;  /* per scan, default 262,144 */
+    uint32_t max_batch;        /* scans registered concurrently by so_register_batch*, default 1 */
+    float line_res;            /* LocalMap::lineRes_  (LocalMap.h:761; node default laserMapping.cpp:102-103) */
+    float plane_res;           /* LocalMap::planeRes_ (LocalMap.h:762) */
+} so_config;
+
+/* Per-call options == the LidarSLAM members laserMapping writes (laserMapping.cpp:102-120,703-711). */
+typedef struct {
+    int32_t max_icp_iters;        /* LidarSLAM::LocalizationICPMaxIter (LidarSlam.h:273); config max_iterations */
+    int32_t max_surface_features; /* OptSet.max_surface_features (LidarSlam.h:118); 0 = uncapped */
+    int32_t lm_max_iterations;    /* ceres options.max_num_iterations = 4 (LidarSlam.cpp:232); 0 -> 4 */
+    float yaw_ratio;              /* OptSet.yaw_ratio (LidarSlam.cpp:905) */
+    int32_t skip_map_checks;      /* 1: do not run shiftMap / hasEnoughFeatures (replay against a frozen map) */
+    int32_t reserved[3];
+} so_icp_opts;
+
+/* Everything the reference leaves in LidarSLAM members after Localization():
+ * T_w_lidar, stats (OptimizationStats.msg), LocalizationUncertainty (RegistrationError, LidarSlam.h:122-148),
+ * PlaneFeatureHistogramObs / MatchRejectionHistogram* (LidarSlam.h:267-269). */
+typedef struct {
+    double pose[7];       /* T_w_lidar after MannualYawCorrection (LidarSlam.cpp:891-913) */
+    double pose_opt[7];   /* optimiser output (pose_parameters) before the RPY round trip */
+    int32_t status;       /* SO_OK / SO_STATUS_* */
+    int32_t n_iterations; /* ICP iterations executed (stats.iterations.size()) */
+    int32_t iter_n_surf[SO_MAX_ICP_ITERS];        /* IterationStats.num_surf_from_scan */
+    int32_t iter_n_edge[SO_MAX_ICP_ITERS];        /* IterationStats.num_corner_from_scan (edge path dormant: 0) */
+    double iter_dtrans[SO_MAX_ICP_ITERS];         /* IterationStats.translation_norm */
+    double iter_drot[SO_MAX_ICP_ITERS];           /* IterationStats.rotation_norm */
+    int32_t iter_lm_steps[SO_MAX_ICP_ITERS];      /* ceres summary: iterations of this solve (diagnostic) */
+    int32_t iter_lm_successful[SO_MAX_ICP_ITERS]; /* ceres summary.num_successful_steps (drives the break, :141) */
+    int32_t iter_lm_termination[SO_MAX_ICP_ITERS];/* 0 max-iter 1 gradient 2 parameter 3 function 4 radius 5 invalid 6 empty */
+    double iter_cost[SO_MAX_ICP_ITERS];           /* final cost of this solve */
+    int32_t hist_obs[9];          /* PlaneFeatureHistogramObs of the last ICP iteration */
+    int32_t hist_reject_plane[7]; /* MatchRejectionHistogramPlane of the last ICP iteration */
+    int32_t hist_reject_line[7];  /* MatchRejectionHistogramLine (edge path dormant: 0) */
+    double cov[36];               /* RegistrationError::Covariance, row-major, order x,y,z,rx,ry,rz */
+    double pos_err, pos_dir[3], pos_inv_cond;     /* PositionError, PositionErrorDirection, PosInverseConditionNum */
+    double ori_err_deg, ori_dir[3], ori_inv_cond; /* OrientationError (degrees), ...Direction, OriInverseConditionNum */
+    double total_translation, total_rotation, translation_from_last, rotation_from_last; /* stats.* (LidarSlam.cpp:198-210) */
+    int32_t map_surf_5x5, map_edge_5x5, scan_surf_num, scan_edge_num; /* stats.laser_cloud_* (LidarSlam.cpp:371-377) */
+    int32_t pos_in_localmap[3];   /* LidarSLAM::pos_in_localmap (shiftMap return) */
+    int32_t pad_;
+    double time_ms;               /* stats.time_elapsed: the ICP loop, device time measured with CUDA events */
+    double time_total_ms;         /* whole so_register call incl. H2D / D2H (host clock) */
+} so_icp_result;
+
+/* One accepted/rejected plane correspondence, for stage-level parity tests
+ * (LidarSLAM::OptimizationParameter, LidarSlam.h:209-222, reduced to what the solver reads). */
+typedef struct {
+    double n[3];      /* NormDir */
+    double d;         /* negative_OA_dot_norm */
+    double w;         /* residualCoefficient */
+    uint32_t nn[5];   /* neighbour ids = index of the map point in the order given to so_map_set_points / so_map_add_surf output */
+    float nn_d2[5];
+    uint8_t status;   /* so_match_result */
+    uint8_t obs[3];   /* Feature_observability labels histogrammed (LidarSlam.cpp:336-339) */
+    uint8_t pad_[4];
+} so_corr;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+/* replaces: LidarSLAM::LidarSLAM() + LocalMap::LocalMap() (LidarSlam.cpp:14-19, LocalMap.h:141-144) */
+so_ctx* so_create(const so_config* cfg);
+void so_destroy(so_ctx* ctx);
+const char* so_last_error(void);
+/* 1 when a CUDA device of compute capability 10.x is usable by this library */
+int so_device_available(void);
+/* Use an externally owned CUDA stream (cudaStream_t as void*) for all work of this context; NULL = own stream. */
+int so_set_stream(so_ctx* ctx, void* cuda_stream);
+
+/* ---- map (LocalMap) ------------------------------------------------------------------------------- */
+/* replaces: slam.localMap.lineRes_/planeRes_ = ... (laserMapping.cpp:102-103,648-649). Rebuilds the neighbour
+ * index when plane_res changes (cell edge derives from sqrt(3*planeRes)). */
+int so_map_set_resolution(so_ctx* ctx, float line_res, float plane_res);
+/* replaces: LocalMap::setOrigin (LocalMap.h:146-164): origin_ = -blockOf(t).  out_origin may be NULL. */
+int so_map_set_origin(so_ctx* ctx, const double t_w_cur[3], int32_t out_origin[3]);
+int so_map_get_origin(so_ctx* ctx, int32_t out_origin[3]);
+/* replaces: LocalMap::shiftMap (LocalMap.h:169-287): roll the 21x21x11 block grid so the sensor block stays in
+ * [3,17]x[3,17]x[3,7]; blocks rolled off the grid are dropped.  Returns the sensor block in out_ijk. */
+int so_map_shift(so_ctx* ctx, const double t_w_cur[3], int32_t out_ijk[3]);
+/* Load an ALREADY voxel-filtered world-frame surf cloud as the whole map (no filtering): replay / localization
+ * mode with a prebuilt map.  Point ids (so_corr.nn) are indices into this array. */
+int so_map_set_points(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset);
+/* replaces: LocalMap::addSurfPointCloud (LocalMap.h:591-645): bin world-frame points into blocks, voxel-centroid
+ * filter every touched block at leaf planeRes (pcl::VoxelGrid semantics), rebuild the neighbour index. */
+int so_map_add_surf(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset);
+/* replaces: LocalMap::get5x5LocalMapFeatureSize (LocalMap.h:291-318) */
+int so_map_counts_5x5(so_ctx* ctx, const int32_t ijk[3], int32_t* n_edge, int32_t* n_surf);
+/* replaces: LocalMap::getAllLocalMap (mode 0, LocalMap.h:647-658) / get5x5LocalMap(pos) (mode 1, :660-687).
+ * Writes packed float4 {x,y,z,intensity} in block order then point-id order; *n_out = points available. */
+int so_map_download(so_ctx* ctx, int mode, const int32_t ijk[3], float* out_xyzi, size_t cap_points, size_t* n_out);
+size_t so_map_size(so_ctx* ctx);
+
+/* ---- registration (LidarSLAM) --------------------------------------------------------------------- */
+/* replaces: LidarSLAM::Localization(true, predictodom, position, edge, planner, t) -> performLocalizationAndMapping
+ * (LidarSlam.cpp:30-51,107-171), excluding the map insert at its end (call so_map_add_surf with the
+ * transformed scan, as transformAndAddToMap does, LidarSlam.cpp:60-80).
+ * edge cloud: accepted and ignored exactly as the reference does today (featureExtraction emits an empty edge
+ * cloud, featureExtraction.cpp:429-436; processEdgeFeatures returns at LidarSlam.cpp:311). */
+int so_register(so_ctx* ctx,
+                const void* surf_xyzi, size_t n_surf, const void* edge_xyzi, size_t n_edge,
+                size_t stride_bytes, size_t intensity_offset,
+                const double pose_in[7], const so_icp_opts* opts, so_icp_result* out);
+
+/* Batched replay against the frozen map (BASELINE cfg4): n_scans independent Localization() calls.
+ * scans: n_scans consecutive clouds, scan s has n_points[s] points starting at point offset sum(n_points[0..s)).
+ * poses_in: n_scans x 7.  results: n_scans structs.  n_scans <= so_config.max_batch. */
+int so_register_batch(so_ctx* ctx, const void* surf_xyzi, const uint32_t* n_points, size_t n_scans,
+                      size_t stride_bytes, size_t intensity_offset,
+                      const double* poses_in, const so_icp_opts* opts, so_icp_result* results);
+/* Same, inputs already resident in device memory: packed float4 points (d_scans_xyzi), host n_points / poses.
+ * Used for the device-resident throughput figure; results are still copied back to host structs. */
+int so_register_batch_device(so_ctx* ctx, const void* d_scans_xyzi, const uint32_t* n_points, size_t n_scans,
+                             const double* poses_in, const so_icp_opts* opts, so_icp_result* results);
+
+/* Stage-level entry points used by the parity tests (same kernels as so_register). */
+/* processPlannerFeatures at a fixed pose (LidarSlam.cpp:323-344): fills corr[n], hist_obs[9], hist_rej[7]. */
+int so_correspond(so_ctx* ctx, const void* surf_xyzi, size_t n, size_t stride_bytes, size_t intensity_offset,
+                  const double pose[7], int32_t max_surface_features, so_corr* corr, int32_t hist_obs[9], int32_t hist_rej[7]);
+/* Robustified normal equations at `pose` over the correspondences of the last so_correspond call:
+ * H = sum rho' J^T J (row-major 6x6), g = sum rho' J^T r, cost = 1/2 sum rho (lidarOptimization.cpp:55-80 + Ceres corrector). */
+int so_evaluate(so_ctx* ctx, const double pose[7], double H[36], double g[6], double* cost);
+
+/* ---- neighbour search (LocalMap::nearestKSearchSurf, LocalMap.h:481-525) --------------------------- */
+/* k nearest map points IN THE QUERY'S OWN 50 m BLOCK for nq world-frame queries (packed xyz floats, 12 B stride or
+ * given stride).  max_d2 > 0: radius-bounded (neighbours with d2 > max_d2 are not returned); max_d2 <= 0: exact,
+ * unbounded.  idx = map point id or 0xFFFFFFFF, d2 = squared distance with the reference's rounding
+ * (flann/octree.h:95-102).  Ordering: ascending (d2, id).  1 <= k <= 8.
+ * so_knn_device takes device pointers for all three arrays (float4 queries). */
+int so_knn(so_ctx* ctx, const float* q_xyz, size_t nq, size_t stride_bytes, int k, float max_d2, uint32_t* idx, float* d2);
+int so_knn_device(so_ctx* ctx, const void* d_q_xyzw, size_t nq, int k, float max_d2, uint32_t* d_idx, float* d_d2);
+
+/* ---- instrumentation ------------------------------------------------------------------------------ */
+/* Number of this library's kernels launched since the last reset (bench.py gpu_launches). */
+uint64_t so_kernel_launches(so_ctx* ctx, int reset);
+/* Accumulated device time (ms, CUDA events on the context stream) and launch count of a kernel class since the last
+ * reset; classes: 0 correspond (k-NN + fit + first evaluation), 1 evaluate (LM step), 2 k-NN only (so_knn), 3 map build.
+ * Profiling mode serialises kernels; enable only for roofline runs. */
+int so_profile_enable(so_ctx* ctx, int on);
+int so_profile_get(so_ctx* ctx, int kernel_class, double* ms, uint64_t* launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUPERODOM_B200_H */

@@ -572,11 +572,12 @@ static void plane_correspondence(const Map& M, const float* sp, const double pos
     }
     float rotq[6], trq[3];
     for (int a = 0; a < 3; ++a) {
-        const double rc = double(cross[0] * axes[a][0] + cross[1] * axes[a][1] + cross[2] * axes[a][2]);  // stored as double
+        // Eigen's unrolled 3-vector dot associates as a0*b0 + (a1*b1 + a2*b2); result stored in a double member
+        const double rc = double(cross[0] * axes[a][0] + (cross[1] * axes[a][1] + cross[2] * axes[a][2]));
         rotq[2 * a] = float(rc); rotq[2 * a + 1] = float(-rc);
     }
     const float planar_sq = float(planar_2 * planar_2);
-    for (int a = 0; a < 3; ++a) trq[a] = float(double(planar_sq * std::fabs(nf[0] * axes[a][0] + nf[1] * axes[a][1] + nf[2] * axes[a][2])));
+    for (int a = 0; a < 3; ++a) trq[a] = float(double(planar_sq * std::fabs(nf[0] * axes[a][0] + (nf[1] * axes[a][1] + nf[2] * axes[a][2]))));
     // std::sort descending on <= 16 elements == insertion sort == stable: top-2 rot labels, top-1 trans label
     int r0 = 0; for (int i = 1; i < 6; ++i) if (rotq[i] > rotq[r0]) r0 = i;
     int r1 = -1; for (int i = 0; i < 6; ++i) { if (i == r0) continue; if (r1 < 0 || rotq[i] > rotq[r1]) r1 = i; }

@@ -1,0 +1,277 @@
+"""Python host-side binding of the C ABI (include/superodom_b200.h) via ctypes.
+
+Used by the parity tests and bench.py; the reference's own host language is C++, whose binding is the header-only
+shim include/superodom_b200/LidarSlam.hpp.  No torch types cross this boundary: numpy arrays for host buffers,
+raw device pointers (ints) for the *_device entry points.  There is no CPU fallback: `Context()` raises if the
+shared library is missing or no sm_100 device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsuperodom_b200.so")
+MAX_ICP_ITERS = 32
+
+EXPORTS = [
+    "so_create", "so_destroy", "so_last_error", "so_device_available", "so_set_stream",
+    "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
+    "so_map_add_surf", "so_map_counts_5x5", "so_map_download", "so_map_size",
+    "so_register", "so_register_batch", "so_register_batch_device", "so_correspond", "so_evaluate",
+    "so_knn", "so_knn_device", "so_kernel_launches", "so_profile_enable", "so_profile_get",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_map_points", C.c_uint32), ("max_scan_points", C.c_uint32),
+                ("max_batch", C.c_uint32), ("line_res", C.c_float), ("plane_res", C.c_float)]
+
+
+class IcpOpts(C.Structure):
+    _fields_ = [("max_icp_iters", C.c_int32), ("max_surface_features", C.c_int32), ("lm_max_iterations", C.c_int32),
+                ("yaw_ratio", C.c_float), ("skip_map_checks", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("pose", C.c_double * 7), ("pose_opt", C.c_double * 7), ("status", C.c_int32), ("n_iterations", C.c_int32),
+                ("iter_n_surf", C.c_int32 * MAX_ICP_ITERS), ("iter_n_edge", C.c_int32 * MAX_ICP_ITERS),
+                ("iter_dtrans", C.c_double * MAX_ICP_ITERS), ("iter_drot", C.c_double * MAX_ICP_ITERS),
+                ("iter_lm_steps", C.c_int32 * MAX_ICP_ITERS), ("iter_lm_successful", C.c_int32 * MAX_ICP_ITERS),
+                ("iter_lm_termination", C.c_int32 * MAX_ICP_ITERS), ("iter_cost", C.c_double * MAX_ICP_ITERS),
+                ("hist_obs", C.c_int32 * 9), ("hist_reject_plane", C.c_int32 * 7), ("hist_reject_line", C.c_int32 * 7),
+                ("cov", C.c_double * 36),
+                ("pos_err", C.c_double), ("pos_dir", C.c_double * 3), ("pos_inv_cond", C.c_double),
+                ("ori_err_deg", C.c_double), ("ori_dir", C.c_double * 3), ("ori_inv_cond", C.c_double),
+                ("total_translation", C.c_double), ("total_rotation", C.c_double),
+                ("translation_from_last", C.c_double), ("rotation_from_last", C.c_double),
+                ("map_surf_5x5", C.c_int32), ("map_edge_5x5", C.c_int32), ("scan_surf_num", C.c_int32), ("scan_edge_num", C.c_int32),
+                ("pos_in_localmap", C.c_int32 * 3), ("pad_", C.c_int32),
+                ("time_ms", C.c_double), ("time_total_ms", C.c_double)]
+
+
+CORR_DTYPE = np.dtype([("n", "<f8", 3), ("d", "<f8"), ("w", "<f8"), ("nn", "<u4", 5), ("nn_d2", "<f4", 5),
+                       ("status", "u1"), ("obs", "u1", 3), ("pad_", "u1", 4)], align=True)
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree shared library and declare signatures.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} missing: run `python -m superodom_b200.build` (no CPU fallback exists)")
+    L = C.CDLL(LIB_PATH)
+    L.so_create.restype = C.c_void_p
+    L.so_create.argtypes = [C.POINTER(Config)]
+    L.so_destroy.argtypes = [C.c_void_p]
+    L.so_last_error.restype = C.c_char_p
+    L.so_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.so_map_set_resolution.argtypes = [C.c_void_p, C.c_float, C.c_float]
+    L.so_map_set_origin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_map_get_origin.argtypes = [C.c_void_p, C.c_void_p]
+    L.so_map_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_map_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
+    L.so_map_add_surf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
+    L.so_map_counts_5x5.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_map_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.so_map_size.restype = C.c_size_t
+    L.so_map_size.argtypes = [C.c_void_p]
+    L.so_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                              C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_register_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_register_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_correspond.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int32,
+                                C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    L.so_knn_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    L.so_kernel_launches.restype = C.c_uint64
+    L.so_kernel_launches.argtypes = [C.c_void_p, C.c_int]
+    L.so_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.so_profile_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    _lib = L
+    return L
+
+
+def device_available() -> bool:
+    return bool(load_library().so_device_available())
+
+
+class SuperOdomError(RuntimeError):
+    pass
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One registration context == one LidarSLAM + LocalMap instance on one GPU."""
+
+    def __init__(self, device: int = 0, max_map_points: int = 4 << 20, max_scan_points: int = 262144, max_batch: int = 1,
+                 plane_res: float = 0.4, line_res: float = 0.2):
+        self.L = load_library()
+        cfg = Config(device, max_map_points, max_scan_points, max_batch, line_res, plane_res)
+        h = self.L.so_create(C.byref(cfg))
+        if not h:
+            raise SuperOdomError("so_create failed: " + self.L.so_last_error().decode())
+        self.h = C.c_void_p(h)
+        self.max_batch = max_batch
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.so_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc < 0:
+            raise SuperOdomError(f"{what} failed ({rc}): " + self.L.so_last_error().decode())
+        return rc
+
+    # ---- stream / instrumentation
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._chk(self.L.so_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)), "so_set_stream")
+
+    def kernel_launches(self, reset: bool = False) -> int:
+        return int(self.L.so_kernel_launches(self.h, int(reset)))
+
+    def profile_enable(self, on: bool):
+        self._chk(self.L.so_profile_enable(self.h, int(on)), "so_profile_enable")
+
+    def profile_get(self, cls: int, reset: bool = False):
+        ms = C.c_double()
+        n = C.c_uint64()
+        self._chk(self.L.so_profile_get(self.h, cls, C.byref(ms), C.byref(n), int(reset)), "so_profile_get")
+        return ms.value, n.value
+
+    # ---- map
+    def map_set_resolution(self, line_res: float, plane_res: float):
+        self._chk(self.L.so_map_set_resolution(self.h, line_res, plane_res), "so_map_set_resolution")
+
+    def map_set_points(self, xyzi: np.ndarray):
+        a = np.ascontiguousarray(xyzi, dtype=np.float32)
+        assert a.ndim == 2 and a.shape[1] >= 3
+        stride = a.shape[1] * 4
+        ioff = 12 if a.shape[1] >= 4 else stride
+        self._chk(self.L.so_map_set_points(self.h, _p(a), a.shape[0], stride, ioff), "so_map_set_points")
+
+    def map_add_surf(self, xyzi: np.ndarray):
+        a = np.ascontiguousarray(xyzi, dtype=np.float32)
+        stride = a.shape[1] * 4
+        self._chk(self.L.so_map_add_surf(self.h, _p(a), a.shape[0], stride, 12 if a.shape[1] >= 4 else stride), "so_map_add_surf")
+
+    def map_set_origin(self, t):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        o = np.zeros(3, np.int32)
+        self._chk(self.L.so_map_set_origin(self.h, _p(t), _p(o)), "so_map_set_origin")
+        return o
+
+    def map_origin(self):
+        o = np.zeros(3, np.int32)
+        self._chk(self.L.so_map_get_origin(self.h, _p(o)), "so_map_get_origin")
+        return o
+
+    def map_shift(self, t):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        o = np.zeros(3, np.int32)
+        self._chk(self.L.so_map_shift(self.h, _p(t), _p(o)), "so_map_shift")
+        return o
+
+    def map_counts_5x5(self, ijk) -> int:
+        ijk = np.ascontiguousarray(ijk, dtype=np.int32)
+        ne, ns = C.c_int32(), C.c_int32()
+        self._chk(self.L.so_map_counts_5x5(self.h, _p(ijk), C.byref(ne), C.byref(ns)), "so_map_counts_5x5")
+        return ns.value
+
+    def map_size(self) -> int:
+        return int(self.L.so_map_size(self.h))
+
+    def map_download(self, mode: int = 0, ijk=None) -> np.ndarray:
+        n = C.c_size_t()
+        cap = self.map_size()
+        out = np.zeros((max(cap, 1), 4), np.float32)
+        ij = np.ascontiguousarray(ijk if ijk is not None else [0, 0, 0], dtype=np.int32)
+        self._chk(self.L.so_map_download(self.h, mode, _p(ij), _p(out), cap, C.byref(n)), "so_map_download")
+        return out[: n.value]
+
+    # ---- registration
+    @staticmethod
+    def _opts(max_icp_iters, max_surface_features=0, lm_max_iterations=4, yaw_ratio=0.0, skip_map_checks=False):
+        return IcpOpts(max_icp_iters, max_surface_features, lm_max_iterations, yaw_ratio, int(skip_map_checks), (C.c_int32 * 3)())
+
+    def register(self, scan_xyzi: np.ndarray, pose7, max_icp_iters: int, max_surface_features: int = 0, **kw) -> IcpResult:
+        s = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        o = self._opts(max_icp_iters, max_surface_features, **kw)
+        r = IcpResult()
+        stride = s.shape[1] * 4
+        self._chk(self.L.so_register(self.h, _p(s), s.shape[0], None, 0, stride, 12 if s.shape[1] >= 4 else stride,
+                                     _p(pose), C.byref(o), C.byref(r)), "so_register")
+        return r
+
+    def register_batch(self, scans_xyzi: np.ndarray, n_points, poses, max_icp_iters: int, max_surface_features: int = 0, **kw):
+        """scans_xyzi: float32 [sum(n_points), 4] host array (pinned or pageable)."""
+        n_points = np.ascontiguousarray(n_points, dtype=np.uint32)
+        poses = np.ascontiguousarray(poses, dtype=np.float64)
+        ns = len(n_points)
+        o = self._opts(max_icp_iters, max_surface_features, **kw)
+        res = (IcpResult * ns)()
+        assert scans_xyzi.dtype == np.float32 and scans_xyzi.flags.c_contiguous
+        stride = scans_xyzi.shape[1] * 4
+        self._chk(self.L.so_register_batch(self.h, _p(scans_xyzi), _p(n_points), ns, stride, 12, _p(poses), C.byref(o), res),
+                  "so_register_batch")
+        return res
+
+    def register_batch_device(self, d_scans_ptr: int, n_points, poses, max_icp_iters: int, max_surface_features: int = 0, **kw):
+        n_points = np.ascontiguousarray(n_points, dtype=np.uint32)
+        poses = np.ascontiguousarray(poses, dtype=np.float64)
+        ns = len(n_points)
+        o = self._opts(max_icp_iters, max_surface_features, **kw)
+        res = (IcpResult * ns)()
+        self._chk(self.L.so_register_batch_device(self.h, C.c_void_p(d_scans_ptr), _p(n_points), ns, _p(poses), C.byref(o), res),
+                  "so_register_batch_device")
+        return res
+
+    def correspond(self, scan_xyzi: np.ndarray, pose7, max_surface_features: int = 0):
+        s = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        corr = np.zeros(s.shape[0], CORR_DTYPE)
+        ho = np.zeros(9, np.int32)
+        hr = np.zeros(7, np.int32)
+        stride = s.shape[1] * 4
+        self._chk(self.L.so_correspond(self.h, _p(s), s.shape[0], stride, 12 if s.shape[1] >= 4 else stride, _p(pose),
+                                       max_surface_features, _p(corr), _p(ho), _p(hr)), "so_correspond")
+        return corr, ho, hr
+
+    def evaluate(self, pose7):
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        H = np.zeros((6, 6))
+        g = np.zeros(6)
+        cost = C.c_double()
+        self._chk(self.L.so_evaluate(self.h, _p(pose), _p(H), _p(g), C.byref(cost)), "so_evaluate")
+        return H, g, cost.value
+
+    # ---- k-NN
+    def knn(self, q_xyz: np.ndarray, k: int = 5, max_d2: float = 0.0):
+        q = np.ascontiguousarray(q_xyz, dtype=np.float32)
+        nq = q.shape[0]
+        idx = np.empty((nq, k), np.uint32)
+        d2 = np.empty((nq, k), np.float32)
+        self._chk(self.L.so_knn(self.h, _p(q), nq, q.shape[1] * 4, k, C.c_float(max_d2), _p(idx), _p(d2)), "so_knn")
+        return idx, d2
+
+    def knn_device(self, d_q_ptr: int, nq: int, k: int, max_d2: float, d_idx_ptr: int, d_d2_ptr: int):
+        self._chk(self.L.so_knn_device(self.h, C.c_void_p(d_q_ptr), nq, k, C.c_float(max_d2), C.c_void_p(d_idx_ptr),
+                                       C.c_void_p(d_d2_ptr)), "so_knn_device")

@@ -1,0 +1,633 @@
+// so_api.cu -- the C ABI (include/superodom_b200.h): context, uploads, the CUDA-graph ICP schedule, results.
+// Host code above the kernels stays C++ (the reference's host language); no torch types anywhere.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "so_ctx.cuh"
+
+namespace so {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+
+static int fail(int code, const std::string& msg) { set_error(msg); return code; }
+
+// ---------------------------------------------------------------------------------------------- host pose helpers
+// tf2 Matrix3x3(q).getRPY + Quaternion::setRPY round trip: LidarSLAM::MannualYawCorrection (LidarSlam.cpp:891-913)
+static void manual_yaw_correction(const double last[7], double T[7], double yaw_ratio) {
+    double tn, rn;
+    rel_motion(last, T, &tn, &rn);
+    const float translation_norm = float(tn);
+    const double x = T[3], y = T[4], z = T[5], w = T[6];
+    const double d = x * x + y * y + z * z + w * w, s = 2.0 / d;
+    const double xs = x * s, ys = y * s, zs = z * s, wx = w * xs, wy = w * ys, wz = w * zs;
+    const double xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+    const double m00 = 1.0 - (yy + zz), m01 = xy - wz, m02 = xz + wy, m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+    double roll, pitch, yaw;
+    if (std::fabs(m20) >= 1) {
+        yaw = 0;
+        if (m20 < 0) { pitch = M_PI / 2.0; roll = std::atan2(m01, m02); }
+        else { pitch = -M_PI / 2.0; roll = std::atan2(-m01, -m02); }
+    } else {
+        pitch = -std::asin(m20);
+        roll = std::atan2(m21 / std::cos(pitch), m22 / std::cos(pitch));
+        yaw = std::atan2(m10 / std::cos(pitch), m00 / std::cos(pitch));
+    }
+    const double cyaw = yaw + double(translation_norm) * yaw_ratio * M_PI / 180;
+    const double hy = cyaw * 0.5, hp = pitch * 0.5, hr = roll * 0.5;
+    const double cy = std::cos(hy), sy = std::sin(hy), cp = std::cos(hp), sp = std::sin(hp), cr = std::cos(hr), sr = std::sin(hr);
+    double q[4] = {sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy};
+    const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; ++i) T[3 + i] = q[i] / n;
+}
+
+static inline int block_coord_h(double v, int origin) { int c = int(v / kBlock); if (v < 0) c--; return c + origin; }
+
+// LocalMap::get5x5LocalMapFeatureSize (LocalMap.h:291-318) on the host mirror of the block counts
+static int counts_5x5(const Ctx* c, const int32_t ijk[3]) {
+    int n = 0;
+    for (int i = ijk[0] - 2; i <= ijk[0] + 2; ++i)
+        for (int j = ijk[1] - 2; j <= ijk[1] + 2; ++j)
+            for (int k = ijk[2] - 1; k <= ijk[2] + 1; ++k)
+                if (i >= 0 && i < kW && j >= 0 && j < kH && k >= 0 && k < kD) n += c->h_block_count[i + kW * j + kW * kH * k];
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------- allocation
+static int ctx_alloc(Ctx* c) {
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    SO_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SO_CUDA_TRY(cudaEventCreate(&c->ev0)); SO_CUDA_TRY(cudaEventCreate(&c->ev1));
+    SO_CUDA_TRY(cudaEventCreate(&c->evp0)); SO_CUDA_TRY(cudaEventCreate(&c->evp1));
+    int rc = map_alloc(c);
+    if (rc) return rc;
+    c->max_batch = c->cfg.max_batch;
+    c->scan_cap = size_t(c->cfg.max_scan_points) * c->max_batch;
+    c->grid_x_cap = (c->cfg.max_scan_points + kThreads - 1) / kThreads;
+    SO_CUDA_TRY(cudaMalloc(&c->d_scan, c->scan_cap * sizeof(float4)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_offset, c->max_batch * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_state, c->max_batch * sizeof(IcpState)));
+    SO_CUDA_TRY(cudaMallocHost(&c->h_state, c->max_batch * sizeof(IcpState)));
+    SO_CUDA_TRY(cudaMallocHost(&c->h_offset, c->max_batch * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_partials, size_t(c->max_batch) * c->grid_x_cap * kAcc * sizeof(double)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_counters, c->max_batch * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_hist, c->max_batch * 16 * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMemset(c->d_counters, 0, c->max_batch * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMemset(c->d_hist, 0, c->max_batch * 16 * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->corr.nd, c->scan_cap * sizeof(double4)));
+    SO_CUDA_TRY(cudaMalloc(&c->corr.w, c->scan_cap * sizeof(double)));
+    SO_CUDA_TRY(cudaMalloc(&c->corr.flags, c->scan_cap * sizeof(uchar4)));
+    SO_CUDA_TRY(cudaMalloc(&c->corr.nn, size_t(c->cfg.max_scan_points) * 5 * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->corr.nn_d2, size_t(c->cfg.max_scan_points) * 5 * sizeof(float)));
+    return SO_OK;
+}
+
+static void ctx_free(Ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->graph) cudaGraphExecDestroy(c->graph);
+    map_free(c);
+    cudaFree(c->d_scan); cudaFree(c->d_offset); cudaFree(c->d_state); cudaFreeHost(c->h_state); cudaFreeHost(c->h_offset);
+    cudaFree(c->d_partials); cudaFree(c->d_counters); cudaFree(c->d_hist);
+    cudaFree(c->corr.nd); cudaFree(c->corr.w); cudaFree(c->corr.flags); cudaFree(c->corr.nn); cudaFree(c->corr.nn_d2);
+    cudaFree(c->d_q); cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evp0) cudaEventDestroy(c->evp0);
+    if (c->evp1) cudaEventDestroy(c->evp1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int ensure_stage(Ctx* c, size_t bytes) {
+    if (bytes <= c->h_stage_bytes) return SO_OK;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->h_stage_bytes = 0;
+    SO_CUDA_TRY(cudaMallocHost(&c->h_stage, bytes));
+    c->h_stage_bytes = bytes;
+    return SO_OK;
+}
+
+// Copy a strided host cloud into device float4 {x,y,z,intensity}.  Packed float4 input goes straight through.
+static int upload_cloud(Ctx* c, const void* src, size_t n, size_t stride, size_t ioff, float4* dst) {
+    if (n == 0) return SO_OK;
+    if (stride == 16 && ioff == 12) {
+        SO_CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        return SO_OK;
+    }
+    int rc = ensure_stage(c, n * sizeof(float4));
+    if (rc) return rc;
+    SO_CUDA_TRY(cudaStreamSynchronize(c->stream));     // staging buffer reuse
+    float4* h = static_cast<float4*>(c->h_stage);
+    const unsigned char* p = static_cast<const unsigned char*>(src);
+    for (size_t i = 0; i < n; ++i, p += stride) {
+        float xyz[3], it = 0.f;
+        std::memcpy(xyz, p, 12);
+        if (ioff + 4 <= stride) std::memcpy(&it, p + ioff, 4);
+        h[i] = make_float4(xyz[0], xyz[1], xyz[2], it);
+    }
+    SO_CUDA_TRY(cudaMemcpyAsync(dst, h, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    return SO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- ICP schedule
+static BatchView batch_view(const Ctx* c, const float4* scan) {
+    BatchView bv;
+    bv.scan = scan; bv.offset = c->d_offset; bv.st = c->d_state; bv.partials = c->d_partials; bv.counters = c->d_counters; bv.hist = c->d_hist;
+    const double a = double(std::sqrt(3 * c->plane_res));     // float sqrt of a float product (LidarSlam.cpp:271)
+    bv.tukey_a2 = a * a;
+    return bv;
+}
+
+static void timed_launch_begin(Ctx* c) { if (c->profiling) cudaEventRecord(c->evp0, c->stream); }
+static void timed_launch_end(Ctx* c, int cls) {
+    c->launches++;
+    if (!c->profiling) return;
+    cudaEventRecord(c->evp1, c->stream);
+    cudaEventSynchronize(c->evp1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->evp0, c->evp1);
+    c->prof[cls].ms += ms; c->prof[cls].launches++;
+}
+
+// [k_correspond, k_evaluate x lm] x icp iterations; every kernel exits at once when its scan is not in the
+// matching phase, so the fixed schedule follows whatever path the device-side state machine takes.
+static int run_schedule(Ctx* c, const float4* d_scan, uint32_t grid_x, uint32_t n_scans, int iters, int lm, bool with_nn) {
+    const MapView mv = map_view(c);
+    const BatchView bv = batch_view(c, d_scan);
+    CorrBuf cb = c->corr;
+    if (!with_nn) { cb.nn = nullptr; cb.nn_d2 = nullptr; }
+    const uint64_t kernels = uint64_t(iters) * (1 + lm);
+    if (c->profiling || with_nn) {
+        // profiling mode: one launch at a time, timed with events, and only launches that have work (the host peeks
+        // at the phases) so that the per-class average is the duration of a kernel that actually ran
+        std::vector<IcpState> peek(n_scans);
+        auto any_in = [&](int ph) -> bool {
+            cudaMemcpyAsync(peek.data(), c->d_state, n_scans * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream);
+            cudaStreamSynchronize(c->stream);
+            for (uint32_t s = 0; s < n_scans; ++s) if (peek[s].phase == ph) return true;
+            return false;
+        };
+        for (int it = 0; it < iters; ++it) {
+            if (any_in(PH_CORR)) { timed_launch_begin(c); launch_correspond(mv, bv, cb, grid_x, n_scans, c->stream); timed_launch_end(c, 0); }
+            for (int k = 0; k < lm; ++k)
+                if (any_in(PH_EVAL)) { timed_launch_begin(c); launch_evaluate(bv, cb, grid_x, n_scans, c->stream); timed_launch_end(c, 1); }
+        }
+        SO_CUDA_TRY(cudaGetLastError());
+        return SO_OK;
+    }
+    const bool hit = c->graph && c->graph_grid_x == grid_x && c->graph_n_scans == n_scans && c->graph_iters == iters && c->graph_lm == lm &&
+                     c->graph_scan_ptr == d_scan && c->graph_map_epoch == c->map_epoch;
+    if (!hit) {
+        if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        SO_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        for (int it = 0; it < iters; ++it) {
+            launch_correspond(mv, bv, cb, grid_x, n_scans, c->stream);
+            for (int k = 0; k < lm; ++k) launch_evaluate(bv, cb, grid_x, n_scans, c->stream);
+        }
+        SO_CUDA_TRY(cudaStreamEndCapture(c->stream, &g));
+        cudaError_t e = cudaGraphInstantiate(&c->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(SO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        c->graph_grid_x = grid_x; c->graph_n_scans = n_scans; c->graph_iters = iters; c->graph_lm = lm; c->graph_scan_ptr = d_scan;
+        c->graph_map_epoch = c->map_epoch;
+    }
+    SO_CUDA_TRY(cudaGraphLaunch(c->graph, c->stream));
+    c->launches += kernels;
+    return SO_OK;
+}
+
+static void init_state(IcpState& s, const double pose[7], uint32_t n, const so_icp_opts& o) {
+    std::memset(&s, 0, sizeof(s));
+    std::memcpy(s.x0, pose, 7 * sizeof(double));
+    std::memcpy(s.x, pose, 7 * sizeof(double));
+    std::memcpy(s.cand, pose, 7 * sizeof(double));
+    s.n_points = int32_t(n);
+    s.max_icp_iters = o.max_icp_iters;
+    s.lm_max_iterations = o.lm_max_iterations;
+    // calculateSamplingRate (LidarSlam.cpp:346-351)
+    s.sampling_rate = (o.max_surface_features > 0 && n > uint32_t(o.max_surface_features)) ? 1.0 * o.max_surface_features / double(n) : -1.0;
+    s.phase = PH_CORR;
+}
+
+static void fill_result(const Ctx* c, const IcpState& s, const double pose_in[7], const so_icp_opts& o, so_icp_result* r) {
+    r->n_iterations = s.n_iterations;
+    for (int i = 0; i < SO_MAX_ICP_ITERS; ++i) {
+        r->iter_n_surf[i] = s.iter_n_surf[i]; r->iter_n_edge[i] = 0; r->iter_dtrans[i] = s.iter_dtrans[i]; r->iter_drot[i] = s.iter_drot[i];
+        r->iter_lm_steps[i] = s.iter_lm_steps[i]; r->iter_lm_successful[i] = s.iter_lm_successful[i];
+        r->iter_lm_termination[i] = s.iter_lm_termination[i]; r->iter_cost[i] = s.iter_cost[i];
+    }
+    std::memcpy(r->hist_obs, s.hist_obs, sizeof(r->hist_obs));
+    std::memcpy(r->hist_reject_plane, s.hist_rej, sizeof(r->hist_reject_plane));
+    std::memset(r->hist_reject_line, 0, sizeof(r->hist_reject_line));
+    std::memcpy(r->cov, s.cov, sizeof(r->cov));
+    r->pos_err = s.pos_err; r->pos_inv_cond = s.pos_inv_cond; r->ori_err_deg = s.ori_err_deg; r->ori_inv_cond = s.ori_inv_cond;
+    for (int i = 0; i < 3; ++i) { r->pos_dir[i] = s.pos_dir[i]; r->ori_dir[i] = s.ori_dir[i]; }
+    if (s.status) r->status = s.status;
+    double T[7];
+    std::memcpy(T, s.x, sizeof(T));
+    std::memcpy(r->pose_opt, T, sizeof(T));
+    // performPostOptimizationProcessing (LidarSlam.cpp:155-171): last_T_w_lidar == T_w_initial_guess == prior (:53-57)
+    manual_yaw_correction(pose_in, T, double(o.yaw_ratio));
+    std::memcpy(r->pose, T, sizeof(T));
+    rel_motion(pose_in, T, &r->total_translation, &r->total_rotation);           // updateOptimizationStats (:198-210)
+    r->translation_from_last = r->total_translation; r->rotation_from_last = r->total_rotation;
+    (void)c;
+}
+
+// Shared tail of so_register / so_register_batch*: scans are on the device at d_scan (packed, back to back).
+static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points, size_t n_scans, const double* poses,
+                         const so_icp_opts* opts_in, so_icp_result* results, bool allow_shift) {
+    so_icp_opts o = *opts_in;
+    if (o.lm_max_iterations <= 0) o.lm_max_iterations = 4;
+    if (o.max_icp_iters <= 0 || o.max_icp_iters > SO_MAX_ICP_ITERS) return fail(SO_ERR_ARG, "max_icp_iters must be in [1,32]");
+    if (o.lm_max_iterations > 16) return fail(SO_ERR_ARG, "lm_max_iterations must be <= 16");
+    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
+    uint32_t max_n = 0, off = 0;
+    bool any = false;
+    for (size_t s = 0; s < n_scans; ++s) {
+        so_icp_result* r = results + s;
+        std::memset(r, 0, sizeof(*r));
+        const double* pose = poses + 7 * s;
+        std::memcpy(r->pose, pose, 7 * sizeof(double));
+        std::memcpy(r->pose_opt, pose, 7 * sizeof(double));
+        r->scan_surf_num = int32_t(n_points[s]);
+        // prepareOptimizationState (LidarSlam.cpp:361-369)
+        int32_t ijk[3];
+        if (allow_shift && !o.skip_map_checks) { int rc = so_map_shift(reinterpret_cast<so_ctx*>(c), pose, ijk); if (rc < 0) return rc; }
+        else for (int a = 0; a < 3; ++a) ijk[a] = block_coord_h(pose[a] + kHalfBlock, c->origin[a]);
+        for (int a = 0; a < 3; ++a) r->pos_in_localmap[a] = ijk[a];
+        r->map_surf_5x5 = counts_5x5(c, ijk);
+        init_state(c->h_state[s], pose, n_points[s], o);
+        c->h_offset[s] = off;
+        off += n_points[s];
+        if (!o.skip_map_checks && !(r->map_surf_5x5 > 50)) {       // hasEnoughFeatures (:379-381): pose stays the prior
+            r->status = SO_STATUS_NOT_ENOUGH_FEATURES;
+            c->h_state[s].phase = PH_DONE;
+        } else if (n_points[s] == 0) {
+            r->status = SO_STATUS_NO_CORRESPONDENCES;
+            c->h_state[s].phase = PH_DONE;
+        } else { any = true; max_n = std::max(max_n, n_points[s]); }
+    }
+    if (any) {
+        SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, n_scans * sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
+        SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, n_scans * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        const uint32_t grid_x = (max_n + kThreads - 1) / kThreads;
+        SO_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+        int rc = run_schedule(c, d_scan, grid_x, uint32_t(n_scans), o.max_icp_iters, o.lm_max_iterations, false);
+        if (rc) return rc;
+        SO_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+        SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, n_scans * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
+        SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        for (size_t s = 0; s < n_scans; ++s) {
+            if (results[s].status == SO_STATUS_NOT_ENOUGH_FEATURES || n_points[s] == 0) continue;
+            fill_result(c, c->h_state[s], poses + 7 * s, o, results + s);
+            results[s].time_ms = double(ms);
+        }
+    }
+    return SO_OK;
+}
+
+}  // namespace so
+
+// =================================================================================================== C ABI
+using namespace so;
+
+extern "C" {
+
+const char* so_last_error(void) { return g_err.c_str(); }
+
+int so_device_available(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return p.major == 10 ? 1 : 0;
+}
+
+so_ctx* so_create(const so_config* cfg_in) {
+    so_config cfg{};
+    if (cfg_in) cfg = *cfg_in;
+    if (cfg.max_map_points == 0) cfg.max_map_points = 4u << 20;
+    if (cfg.max_scan_points == 0) cfg.max_scan_points = 262144;
+    if (cfg.max_batch == 0) cfg.max_batch = 1;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); set_error("no CUDA device: this library has no CPU fallback"); return nullptr; }
+    if (cfg.device < 0 || cfg.device >= n) { set_error("bad device ordinal"); return nullptr; }
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, cfg.device);
+    if (p.major != 10) { set_error("device is not compute capability 10.x (kernels are built for sm_100a only)"); return nullptr; }
+    Ctx* c = new Ctx();
+    c->device = cfg.device;
+    c->cfg = cfg;
+    if (cfg.plane_res > 0) c->plane_res = cfg.plane_res;
+    if (cfg.line_res > 0) c->line_res = cfg.line_res;
+    if (ctx_alloc(c) != SO_OK) { ctx_free(c); return nullptr; }
+    return reinterpret_cast<so_ctx*>(c);
+}
+
+void so_destroy(so_ctx* ctx) { ctx_free(reinterpret_cast<Ctx*>(ctx)); }
+
+int so_set_stream(so_ctx* ctx, void* cuda_stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return fail(SO_ERR_ARG, "null ctx");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+    if (cuda_stream) {
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        c->stream = static_cast<cudaStream_t>(cuda_stream); c->own_stream = false;
+    } else if (!c->own_stream) {
+        SO_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true;
+    }
+    return SO_OK;
+}
+
+// ---- map -------------------------------------------------------------------------------------------------------
+int so_map_set_resolution(so_ctx* ctx, float line_res, float plane_res) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !(plane_res > 0)) return fail(SO_ERR_ARG, "bad args");
+    if (line_res > 0) c->line_res = line_res;
+    if (plane_res != c->plane_res) {
+        const int nb_old = c->nb;
+        c->plane_res = plane_res;
+        c->map_epoch++;                                     // bound_d2 / plane_res live in the captured MapView
+        if (map_cells_per_block(plane_res) != nb_old) c->map_dirty = true;
+    }
+    return SO_OK;
+}
+
+int so_map_set_origin(so_ctx* ctx, const double t[3], int32_t out_origin[3]) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !t) return fail(SO_ERR_ARG, "bad args");
+    for (int a = 0; a < 3; ++a) {                           // LocalMap::setOrigin (LocalMap.h:146-164)
+        int cc = int((t[a] + kHalfBlock) / kBlock);
+        if (t[a] + kHalfBlock < 0) cc--;
+        c->origin[a] = -cc;
+        if (out_origin) out_origin[a] = c->origin[a];
+    }
+    c->map_dirty = true;
+    return SO_OK;
+}
+
+int so_map_get_origin(so_ctx* ctx, int32_t out[3]) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !out) return fail(SO_ERR_ARG, "bad args");
+    for (int a = 0; a < 3; ++a) out[a] = c->origin[a];
+    return SO_OK;
+}
+
+int so_map_shift(so_ctx* ctx, const double t[3], int32_t out_ijk[3]) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !t || !out_ijk) return fail(SO_ERR_ARG, "bad args");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    int cc[3], shift[3] = {0, 0, 0};
+    const int dims[3] = {kW, kH, kD};
+    for (int a = 0; a < 3; ++a) {                           // LocalMap::shiftMap (LocalMap.h:169-287)
+        cc[a] = block_coord_h(t[a] + kHalfBlock, c->origin[a]);
+        while (cc[a] < 3) { cc[a]++; shift[a]++; }
+        while (cc[a] >= dims[a] - 3) { cc[a]--; shift[a]--; }
+    }
+    if (shift[0] || shift[1] || shift[2]) {
+        for (int a = 0; a < 3; ++a) c->origin[a] += shift[a];
+        c->map_dirty = true;
+    }
+    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
+    for (int a = 0; a < 3; ++a) out_ijk[a] = cc[a];
+    return SO_OK;
+}
+
+int so_map_set_points(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || (!xyzi && n) || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (n > c->cfg.max_map_points) return fail(SO_ERR_CAPACITY, "map larger than so_config.max_map_points");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    int rc = upload_cloud(c, xyzi, n, stride, ioff, c->d_map_xyzi);
+    if (rc) return rc;
+    c->map_n = uint32_t(n);
+    return map_rebuild(c);
+}
+
+int so_map_add_surf(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff) {
+    (void)ctx; (void)xyzi; (void)n; (void)stride; (void)ioff;
+    return fail(SO_ERR_ARG, "so_map_add_surf: voxel-filter insert not built yet (SURVEY 8f row 1)");
+}
+
+int so_map_counts_5x5(so_ctx* ctx, const int32_t ijk[3], int32_t* n_edge, int32_t* n_surf) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !ijk) return fail(SO_ERR_ARG, "bad args");
+    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
+    if (n_edge) *n_edge = 0;
+    if (n_surf) *n_surf = counts_5x5(c, ijk);
+    return SO_OK;
+}
+
+size_t so_map_size(so_ctx* ctx) { Ctx* c = reinterpret_cast<Ctx*>(ctx); return c ? c->map_n : 0; }
+
+int so_map_download(so_ctx* ctx, int mode, const int32_t ijk[3], float* out, size_t cap, size_t* n_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !n_out) return fail(SO_ERR_ARG, "bad args");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
+    // raw order is (block, point id) already for set_points / add_surf output, so mode 0 is a plain copy
+    std::vector<float4> h(c->map_n);
+    if (c->map_n) SO_CUDA_TRY(cudaMemcpy(h.data(), c->d_map_xyzi, size_t(c->map_n) * sizeof(float4), cudaMemcpyDeviceToHost));
+    size_t k = 0;
+    for (uint32_t i = 0; i < c->map_n; ++i) {
+        if (mode == 1) {
+            if (!ijk) return fail(SO_ERR_ARG, "mode 1 needs ijk");
+            int g[3]; const float q[3] = {h[i].x, h[i].y, h[i].z};
+            for (int a = 0; a < 3; ++a) g[a] = block_coord_h(double(q[a]) + kHalfBlock, c->origin[a]);
+            if (std::abs(g[0] - ijk[0]) > 2 || std::abs(g[1] - ijk[1]) > 2 || std::abs(g[2] - ijk[2]) > 1) continue;
+        }
+        if (out && k < cap) std::memcpy(out + 4 * k, &h[i], sizeof(float4));
+        ++k;
+    }
+    *n_out = k;
+    return SO_OK;
+}
+
+// ---- registration ----------------------------------------------------------------------------------------------
+int so_register(so_ctx* ctx, const void* surf, size_t n_surf, const void* edge, size_t n_edge, size_t stride, size_t ioff,
+                const double pose_in[7], const so_icp_opts* opts, so_icp_result* out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    (void)edge;
+    if (!c || !pose_in || !opts || !out || (!surf && n_surf) || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (n_surf > c->cfg.max_scan_points) return fail(SO_ERR_CAPACITY, "scan larger than so_config.max_scan_points");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = upload_cloud(c, surf, n_surf, stride, ioff, c->d_scan);
+    if (rc) return rc;
+    const uint32_t n = uint32_t(n_surf);
+    rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true);
+    if (rc) return rc;
+    out->scan_edge_num = int32_t(n_edge);
+    out->time_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return out->status;
+}
+
+int so_register_batch(so_ctx* ctx, const void* surf, const uint32_t* n_points, size_t n_scans, size_t stride, size_t ioff,
+                      const double* poses_in, const so_icp_opts* opts, so_icp_result* results) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !surf || !n_points || !poses_in || !opts || !results || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (n_scans == 0 || n_scans > c->max_batch) return fail(SO_ERR_CAPACITY, "n_scans exceeds so_config.max_batch");
+    size_t total = 0;
+    for (size_t s = 0; s < n_scans; ++s) { if (n_points[s] > c->cfg.max_scan_points) return fail(SO_ERR_CAPACITY, "scan too large"); total += n_points[s]; }
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = upload_cloud(c, surf, total, stride, ioff, c->d_scan);
+    if (rc) return rc;
+    rc = register_core(c, c->d_scan, n_points, n_scans, poses_in, opts, results, false);
+    if (rc) return rc;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (size_t s = 0; s < n_scans; ++s) results[s].time_total_ms = ms;
+    return SO_OK;
+}
+
+int so_register_batch_device(so_ctx* ctx, const void* d_scans, const uint32_t* n_points, size_t n_scans, const double* poses_in,
+                             const so_icp_opts* opts, so_icp_result* results) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !d_scans || !n_points || !poses_in || !opts || !results) return fail(SO_ERR_ARG, "bad args");
+    if (n_scans == 0 || n_scans > c->max_batch) return fail(SO_ERR_CAPACITY, "n_scans exceeds so_config.max_batch");
+    for (size_t s = 0; s < n_scans; ++s) if (n_points[s] > c->cfg.max_scan_points) return fail(SO_ERR_CAPACITY, "scan too large");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = register_core(c, static_cast<const float4*>(d_scans), n_points, n_scans, poses_in, opts, results, false);
+    if (rc) return rc;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (size_t s = 0; s < n_scans; ++s) results[s].time_total_ms = ms;
+    return SO_OK;
+}
+
+// ---- stage-level entry points ------------------------------------------------------------------------------------
+int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t ioff, const double pose[7], int32_t max_surface_features,
+                  so_corr* corr, int32_t hist_obs[9], int32_t hist_rej[7]) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !surf || !pose || !corr || n == 0 || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (n > c->cfg.max_scan_points) return fail(SO_ERR_CAPACITY, "scan larger than so_config.max_scan_points");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
+    int rc = upload_cloud(c, surf, n, stride, ioff, c->d_scan);
+    if (rc) return rc;
+    so_icp_opts o{}; o.max_icp_iters = -1; o.lm_max_iterations = 4; o.max_surface_features = max_surface_features;
+    init_state(c->h_state[0], pose, uint32_t(n), o);
+    c->h_offset[0] = 0;
+    SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    const uint32_t grid_x = (uint32_t(n) + kThreads - 1) / kThreads;
+    const MapView mv = map_view(c);
+    const BatchView bv = batch_view(c, c->d_scan);
+    timed_launch_begin(c); launch_correspond(mv, bv, c->corr, grid_x, 1, c->stream); timed_launch_end(c, 0);
+    SO_CUDA_TRY(cudaGetLastError());
+    std::vector<double4> nd(n); std::vector<double> w(n); std::vector<uchar4> fl(n); std::vector<uint32_t> nn(n * 5); std::vector<float> d2(n * 5);
+    SO_CUDA_TRY(cudaMemcpyAsync(nd.data(), c->corr.nd, n * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(w.data(), c->corr.w, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(fl.data(), c->corr.flags, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(nn.data(), c->corr.nn, n * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(d2.data(), c->corr.nn_d2, n * 5 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; ++i) {
+        so_corr& r = corr[i];
+        std::memset(&r, 0, sizeof(r));
+        r.n[0] = nd[i].x; r.n[1] = nd[i].y; r.n[2] = nd[i].z; r.d = nd[i].w; r.w = w[i];
+        for (int j = 0; j < 5; ++j) { r.nn[j] = nn[i * 5 + j]; r.nn_d2[j] = d2[i * 5 + j]; }
+        r.status = fl[i].x; r.obs[0] = fl[i].y; r.obs[1] = fl[i].z; r.obs[2] = fl[i].w;
+    }
+    if (hist_obs) std::memcpy(hist_obs, c->h_state[0].hist_obs, 9 * sizeof(int32_t));
+    if (hist_rej) std::memcpy(hist_rej, c->h_state[0].hist_rej, 7 * sizeof(int32_t));
+    return SO_OK;
+}
+
+int so_evaluate(so_ctx* ctx, const double pose[7], double H[36], double g[6], double* cost) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !pose) return fail(SO_ERR_ARG, "bad args");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    IcpState& s = c->h_state[0];
+    const uint32_t n = uint32_t(s.n_points);
+    if (n == 0) return fail(SO_ERR_ARG, "so_evaluate needs a preceding so_correspond");
+    std::memcpy(s.cand, pose, 7 * sizeof(double));
+    s.phase = PH_EVAL; s.max_icp_iters = -1;
+    SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
+    const uint32_t grid_x = (n + kThreads - 1) / kThreads;
+    const BatchView bv = batch_view(c, c->d_scan);
+    timed_launch_begin(c); launch_evaluate(bv, c->corr, grid_x, 1, c->stream); timed_launch_end(c, 1);
+    SO_CUDA_TRY(cudaGetLastError());
+    SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (H) for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) H[i * 6 + j] = s.H[i <= j ? tri(i, j) : tri(j, i)];
+    if (g) for (int i = 0; i < 6; ++i) g[i] = s.g[i];
+    if (cost) *cost = s.cost;
+    return SO_OK;
+}
+
+// ---- k-NN --------------------------------------------------------------------------------------------------------
+int so_knn_device(so_ctx* ctx, const void* d_q, size_t nq, int k, float max_d2, uint32_t* d_idx, float* d_d2) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !d_q || !d_idx || !d_d2 || k < 1 || k > 8) return fail(SO_ERR_ARG, "bad args");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
+    if (nq == 0) return SO_OK;
+    timed_launch_begin(c);
+    if (launch_knn(map_view(c), static_cast<const float4*>(d_q), nq, k, max_d2, d_idx, d_d2, c->stream)) return fail(SO_ERR_ARG, "bad k");
+    timed_launch_end(c, 2);
+    SO_CUDA_TRY(cudaGetLastError());
+    return SO_OK;
+}
+
+int so_knn(so_ctx* ctx, const float* q_xyz, size_t nq, size_t stride, int k, float max_d2, uint32_t* idx, float* d2) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !q_xyz || !idx || !d2 || k < 1 || k > 8 || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    if (nq > c->knn_cap) {
+        cudaFree(c->d_q); cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2);
+        c->d_q = nullptr; c->d_knn_idx = nullptr; c->d_knn_d2 = nullptr; c->knn_cap = 0;
+        SO_CUDA_TRY(cudaMalloc(&c->d_q, nq * sizeof(float4)));
+        SO_CUDA_TRY(cudaMalloc(&c->d_knn_idx, nq * 8 * sizeof(uint32_t)));
+        SO_CUDA_TRY(cudaMalloc(&c->d_knn_d2, nq * 8 * sizeof(float)));
+        c->knn_cap = nq;
+    }
+    int rc = upload_cloud(c, q_xyz, nq, stride, stride /* no intensity */, c->d_q);
+    if (rc) return rc;
+    rc = so_knn_device(ctx, c->d_q, nq, k, max_d2, c->d_knn_idx, c->d_knn_d2);
+    if (rc) return rc;
+    SO_CUDA_TRY(cudaMemcpyAsync(idx, c->d_knn_idx, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(d2, c->d_knn_d2, nq * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SO_OK;
+}
+
+// ---- instrumentation -----------------------------------------------------------------------------------------------
+uint64_t so_kernel_launches(so_ctx* ctx, int reset) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return 0;
+    const uint64_t v = c->launches;
+    if (reset) c->launches = 0;
+    return v;
+}
+
+int so_profile_enable(so_ctx* ctx, int on) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return fail(SO_ERR_ARG, "null ctx");
+    c->profiling = on != 0;
+    return SO_OK;
+}
+
+int so_profile_get(so_ctx* ctx, int cls, double* ms, uint64_t* launches, int reset) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || cls < 0 || cls > 3) return fail(SO_ERR_ARG, "bad args");
+    if (ms) *ms = c->prof[cls].ms;
+    if (launches) *launches = c->prof[cls].launches;
+    if (reset) c->prof[cls] = ProfileSlot{};
+    return SO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// so_ctx.cuh -- the context behind the C ABI: owns every device buffer, the stream, CUDA graphs and host mirrors.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "so_icp.cuh"
+
+namespace so {
+
+#define SO_CUDA_TRY(expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            so::set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
+            return SO_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+void set_error(const std::string& s);
+
+struct ProfileSlot { double ms = 0.0; uint64_t launches = 0; };
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    so_config cfg{};
+    float plane_res = 0.4f, line_res = 0.2f;       // LocalMap defaults (LocalMap.h:761-762)
+
+    // ---- map: raw (id order) + sorted hash grid --------------------------------------------------------------
+    int32_t origin[3] = {kW / 2, kH / 2, kD / 2};  // LocalMap() ctor (LocalMap.h:141-144)
+    uint32_t map_n = 0;                            // points held (on-grid)
+    float4* d_map_xyzi = nullptr;                  // [max_map] id order, w = intensity
+    float4* d_map_sorted = nullptr;                // [max_map] sorted by (slot, cell), w = bitcast(id)
+    uint64_t* d_keys = nullptr;                    // [max_map] sort keys (in)
+    uint64_t* d_keys_out = nullptr;                // [max_map]
+    uint32_t* d_vals = nullptr;                    // [max_map] ids (in)
+    uint32_t* d_vals_out = nullptr;                // [max_map]
+    int32_t* d_block_of_point = nullptr;           // [max_map] grid block of each raw point or -1
+    int32_t* d_block_slot = nullptr;               // [4851]
+    int32_t* d_block_count = nullptr;              // [4851]
+    uint32_t* d_cell_start = nullptr;              // [cell_cap + 1]
+    size_t cell_cap = 0;
+    void* d_cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    std::vector<int32_t> h_block_count, h_block_slot;   // host mirrors
+    int n_slots = 0;
+    int nb = 64;                                   // cells per block axis
+    bool map_dirty = true;
+
+    // ---- scans / correspondences / optimiser state -------------------------------------------------------------
+    uint32_t max_batch = 1;
+    size_t scan_cap = 0;                           // points over the whole batch
+    float4* d_scan = nullptr;
+    uint32_t* d_offset = nullptr;
+    IcpState* d_state = nullptr;
+    IcpState* h_state = nullptr;                   // pinned
+    uint32_t* h_offset = nullptr;                  // pinned
+    double* d_partials = nullptr;
+    uint32_t* d_counters = nullptr;
+    int32_t* d_hist = nullptr;
+    CorrBuf corr{};
+    uint32_t grid_x_cap = 0;
+    void* h_stage = nullptr;                       // pinned staging for strided host clouds
+    size_t h_stage_bytes = 0;
+
+    // ---- k-NN scratch -------------------------------------------------------------------------------------------
+    float4* d_q = nullptr; uint32_t* d_knn_idx = nullptr; float* d_knn_d2 = nullptr; size_t knn_cap = 0;
+
+    // ---- CUDA graph cache for the ICP schedule ------------------------------------------------------------------
+    cudaGraphExec_t graph = nullptr;
+    uint32_t graph_grid_x = 0, graph_n_scans = 0; int graph_iters = 0, graph_lm = 0; const void* graph_scan_ptr = nullptr;
+    uint64_t graph_map_epoch = 0, map_epoch = 1;
+
+    // ---- instrumentation ----------------------------------------------------------------------------------------
+    uint64_t launches = 0;
+    bool profiling = false;
+    ProfileSlot prof[4];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+};
+
+// so_map.cu
+int map_alloc(Ctx* c);
+void map_free(Ctx* c);
+int map_rebuild(Ctx* c);                 // (re)bin, drop off-grid points, sort, build cell table
+MapView map_view(const Ctx* c);
+int map_cells_per_block(float plane_res);
+
+}  // namespace so

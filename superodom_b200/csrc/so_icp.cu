@@ -1,0 +1,674 @@
+// so_icp.cu -- sm_100a kernels of the per-scan ICP registration path.
+//
+//   k_correspond : per scan point -- pose transform, block lookup, radius-bounded 5-NN in the sorted hash grid,
+//                  3x3 PCA + 5x3 column-pivoted QR plane fit with the reference's accept/reject gates, observability
+//                  labels + histograms, AND the first residual/Jacobian evaluation of the following ceres::Solve,
+//                  warp/CTA-reduced in FP64 (21+6+1 accumulators).                       [SURVEY 2.3: K2+K3+K4+K5]
+//   k_evaluate   : per correspondence -- residual, 1x6 Jacobian, Tukey/Scaled robust weight at the LM candidate pose,
+//                  same reduction.                                                          [K5]
+//   last CTA of either kernel: fixed-order final reduction, then ONE thread advances the device-resident state
+//                  machine: Ceres' trust-region LM (step solve by 6x6 Cholesky, accept/reject, tolerances), the outer
+//                  ICP convergence rule, and at the end the covariance pseudo-inverse + 3x3 eigen analysis. [K6+K7]
+//   k_knn        : stand-alone k-NN (so_knn*), radius-bounded or exact with ring expansion.
+//
+// Reference citations are relative to /root/reference/super_odometry/.
+#include "so_icp.cuh"
+
+namespace so {
+
+// ------------------------------------------------------------------------------------------------------------------
+// k-NN core.  Lists are kept ascending by (d2, id); d2 carries the reference's rounding float(double sum of squares)
+// (flann/octree.h:95-102).  Sentinel id 0xFFFFFFFF marks empty slots; d2 slots start at `bound` so that the
+// NEIGHBORS_TOO_FAR gate (d2 > 3*planeRes, LidarSlam.cpp:741) doubles as the search radius.
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+struct TopK {
+    float d2[K]; uint32_t id[K]; uint32_t pos[K];
+    __device__ __forceinline__ void init(float bound) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) { d2[j] = bound; id[j] = 0xFFFFFFFFu; pos[j] = 0; }
+    }
+    __device__ __forceinline__ float worst() const { return d2[K - 1]; }
+    __device__ __forceinline__ void offer(float d, uint32_t i, uint32_t p) {
+        if (d < d2[K - 1] || (d == d2[K - 1] && i < id[K - 1])) {
+            d2[K - 1] = d; id[K - 1] = i; pos[K - 1] = p;
+#pragma unroll
+            for (int j = K - 1; j > 0; --j) {
+                const bool lt = d2[j] < d2[j - 1] || (d2[j] == d2[j - 1] && id[j] < id[j - 1]);
+                if (lt) {
+                    const float td = d2[j]; d2[j] = d2[j - 1]; d2[j - 1] = td;
+                    const uint32_t ti = id[j]; id[j] = id[j - 1]; id[j - 1] = ti;
+                    const uint32_t tp = pos[j]; pos[j] = pos[j - 1]; pos[j - 1] = tp;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ int count() const {
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) c += (id[j] != 0xFFFFFFFFu);
+        return c;
+    }
+};
+
+struct QueryCell {
+    int32_t slot;        // block slot or -1
+    int32_t c[3];        // cell inside the block
+    float f[3];          // offset of the query inside its cell, metres, in [0, cs]
+    int32_t nblock;      // points in the block
+};
+
+// LocalMap::nearestKSearchSurf block lookup (LocalMap.h:488-507) + cell inside the block.
+__device__ __forceinline__ void locate(const MapView& m, float qx, float qy, float qz, QueryCell& qc) {
+    const float q[3] = {qx, qy, qz};
+    int g[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double v = double(q[a]) + kHalfBlock;
+        int b = int(v / kBlock);
+        if (v < 0) b--;
+        g[a] = b + m.origin[a];
+        const double u = (v - kBlock * double(b)) * m.inv_cs;
+        int c = int(u);
+        c = c < 0 ? 0 : (c > m.nb - 1 ? m.nb - 1 : c);
+        qc.c[a] = c;
+        const float f = float(u - double(c)) * m.cs;
+        qc.f[a] = fminf(fmaxf(f, 0.f), m.cs);
+    }
+    const bool ok = g[0] >= 0 && g[0] < kW && g[1] >= 0 && g[1] < kH && g[2] >= 0 && g[2] < kD;
+    qc.slot = -1; qc.nblock = 0;
+    if (ok) {
+        const int lin = g[0] + kW * g[1] + kW * kH * g[2];
+        qc.slot = __ldg(&m.block_slot[lin]);
+        qc.nblock = __ldg(&m.block_count[lin]);
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void scan_range(const MapView& m, uint32_t beg, uint32_t end, float qx, float qy, float qz, TopK<K>& tk) {
+    for (uint32_t t = beg; t < end; ++t) {
+        const float4 c = __ldg(&m.pts[t]);
+        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+        const float approx = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        // cheap FP32 filter (relative error < 4e-7), then the reference's exact rounding for real contenders
+        if (approx <= tk.worst() * 1.000002f) {
+            const float d2 = float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz));
+            tk.offer(d2, __float_as_uint(c.w), t);
+        }
+    }
+}
+
+// Cube of cells [c-R, c+R]^3 clipped to the block, as (2R+1)^2 contiguous x-rows.  For R == 1 rows are visited
+// nearest-first and pruned against the current k-th distance (exact for all neighbours with d2 <= bound <= cs^2).
+template <int K>
+__device__ __forceinline__ void knn_ring(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, int R, TopK<K>& tk) {
+    const int nb = m.nb;
+    const uint32_t base = uint32_t(qc.slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
+    const float cs = m.cs;
+    const float fx = qc.f[0], fy = qc.f[1], fz = qc.f[2];
+    if (R == 1) {
+        // row order: centre, 4 edge neighbours, 4 corners; 2-bit codes 0 -> 0, 1 -> -1, 2 -> +1
+        constexpr uint32_t DY = 0u | 1u << 2 | 2u << 4 | 0u << 6 | 0u << 8 | 1u << 10 | 2u << 12 | 1u << 14 | 2u << 16;
+        constexpr uint32_t DZ = 0u | 0u << 2 | 0u << 4 | 1u << 6 | 2u << 8 | 1u << 10 | 1u << 12 | 2u << 14 | 2u << 16;
+#pragma unroll 1
+        for (int r = 0; r < 9; ++r) {
+            const int cy = (DY >> (2 * r)) & 3, cz = (DZ >> (2 * r)) & 3;
+            const int oy = cy == 0 ? 0 : (cy == 1 ? -1 : 1);
+            const int oz = cz == 0 ? 0 : (cz == 1 ? -1 : 1);
+            const int yy = qc.c[1] + oy, zz = qc.c[2] + oz;
+            if (yy < 0 || yy >= nb || zz < 0 || zz >= nb) continue;   // stay inside the query's block (LocalMap.h:488-507)
+            const float ly = oy < 0 ? fy : (oy > 0 ? cs - fy : 0.f);
+            const float lz = oz < 0 ? fz : (oz > 0 ? cs - fz : 0.f);
+            const float lb = ly * ly + lz * lz;
+            const float w = tk.worst();
+            if (lb * 0.9999f > w) continue;
+            int xlo = qc.c[0], xhi = qc.c[0];
+            if (xlo > 0 && (lb + fx * fx) * 0.9999f <= w) xlo--;
+            if (xhi < nb - 1 && (lb + (cs - fx) * (cs - fx)) * 0.9999f <= w) xhi++;
+            const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
+            const uint32_t beg = __ldg(&m.cell_start[row + xlo]);
+            const uint32_t end = __ldg(&m.cell_start[row + xhi + 1]);
+            scan_range<K>(m, beg, end, qx, qy, qz, tk);
+        }
+    } else {
+        const int xlo = max(qc.c[0] - R, 0), xhi = min(qc.c[0] + R, nb - 1);
+        for (int zz = max(qc.c[2] - R, 0); zz <= min(qc.c[2] + R, nb - 1); ++zz)
+            for (int yy = max(qc.c[1] - R, 0); yy <= min(qc.c[1] + R, nb - 1); ++yy) {
+                const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
+                scan_range<K>(m, __ldg(&m.cell_start[row + xlo]), __ldg(&m.cell_start[row + xhi + 1]), qx, qy, qz, tk);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTA reduction of kAcc doubles per thread + "last CTA" hand-off.
+// Returns true in exactly one CTA per scan (the last to arrive), with the fully reduced sums in s_out[kAcc]
+// (valid for thread 0).  Fixed thread->point mapping + fixed reduction trees => run-to-run deterministic sums.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool reduce_and_elect(double acc[kAcc], const BatchView& bv, int s, double* s_out) {
+    __shared__ double s_red[kThreads / 32][kAcc];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][k] = v;
+    }
+    __syncthreads();
+    double* part = bv.partials + (size_t(s) * gridDim.x + blockIdx.x) * kAcc;
+    if (threadIdx.x < kAcc) {
+        double v = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < kThreads / 32; ++wv) v += s_red[wv][threadIdx.x];
+        part[threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(&bv.counters[s], 1u);
+        s_last = (prev == gridDim.x - 1);
+        if (s_last) bv.counters[s] = 0;          // self-reset for the next kernel
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    // final reduction over CTAs: thread t sums component (t & 31) over CTAs t>>5, t>>5 + 8, ...
+    const int comp = threadIdx.x & 31, sub = threadIdx.x >> 5;
+    double v = 0.0;
+    if (comp < kAcc) {
+        const double* base = bv.partials + size_t(s) * gridDim.x * kAcc;
+        for (uint32_t b = sub; b < gridDim.x; b += kThreads / 32) v += __ldcg(&base[size_t(b) * kAcc + comp]);
+    }
+    __syncthreads();
+    if (comp < kAcc) s_red[sub][comp] = v;
+    __syncthreads();
+    if (threadIdx.x < kAcc) {
+        double t = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < kThreads / 32; ++wv) t += s_red[wv][threadIdx.x];
+        s_out[threadIdx.x] = t;
+    }
+    __syncthreads();
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Device-resident optimiser state machine (runs on one thread of the last CTA).
+// Restates ceres::Solve {max_num_iterations=4, DENSE_QR, defaults} of Ceres 2.0.0 as called at LidarSlam.cpp:230-240:
+// TrustRegionMinimizer::Minimize, LevenbergMarquardtStrategy::ComputeStep/StepAccepted/StepRejected and the monotonic
+// TrustRegionStepEvaluator, expressed on the robustified normal equations H = sum rho' J^T J, g = sum rho' J^T r
+// (the QR of [J;D] that DENSE_QR performs solves exactly (H + D^2) y = g).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ double grad_max_norm(const double x[7], const double g[6]) {
+    // ||x - Plus(x, -g)||_inf  (TrustRegionMinimizer::EvaluateGradientAndJacobian)
+    double neg[6], xp[7];
+    for (int j = 0; j < 6; ++j) neg[j] = -g[j];
+    pose_plus(x, neg, xp);
+    double m = 0.0;
+    for (int i = 0; i < 7; ++i) m = fmax(m, fabs(x[i] - xp[i]));
+    return m;
+}
+
+__device__ void covariance_and_errors(IcpState& st) {
+    // ceres::Covariance{apply_loss_function, DENSE_SVD, null_space_rank=-1} in tangent space (LidarSlam.cpp:854-871):
+    // pseudo-inverse of J^T J dropping singular directions with s_i/s_max < sqrt(1e-14) (covariance_impl.cc).
+    double A[36], V[36], w[6];
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) A[i * 6 + j] = st.H[i <= j ? tri(i, j) : tri(j, i)];
+    jacobi_eig<6, 30>(A, V, w);
+    const double lmax = w[5];
+    double inv[6];
+    bool cut = false;
+    for (int k = 5; k >= 0; --k) {          // descending singular values = descending eigenvalues
+        const double ratio = (w[k] > 0.0 && lmax > 0.0) ? sqrt(w[k] / lmax) : 0.0;
+        if (cut || ratio < 1e-7) { cut = true; inv[k] = 0.0; } else inv[k] = 1.0 / w[k];
+    }
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
+        double t = 0.0;
+        for (int k = 0; k < 6; ++k) t += V[i * 6 + k] * inv[k] * V[j * 6 + k];
+        st.cov[i * 6 + j] = t;
+    }
+    // EstimateRegistrationError (LidarSlam.cpp:873-884): 3x3 eigen of the position / orientation blocks
+    double P[9], O[9], E[9], e[3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { P[i * 3 + j] = st.cov[i * 6 + j]; O[i * 3 + j] = st.cov[(i + 3) * 6 + (j + 3)]; }
+    jacobi_eig<3, 20>(P, E, e);
+    st.pos_err = sqrt(e[2]); st.pos_dir[0] = E[2]; st.pos_dir[1] = E[5]; st.pos_dir[2] = E[8];
+    st.pos_inv_cond = sqrt(e[0]) / sqrt(e[2]);
+    jacobi_eig<3, 20>(O, E, e);
+    st.ori_err_deg = sqrt(e[2]) / M_PI * 180.0; st.ori_dir[0] = E[2]; st.ori_dir[1] = E[5]; st.ori_dir[2] = E[8];
+    st.ori_inv_cond = sqrt(e[0]) / sqrt(e[2]);
+}
+
+// End of one ceres::Solve == end of one ICP iteration (LidarSlam.cpp:134-146).
+__device__ void end_solve(IcpState& st) {
+    const int it = st.icp_iter;
+    st.iter_n_surf[it] = st.n_ok;
+    rel_motion(st.x_iter_start, st.x, &st.iter_dtrans[it], &st.iter_drot[it]);      // recordIterationStats (:242-251)
+    st.iter_lm_steps[it] = st.lm_iter;
+    st.iter_lm_successful[it] = st.num_successful;
+    st.iter_lm_termination[it] = st.termination;
+    st.iter_cost[it] = st.cost;
+    st.n_iterations = it + 1;
+    if (st.n_ok == 0) {          // reference: ceres::Covariance CHECK-fails on an empty problem; we stop with a status
+        st.status = SO_STATUS_NO_CORRESPONDENCES; st.phase = PH_DONE; return;
+    }
+    if (st.num_successful == 1 || it == st.max_icp_iters - 1) {      // (:141)
+        covariance_and_errors(st);
+        st.phase = PH_DONE;
+    } else {
+        st.icp_iter = it + 1;
+        st.phase = PH_CORR;
+    }
+}
+
+// TrustRegionMinimizer loop from FinalizeIterationAndCheckIfMinimizerCanContinue up to the next cost evaluation.
+__device__ void lm_continue(IcpState& st, bool step_successful) {
+    for (;;) {
+        if (step_successful) st.num_successful++; else st.num_unsuccessful++;
+        if (st.lm_iter >= st.lm_max_iterations) { st.termination = 0; end_solve(st); return; }
+        if (st.gmax <= 1e-10) { st.termination = 1; end_solve(st); return; }
+        if (st.radius <= 1e-32) { st.termination = 4; end_solve(st); return; }
+        st.lm_iter++;
+        step_successful = false;
+        // LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system
+        double Hs[36], gs[6];
+        for (int i = 0; i < 6; ++i) {
+            gs[i] = st.g[i] * st.scale[i];
+            for (int j = 0; j < 6; ++j) Hs[i * 6 + j] = st.H[i <= j ? tri(i, j) : tri(j, i)] * st.scale[i] * st.scale[j];
+        }
+        if (!st.reuse_diagonal)
+            for (int j = 0; j < 6; ++j) st.diag[j] = fmin(fmax(Hs[j * 6 + j], 1e-6), 1e32);
+        st.reuse_diagonal = 1;
+        double M[36], y[6];
+        for (int i = 0; i < 36; ++i) M[i] = Hs[i];
+        for (int j = 0; j < 6; ++j) M[j * 6 + j] += st.diag[j] / st.radius;       // lm_diagonal^2 = diagonal / radius
+        bool valid = chol6_solve(M, gs, y);
+        double step[6], mcc = 0.0;
+        if (valid) {
+            for (int j = 0; j < 6; ++j) { step[j] = -y[j]; valid = valid && isfinite(step[j]); }
+            // model_cost_change = -(J step)'(f + J step / 2) = -step'gs - step'Hs step / 2
+            double sg = 0.0, sHs = 0.0;
+            for (int i = 0; i < 6; ++i) { sg += step[i] * gs[i]; double t = 0.0; for (int j = 0; j < 6; ++j) t += Hs[i * 6 + j] * step[j]; sHs += step[i] * t; }
+            mcc = -sg - 0.5 * sHs;
+        }
+        if (!valid || !(mcc > 0.0)) {           // HandleInvalidStep
+            if (++st.consecutive_invalid >= 5) { st.termination = 5; end_solve(st); return; }
+            st.radius *= 0.5; st.reuse_diagonal = 1;
+            continue;
+        }
+        st.consecutive_invalid = 0;
+        st.model_cost_change = mcc;
+        double delta[6];
+        for (int j = 0; j < 6; ++j) delta[j] = step[j] * st.scale[j];
+        pose_plus(st.x, delta, st.cand);
+        st.phase = PH_EVAL;
+        return;
+    }
+}
+
+// IterationZero of a new solve, fed by k_correspond's reduction.
+__device__ void lm_begin_solve(IcpState& st, const double* acc, int n_ok) {
+    for (int k = 0; k < 21; ++k) st.H[k] = acc[k];
+    for (int k = 0; k < 6; ++k) st.g[k] = acc[21 + k];
+    st.cost = acc[27];
+    st.n_ok = n_ok;
+    for (int i = 0; i < 7; ++i) st.x_iter_start[i] = st.x[i];
+    st.lm_iter = 0; st.num_successful = 0; st.num_unsuccessful = 0; st.consecutive_invalid = 0; st.termination = 0;
+    if (n_ok == 0) { st.termination = 6; end_solve(st); return; }
+    for (int j = 0; j < 6; ++j) st.scale[j] = 1.0 / (1.0 + sqrt(st.H[tri(j, j)]));      // jacobi_scaling at iteration 0
+    double xn = 0.0; for (int i = 0; i < 7; ++i) xn += st.x[i] * st.x[i];
+    st.x_norm = sqrt(xn);
+    st.gmax = grad_max_norm(st.x, st.g);
+    st.radius = 1e4; st.decrease_factor = 2.0; st.reuse_diagonal = 0;
+    lm_continue(st, false);
+}
+
+// After the cost (and H, g) at the candidate are known.
+__device__ void lm_after_eval(IcpState& st, const double* acc) {
+    const double cand_cost = acc[27];
+    // ParameterToleranceReached
+    double sn = 0.0; for (int i = 0; i < 7; ++i) { const double d = st.x[i] - st.cand[i]; sn += d * d; }
+    sn = sqrt(sn);
+    if (sn <= 1e-8 * (st.x_norm + 1e-8)) { st.termination = 2; end_solve(st); return; }
+    // FunctionToleranceReached
+    const double cost_change = st.cost - cand_cost;
+    if (fabs(cost_change) <= 1e-6 * st.cost) { st.termination = 3; end_solve(st); return; }
+    const double rd = cost_change / st.model_cost_change;
+    if (rd > 1e-3) {        // HandleSuccessfulStep
+        for (int i = 0; i < 7; ++i) st.x[i] = st.cand[i];
+        double xn = 0.0; for (int i = 0; i < 7; ++i) xn += st.x[i] * st.x[i];
+        st.x_norm = sqrt(xn);
+        for (int k = 0; k < 21; ++k) st.H[k] = acc[k];
+        for (int k = 0; k < 6; ++k) st.g[k] = acc[21 + k];
+        st.cost = cand_cost;
+        st.gmax = grad_max_norm(st.x, st.g);
+        const double t = 2.0 * rd - 1.0;
+        st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
+        st.radius = fmin(1e16, st.radius);
+        st.decrease_factor = 2.0; st.reuse_diagonal = 0;
+        lm_continue(st, true);
+    } else {                // StepRejected
+        st.radius = st.radius / st.decrease_factor; st.decrease_factor *= 2.0; st.reuse_diagonal = 1;
+        lm_continue(st, false);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// residual + Jacobian + robust weight accumulation for one correspondence at pose (q, t) with rotation matrix R.
+// SurfNormAnalyticCostFunction::Evaluate (lidarOptimization.cpp:55-80); ScaledLoss(TukeyLoss(a), w) through Ceres'
+// Corrector: Tukey has rho'' <= 0, so residual and Jacobian are both scaled by sqrt(rho') (corrector.cc);
+// TukeyLoss of Ceres 2.0.0: rho = a^2/6 (1-(1-s/a^2)^3), rho' = (1-s/a^2)^2 / 2 for s <= a^2.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void accumulate(double acc[kAcc], const double n[3], double d, double w, const double p[3],
+                                           const double pw[3], const double R[9], double a2) {
+    const double r = n[0] * pw[0] + n[1] * pw[1] + n[2] * pw[2] + d;
+    const double s = r * r;
+    double rho0, rho1;
+    if (s <= a2) { const double v = 1.0 - s / a2, v2 = v * v; rho0 = a2 / 6.0 * (1.0 - v2 * v); rho1 = 0.5 * v2; }
+    else { rho0 = a2 / 6.0; rho1 = 0.0; }
+    rho0 *= w; rho1 *= w;
+    // J = [ n^T , -n^T R [p]x ] ;  -a^T [p]x = p x a  with a = R^T n
+    const double a0 = R[0] * n[0] + R[3] * n[1] + R[6] * n[2];
+    const double a1 = R[1] * n[0] + R[4] * n[1] + R[7] * n[2];
+    const double a2v = R[2] * n[0] + R[5] * n[1] + R[8] * n[2];
+    const double J[6] = {n[0], n[1], n[2], p[1] * a2v - p[2] * a1, p[2] * a0 - p[0] * a2v, p[0] * a1 - p[1] * a0};
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double wi = rho1 * J[i];
+#pragma unroll
+        for (int j = i; j < 6; ++j) acc[k++] += wi * J[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[21 + i] += rho1 * J[i] * r;
+    acc[27] += 0.5 * rho0;
+}
+
+// shouldProcessPoint (LidarSlam.cpp:353-359)
+__device__ __forceinline__ bool should_process(uint32_t i, double rate) {
+    if (rate < 0.0) return true;
+    const double rem = fmod(double(i) * rate, 1.0);
+    return !(rem + 0.001 > rate);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_correspond: LidarSLAM::ComputePlaneDistanceParameters for every scan point (LidarSlam.cpp:514-572)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_correspond(MapView m, BatchView bv, CorrBuf cb) {
+    const int s = blockIdx.y;
+    IcpState* st = bv.st + s;
+    if (st->phase != PH_CORR) return;
+    __shared__ double s_pose[7];
+    __shared__ double s_R[9];
+    __shared__ int s_hist[16];
+    __shared__ double s_sum[kAcc];
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
+    if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) qtoR(s_pose + 3, s_R);
+    __syncthreads();
+    const uint32_t n = uint32_t(st->n_points);
+    const double rate = st->sampling_rate;
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    const size_t gi = size_t(bv.offset[s]) + i;
+
+    double acc[kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+
+    if (i < n) {
+        int status = SO_MATCH_SKIPPED;
+        int o0 = 0, o1 = 0, o2 = 0;
+        double nrm[3] = {0, 0, 0}, dpl = 0.0, wq = 0.0;
+        TopK<5> tk;
+        tk.init(m.bound_d2);
+        if (should_process(i, rate)) {
+            const float4 sp = __ldg(&bv.scan[gi]);
+            // ComputePointInitAndFinalPose (:382-400): pInit = double(p), pFinal = T_w_lidar * pInit
+            const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+            double pf[3];
+            qrot(s_pose + 3, pin, pf);
+            pf[0] += s_pose[0]; pf[1] += s_pose[1]; pf[2] += s_pose[2];
+            const float qx = float(pf[0]), qy = float(pf[1]), qz = float(pf[2]);      // findNearestNeighbors (:728-731)
+            QueryCell qc;
+            locate(m, qx, qy, qz, qc);
+            if (qc.slot < 0 || qc.nblock < 5) status = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
+            else {
+                knn_ring<5>(m, qc, qx, qy, qz, 1, tk);
+                if (tk.count() < 5) status = SO_MATCH_NEIGHBORS_TOO_FAR;            // d2[4] > 3*planeRes_ (:741-744)
+                else {
+                    // computePCAForFeature (:749-790) + utils::ComputePCA (superodom_utils.h:143-151)
+                    double mm[5][3];
+                    double mean[3] = {0, 0, 0};
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const float4 c = __ldg(&m.pts[tk.pos[j]]);
+                        mm[j][0] = double(c.x); mm[j][1] = double(c.y); mm[j][2] = double(c.z);
+                        mean[0] += mm[j][0]; mean[1] += mm[j][1]; mean[2] += mm[j][2];
+                    }
+                    mean[0] /= 5.0; mean[1] /= 5.0; mean[2] /= 5.0;
+                    double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const double c0 = mm[j][0] - mean[0], c1 = mm[j][1] - mean[1], c2 = mm[j][2] - mean[2];
+                        S[0] += c0 * c0; S[1] += c0 * c1; S[2] += c0 * c2; S[4] += c1 * c1; S[5] += c1 * c2; S[8] += c2 * c2;
+                    }
+                    S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
+                    double V[9], ev[3];
+                    jacobi_eig<3, 12>(S, V, ev);
+                    if (ev[0] < 1e-6 || ev[1] / ev[2] < 0.1) status = SO_MATCH_BAD_PCA_STRUCTURE;      // (:772)
+                    else {
+                        // computePlaneQualityMetrics (:792-844)
+                        double A[5][3], b[5];
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) { A[j][0] = mm[j][0]; A[j][1] = mm[j][1]; A[j][2] = mm[j][2]; b[j] = -1.0; }
+                        double x[3];
+                        colpiv_qr_solve_5x3(A, b, x);
+                        if (!(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]))) status = SO_MATCH_INVALID_NUMERICAL;
+                        else {
+                            const double nn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+                            const double dd = 1.0 / nn;
+                            x[0] /= nn; x[1] /= nn; x[2] /= nn;
+                            const double maxd = double(m.plane_res) / 2.0;
+                            double msum = 0.0;
+                            bool ok = true;
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) {
+                                const double dist = fabs(x[0] * mm[j][0] + x[1] * mm[j][1] + x[2] * mm[j][2] + dd);
+                                if (ok && dist > maxd) ok = false;
+                                msum += dist;
+                            }
+                            if (!ok) status = SO_MATCH_MSE_TOO_LARGE;
+                            else {
+                                const double mean_dist = msum / 5.0;
+                                // normal orientation (:553-561) on the PCA normal, then FeatureObservabilityAnalysis (:574-693)
+                                double no[3] = {V[0], V[3], V[6]};
+                                if (pf[0] * no[0] + pf[1] * no[1] + pf[2] * no[2] < 0) { no[0] = -no[0]; no[1] = -no[1]; no[2] = -no[2]; }
+                                const double l1 = sqrt(ev[2]), l2 = sqrt(ev[1]), l3 = sqrt(ev[0]);
+                                const double planar_2 = (l2 - l3) / l1;
+                                const float nf[3] = {float(no[0]), float(no[1]), float(no[2])};
+                                const float cr[3] = {__fmul_rn(qy, nf[2]) - __fmul_rn(qz, nf[1]), __fmul_rn(qz, nf[0]) - __fmul_rn(qx, nf[2]),
+                                                     __fmul_rn(qx, nf[1]) - __fmul_rn(qy, nf[0])};
+                                const float fq[4] = {float(s_pose[3]), float(s_pose[4]), float(s_pose[5]), float(s_pose[6])};
+                                float rotq[6], trq[3];
+                                const float planar_sq = float(planar_2 * planar_2);
+#pragma unroll
+                                for (int a = 0; a < 3; ++a) {
+                                    // computeRotatedAxes (:624-638): float quaternion * e_a, no FMA contraction (host code is plain IEEE)
+                                    const float v0 = a == 0 ? 1.f : 0.f, v1 = a == 1 ? 1.f : 0.f, v2 = a == 2 ? 1.f : 0.f;
+                                    float ux = __fsub_rn(__fmul_rn(fq[1], v2), __fmul_rn(fq[2], v1));
+                                    float uy = __fsub_rn(__fmul_rn(fq[2], v0), __fmul_rn(fq[0], v2));
+                                    float uz = __fsub_rn(__fmul_rn(fq[0], v1), __fmul_rn(fq[1], v0));
+                                    ux = __fadd_rn(ux, ux); uy = __fadd_rn(uy, uy); uz = __fadd_rn(uz, uz);
+                                    const float ax = __fadd_rn(__fadd_rn(v0, __fmul_rn(fq[3], ux)), __fsub_rn(__fmul_rn(fq[1], uz), __fmul_rn(fq[2], uy)));
+                                    const float ay = __fadd_rn(__fadd_rn(v1, __fmul_rn(fq[3], uy)), __fsub_rn(__fmul_rn(fq[2], ux), __fmul_rn(fq[0], uz)));
+                                    const float az = __fadd_rn(__fadd_rn(v2, __fmul_rn(fq[3], uz)), __fsub_rn(__fmul_rn(fq[0], uy), __fmul_rn(fq[1], ux)));
+                                    // Eigen's unrolled 3-vector dot associates as a0*b0 + (a1*b1 + a2*b2)
+                                    const float rc = __fadd_rn(__fmul_rn(cr[0], ax), __fadd_rn(__fmul_rn(cr[1], ay), __fmul_rn(cr[2], az)));
+                                    rotq[2 * a] = rc; rotq[2 * a + 1] = -rc;
+                                    const float dn = __fadd_rn(__fmul_rn(nf[0], ax), __fadd_rn(__fmul_rn(nf[1], ay), __fmul_rn(nf[2], az)));
+                                    trq[a] = __fmul_rn(planar_sq, fabsf(dn));
+                                }
+                                // top-2 rotation labels and top-1 translation label of a stable descending sort (:654-679)
+                                int r0 = 0;
+#pragma unroll
+                                for (int q = 1; q < 6; ++q) if (rotq[q] > rotq[r0]) r0 = q;
+                                int r1 = (r0 == 0) ? 1 : 0;
+#pragma unroll
+                                for (int q = 0; q < 6; ++q) if (q != r0 && q != r1 && (rotq[q] > rotq[r1] || (rotq[q] == rotq[r1] && q < r1))) r1 = q;
+                                int t0 = 0;
+#pragma unroll
+                                for (int q = 1; q < 3; ++q) if (trq[q] > trq[t0]) t0 = q;
+                                o0 = r0; o1 = r1; o2 = 6 + t0;
+                                nrm[0] = x[0]; nrm[1] = x[1]; nrm[2] = x[2]; dpl = dd;
+                                wq = 1.0 - sqrt(mean_dist / double(m.bound_d2));        // fitQualityCoeff (:568)
+                                status = SO_MATCH_SUCCESS;
+                                accumulate(acc, nrm, dpl, wq, pin, pf, s_R, bv.tukey_a2);
+                            }
+                        }
+                    }
+                }
+            }
+            if (status == SO_MATCH_SUCCESS) { atomicAdd(&s_hist[o0], 1); atomicAdd(&s_hist[o1], 1); atomicAdd(&s_hist[o2], 1); }
+            atomicAdd(&s_hist[9 + status], 1);
+        }
+        cb.nd[gi] = make_double4(nrm[0], nrm[1], nrm[2], dpl);
+        cb.w[gi] = wq;
+        cb.flags[gi] = make_uchar4((unsigned char)status, (unsigned char)o0, (unsigned char)o1, (unsigned char)o2);
+        if (cb.nn) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) { cb.nn[gi * 5 + j] = tk.id[j]; cb.nn_d2[gi * 5 + j] = tk.id[j] != 0xFFFFFFFFu ? tk.d2[j] : 0.f; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&bv.hist[s * 16 + threadIdx.x], s_hist[threadIdx.x]);
+
+    if (!reduce_and_elect(acc, bv, s, s_sum)) return;
+    if (threadIdx.x == 0) {
+        // histograms of this ICP iteration (ResetDistanceParameters + processPlannerFeatures, :847-852,:336-341)
+        int n_ok = 0;
+        for (int k = 0; k < 9; ++k) { st->hist_obs[k] = __ldcg(&bv.hist[s * 16 + k]); }
+        for (int k = 0; k < 7; ++k) { st->hist_rej[k] = __ldcg(&bv.hist[s * 16 + 9 + k]); }
+        n_ok = st->hist_rej[0];
+        for (int k = 0; k < 16; ++k) bv.hist[s * 16 + k] = 0;
+        if (st->max_icp_iters < 0) {          // stage mode (so_correspond): stop here
+            for (int k = 0; k < 21; ++k) st->H[k] = s_sum[k];
+            for (int k = 0; k < 6; ++k) st->g[k] = s_sum[21 + k];
+            st->cost = s_sum[27]; st->n_ok = n_ok; st->phase = PH_DONE;
+        } else lm_begin_solve(*st, s_sum, n_ok);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_evaluate: robustified normal equations at the candidate pose over the stored correspondences
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_evaluate(BatchView bv, CorrBuf cb) {
+    const int s = blockIdx.y;
+    IcpState* st = bv.st + s;
+    if (st->phase != PH_EVAL) return;
+    __shared__ double s_pose[7];
+    __shared__ double s_R[9];
+    __shared__ double s_sum[kAcc];
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = st->cand[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) qtoR(s_pose + 3, s_R);
+    __syncthreads();
+    const uint32_t n = uint32_t(st->n_points);
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    const size_t gi = size_t(bv.offset[s]) + i;
+    double acc[kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+    if (i < n) {
+        const double w = cb.w[gi];
+        if (w != 0.0) {
+            const double4 nd = cb.nd[gi];
+            const float4 sp = __ldg(&bv.scan[gi]);
+            const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+            double pw[3];
+            qrot(s_pose + 3, pin, pw);
+            pw[0] += s_pose[0]; pw[1] += s_pose[1]; pw[2] += s_pose[2];
+            const double nn[3] = {nd.x, nd.y, nd.z};
+            accumulate(acc, nn, nd.w, w, pin, pw, s_R, bv.tukey_a2);
+        }
+    }
+    if (!reduce_and_elect(acc, bv, s, s_sum)) return;
+    if (threadIdx.x == 0) {
+        if (st->max_icp_iters < 0) {          // stage mode (so_evaluate): report and stop
+            for (int k = 0; k < 21; ++k) st->H[k] = s_sum[k];
+            for (int k = 0; k < 6; ++k) st->g[k] = s_sum[21 + k];
+            st->cost = s_sum[27]; st->phase = PH_DONE;
+        } else lm_after_eval(*st, s_sum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_knn: LocalMap::nearestKSearchSurf for a batch of world-frame queries (so_knn / so_knn_device)
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __restrict__ q, size_t nq, float max_d2,
+                                                  uint32_t* __restrict__ idx, float* __restrict__ d2) {
+    const size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    if (i >= nq) return;
+    const float4 p = __ldg(&q[i]);
+    TopK<K> tk;
+    const bool bounded = max_d2 > 0.f;
+    tk.init(bounded ? max_d2 : FLT_MAX);
+    QueryCell qc;
+    locate(m, p.x, p.y, p.z, qc);
+    if (qc.slot >= 0) {
+        // rings needed so that a bounded search is complete: R * cs >= sqrt(max_d2)
+        int R = 1;
+        if (bounded) { const float r = sqrtf(max_d2); while (float(R) * m.cs < r && R < m.nb) ++R; }
+        for (;;) {
+            if (R > 1 || !bounded) tk.init(bounded ? max_d2 : FLT_MAX);
+            knn_ring<K>(m, qc, p.x, p.y, p.z, R, tk);
+            if (bounded) break;
+            // exact: done when the k-th distance is inside the guaranteed-complete radius, or the cube covers the block
+            float reach = FLT_MAX;
+            bool covers = true;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (qc.c[a] - R > 0) { covers = false; reach = fminf(reach, qc.f[a] + float(R) * m.cs); }
+                if (qc.c[a] + R < m.nb - 1) { covers = false; reach = fminf(reach, (m.cs - qc.f[a]) + float(R) * m.cs); }
+            }
+            if (covers) break;
+            if (tk.count() == K && tk.worst() < reach * reach * 0.999f) break;
+            R = (R < 4) ? R + 1 : R * 2;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const bool ok = tk.id[j] != 0xFFFFFFFFu;
+        idx[i * K + j] = tk.id[j];
+        d2[i * K + j] = ok ? tk.d2[j] : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------------------------
+void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+    k_correspond<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, cb);
+}
+void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+    k_evaluate<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(bv, cb);
+}
+int launch_knn(const MapView& m, const float4* q, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st) {
+    const uint32_t grid = uint32_t((nq + kThreads - 1) / kThreads);
+    switch (k) {
+        case 1: k_knn<1><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
+        case 2: k_knn<2><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
+        case 3: k_knn<3><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
+        case 4: k_knn<4><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
+        case 5: k_knn<5><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
+        case 6: k_knn<6><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
+        case 7: k_knn<7><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
+        case 8: k_knn<8><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
+        default: return -1;
+    }
+    return 0;
+}
+
+}  // namespace so

@@ -1,0 +1,29 @@
+// so_icp.cuh -- kernel-side views and host launchers shared by so_icp.cu / so_api.cu.
+#pragma once
+#include "so_internal.cuh"
+
+namespace so {
+
+struct CorrBuf {
+    double4* nd;        // {n.x,n.y,n.z,d}; all zero for rejected points
+    double* w;          // residualCoefficient (0 for rejected)
+    uchar4* flags;      // {status, obs0, obs1, obs2}
+    uint32_t* nn;       // optional [5 per point] neighbour ids (stage tests); may be null
+    float* nn_d2;       // optional [5 per point]
+};
+
+struct BatchView {
+    const float4* scan;       // all scans back to back
+    const uint32_t* offset;   // [n_scans] first point of each scan
+    IcpState* st;             // [n_scans]
+    double* partials;         // [n_scans][grid.x][kAcc]
+    uint32_t* counters;       // [n_scans] CTA arrival counters (self-resetting)
+    int32_t* hist;            // [n_scans][16] histogram accumulators (self-resetting): 9 obs + 7 rejection causes
+    double tukey_a2;          // a^2, a = double(sqrtf(3*planeRes_))  (LidarSlam.cpp:271)
+};
+
+void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
+void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
+int launch_knn(const MapView& m, const float4* q, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st);
+
+}  // namespace so

@@ -1,0 +1,196 @@
+// so_map.cu -- device-resident LocalMap: block binning + sorted spatial hash grid (K1).
+//
+// Replaces the per-block nanoflann::Octree build (flann/octree.h:355-400,536-738, called from LocalMap.h:580,638):
+// points are keyed by (block slot, cell inside the block), radix-sorted, and a dense per-slot cell-start table is
+// built by histogram + exclusive scan.  Cells have edge cs = 50/nb >= sqrt(3*planeRes): every neighbour that can
+// pass the NEIGHBORS_TOO_FAR gate lies in the 27 cells around the query's cell, and because nb divides the 50 m
+// block exactly, "same block" (LocalMap.h:488-507) is "same slot".
+#include <cub/cub.cuh>
+
+#include "so_ctx.cuh"
+
+namespace so {
+
+int map_cells_per_block(float plane_res) {
+    const float bound = 3 * plane_res;                               // float product, as LidarSlam.cpp:526
+    const double r = std::sqrt(double(bound)) * (1.0 + 1e-4);
+    int nb = int(kBlock / r);
+    if (nb < 1) nb = 1;
+    if (nb > 128) nb = 128;
+    return nb;
+}
+
+__device__ __forceinline__ int block_coord(double v, int origin) {   // LocalMap.h:594-605
+    int c = int(v / kBlock);
+    if (v < 0) c--;
+    return c + origin;
+}
+
+__global__ void k_block_of(const float4* __restrict__ raw, uint32_t n, int3 origin, int32_t* __restrict__ block_of_point,
+                           int32_t* __restrict__ block_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = raw[i];
+    const int gx = block_coord(double(p.x) + kHalfBlock, origin.x);
+    const int gy = block_coord(double(p.y) + kHalfBlock, origin.y);
+    const int gz = block_coord(double(p.z) + kHalfBlock, origin.z);
+    int lin = -1;
+    if (gx >= 0 && gx < kW && gy >= 0 && gy < kH && gz >= 0 && gz < kD && isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        lin = gx + kW * gy + kW * kH * gz;
+        atomicAdd(&block_count[lin], 1);
+    }
+    block_of_point[i] = lin;
+}
+
+__global__ void k_flags(const int32_t* __restrict__ block_of_point, uint32_t n, uint8_t* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = block_of_point[i] >= 0;
+}
+
+__global__ void k_keys(const float4* __restrict__ raw, uint32_t n, int3 origin, const int32_t* __restrict__ block_slot,
+                       int nb, double inv_cs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                       uint32_t* __restrict__ cell_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = raw[i];
+    const float q[3] = {p.x, p.y, p.z};
+    const int o[3] = {origin.x, origin.y, origin.z};
+    int g[3], c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double v = double(q[a]) + kHalfBlock;
+        int b = int(v / kBlock);
+        if (v < 0) b--;
+        g[a] = b + o[a];
+        int cc = int((v - kBlock * double(b)) * inv_cs);
+        c[a] = cc < 0 ? 0 : (cc > nb - 1 ? nb - 1 : cc);
+    }
+    const int lin = g[0] + kW * g[1] + kW * kH * g[2];
+    const uint64_t slot = uint64_t(block_slot[lin]);
+    const uint64_t key = slot * uint64_t(nb) * uint64_t(nb) * uint64_t(nb) + uint64_t((c[2] * nb + c[1]) * nb + c[0]);
+    keys[i] = key;
+    vals[i] = i;
+    atomicAdd(&cell_count[key], 1u);
+}
+
+__global__ void k_gather(const float4* __restrict__ raw, const uint32_t* __restrict__ vals, uint32_t n, float4* __restrict__ sorted) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = vals[i];
+    const float4 p = raw[id];
+    sorted[i] = make_float4(p.x, p.y, p.z, __uint_as_float(id));
+}
+
+int map_alloc(Ctx* c) {
+    const size_t M = c->cfg.max_map_points;
+    SO_CUDA_TRY(cudaMalloc(&c->d_map_xyzi, M * sizeof(float4)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_map_sorted, M * sizeof(float4)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_keys, M * sizeof(uint64_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_keys_out, M * sizeof(uint64_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_vals, M * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_vals_out, M * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_block_of_point, M * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_block_slot, kNumBlocks * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_block_count, kNumBlocks * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMemset(c->d_block_slot, 0xFF, kNumBlocks * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMemset(c->d_block_count, 0, kNumBlocks * sizeof(int32_t)));
+    c->h_block_count.assign(kNumBlocks, 0);
+    c->h_block_slot.assign(kNumBlocks, -1);
+    // cub temp: the larger of sort / scan / select requirements at full capacity
+    size_t a = 0, b = 0, d = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, c->d_keys, c->d_keys_out, c->d_vals, c->d_vals_out, int(M), 0, 64);
+    cub::DeviceSelect::Flagged(nullptr, d, c->d_map_xyzi, (uint8_t*)nullptr, c->d_map_sorted, (uint32_t*)nullptr, int(M));
+    const size_t max_cells = size_t(64) * 128 * 128 * 128 + 1;     // scan temp is tiny; size for a generous table
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, int(std::min<size_t>(max_cells, size_t(1) << 30)));
+    c->cub_tmp_bytes = std::max(a, std::max(b, d)) + 256;
+    SO_CUDA_TRY(cudaMalloc(&c->d_cub_tmp, c->cub_tmp_bytes));
+    return SO_OK;
+}
+
+void map_free(Ctx* c) {
+    cudaFree(c->d_map_xyzi); cudaFree(c->d_map_sorted); cudaFree(c->d_keys); cudaFree(c->d_keys_out);
+    cudaFree(c->d_vals); cudaFree(c->d_vals_out); cudaFree(c->d_block_of_point); cudaFree(c->d_block_slot);
+    cudaFree(c->d_block_count); cudaFree(c->d_cell_start); cudaFree(c->d_cub_tmp);
+}
+
+MapView map_view(const Ctx* c) {
+    MapView m;
+    m.pts = c->d_map_sorted; m.block_slot = c->d_block_slot; m.block_count = c->d_block_count; m.cell_start = c->d_cell_start;
+    m.origin[0] = c->origin[0]; m.origin[1] = c->origin[1]; m.origin[2] = c->origin[2];
+    m.nb = c->nb; m.inv_cs = double(c->nb) / kBlock; m.cs = float(kBlock / double(c->nb));
+    m.bound_d2 = 3 * c->plane_res;        // float product (LidarSlam.cpp:526)
+    m.plane_res = c->plane_res;
+    return m;
+}
+
+// (Re)build the index from d_map_xyzi[0..map_n): bin to blocks under the current origin, drop off-grid points
+// (what LocalMap::shiftMap does to blocks rolled off the grid, LocalMap.h:169-287), sort, build the cell table.
+int map_rebuild(Ctx* c) {
+    cudaStream_t st = c->stream;
+    c->nb = map_cells_per_block(c->plane_res);
+    c->map_epoch++;
+    c->map_dirty = false;
+    const int3 origin = make_int3(c->origin[0], c->origin[1], c->origin[2]);
+    SO_CUDA_TRY(cudaMemsetAsync(c->d_block_count, 0, kNumBlocks * sizeof(int32_t), st));
+    std::fill(c->h_block_count.begin(), c->h_block_count.end(), 0);
+    std::fill(c->h_block_slot.begin(), c->h_block_slot.end(), -1);
+    c->n_slots = 0;
+    if (c->map_n == 0) {
+        SO_CUDA_TRY(cudaMemsetAsync(c->d_block_slot, 0xFF, kNumBlocks * sizeof(int32_t), st));
+        SO_CUDA_TRY(cudaStreamSynchronize(st));
+        return SO_OK;
+    }
+    const uint32_t n = c->map_n;
+    const uint32_t grid = (n + 255) / 256;
+    k_block_of<<<grid, 256, 0, st>>>(c->d_map_xyzi, n, origin, c->d_block_of_point, c->d_block_count);
+    c->launches++;
+    SO_CUDA_TRY(cudaMemcpyAsync(c->h_block_count.data(), c->d_block_count, kNumBlocks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SO_CUDA_TRY(cudaStreamSynchronize(st));
+    uint64_t kept = 0;
+    for (int b = 0; b < kNumBlocks; ++b) if (c->h_block_count[b] > 0) { c->h_block_slot[b] = c->n_slots++; kept += uint64_t(c->h_block_count[b]); }
+    SO_CUDA_TRY(cudaMemcpyAsync(c->d_block_slot, c->h_block_slot.data(), kNumBlocks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (kept < n) {
+        // compact away the points whose block rolled off the grid, preserving order (ids are ranks in this order)
+        uint8_t* flags = reinterpret_cast<uint8_t*>(c->d_vals_out);
+        uint32_t* d_num = reinterpret_cast<uint32_t*>(c->d_keys_out);
+        k_flags<<<grid, 256, 0, st>>>(c->d_block_of_point, n, flags);
+        size_t tmp = c->cub_tmp_bytes;
+        SO_CUDA_TRY(cub::DeviceSelect::Flagged(c->d_cub_tmp, tmp, c->d_map_xyzi, flags, c->d_map_sorted, d_num, int(n), st));
+        SO_CUDA_TRY(cudaMemcpyAsync(c->d_map_xyzi, c->d_map_sorted, kept * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        c->launches += 3;
+        c->map_n = uint32_t(kept);
+    }
+    if (kept == 0) { SO_CUDA_TRY(cudaStreamSynchronize(st)); return SO_OK; }
+    const uint32_t m = c->map_n;
+    const size_t cells = size_t(c->n_slots) * c->nb * c->nb * c->nb;
+    if (cells + 1 > c->cell_cap) {
+        SO_CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(c->d_cell_start);
+        c->d_cell_start = nullptr;
+        c->cell_cap = cells + 1 + cells / 4;
+        SO_CUDA_TRY(cudaMalloc(&c->d_cell_start, c->cell_cap * sizeof(uint32_t)));
+        size_t need = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need, c->d_cell_start, c->d_cell_start, int(c->cell_cap));
+        if (need > c->cub_tmp_bytes) {
+            cudaFree(c->d_cub_tmp);
+            c->cub_tmp_bytes = need + 256;
+            SO_CUDA_TRY(cudaMalloc(&c->d_cub_tmp, c->cub_tmp_bytes));
+        }
+    }
+    SO_CUDA_TRY(cudaMemsetAsync(c->d_cell_start, 0, (cells + 1) * sizeof(uint32_t), st));
+    const uint32_t g2 = (m + 255) / 256;
+    k_keys<<<g2, 256, 0, st>>>(c->d_map_xyzi, m, origin, c->d_block_slot, c->nb, double(c->nb) / kBlock, c->d_keys, c->d_vals, c->d_cell_start);
+    int bits = 1;
+    while ((uint64_t(1) << bits) < uint64_t(cells)) ++bits;
+    size_t tmp = c->cub_tmp_bytes;
+    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, tmp, c->d_keys, c->d_keys_out, c->d_vals, c->d_vals_out, int(m), 0, bits, st));
+    k_gather<<<g2, 256, 0, st>>>(c->d_map_xyzi, c->d_vals_out, m, c->d_map_sorted);
+    tmp = c->cub_tmp_bytes;
+    SO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, tmp, c->d_cell_start, c->d_cell_start, int(cells + 1), st));
+    c->launches += 8;
+    SO_CUDA_TRY(cudaGetLastError());
+    SO_CUDA_TRY(cudaStreamSynchronize(st));
+    return SO_OK;
+}
+
+}  // namespace so
