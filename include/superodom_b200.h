@@ -192,6 +192,9 @@ int so_knn_device(so_ctx* ctx, const void* d_q_xyzw, size_t nq, int k, float max
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 /* Number of this library's kernels launched since the last reset (bench.py gpu_launches). */
 uint64_t so_kernel_launches(so_ctx* ctx, int reset);
+/* Bytes this library copied host->device / device->host for scans, poses, optimiser state and results since the
+ * last reset (bench.py e2e accounting). */
+int so_bytes_copied(so_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);
 /* Accumulated device time (ms, CUDA events on the context stream) and launch count of a kernel class since the last
  * reset; classes: 0 correspond (k-NN + fit + first evaluation), 1 evaluate (LM step), 2 k-NN only (so_knn), 3 map build.
  * Profiling mode serialises kernels; enable only for roofline runs. */

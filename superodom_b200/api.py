@@ -21,7 +21,7 @@ EXPORTS = [
     "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
     "so_map_add_surf", "so_map_counts_5x5", "so_map_download", "so_map_size",
     "so_register", "so_register_batch", "so_register_batch_device", "so_correspond", "so_evaluate",
-    "so_knn", "so_knn_device", "so_kernel_launches", "so_profile_enable", "so_profile_get",
+    "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_profile_enable", "so_profile_get",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library():
     L.so_knn_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
     L.so_kernel_launches.restype = C.c_uint64
     L.so_kernel_launches.argtypes = [C.c_void_p, C.c_int]
+    L.so_bytes_copied.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.so_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.so_profile_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     _lib = L
@@ -146,6 +147,11 @@ class Context:
 
     def kernel_launches(self, reset: bool = False) -> int:
         return int(self.L.so_kernel_launches(self.h, int(reset)))
+
+    def bytes_copied(self, reset: bool = False):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._chk(self.L.so_bytes_copied(self.h, C.byref(a), C.byref(b), int(reset)), "so_bytes_copied")
+        return a.value, b.value
 
     def profile_enable(self, on: bool):
         self._chk(self.L.so_profile_enable(self.h, int(on)), "so_profile_enable")

@@ -118,6 +118,7 @@ static int upload_cloud(Ctx* c, const void* src, size_t n, size_t stride, size_t
     if (n == 0) return SO_OK;
     if (stride == 16 && ioff == 12) {
         SO_CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        c->bytes_h2d += n * sizeof(float4);
         return SO_OK;
     }
     int rc = ensure_stage(c, n * sizeof(float4));
@@ -132,6 +133,7 @@ static int upload_cloud(Ctx* c, const void* src, size_t n, size_t stride, size_t
         h[i] = make_float4(xyz[0], xyz[1], xyz[2], it);
     }
     SO_CUDA_TRY(cudaMemcpyAsync(dst, h, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    c->bytes_h2d += n * sizeof(float4);
     return SO_OK;
 }
 
@@ -143,6 +145,9 @@ static BatchView batch_view(const Ctx* c, const float4* scan) {
     bv.tukey_a2 = a * a;
     return bv;
 }
+
+static inline void count_h2d(Ctx* c, size_t b) { c->bytes_h2d += b; }
+static inline void count_d2h(Ctx* c, size_t b) { c->bytes_d2h += b; }
 
 static void timed_launch_begin(Ctx* c) { if (c->profiling) cudaEventRecord(c->evp0, c->stream); }
 static void timed_launch_end(Ctx* c, int cls) {
@@ -278,12 +283,14 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
     if (any) {
         SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, n_scans * sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
         SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, n_scans * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        count_h2d(c, n_scans * (sizeof(IcpState) + sizeof(uint32_t)));
         const uint32_t grid_x = (max_n + kThreads - 1) / kThreads;
         SO_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
         int rc = run_schedule(c, d_scan, grid_x, uint32_t(n_scans), o.max_icp_iters, o.lm_max_iterations, false);
         if (rc) return rc;
         SO_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, n_scans * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
+        count_d2h(c, n_scans * sizeof(IcpState));
         SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->ev0, c->ev1);
@@ -612,6 +619,15 @@ uint64_t so_kernel_launches(so_ctx* ctx, int reset) {
     const uint64_t v = c->launches;
     if (reset) c->launches = 0;
     return v;
+}
+
+int so_bytes_copied(so_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return fail(SO_ERR_ARG, "null ctx");
+    if (h2d) *h2d = c->bytes_h2d;
+    if (d2h) *d2h = c->bytes_d2h;
+    if (reset) { c->bytes_h2d = 0; c->bytes_d2h = 0; }
+    return SO_OK;
 }
 
 int so_profile_enable(so_ctx* ctx, int on) {

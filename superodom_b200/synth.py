@@ -52,16 +52,25 @@ class Scene:
         return not bool(inside.any())
 
 
-def make_scene(half_extent: float, seed: int = 77, aisle: float = 5.0) -> Scene:
-    """Room [-h,h]^2 x [-1.8,6] with shelving rows every `aisle` metres and pillars."""
-    h = float(half_extent)
+def make_scene(half_extent: float, seed: int = 77, aisle: float = 5.0, half_extent_y: float | None = None,
+               center=(0.0, 0.0)) -> Scene:
+    """Room [-h,h] x [-hy,hy] x [-1.8,6] (then translated by `center`) with shelving rows every `aisle` metres and pillars."""
+    sc = _make_scene_centered(float(half_extent), float(half_extent if half_extent_y is None else half_extent_y), seed, aisle)
+    cx, cy = float(center[0]), float(center[1])
+    if cx or cy:
+        sh = np.array([cx, cx, cy, cy, 0.0, 0.0])
+        sc = Scene(room=sc.room + sh, boxes=sc.boxes + sh)
+    return sc
+
+
+def _make_scene_centered(h: float, hy: float, seed: int, aisle: float) -> Scene:
     rng = np.random.default_rng(seed)
-    room = np.array([-h, h, -h, h, -1.8, 6.0])
+    room = np.array([-h, h, -hy, hy, -1.8, 6.0])
     boxes = []
     # shelving rows: long boxes parallel to x, broken into segments with gaps
-    y = -h + aisle
+    y = -hy + aisle
     row = 0
-    while y < h - aisle + 1e-9:
+    while y < hy - aisle + 1e-9:
         if abs(y) >= 2.0:           # keep faces |y| >= 1 and the origin aisle free
             x = -h + 2.0
             while x < h - 2.0:
@@ -77,7 +86,7 @@ def make_scene(half_extent: float, seed: int = 77, aisle: float = 5.0) -> Scene:
     # pillars (floor to ceiling) on a coarse lattice, jittered
     step = max(10.0, h / 4)
     for px in np.arange(-h + step / 2, h, step):
-        for py in np.arange(-h + step / 2 + 2.5, h, step):
+        for py in np.arange(-hy + step / 2 + 2.5, hy, step):
             cx = float(px + rng.uniform(-1, 1))
             cy = float(py + rng.uniform(-1, 1))
             if abs(cx) < 2.0 or abs(cy) < 2.0:
@@ -104,6 +113,35 @@ def _face_samples(lo_u, hi_u, lo_v, hi_v, pitch):
     return uu.ravel(), vv.ravel()
 
 
+def _inside_any_numpy(pts, boxes, eps):
+    ins_any = np.zeros(len(pts), dtype=bool)
+    for b in boxes:
+        ins_any |= ((pts[:, 0] > b[0] + eps) & (pts[:, 0] < b[1] - eps) & (pts[:, 1] > b[2] + eps) &
+                    (pts[:, 1] < b[3] - eps) & (pts[:, 2] > b[4] + eps) & (pts[:, 2] < b[5] - eps))
+    return ins_any
+
+
+try:
+    import numba as _nb0
+
+    @_nb0.njit(parallel=True, cache=True)
+    def _inside_any(pts, boxes, eps):
+        n = pts.shape[0]
+        out = np.zeros(n, np.bool_)
+        for i in _nb0.prange(n):
+            x = pts[i, 0]
+            y = pts[i, 1]
+            z = pts[i, 2]
+            for b in range(boxes.shape[0]):
+                if (x > boxes[b, 0] + eps and x < boxes[b, 1] - eps and y > boxes[b, 2] + eps and y < boxes[b, 3] - eps
+                        and z > boxes[b, 4] + eps and z < boxes[b, 5] - eps):
+                    out[i] = True
+                    break
+        return out
+except Exception:                                             # pragma: no cover
+    _inside_any = _inside_any_numpy
+
+
 def sample_surfaces(scene: Scene, pitch: float, seed: int = 1234, noise: float = 0.02) -> np.ndarray:
     """Raw (unfiltered) surface samples, float32 [M,3]."""
     rng = np.random.default_rng(seed)
@@ -125,14 +163,8 @@ def sample_surfaces(scene: Scene, pitch: float, seed: int = 1234, noise: float =
     for b in scene.boxes:
         add_box_faces(b, False)
     pts = np.concatenate(chunks, 0)
-    # drop samples strictly inside another box (hidden) -- cheap chunked test
-    keep = np.ones(len(pts), dtype=bool)
-    eps = 1e-6
-    for b in scene.boxes:
-        ins = ((pts[:, 0] > b[0] + eps) & (pts[:, 0] < b[1] - eps) & (pts[:, 1] > b[2] + eps) &
-               (pts[:, 1] < b[3] - eps) & (pts[:, 2] > b[4] + eps) & (pts[:, 2] < b[5] - eps))
-        keep &= ~ins
-    pts = pts[keep]
+    # drop samples strictly inside another box (hidden)
+    pts = pts[~_inside_any(pts, np.ascontiguousarray(scene.boxes), 1e-6)]
     pts = pts + rng.normal(0.0, noise, size=pts.shape)
     return pts.astype(np.float32)
 
@@ -192,8 +224,8 @@ def voxel_filter_blocks(xyzi: np.ndarray, leaf: float, origin=ORIGIN0) -> np.nda
     return (acc / cnt[:, None]).astype(np.float32)
 
 
-def make_map(half_extent: float, leaf: float, scene_seed: int = 77, map_seed: int = 1234):
-    scene = make_scene(half_extent, seed=scene_seed)
+def make_map(half_extent: float, leaf: float, scene_seed: int = 77, map_seed: int = 1234, half_extent_y=None, center=(0.0, 0.0)):
+    scene = make_scene(half_extent, seed=scene_seed, half_extent_y=half_extent_y, center=center)
     raw = sample_surfaces(scene, leaf, seed=map_seed)
     xyzi = np.concatenate([raw, np.ones((len(raw), 1), np.float32)], 1)
     return scene, voxel_filter_blocks(xyzi, leaf)
@@ -228,10 +260,12 @@ def quat_to_R(q):
 
 def random_sensor_pose(scene: Scene, seed: int, max_radius: float = 20.0) -> np.ndarray:
     rng = np.random.default_rng(seed)
+    cx = 0.5 * (scene.room[0] + scene.room[1])
+    cy = 0.5 * (scene.room[2] + scene.room[3])
     for _ in range(1000):
         r = rng.uniform(0.0, max_radius)
         a = rng.uniform(0, 2 * math.pi)
-        p = np.array([r * math.cos(a), r * math.sin(a), rng.uniform(-0.6, 0.6)])
+        p = np.array([cx + r * math.cos(a), cy + r * math.sin(a), rng.uniform(-0.6, 0.6)])
         if scene.free(p):
             break
     else:
@@ -256,7 +290,17 @@ def perturb_pose(pose7: np.ndarray, seed: int, dt: float = 0.10, dth_deg: float 
 # --------------------------------------------------------------------------
 # sensors + ray casting
 # --------------------------------------------------------------------------
+_DIRS_CACHE = {}
+
+
 def sensor_dirs(sensor: str, seed: int = 0) -> np.ndarray:
+    key = (sensor, seed if sensor == "mid360" else 0)
+    if key not in _DIRS_CACHE:
+        _DIRS_CACHE[key] = _sensor_dirs(sensor, seed)
+    return _DIRS_CACHE[key]
+
+
+def _sensor_dirs(sensor: str, seed: int = 0) -> np.ndarray:
     if sensor == "vlp16":
         el = np.deg2rad(np.arange(-15.0, 15.1, 2.0))
         az = np.arange(1800) * (2 * math.pi / 1800)
@@ -276,18 +320,15 @@ def sensor_dirs(sensor: str, seed: int = 0) -> np.ndarray:
     return np.stack([np.cos(E) * np.cos(A), np.cos(E) * np.sin(A), np.sin(E)], -1).reshape(-1, 3)
 
 
-def raycast(scene: Scene, o: np.ndarray, d: np.ndarray) -> np.ndarray:
-    """Range to the first surface along each ray (origin o [3], dirs d [n,3]); inf if none."""
+def _raycast_numpy(room, boxes, o, d):
     with np.errstate(divide="ignore", invalid="ignore"):
         inv = 1.0 / d
-        r = scene.room
-        lo = np.array([r[0], r[2], r[4]])
-        hi = np.array([r[1], r[3], r[5]])
+        lo = np.array([room[0], room[2], room[4]])
+        hi = np.array([room[1], room[3], room[5]])
         t1 = (lo - o) * inv
         t2 = (hi - o) * inv
-        t_exit = np.min(np.maximum(t1, t2), axis=1)          # inside the room: exit distance
-        best = t_exit
-        for b in scene.boxes:
+        best = np.min(np.maximum(t1, t2), axis=1)            # inside the room: exit distance
+        for b in boxes:
             lo = np.array([b[0], b[2], b[4]])
             hi = np.array([b[1], b[3], b[5]])
             t1 = (lo - o) * inv
@@ -297,6 +338,78 @@ def raycast(scene: Scene, o: np.ndarray, d: np.ndarray) -> np.ndarray:
             hit = (tn <= tf) & (tn > 0)
             best = np.where(hit & (tn < best), tn, best)
     return best
+
+
+try:                                                          # numba (in the image) makes scan generation ~100x faster
+    import numba as _nb
+
+    @_nb.njit(parallel=True, cache=True)
+    def _raycast_numba(room, boxes, o, d):
+        n = d.shape[0]
+        nb = boxes.shape[0]
+        out = np.empty(n, np.float64)
+        # box bounds relative to the ray origin
+        rel = np.empty((nb, 6), np.float64)
+        for b in range(nb):
+            for a in range(3):
+                rel[b, 2 * a] = boxes[b, 2 * a] - o[a]
+                rel[b, 2 * a + 1] = boxes[b, 2 * a + 1] - o[a]
+        for i in _nb.prange(n):
+            inv0 = 1.0 / d[i, 0] if d[i, 0] != 0.0 else np.inf
+            inv1 = 1.0 / d[i, 1] if d[i, 1] != 0.0 else np.inf
+            inv2 = 1.0 / d[i, 2] if d[i, 2] != 0.0 else np.inf
+            # room (we are inside): exit distance
+            best = np.inf
+            for a in range(3):
+                da = d[i, a]
+                if da != 0.0:
+                    t1 = (room[2 * a] - o[a]) / da
+                    t2 = (room[2 * a + 1] - o[a]) / da
+                    tm = t1 if t1 > t2 else t2
+                    if tm < best:
+                        best = tm
+            for b in range(nb):
+                # slab test; a zero direction component gives +-inf (or nan when the origin lies on the slab plane,
+                # which the comparisons below treat as a miss)
+                t1 = rel[b, 0] * inv0
+                t2 = rel[b, 1] * inv0
+                tn = t1 if t1 < t2 else t2
+                tf = t1 if t1 > t2 else t2
+                if tn >= best:
+                    continue
+                t1 = rel[b, 2] * inv1
+                t2 = rel[b, 3] * inv1
+                lo = t1 if t1 < t2 else t2
+                hi = t1 if t1 > t2 else t2
+                if lo > tn:
+                    tn = lo
+                if hi < tf:
+                    tf = hi
+                if tn > tf or tn >= best:
+                    continue
+                t1 = rel[b, 4] * inv2
+                t2 = rel[b, 5] * inv2
+                lo = t1 if t1 < t2 else t2
+                hi = t1 if t1 > t2 else t2
+                if lo > tn:
+                    tn = lo
+                if hi < tf:
+                    tf = hi
+                if tn <= tf and tn > 0.0 and tn < best:
+                    best = tn
+            out[i] = best
+        return out
+except Exception:                                             # pragma: no cover
+    _raycast_numba = None
+
+
+def raycast(scene: Scene, o: np.ndarray, d: np.ndarray) -> np.ndarray:
+    """Range to the first surface along each ray (origin o [3], dirs d [n,3]); inf if none."""
+    o = np.ascontiguousarray(o, dtype=np.float64)
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    if _raycast_numba is not None:
+        return _raycast_numba(np.ascontiguousarray(scene.room), np.ascontiguousarray(scene.boxes), o, d)
+    return _raycast_numpy(scene.room, scene.boxes, o, d)
 
 
 def make_scan(scene: Scene, sensor: str, pose7: np.ndarray, seed: int,
@@ -323,20 +436,28 @@ CONFIGS = {
     "cfg2": dict(half_extent=52.0, plane_res=0.2, sensor="os1_128", max_iterations=20, max_surface_features=0),
     "cfg3": dict(half_extent=36.5, plane_res=0.1, sensor="mid360", max_iterations=20, max_surface_features=0),
     "tiny": dict(half_extent=9.0, plane_res=0.2, sensor="vlp16", max_iterations=5, max_surface_features=0),
+    # x-dominant single-block hall far from the world diagonal: the layout on which the reference octree's two bugs
+    # (flann/octree.h:383-385, :984-1001) cannot fire, so reference k-NN == exact k-NN (tests assert this)
+    "hall": dict(half_extent=23.0, half_extent_y=9.0, center=(100.0, 0.0), plane_res=0.2, sensor="vlp16",
+                 max_iterations=5, max_surface_features=0),
 }
 
 
 def make_case(name: str, scan_index: int = 0, max_radius: float | None = None):
     """-> dict(scene, map_xyzi [M,4] f32, scan_xyzi [N,4] f32, pose_true [7], pose_prior [7], cfg)."""
-    cfg = CONFIGS[name]
-    scene, map_xyzi = make_map(cfg["half_extent"], cfg["plane_res"])
+    scene, map_xyzi = make_map_for(name)
     return make_case_on(scene, map_xyzi, name, scan_index, max_radius)
+
+
+def make_map_for(name: str):
+    cfg = CONFIGS[name]
+    return make_map(cfg["half_extent"], cfg["plane_res"], half_extent_y=cfg.get("half_extent_y"), center=cfg.get("center", (0.0, 0.0)))
 
 
 def make_case_on(scene, map_xyzi, name: str, scan_index: int = 0, max_radius: float | None = None):
     cfg = CONFIGS[name]
     if max_radius is None:
-        max_radius = min(20.0, cfg["half_extent"] * 0.6)
+        max_radius = min(20.0, min(cfg["half_extent"], cfg.get("half_extent_y") or cfg["half_extent"]) * 0.6)
     pose_true = random_sensor_pose(scene, 900 + scan_index, max_radius)
     scan = make_scan(scene, cfg["sensor"], pose_true, 1000 + scan_index)
     prior = perturb_pose(pose_true, 2000 + scan_index)

@@ -1,0 +1,71 @@
+"""CPU-side checks of the drop-in boundary: the in-tree shared library builds for sm_100a, loads, exports every
+symbol include/superodom_b200.h declares, and refuses to work (loudly) without a GPU -- there is no CPU fallback."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "superodom_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(so_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_compiles_as_c_and_cpp(tmp_path):
+    for comp, flag, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++17", "cpp")):
+        f = tmp_path / f"t.{ext}"
+        f.write_text('#include "superodom_b200.h"\nint main(void){ so_icp_result r; (void)r; return 0; }\n')
+        subprocess.check_call([comp, flag, "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(f), "-o", str(tmp_path / "t.o")])
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from superodom_b200 import api, build
+    lib_path = build.build()
+    assert os.path.exists(lib_path)
+    L = C.CDLL(lib_path)
+    decl = _declared()
+    assert len(decl) >= 20
+    for name in decl:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert sorted(api.EXPORTS) == decl, "python binding and header disagree on the ABI surface"
+    # SASS is sm_100a
+    out = subprocess.run(["cuobjdump", "--list-elf", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_struct_layouts_match_header(tmp_path):
+    from superodom_b200 import api
+    f = tmp_path / "sz.c"
+    f.write_text('#include <stdio.h>\n#include "superodom_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(so_config), sizeof(so_icp_opts), sizeof(so_icp_result), sizeof(so_corr));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(f), "-o", str(exe)])
+    a, b, c, d = map(int, subprocess.check_output([str(exe)]).split())
+    assert (a, b, c, d) == (C.sizeof(api.Config), C.sizeof(api.IcpOpts), C.sizeof(api.IcpResult), api.CORR_DTYPE.itemsize)
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly, never compute on the CPU."""
+    import torch
+    from superodom_b200 import api
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the loud-failure path is not reachable")
+    assert not api.device_available()
+    with pytest.raises(api.SuperOdomError):
+        api.Context()
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under superodom_b200/ or include/ may reference it."""
+    for base in ("superodom_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            for fn in fs:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    txt = open(os.path.join(dp, fn), errors="ignore").read()
+                    assert "so_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, fn

@@ -1,0 +1,327 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI, against the CPU oracle on identical inputs.
+
+Bars (task section 3): bit-exact for integer / index work (neighbour ids, float d2, status codes, histograms,
+iteration counts); FP64 quantities within the stated tolerances (normal equations 1e-10 relative, pose 1e-4 m /
+1e-4 rad per BASELINE.json north_star -- observed ~1e-15)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import get_case, quat_angle
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_M = 1e-4       # north_star
+POSE_TOL_RAD = 1e-4
+
+
+def _ctx(api, case, **kw):
+    ctx = api.Context(max_map_points=max(1 << 20, len(case["map_xyzi"]) + 1024), max_scan_points=262144,
+                      plane_res=case["cfg"]["plane_res"], **kw)
+    ctx.map_set_points(case["map_xyzi"])
+    return ctx
+
+
+def _gi(idx):
+    g = idx.astype(np.int64)
+    g[idx == 0xFFFFFFFF] = -1
+    return g
+
+
+def _assert_pose_close(pg, po, tol_m=POSE_TOL_M, tol_r=POSE_TOL_RAD):
+    assert np.abs(pg[:3] - po[:3]).max() <= tol_m, (pg, po)
+    assert quat_angle(pg[3:], po[3:]) <= tol_r, (pg, po)
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1", "hall"])
+def test_knn_bit_exact(gpu_api, oracle_mod, name):
+    case = get_case(name)
+    ctx = _ctx(gpu_api, case)
+    om = oracle_mod.OracleMap(case["map_xyzi"])
+    rng = np.random.default_rng(0)
+    base = case["map_xyzi"][::7, :3]
+    q = base + rng.normal(0, 0.12, size=base.shape).astype(np.float32)
+    q = np.concatenate([q, rng.uniform(-30, 30, size=(500, 3)).astype(np.float32) + q.mean(0)])     # incl. far-away queries
+    gi, gd = ctx.knn(q, 5, 0.0)                           # exact, unbounded
+    oi, od, of = om.knn(q, 5, 0)
+    assert np.array_equal(_gi(gi)[of], oi[of]) and np.array_equal(gd[of], od[of])
+    assert (gi[~of] == 0xFFFFFFFF).all()
+    bound = np.float32(3 * np.float32(case["cfg"]["plane_res"]))
+    gi, gd = ctx.knn(q, 5, float(bound))                  # radius-bounded: same neighbours up to the bound
+    keep = od <= bound
+    assert np.array_equal(_gi(gi)[keep & of[:, None]], oi[keep & of[:, None]])
+    assert (gi[~keep | ~of[:, None]] == 0xFFFFFFFF).all()
+    for k in (1, 3, 8):
+        gi, gd = ctx.knn(q[:2000], k, 0.0)
+        oi, od, of = om.knn(q[:2000], k, 0)
+        assert np.array_equal(_gi(gi)[of], oi[of]) and np.array_equal(gd[of], od[of])
+    if name == "hall" and oracle_mod.has_ref_octree():    # reference's own octree (verbatim) agrees here
+        ri, rd, rf = om.knn(q[:-500], 5, 2)
+        gi, gd = ctx.knn(q[:-500], 5, 0.0)
+        assert np.array_equal(_gi(gi), ri) and np.array_equal(gd, rd)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,cap", [("tiny", 0), ("cfg1", 2000), ("cfg1", 0), ("hall", 0)])
+def test_correspondences_and_normal_equations(gpu_api, oracle_mod, name, cap):
+    case = get_case(name)
+    pr = case["cfg"]["plane_res"]
+    ctx = _ctx(gpu_api, case)
+    om = oracle_mod.OracleMap(case["map_xyzi"])
+    gc, gho, ghr = ctx.correspond(case["scan_xyzi"], case["pose_prior"], cap)
+    oc, oho, ohr = om.correspond(case["scan_xyzi"], case["pose_prior"], pr, cap, 0)
+    ost = oc["status"].astype(np.int64)
+    ost[ost < 0] = 255
+    assert np.array_equal(gc["status"].astype(np.int64), ost)                  # every accept/reject gate agrees
+    assert np.array_equal(gho, oho) and np.array_equal(ghr, ohr)
+    ok = ost == 0
+    assert ok.sum() > 100
+    searched = (ost != 255) & (ost != 1)
+    found5 = searched & (ost != 2)
+    assert np.array_equal(gc["nn"][found5].astype(np.int64), oc["nn"][found5])
+    assert np.array_equal(gc["nn_d2"][found5], oc["nn_d2"][found5])
+    assert np.array_equal(gc["obs"][ok], oc["obs"][ok].astype(np.uint8))
+    assert np.allclose(gc["n"][ok], oc["n"][ok], rtol=0, atol=1e-8)
+    assert np.allclose(gc["d"][ok], oc["d"][ok], rtol=1e-10, atol=0)
+    assert np.allclose(gc["w"][ok], oc["w"][ok], rtol=1e-10, atol=0)
+    assert (gc["w"][~ok] == 0).all() and (gc["n"][~ok] == 0).all()
+    for pose in (case["pose_prior"], case["pose_true"]):
+        H, g, cost = ctx.evaluate(pose)
+        oH, og, ocost, nok = oracle_mod.evaluate(oc, pose, pr)
+        assert np.abs(H - oH).max() <= 1e-10 * np.abs(oH).max()
+        assert np.abs(g - og).max() <= 1e-10 * max(np.abs(og).max(), 1e-3 * np.abs(oH).max())
+        assert abs(cost - ocost) <= 1e-10 * ocost
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,cap", [("tiny", 0), ("cfg1", 2000), ("cfg1", 0), ("hall", 0)])
+def test_register_pose_parity(gpu_api, oracle_mod, name, cap):
+    case = get_case(name)
+    cfg = case["cfg"]
+    ctx = _ctx(gpu_api, case)
+    om = oracle_mod.OracleMap(case["map_xyzi"])
+    r = ctx.register(case["scan_xyzi"], case["pose_prior"], cfg["max_iterations"], cap)
+    ro = om.register(case["scan_xyzi"], case["pose_prior"], cfg["plane_res"], cfg["max_iterations"], cap, knn_mode=0)
+    assert r.status == 0 and ro.status == 0
+    _assert_pose_close(np.array(r.pose), np.array(ro.pose))
+    _assert_pose_close(np.array(r.pose_opt), np.array(ro.pose_opt))
+    n = ro.n_iterations
+    assert r.n_iterations == n                                                    # same ICP trip count
+    assert list(r.iter_n_surf[:n]) == list(ro.iter_n_surf[:n])
+    assert list(r.iter_lm_steps[:n]) == list(ro.iter_lm_steps[:n])              # same Ceres control flow
+    assert list(r.iter_lm_successful[:n]) == list(ro.iter_lm_successful[:n])
+    assert list(r.iter_lm_termination[:n]) == list(ro.iter_lm_termination[:n])
+    assert np.allclose(r.iter_cost[:n], ro.iter_cost[:n], rtol=1e-9)
+    assert np.allclose(r.iter_dtrans[:n], ro.iter_dtrans[:n], atol=1e-9) and np.allclose(r.iter_drot[:n], ro.iter_drot[:n], atol=1e-9)
+    assert list(r.hist_obs) == list(ro.hist_obs) and list(r.hist_reject_plane) == list(ro.hist_reject_plane)
+    cg, co = np.array(r.cov).reshape(6, 6), np.array(ro.cov).reshape(6, 6)
+    assert np.abs(cg - co).max() <= 1e-6 * np.abs(co).max()                      # ||dC||/||C|| <= 1e-6
+    for f in ("pos_err", "pos_inv_cond", "ori_err_deg", "ori_inv_cond", "total_translation", "total_rotation"):
+        assert abs(getattr(r, f) - getattr(ro, f)) <= 1e-6 * abs(getattr(ro, f)) + 1e-12, f
+    assert abs(abs(np.dot(r.pos_dir, ro.pos_dir)) - 1) < 1e-6 and abs(abs(np.dot(r.ori_dir, ro.ori_dir)) - 1) < 1e-6
+    assert r.map_surf_5x5 == ro.map_surf_5x5 and list(r.pos_in_localmap) == list(ro.pos_in_localmap)
+    # truth is recovered (the oracle is, too) and the run is bit-reproducible
+    assert np.linalg.norm(np.array(r.pose)[:3] - case["pose_true"][:3]) < 0.02
+    r2 = ctx.register(case["scan_xyzi"], case["pose_prior"], cfg["max_iterations"], cap)
+    assert np.array_equal(np.array(r.pose), np.array(r2.pose)) and np.array_equal(np.array(r.cov), np.array(r2.cov))
+    if name == "hall" and oracle_mod.has_ref_octree():
+        # the reference's own (verbatim) octree in the loop: same pose, because on this layout the octree is exact
+        rr = om.register(case["scan_xyzi"], case["pose_prior"], cfg["plane_res"], cfg["max_iterations"], cap, knn_mode=2)
+        _assert_pose_close(np.array(r.pose), np.array(rr.pose))
+        assert rr.n_iterations == r.n_iterations
+    ctx.close()
+
+
+def test_golden_fixture_through_the_abi(gpu_api):
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_case.npz"))
+    ctx = gpu_api.Context(max_map_points=1 << 20, max_scan_points=65536, plane_res=float(G["plane_res"]))
+    ctx.map_set_points(G["map_xyzi"])
+    gc, gho, ghr = ctx.correspond(G["scan_xyzi"], G["pose_prior"], 0)
+    assert np.array_equal(gc["status"].astype(np.int32), G["status"])
+    ok = G["status"] == 0
+    assert np.array_equal(gc["nn"][ok].astype(np.int64), G["nn"][ok])
+    assert np.array_equal(gho, G["hist_obs"]) and np.array_equal(ghr, G["hist_rej"])
+    H, g, cost = ctx.evaluate(G["pose_prior"])
+    assert np.allclose(H, G["H"], rtol=1e-9) and abs(cost - G["cost"]) < 1e-9 * G["cost"]
+    r = ctx.register(G["scan_xyzi"], G["pose_prior"], int(G["max_iterations"]), 0)
+    _assert_pose_close(np.array(r.pose), G["pose_exact"])
+    assert r.n_iterations == int(G["n_iterations_exact"])
+    ctx.close()
+
+
+def test_pcl_point_layout_and_stride(gpu_api):
+    """pcl::PointXYZI layout: 32-byte stride, intensity at byte 16 -- what the C++ shim passes (points.data())."""
+    case = get_case("tiny")
+    ctx = _ctx(gpu_api, case)
+    s = case["scan_xyzi"]
+    r0 = ctx.register(s, case["pose_prior"], 5)
+    pcl = np.zeros((len(s), 8), np.float32)
+    pcl[:, :3] = s[:, :3]
+    pcl[:, 3] = 1.0
+    pcl[:, 4] = s[:, 3]
+    o = ctx._opts(5)
+    r1 = gpu_api.IcpResult()
+    pose = np.ascontiguousarray(case["pose_prior"])
+    rc = ctx.L.so_register(ctx.h, pcl.ctypes.data_as(C.c_void_p), len(s), None, 0, 32, 16, pose.ctypes.data_as(C.c_void_p), C.byref(o), C.byref(r1))
+    assert rc == 0 and np.array_equal(np.array(r0.pose), np.array(r1.pose))
+    ctx.close()
+
+
+def test_soft_statuses_and_edge_cases(gpu_api):
+    case = get_case("tiny")
+    api = gpu_api
+    # map with too few points: hasEnoughFeatures false -> status 1, pose = prior (LidarSlam.cpp:113-116)
+    ctx = api.Context(max_map_points=1 << 16, max_scan_points=65536, plane_res=0.2)
+    ctx.map_set_points(case["map_xyzi"][:40])
+    r = ctx.register(case["scan_xyzi"], case["pose_prior"], 5)
+    assert r.status == 1 and np.array_equal(np.array(r.pose), case["pose_prior"])
+    # empty map
+    ctx.map_set_points(np.zeros((0, 4), np.float32))
+    r = ctx.register(case["scan_xyzi"], case["pose_prior"], 5)
+    assert r.status == 1
+    ctx.close()
+    ctx = _ctx(api, case)
+    # scan nowhere near the map -> every point rejected -> status 2, pose = prior
+    far = case["scan_xyzi"].copy()
+    far[:, :3] += 400.0
+    r = ctx.register(far, case["pose_prior"], 5, skip_map_checks=True)
+    assert r.status == 2 and np.allclose(np.array(r.pose_opt), case["pose_prior"])
+    assert r.hist_reject_plane[1] + r.hist_reject_plane[2] == len(far)
+    # empty scan
+    r = ctx.register(np.zeros((0, 4), np.float32), case["pose_prior"], 5)
+    assert r.status == 2
+    # ragged tiny scans (1, 31, 257 points) run and match the full-scan machinery
+    for n in (1, 31, 257):
+        r = ctx.register(case["scan_xyzi"][:n], case["pose_true"], 5)
+        assert r.status in (0, 2)
+    # argument errors are reported, not thrown
+    assert ctx.L.so_register(ctx.h, None, 10, None, 0, 16, 12, None, None, None) < 0
+    assert b"bad args" in ctx.L.so_last_error()
+    with pytest.raises(api.SuperOdomError):
+        ctx.register(np.zeros((300000, 4), np.float32), case["pose_prior"], 5)       # over max_scan_points
+    ctx.close()
+
+
+def test_block_boundary_restriction(gpu_api, oracle_mod):
+    """Neighbours come only from the query's own 50 m block (LocalMap.h:488-525): straddle x = 25."""
+    rng = np.random.default_rng(4)
+    n = 60000
+    p = np.stack([rng.uniform(20, 30, n), rng.uniform(-5, 5, n), rng.uniform(-1, 1, n) * 0.02 - 1.5], 1).astype(np.float32)
+    xyzi = np.concatenate([p, np.ones((n, 1), np.float32)], 1)
+    ctx = gpu_api.Context(max_map_points=1 << 20, max_scan_points=65536, plane_res=0.2)
+    ctx.map_set_points(xyzi)
+    om = oracle_mod.OracleMap(xyzi)
+    q = np.stack([rng.uniform(24.5, 25.5, 4000), rng.uniform(-4, 4, 4000), np.full(4000, -1.5)], 1).astype(np.float32)
+    q[:8, 0] = np.float32([25.0, 24.999998, 25.000002, 24.99, 25.01, 25.0, 25.0, 25.0])
+    gi, gd = ctx.knn(q, 5, 0.0)
+    oi, od, of = om.knn(q, 5, 0)
+    assert np.array_equal(_gi(gi), oi) and np.array_equal(gd, od)
+    side_q = q[:, 0].astype(np.float64) + 25.0 >= 50.0
+    side_n = p[gi.astype(np.int64), 0].astype(np.float64) + 25.0 >= 50.0
+    assert (side_n == side_q[:, None]).all()
+    ctx.close()
+
+
+def test_map_shift_and_counts(gpu_api, oracle_mod):
+    case = get_case("tiny")
+    ctx = _ctx(gpu_api, case)
+    om = oracle_mod.OracleMap(case["map_xyzi"])
+    assert list(ctx.map_origin()) == [10, 10, 5]
+    for t in ([0, 0, 0], [-400.0, 0, 0], [30.0, 460.0, 0.0]):
+        assert list(ctx.map_shift(t)) == list(om.shift(t))
+        assert list(ctx.map_origin()) == list(om.origin())
+        ijk = ctx.map_shift(t)
+        assert ctx.map_counts_5x5(ijk) == om.counts_5x5(ijk)
+    assert ctx.map_size() == len(case["map_xyzi"])
+    r = ctx.register(case["scan_xyzi"], case["pose_prior"], 5)        # still registers after the rolls
+    ro = om.register(case["scan_xyzi"], case["pose_prior"], 0.2, 5)
+    _assert_pose_close(np.array(r.pose), np.array(ro.pose))
+    ijk = ctx.map_shift([900.0, 0, 0])                                # far away: the map's block rolls off the grid
+    assert ctx.map_size() == 0 and list(ijk) == list(om.shift([900.0, 0, 0]))
+    back = ctx.map_download(0)
+    assert len(back) == 0
+    ctx.close()
+
+
+def test_batch_equals_singles(gpu_api):
+    case0 = get_case("tiny", 0)
+    scans, poses = [], []
+    for i in range(5):
+        c = get_case("tiny", i)
+        s = c["scan_xyzi"][: len(c["scan_xyzi"]) - 37 * i]           # ragged lengths
+        scans.append(s)
+        poses.append(c["pose_prior"])
+    ctx = _ctx(gpu_api, case0, max_batch=8)
+    singles = [ctx.register(s, p, 5, skip_map_checks=True) for s, p in zip(scans, poses)]
+    flat = np.ascontiguousarray(np.concatenate(scans, 0))
+    res = ctx.register_batch(flat, [len(s) for s in scans], np.stack(poses), 5, skip_map_checks=True)
+    for a, b in zip(singles, res):
+        assert np.array_equal(np.array(a.pose), np.array(b.pose)) and a.n_iterations == b.n_iterations
+        assert np.array_equal(np.array(a.cov), np.array(b.cov))
+    import torch
+    d = torch.from_numpy(flat).cuda()
+    res2 = ctx.register_batch_device(d.data_ptr(), [len(s) for s in scans], np.stack(poses), 5, skip_map_checks=True)
+    for a, b in zip(singles, res2):
+        assert np.array_equal(np.array(a.pose), np.array(b.pose))
+    ctx.close()
+
+
+def test_full_size_properties_cfg2(gpu_api, oracle_mod):
+    """BASELINE cfg2 (131 072-pt scan vs 1 M-pt map, 20 ICP iterations): size-independent properties, plus direct
+    oracle parity for the first ICP iteration's correspondences (one oracle pass is ~1 s)."""
+    case = get_case("cfg2")
+    cfg = case["cfg"]
+    ctx = api_ctx = _ctx(gpu_api, case)
+    r = ctx.register(case["scan_xyzi"], case["pose_prior"], cfg["max_iterations"], 0)
+    pose = np.array(r.pose)
+    assert r.status == 0
+    assert np.linalg.norm(pose[:3] - case["pose_true"][:3]) < 0.01 and quat_angle(pose[3:], case["pose_true"][3:]) < 2e-3
+    # idempotence: registering again from the converged pose moves < 1 mm
+    r2 = ctx.register(case["scan_xyzi"], pose, cfg["max_iterations"], 0)
+    assert np.linalg.norm(np.array(r2.pose)[:3] - pose[:3]) < 1e-3
+    # histogram bookkeeping: every processed point lands in exactly one rejection bin; 3 obs labels per accepted point
+    assert sum(r.hist_reject_plane) == len(case["scan_xyzi"]) and sum(r.hist_obs) == 3 * r.hist_reject_plane[0]
+    assert r.iter_n_surf[r.n_iterations - 1] == r.hist_reject_plane[0]
+    # rigid-motion equivariance is NOT exact for this algorithm (block grid, float rounding), but a different prior must
+    # land on the same optimum to well under the tolerance
+    from superodom_b200 import synth
+    r3 = ctx.register(case["scan_xyzi"], synth.perturb_pose(case["pose_true"], 4242), cfg["max_iterations"], 0)
+    assert np.linalg.norm(np.array(r3.pose)[:3] - pose[:3]) < 2e-3
+    # one oracle pass at full size
+    om = oracle_mod.OracleMap(case["map_xyzi"], ref_octree=False)
+    gc, gho, ghr = ctx.correspond(case["scan_xyzi"], case["pose_prior"], 0)
+    oc, oho, ohr = om.correspond(case["scan_xyzi"], case["pose_prior"], cfg["plane_res"], 0, 0, n_threads=8)
+    assert np.array_equal(gc["status"].astype(np.int64), oc["status"].astype(np.int64))
+    assert np.array_equal(gho, oho) and np.array_equal(ghr, ohr)
+    ok = oc["status"] == 0
+    assert np.array_equal(gc["nn"][ok].astype(np.int64), oc["nn"][ok])
+    H, g, cost = ctx.evaluate(case["pose_prior"])
+    oH, og, ocost, _ = oracle_mod.evaluate(oc, case["pose_prior"], cfg["plane_res"])
+    assert np.abs(H - oH).max() <= 1e-10 * np.abs(oH).max() and abs(cost - ocost) <= 1e-10 * ocost
+    # and the whole registration against the oracle (about 10 s of CPU)
+    ro = om.register(case["scan_xyzi"], case["pose_prior"], cfg["plane_res"], cfg["max_iterations"], 0, knn_mode=0, n_threads=8)
+    _assert_pose_close(pose, np.array(ro.pose))
+    assert r.n_iterations == ro.n_iterations
+    api_ctx.close()
+
+
+def test_cfg3_mid360_with_covariance(gpu_api, oracle_mod):
+    """BASELINE cfg3: 240 000-pt Mid-360 scan vs 2 M-pt map at planeRes 0.1, covariance / eigen outputs checked."""
+    case = get_case("cfg3")
+    cfg = case["cfg"]
+    ctx = gpu_api.Context(max_map_points=len(case["map_xyzi"]) + 1024, max_scan_points=262144, plane_res=cfg["plane_res"])
+    ctx.map_set_points(case["map_xyzi"])
+    r = ctx.register(case["scan_xyzi"], case["pose_prior"], cfg["max_iterations"], 0)
+    om = oracle_mod.OracleMap(case["map_xyzi"], ref_octree=False)
+    ro = om.register(case["scan_xyzi"], case["pose_prior"], cfg["plane_res"], cfg["max_iterations"], 0, knn_mode=0, n_threads=8)
+    assert r.status == 0 and ro.status == 0
+    _assert_pose_close(np.array(r.pose), np.array(ro.pose))
+    assert r.n_iterations == ro.n_iterations
+    cg, co = np.array(r.cov).reshape(6, 6), np.array(ro.cov).reshape(6, 6)
+    assert np.abs(cg - co).max() <= 1e-6 * np.abs(co).max()
+    for f in ("pos_err", "pos_inv_cond", "ori_err_deg", "ori_inv_cond"):
+        assert abs(getattr(r, f) - getattr(ro, f)) <= 1e-6 * abs(getattr(ro, f))
+    assert np.linalg.norm(np.array(r.pose)[:3] - case["pose_true"][:3]) < 0.01
+    ctx.close()
