@@ -68,6 +68,15 @@ static int ctx_alloc(Ctx* c) {
     c->scan_cap = size_t(c->cfg.max_scan_points) * c->max_batch;
     c->grid_x_cap = (c->cfg.max_scan_points + kThreads - 1) / kThreads;
     SO_CUDA_TRY(cudaMalloc(&c->d_scan, c->scan_cap * sizeof(float4)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_scan_sorted, c->scan_cap * sizeof(float4)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_skeys, c->scan_cap * sizeof(uint64_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_skeys_out, c->scan_cap * sizeof(uint64_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_svals, c->scan_cap * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_svals_out, c->scan_cap * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->nn.pos, c->scan_cap * 5 * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->nn.pre, c->scan_cap));
+    c->nn.cap = c->scan_cap;
+    { int rc2 = scan_sort_alloc(c); if (rc2) return rc2; }
     SO_CUDA_TRY(cudaMalloc(&c->d_offset, c->max_batch * sizeof(uint32_t)));
     SO_CUDA_TRY(cudaMalloc(&c->d_state, c->max_batch * sizeof(IcpState)));
     SO_CUDA_TRY(cudaMallocHost(&c->h_state, c->max_batch * sizeof(IcpState)));
@@ -91,6 +100,8 @@ static void ctx_free(Ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->graph) cudaGraphExecDestroy(c->graph);
     map_free(c);
+    cudaFree(c->d_scan_sorted); cudaFree(c->d_skeys); cudaFree(c->d_skeys_out); cudaFree(c->d_svals); cudaFree(c->d_svals_out);
+    cudaFree(c->d_sort_tmp); cudaFree(c->nn.pos); cudaFree(c->nn.pre);
     cudaFree(c->d_scan); cudaFree(c->d_offset); cudaFree(c->d_state); cudaFreeHost(c->h_state); cudaFreeHost(c->h_offset);
     cudaFree(c->d_partials); cudaFree(c->d_counters); cudaFree(c->d_hist);
     cudaFree(c->corr.nd); cudaFree(c->corr.w); cudaFree(c->corr.flags); cudaFree(c->corr.nn); cudaFree(c->corr.nn_d2);
@@ -162,12 +173,28 @@ static void timed_launch_end(Ctx* c, int cls) {
 
 // [k_correspond, k_evaluate x lm] x icp iterations; every kernel exits at once when its scan is not in the
 // matching phase, so the fixed schedule follows whatever path the device-side state machine takes.
-static int run_schedule(Ctx* c, const float4* d_scan, uint32_t grid_x, uint32_t n_scans, int iters, int lm, bool with_nn) {
+// Once per registration: order every scan by map cell at its prior pose (k_scan_keys -> radix sort -> k_scan_gather).
+static int prepare_scans(Ctx* c, const float4* d_scan_in, uint32_t grid_x, uint32_t n_scans, size_t total) {
+    const MapView mv = map_view(c);
+    const BatchView bv = batch_view(c, d_scan_in);
+    timed_launch_begin(c);
+    launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, grid_x, n_scans, c->stream);
+    int rc = scan_sort(c, total, int(n_scans));
+    if (rc) return rc;
+    launch_scan_gather(d_scan_in, c->d_svals_out, c->d_skeys_out, c->d_offset, total, c->d_scan_sorted, c->stream);
+    c->launches++;
+    timed_launch_end(c, 3);
+    SO_CUDA_TRY(cudaGetLastError());
+    return SO_OK;
+}
+
+static int run_schedule(Ctx* c, uint32_t grid_x, uint32_t n_scans, int iters, int lm, bool with_nn) {
+    const float4* d_scan = c->d_scan_sorted;
     const MapView mv = map_view(c);
     const BatchView bv = batch_view(c, d_scan);
     CorrBuf cb = c->corr;
     if (!with_nn) { cb.nn = nullptr; cb.nn_d2 = nullptr; }
-    const uint64_t kernels = uint64_t(iters) * (1 + lm);
+    const uint64_t kernels = uint64_t(iters) * (2 + lm);
     if (c->profiling || with_nn) {
         // profiling mode: one launch at a time, timed with events, and only launches that have work (the host peeks
         // at the phases) so that the per-class average is the duration of a kernel that actually ran
@@ -179,7 +206,7 @@ static int run_schedule(Ctx* c, const float4* d_scan, uint32_t grid_x, uint32_t 
             return false;
         };
         for (int it = 0; it < iters; ++it) {
-            if (any_in(PH_CORR)) { timed_launch_begin(c); launch_correspond(mv, bv, cb, grid_x, n_scans, c->stream); timed_launch_end(c, 0); }
+            if (any_in(PH_CORR)) { timed_launch_begin(c); launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream); c->launches++; timed_launch_end(c, 0); }
             for (int k = 0; k < lm; ++k)
                 if (any_in(PH_EVAL)) { timed_launch_begin(c); launch_evaluate(bv, cb, grid_x, n_scans, c->stream); timed_launch_end(c, 1); }
         }
@@ -193,7 +220,7 @@ static int run_schedule(Ctx* c, const float4* d_scan, uint32_t grid_x, uint32_t 
         cudaGraph_t g = nullptr;
         SO_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         for (int it = 0; it < iters; ++it) {
-            launch_correspond(mv, bv, cb, grid_x, n_scans, c->stream);
+            launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream);
             for (int k = 0; k < lm; ++k) launch_evaluate(bv, cb, grid_x, n_scans, c->stream);
         }
         SO_CUDA_TRY(cudaStreamEndCapture(c->stream, &g));
@@ -286,7 +313,9 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         count_h2d(c, n_scans * (sizeof(IcpState) + sizeof(uint32_t)));
         const uint32_t grid_x = (max_n + kThreads - 1) / kThreads;
         SO_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-        int rc = run_schedule(c, d_scan, grid_x, uint32_t(n_scans), o.max_icp_iters, o.lm_max_iterations, false);
+        int rc = prepare_scans(c, d_scan, grid_x, uint32_t(n_scans), size_t(off));
+        if (rc) return rc;
+        rc = run_schedule(c, grid_x, uint32_t(n_scans), o.max_icp_iters, o.lm_max_iterations, false);
         if (rc) return rc;
         SO_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, n_scans * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
@@ -530,24 +559,30 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     const uint32_t grid_x = (uint32_t(n) + kThreads - 1) / kThreads;
+    rc = prepare_scans(c, c->d_scan, grid_x, 1, n);
+    if (rc) return rc;
     const MapView mv = map_view(c);
-    const BatchView bv = batch_view(c, c->d_scan);
-    timed_launch_begin(c); launch_correspond(mv, bv, c->corr, grid_x, 1, c->stream); timed_launch_end(c, 0);
+    const BatchView bv = batch_view(c, c->d_scan_sorted);
+    timed_launch_begin(c); launch_correspond(mv, bv, c->corr, c->nn, grid_x, 1, c->stream); c->launches++; timed_launch_end(c, 0);
     SO_CUDA_TRY(cudaGetLastError());
     std::vector<double4> nd(n); std::vector<double> w(n); std::vector<uchar4> fl(n); std::vector<uint32_t> nn(n * 5); std::vector<float> d2(n * 5);
+    std::vector<float4> sorted(n);
     SO_CUDA_TRY(cudaMemcpyAsync(nd.data(), c->corr.nd, n * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
     SO_CUDA_TRY(cudaMemcpyAsync(w.data(), c->corr.w, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SO_CUDA_TRY(cudaMemcpyAsync(fl.data(), c->corr.flags, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
     SO_CUDA_TRY(cudaMemcpyAsync(nn.data(), c->corr.nn, n * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     SO_CUDA_TRY(cudaMemcpyAsync(d2.data(), c->corr.nn_d2, n * 5 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(sorted.data(), c->d_scan_sorted, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
     SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
     SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    for (size_t i = 0; i < n; ++i) {
-        so_corr& r = corr[i];
+    for (size_t j = 0; j < n; ++j) {          // kernels work in cell order; report in the caller's order
+        uint32_t orig;
+        std::memcpy(&orig, &sorted[j].w, 4);
+        so_corr& r = corr[orig];
         std::memset(&r, 0, sizeof(r));
-        r.n[0] = nd[i].x; r.n[1] = nd[i].y; r.n[2] = nd[i].z; r.d = nd[i].w; r.w = w[i];
-        for (int j = 0; j < 5; ++j) { r.nn[j] = nn[i * 5 + j]; r.nn_d2[j] = d2[i * 5 + j]; }
-        r.status = fl[i].x; r.obs[0] = fl[i].y; r.obs[1] = fl[i].z; r.obs[2] = fl[i].w;
+        r.n[0] = nd[j].x; r.n[1] = nd[j].y; r.n[2] = nd[j].z; r.d = nd[j].w; r.w = w[j];
+        for (int k = 0; k < 5; ++k) { r.nn[k] = nn[j * 5 + k]; r.nn_d2[k] = d2[j * 5 + k]; }
+        r.status = fl[j].x; r.obs[0] = fl[j].y; r.obs[1] = fl[j].z; r.obs[2] = fl[j].w;
     }
     if (hist_obs) std::memcpy(hist_obs, c->h_state[0].hist_obs, 9 * sizeof(int32_t));
     if (hist_rej) std::memcpy(hist_rej, c->h_state[0].hist_rej, 7 * sizeof(int32_t));
@@ -565,7 +600,7 @@ int so_evaluate(so_ctx* ctx, const double pose[7], double H[36], double g[6], do
     s.phase = PH_EVAL; s.max_icp_iters = -1;
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
     const uint32_t grid_x = (n + kThreads - 1) / kThreads;
-    const BatchView bv = batch_view(c, c->d_scan);
+    const BatchView bv = batch_view(c, c->d_scan_sorted);
     timed_launch_begin(c); launch_evaluate(bv, c->corr, grid_x, 1, c->stream); timed_launch_end(c, 1);
     SO_CUDA_TRY(cudaGetLastError());
     SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));

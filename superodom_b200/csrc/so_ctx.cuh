@@ -51,7 +51,12 @@ struct Ctx {
     // ---- scans / correspondences / optimiser state -------------------------------------------------------------
     uint32_t max_batch = 1;
     size_t scan_cap = 0;                           // points over the whole batch
-    float4* d_scan = nullptr;
+    float4* d_scan = nullptr;                      // upload target for host scans (original order)
+    float4* d_scan_sorted = nullptr;               // cell-ordered copy the kernels read; w = original index
+    uint64_t* d_skeys = nullptr; uint64_t* d_skeys_out = nullptr;   // scan sort keys (scan id << 32 | cell)
+    uint32_t* d_svals = nullptr; uint32_t* d_svals_out = nullptr;
+    void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
+    NnBuf nn{};
     uint32_t* d_offset = nullptr;
     IcpState* d_state = nullptr;
     IcpState* h_state = nullptr;                   // pinned
@@ -86,5 +91,7 @@ void map_free(Ctx* c);
 int map_rebuild(Ctx* c);                 // (re)bin, drop off-grid points, sort, build cell table
 MapView map_view(const Ctx* c);
 int map_cells_per_block(float plane_res);
+int scan_sort_alloc(Ctx* c);             // temp storage for the per-registration scan sort
+int scan_sort(Ctx* c, size_t n, int n_scans);   // d_skeys/d_svals -> d_skeys_out/d_svals_out
 
 }  // namespace so

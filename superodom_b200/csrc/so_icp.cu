@@ -1,9 +1,10 @@
 // so_icp.cu -- sm_100a kernels of the per-scan ICP registration path.
 //
-//   k_correspond : per scan point -- pose transform, block lookup, radius-bounded 5-NN in the sorted hash grid,
-//                  3x3 PCA + 5x3 column-pivoted QR plane fit with the reference's accept/reject gates, observability
+//   k_scan_keys / k_scan_gather : order the scan by map cell once per registration (warp-coherent cell walks).
+//   k_knn_scan   : per scan point -- pose transform, block lookup, radius-bounded 5-NN in the sorted hash grid.   [K2]
+//   k_fit        : 3x3 PCA + 5x3 column-pivoted QR plane fit with the reference's accept/reject gates, observability
 //                  labels + histograms, AND the first residual/Jacobian evaluation of the following ceres::Solve,
-//                  warp/CTA-reduced in FP64 (21+6+1 accumulators).                       [SURVEY 2.3: K2+K3+K4+K5]
+//                  warp/CTA-reduced in FP64 (21+6+1 accumulators).                                  [K3+K4+K5]
 //   k_evaluate   : per correspondence -- residual, 1x6 Jacobian, Tukey/Scaled robust weight at the LM candidate pose,
 //                  same reduction.                                                          [K5]
 //   last CTA of either kernel: fixed-order final reduction, then ONE thread advances the device-resident state
@@ -85,17 +86,27 @@ __device__ __forceinline__ void locate(const MapView& m, float qx, float qy, flo
 }
 
 template <int K>
-__device__ __forceinline__ void scan_range(const MapView& m, uint32_t beg, uint32_t end, float qx, float qy, float qz, TopK<K>& tk) {
-    for (uint32_t t = beg; t < end; ++t) {
-        const float4 c = __ldg(&m.pts[t]);
-        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-        const float approx = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        // cheap FP32 filter (relative error < 4e-7), then the reference's exact rounding for real contenders
-        if (approx <= tk.worst() * 1.000002f) {
-            const float d2 = float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz));
-            tk.offer(d2, __float_as_uint(c.w), t);
-        }
+__device__ __forceinline__ void offer_candidate(const float4 c, uint32_t t, float qx, float qy, float qz, TopK<K>& tk) {
+    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+    const float approx = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    // cheap FP32 filter (relative error < 4e-7), then the reference's exact rounding for real contenders
+    if (approx <= tk.worst() * 1.000002f) {
+        const float d2 = float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz));
+        tk.offer(d2, __float_as_uint(c.w), t);
     }
+}
+
+template <int K>
+__device__ __forceinline__ void scan_range(const MapView& m, uint32_t beg, uint32_t end, float qx, float qy, float qz, TopK<K>& tk) {
+    uint32_t t = beg;
+    for (; t + 4 <= end; t += 4) {          // four independent 16-byte loads in flight per lane
+        const float4 c0 = __ldg(&m.pts[t]), c1 = __ldg(&m.pts[t + 1]), c2 = __ldg(&m.pts[t + 2]), c3 = __ldg(&m.pts[t + 3]);
+        offer_candidate<K>(c0, t, qx, qy, qz, tk);
+        offer_candidate<K>(c1, t + 1, qx, qy, qz, tk);
+        offer_candidate<K>(c2, t + 2, qx, qy, qz, tk);
+        offer_candidate<K>(c3, t + 3, qx, qy, qz, tk);
+    }
+    for (; t < end; ++t) offer_candidate<K>(__ldg(&m.pts[t]), t, qx, qy, qz, tk);
 }
 
 // Cube of cells [c-R, c+R]^3 clipped to the block, as (2R+1)^2 contiguous x-rows.  For R == 1 rows are visited
@@ -201,7 +212,7 @@ __device__ __forceinline__ bool reduce_and_elect(double acc[kAcc], const BatchVi
 // TrustRegionStepEvaluator, expressed on the robustified normal equations H = sum rho' J^T J, g = sum rho' J^T r
 // (the QR of [J;D] that DENSE_QR performs solves exactly (H + D^2) y = g).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ double grad_max_norm(const double x[7], const double g[6]) {
+__device__ __noinline__ double grad_max_norm(const double x[7], const double g[6]) {
     // ||x - Plus(x, -g)||_inf  (TrustRegionMinimizer::EvaluateGradientAndJacobian)
     double neg[6], xp[7];
     for (int j = 0; j < 6; ++j) neg[j] = -g[j];
@@ -211,7 +222,7 @@ __device__ double grad_max_norm(const double x[7], const double g[6]) {
     return m;
 }
 
-__device__ void covariance_and_errors(IcpState& st) {
+__device__ __noinline__ void covariance_and_errors(IcpState& st) {
     // ceres::Covariance{apply_loss_function, DENSE_SVD, null_space_rank=-1} in tangent space (LidarSlam.cpp:854-871):
     // pseudo-inverse of J^T J dropping singular directions with s_i/s_max < sqrt(1e-14) (covariance_impl.cc).
     double A[36], V[36], w[6];
@@ -241,7 +252,7 @@ __device__ void covariance_and_errors(IcpState& st) {
 }
 
 // End of one ceres::Solve == end of one ICP iteration (LidarSlam.cpp:134-146).
-__device__ void end_solve(IcpState& st) {
+__device__ __noinline__ void end_solve(IcpState& st) {
     const int it = st.icp_iter;
     st.iter_n_surf[it] = st.n_ok;
     rel_motion(st.x_iter_start, st.x, &st.iter_dtrans[it], &st.iter_drot[it]);      // recordIterationStats (:242-251)
@@ -263,7 +274,7 @@ __device__ void end_solve(IcpState& st) {
 }
 
 // TrustRegionMinimizer loop from FinalizeIterationAndCheckIfMinimizerCanContinue up to the next cost evaluation.
-__device__ void lm_continue(IcpState& st, bool step_successful) {
+__device__ __noinline__ void lm_continue(IcpState& st, bool step_successful) {
     for (;;) {
         if (step_successful) st.num_successful++; else st.num_unsuccessful++;
         if (st.lm_iter >= st.lm_max_iterations) { st.termination = 0; end_solve(st); return; }
@@ -308,7 +319,7 @@ __device__ void lm_continue(IcpState& st, bool step_successful) {
 }
 
 // IterationZero of a new solve, fed by k_correspond's reduction.
-__device__ void lm_begin_solve(IcpState& st, const double* acc, int n_ok) {
+__device__ __noinline__ void lm_begin_solve(IcpState& st, const double* acc, int n_ok) {
     for (int k = 0; k < 21; ++k) st.H[k] = acc[k];
     for (int k = 0; k < 6; ++k) st.g[k] = acc[21 + k];
     st.cost = acc[27];
@@ -325,7 +336,7 @@ __device__ void lm_begin_solve(IcpState& st, const double* acc, int n_ok) {
 }
 
 // After the cost (and H, g) at the candidate are known.
-__device__ void lm_after_eval(IcpState& st, const double* acc) {
+__device__ __noinline__ void lm_after_eval(IcpState& st, const double* acc) {
     const double cand_cost = acc[27];
     // ParameterToleranceReached
     double sn = 0.0; for (int i = 0; i < 7; ++i) { const double d = st.x[i] - st.cand[i]; sn += d * d; }
@@ -393,9 +404,85 @@ __device__ __forceinline__ bool should_process(uint32_t i, double rate) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_correspond: LidarSLAM::ComputePlaneDistanceParameters for every scan point (LidarSlam.cpp:514-572)
+// Scan preparation (once per registration): order the scan points by the map cell they fall into at the PRIOR pose,
+// so that the 32 lanes of a warp walk the same cell rows in lock-step (identical addresses -> one L1 wavefront per
+// load instead of 32).  Pose updates inside one registration are a few cm against 0.78 m cells, so the order stays
+// coherent for all ICP iterations.  The sorted copy carries the point's original index in .w (the reference's
+// shouldProcessPoint() decimation is defined on the original index, LidarSlam.cpp:353-359).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_correspond(MapView m, BatchView bv, CorrBuf cb) {
+__global__ void __launch_bounds__(kThreads) k_scan_keys(MapView m, BatchView bv, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int s = blockIdx.y;
+    const IcpState* st = bv.st + s;
+    const uint32_t n = uint32_t(st->n_points);
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const size_t gi = size_t(bv.offset[s]) + i;
+    const float4 sp = __ldg(&bv.scan[gi]);
+    const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+    double pf[3];
+    qrot(st->x + 3, pin, pf);
+    QueryCell qc;
+    locate(m, float(pf[0] + st->x[0]), float(pf[1] + st->x[1]), float(pf[2] + st->x[2]), qc);
+    uint32_t cell = 0xFFFFFFFFu;
+    if (qc.slot >= 0) cell = uint32_t(qc.slot) * uint32_t(m.nb * m.nb * m.nb) + uint32_t((qc.c[2] * m.nb + qc.c[1]) * m.nb + qc.c[0]);
+    keys[gi] = (uint64_t(s) << 32) | uint64_t(cell);
+    vals[gi] = uint32_t(gi);
+}
+
+__global__ void __launch_bounds__(kThreads) k_scan_gather(const float4* __restrict__ in, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ keys,
+                                                          const uint32_t* __restrict__ offset, size_t total, float4* __restrict__ out) {
+    const size_t j = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    if (j >= total) return;
+    const uint32_t g = vals[j];
+    const uint32_t s = uint32_t(keys[j] >> 32);
+    const float4 p = __ldg(&in[g]);
+    out[j] = make_float4(p.x, p.y, p.z, __uint_as_float(g - offset[s]));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_knn_scan: findNearestNeighbors (LidarSlam.cpp:720-747) for every processed scan point at the current pose.
+// Light on registers (FP32 search, FP64 only for the pose transform and the exact d2 of real contenders) so that
+// many warps per SM hide the L1/L2 latency of the cell walks.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, NnBuf nb) {
+    const int s = blockIdx.y;
+    const IcpState* st = bv.st + s;
+    if (st->phase != PH_CORR) return;
+    __shared__ double s_pose[7];
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
+    __syncthreads();
+    const uint32_t n = uint32_t(st->n_points);
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const size_t gi = size_t(bv.offset[s]) + i;
+    const float4 sp = __ldg(&bv.scan[gi]);
+    int pre = SO_MATCH_SKIPPED;
+    TopK<5> tk;
+    tk.init(m.bound_d2);
+    if (should_process(__float_as_uint(sp.w), st->sampling_rate)) {
+        const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+        double pf[3];
+        qrot(s_pose + 3, pin, pf);
+        const float qx = float(pf[0] + s_pose[0]), qy = float(pf[1] + s_pose[1]), qz = float(pf[2] + s_pose[2]);
+        QueryCell qc;
+        locate(m, qx, qy, qz, qc);
+        if (qc.slot < 0 || qc.nblock < 5) pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
+        else {
+            knn_ring<5>(m, qc, qx, qy, qz, 1, tk);
+            pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
+        }
+    }
+    nb.pre[gi] = (unsigned char)pre;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) nb.pos[size_t(j) * nb.cap + gi] = tk.id[j] != 0xFFFFFFFFu ? tk.pos[j] : 0xFFFFFFFFu;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_fit: the rest of LidarSLAM::ComputePlaneDistanceParameters (LidarSlam.cpp:536-572) for every point that has its
+// five neighbours -- PCA, plane fit, gates, observability -- plus the first residual/Jacobian evaluation of the
+// following ceres::Solve and the histogram / normal-equation reductions.  FP64 throughout.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_fit(MapView m, BatchView bv, CorrBuf cb, NnBuf nb) {
     const int s = blockIdx.y;
     IcpState* st = bv.st + s;
     if (st->phase != PH_CORR) return;
@@ -409,7 +496,6 @@ __global__ void __launch_bounds__(kThreads) k_correspond(MapView m, BatchView bv
     if (threadIdx.x == 0) qtoR(s_pose + 3, s_R);
     __syncthreads();
     const uint32_t n = uint32_t(st->n_points);
-    const double rate = st->sampling_rate;
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
     const size_t gi = size_t(bv.offset[s]) + i;
 
@@ -418,128 +504,128 @@ __global__ void __launch_bounds__(kThreads) k_correspond(MapView m, BatchView bv
     for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
 
     if (i < n) {
-        int status = SO_MATCH_SKIPPED;
+        int status = nb.pre[gi];
         int o0 = 0, o1 = 0, o2 = 0;
         double nrm[3] = {0, 0, 0}, dpl = 0.0, wq = 0.0;
-        TopK<5> tk;
-        tk.init(m.bound_d2);
-        if (should_process(i, rate)) {
+        if (status == SO_MATCH_SUCCESS) {
             const float4 sp = __ldg(&bv.scan[gi]);
             // ComputePointInitAndFinalPose (:382-400): pInit = double(p), pFinal = T_w_lidar * pInit
             const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
             double pf[3];
             qrot(s_pose + 3, pin, pf);
             pf[0] += s_pose[0]; pf[1] += s_pose[1]; pf[2] += s_pose[2];
-            const float qx = float(pf[0]), qy = float(pf[1]), qz = float(pf[2]);      // findNearestNeighbors (:728-731)
-            QueryCell qc;
-            locate(m, qx, qy, qz, qc);
-            if (qc.slot < 0 || qc.nblock < 5) status = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
+            const float qx = float(pf[0]), qy = float(pf[1]), qz = float(pf[2]);
+            // computePCAForFeature (:749-790) + utils::ComputePCA (superodom_utils.h:143-151)
+            double mm[5][3];
+            double mean[3] = {0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const uint32_t pos = nb.pos[size_t(j) * nb.cap + gi];
+                const float4 c = __ldg(&m.pts[pos]);
+                mm[j][0] = double(c.x); mm[j][1] = double(c.y); mm[j][2] = double(c.z);
+                mean[0] += mm[j][0]; mean[1] += mm[j][1]; mean[2] += mm[j][2];
+                if (cb.nn) {
+                    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+                    cb.nn[gi * 5 + j] = __float_as_uint(c.w);
+                    cb.nn_d2[gi * 5 + j] = float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz));
+                }
+            }
+            mean[0] /= 5.0; mean[1] /= 5.0; mean[2] /= 5.0;
+            double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const double c0 = mm[j][0] - mean[0], c1 = mm[j][1] - mean[1], c2 = mm[j][2] - mean[2];
+                S[0] += c0 * c0; S[1] += c0 * c1; S[2] += c0 * c2; S[4] += c1 * c1; S[5] += c1 * c2; S[8] += c2 * c2;
+            }
+            S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
+            double V[9], ev[3];
+            jacobi_eig<3, 12>(S, V, ev);
+            if (ev[0] < 1e-6 || ev[1] / ev[2] < 0.1) status = SO_MATCH_BAD_PCA_STRUCTURE;      // (:772)
             else {
-                knn_ring<5>(m, qc, qx, qy, qz, 1, tk);
-                if (tk.count() < 5) status = SO_MATCH_NEIGHBORS_TOO_FAR;            // d2[4] > 3*planeRes_ (:741-744)
+                // computePlaneQualityMetrics (:792-844)
+                double A[5][3], b[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) { A[j][0] = mm[j][0]; A[j][1] = mm[j][1]; A[j][2] = mm[j][2]; b[j] = -1.0; }
+                double x[3];
+                colpiv_qr_solve_5x3(A, b, x);
+                if (!(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]))) status = SO_MATCH_INVALID_NUMERICAL;
                 else {
-                    // computePCAForFeature (:749-790) + utils::ComputePCA (superodom_utils.h:143-151)
-                    double mm[5][3];
-                    double mean[3] = {0, 0, 0};
+                    const double nn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+                    const double dd = 1.0 / nn;
+                    x[0] /= nn; x[1] /= nn; x[2] /= nn;
+                    const double maxd = double(m.plane_res) / 2.0;
+                    double msum = 0.0;
+                    bool ok = true;
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
-                        const float4 c = __ldg(&m.pts[tk.pos[j]]);
-                        mm[j][0] = double(c.x); mm[j][1] = double(c.y); mm[j][2] = double(c.z);
-                        mean[0] += mm[j][0]; mean[1] += mm[j][1]; mean[2] += mm[j][2];
+                        const double dist = fabs(x[0] * mm[j][0] + x[1] * mm[j][1] + x[2] * mm[j][2] + dd);
+                        if (ok && dist > maxd) ok = false;
+                        msum += dist;
                     }
-                    mean[0] /= 5.0; mean[1] /= 5.0; mean[2] /= 5.0;
-                    double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) {
-                        const double c0 = mm[j][0] - mean[0], c1 = mm[j][1] - mean[1], c2 = mm[j][2] - mean[2];
-                        S[0] += c0 * c0; S[1] += c0 * c1; S[2] += c0 * c2; S[4] += c1 * c1; S[5] += c1 * c2; S[8] += c2 * c2;
-                    }
-                    S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
-                    double V[9], ev[3];
-                    jacobi_eig<3, 12>(S, V, ev);
-                    if (ev[0] < 1e-6 || ev[1] / ev[2] < 0.1) status = SO_MATCH_BAD_PCA_STRUCTURE;      // (:772)
+                    if (!ok) status = SO_MATCH_MSE_TOO_LARGE;
                     else {
-                        // computePlaneQualityMetrics (:792-844)
-                        double A[5][3], b[5];
+                        const double mean_dist = msum / 5.0;
+                        // normal orientation (:553-561) on the PCA normal, then FeatureObservabilityAnalysis (:574-693)
+                        double no[3] = {V[0], V[3], V[6]};
+                        if (pf[0] * no[0] + pf[1] * no[1] + pf[2] * no[2] < 0) { no[0] = -no[0]; no[1] = -no[1]; no[2] = -no[2]; }
+                        const double l1 = sqrt(ev[2]), l2 = sqrt(ev[1]), l3 = sqrt(ev[0]);
+                        const double planar_2 = (l2 - l3) / l1;
+                        const float nf[3] = {float(no[0]), float(no[1]), float(no[2])};
+                        const float cr[3] = {__fmul_rn(qy, nf[2]) - __fmul_rn(qz, nf[1]), __fmul_rn(qz, nf[0]) - __fmul_rn(qx, nf[2]),
+                                             __fmul_rn(qx, nf[1]) - __fmul_rn(qy, nf[0])};
+                        const float fq[4] = {float(s_pose[3]), float(s_pose[4]), float(s_pose[5]), float(s_pose[6])};
+                        float rotq[6], trq[3];
+                        const float planar_sq = float(planar_2 * planar_2);
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) { A[j][0] = mm[j][0]; A[j][1] = mm[j][1]; A[j][2] = mm[j][2]; b[j] = -1.0; }
-                        double x[3];
-                        colpiv_qr_solve_5x3(A, b, x);
-                        if (!(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]))) status = SO_MATCH_INVALID_NUMERICAL;
-                        else {
-                            const double nn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-                            const double dd = 1.0 / nn;
-                            x[0] /= nn; x[1] /= nn; x[2] /= nn;
-                            const double maxd = double(m.plane_res) / 2.0;
-                            double msum = 0.0;
-                            bool ok = true;
-#pragma unroll
-                            for (int j = 0; j < 5; ++j) {
-                                const double dist = fabs(x[0] * mm[j][0] + x[1] * mm[j][1] + x[2] * mm[j][2] + dd);
-                                if (ok && dist > maxd) ok = false;
-                                msum += dist;
-                            }
-                            if (!ok) status = SO_MATCH_MSE_TOO_LARGE;
-                            else {
-                                const double mean_dist = msum / 5.0;
-                                // normal orientation (:553-561) on the PCA normal, then FeatureObservabilityAnalysis (:574-693)
-                                double no[3] = {V[0], V[3], V[6]};
-                                if (pf[0] * no[0] + pf[1] * no[1] + pf[2] * no[2] < 0) { no[0] = -no[0]; no[1] = -no[1]; no[2] = -no[2]; }
-                                const double l1 = sqrt(ev[2]), l2 = sqrt(ev[1]), l3 = sqrt(ev[0]);
-                                const double planar_2 = (l2 - l3) / l1;
-                                const float nf[3] = {float(no[0]), float(no[1]), float(no[2])};
-                                const float cr[3] = {__fmul_rn(qy, nf[2]) - __fmul_rn(qz, nf[1]), __fmul_rn(qz, nf[0]) - __fmul_rn(qx, nf[2]),
-                                                     __fmul_rn(qx, nf[1]) - __fmul_rn(qy, nf[0])};
-                                const float fq[4] = {float(s_pose[3]), float(s_pose[4]), float(s_pose[5]), float(s_pose[6])};
-                                float rotq[6], trq[3];
-                                const float planar_sq = float(planar_2 * planar_2);
-#pragma unroll
-                                for (int a = 0; a < 3; ++a) {
-                                    // computeRotatedAxes (:624-638): float quaternion * e_a, no FMA contraction (host code is plain IEEE)
-                                    const float v0 = a == 0 ? 1.f : 0.f, v1 = a == 1 ? 1.f : 0.f, v2 = a == 2 ? 1.f : 0.f;
-                                    float ux = __fsub_rn(__fmul_rn(fq[1], v2), __fmul_rn(fq[2], v1));
-                                    float uy = __fsub_rn(__fmul_rn(fq[2], v0), __fmul_rn(fq[0], v2));
-                                    float uz = __fsub_rn(__fmul_rn(fq[0], v1), __fmul_rn(fq[1], v0));
-                                    ux = __fadd_rn(ux, ux); uy = __fadd_rn(uy, uy); uz = __fadd_rn(uz, uz);
-                                    const float ax = __fadd_rn(__fadd_rn(v0, __fmul_rn(fq[3], ux)), __fsub_rn(__fmul_rn(fq[1], uz), __fmul_rn(fq[2], uy)));
-                                    const float ay = __fadd_rn(__fadd_rn(v1, __fmul_rn(fq[3], uy)), __fsub_rn(__fmul_rn(fq[2], ux), __fmul_rn(fq[0], uz)));
-                                    const float az = __fadd_rn(__fadd_rn(v2, __fmul_rn(fq[3], uz)), __fsub_rn(__fmul_rn(fq[0], uy), __fmul_rn(fq[1], ux)));
-                                    // Eigen's unrolled 3-vector dot associates as a0*b0 + (a1*b1 + a2*b2)
-                                    const float rc = __fadd_rn(__fmul_rn(cr[0], ax), __fadd_rn(__fmul_rn(cr[1], ay), __fmul_rn(cr[2], az)));
-                                    rotq[2 * a] = rc; rotq[2 * a + 1] = -rc;
-                                    const float dn = __fadd_rn(__fmul_rn(nf[0], ax), __fadd_rn(__fmul_rn(nf[1], ay), __fmul_rn(nf[2], az)));
-                                    trq[a] = __fmul_rn(planar_sq, fabsf(dn));
-                                }
-                                // top-2 rotation labels and top-1 translation label of a stable descending sort (:654-679)
-                                int r0 = 0;
-#pragma unroll
-                                for (int q = 1; q < 6; ++q) if (rotq[q] > rotq[r0]) r0 = q;
-                                int r1 = (r0 == 0) ? 1 : 0;
-#pragma unroll
-                                for (int q = 0; q < 6; ++q) if (q != r0 && q != r1 && (rotq[q] > rotq[r1] || (rotq[q] == rotq[r1] && q < r1))) r1 = q;
-                                int t0 = 0;
-#pragma unroll
-                                for (int q = 1; q < 3; ++q) if (trq[q] > trq[t0]) t0 = q;
-                                o0 = r0; o1 = r1; o2 = 6 + t0;
-                                nrm[0] = x[0]; nrm[1] = x[1]; nrm[2] = x[2]; dpl = dd;
-                                wq = 1.0 - sqrt(mean_dist / double(m.bound_d2));        // fitQualityCoeff (:568)
-                                status = SO_MATCH_SUCCESS;
-                                accumulate(acc, nrm, dpl, wq, pin, pf, s_R, bv.tukey_a2);
-                            }
+                        for (int a = 0; a < 3; ++a) {
+                            // computeRotatedAxes (:624-638): float quaternion * e_a, no FMA contraction (host code is plain IEEE)
+                            const float v0 = a == 0 ? 1.f : 0.f, v1 = a == 1 ? 1.f : 0.f, v2 = a == 2 ? 1.f : 0.f;
+                            float ux = __fsub_rn(__fmul_rn(fq[1], v2), __fmul_rn(fq[2], v1));
+                            float uy = __fsub_rn(__fmul_rn(fq[2], v0), __fmul_rn(fq[0], v2));
+                            float uz = __fsub_rn(__fmul_rn(fq[0], v1), __fmul_rn(fq[1], v0));
+                            ux = __fadd_rn(ux, ux); uy = __fadd_rn(uy, uy); uz = __fadd_rn(uz, uz);
+                            const float ax = __fadd_rn(__fadd_rn(v0, __fmul_rn(fq[3], ux)), __fsub_rn(__fmul_rn(fq[1], uz), __fmul_rn(fq[2], uy)));
+                            const float ay = __fadd_rn(__fadd_rn(v1, __fmul_rn(fq[3], uy)), __fsub_rn(__fmul_rn(fq[2], ux), __fmul_rn(fq[0], uz)));
+                            const float az = __fadd_rn(__fadd_rn(v2, __fmul_rn(fq[3], uz)), __fsub_rn(__fmul_rn(fq[0], uy), __fmul_rn(fq[1], ux)));
+                            // Eigen's unrolled 3-vector dot associates as a0*b0 + (a1*b1 + a2*b2)
+                            const float rc = __fadd_rn(__fmul_rn(cr[0], ax), __fadd_rn(__fmul_rn(cr[1], ay), __fmul_rn(cr[2], az)));
+                            rotq[2 * a] = rc; rotq[2 * a + 1] = -rc;
+                            const float dn = __fadd_rn(__fmul_rn(nf[0], ax), __fadd_rn(__fmul_rn(nf[1], ay), __fmul_rn(nf[2], az)));
+                            trq[a] = __fmul_rn(planar_sq, fabsf(dn));
                         }
+                        // top-2 rotation labels and top-1 translation label of a stable descending sort (:654-679)
+                        int r0 = 0;
+#pragma unroll
+                        for (int q = 1; q < 6; ++q) if (rotq[q] > rotq[r0]) r0 = q;
+                        int r1 = (r0 == 0) ? 1 : 0;
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) if (q != r0 && q != r1 && rotq[q] > rotq[r1]) r1 = q;
+                        int t0 = 0;
+#pragma unroll
+                        for (int q = 1; q < 3; ++q) if (trq[q] > trq[t0]) t0 = q;
+                        o0 = r0; o1 = r1; o2 = 6 + t0;
+                        nrm[0] = x[0]; nrm[1] = x[1]; nrm[2] = x[2]; dpl = dd;
+                        wq = 1.0 - sqrt(mean_dist / double(m.bound_d2));        // fitQualityCoeff (:568)
+                        status = SO_MATCH_SUCCESS;
+                        accumulate(acc, nrm, dpl, wq, pin, pf, s_R, bv.tukey_a2);
                     }
                 }
             }
+        } else if (cb.nn) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const uint32_t pos = nb.pos[size_t(j) * nb.cap + gi];
+                cb.nn[gi * 5 + j] = pos != 0xFFFFFFFFu ? __float_as_uint(__ldg(&m.pts[pos]).w) : 0xFFFFFFFFu;
+                cb.nn_d2[gi * 5 + j] = 0.f;
+            }
+        }
+        if (status != SO_MATCH_SKIPPED) {
             if (status == SO_MATCH_SUCCESS) { atomicAdd(&s_hist[o0], 1); atomicAdd(&s_hist[o1], 1); atomicAdd(&s_hist[o2], 1); }
             atomicAdd(&s_hist[9 + status], 1);
         }
         cb.nd[gi] = make_double4(nrm[0], nrm[1], nrm[2], dpl);
         cb.w[gi] = wq;
         cb.flags[gi] = make_uchar4((unsigned char)status, (unsigned char)o0, (unsigned char)o1, (unsigned char)o2);
-        if (cb.nn) {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) { cb.nn[gi * 5 + j] = tk.id[j]; cb.nn_d2[gi * 5 + j] = tk.id[j] != 0xFFFFFFFFu ? tk.d2[j] : 0.f; }
-        }
     }
     __syncthreads();
     if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&bv.hist[s * 16 + threadIdx.x], s_hist[threadIdx.x]);
@@ -547,10 +633,9 @@ __global__ void __launch_bounds__(kThreads) k_correspond(MapView m, BatchView bv
     if (!reduce_and_elect(acc, bv, s, s_sum)) return;
     if (threadIdx.x == 0) {
         // histograms of this ICP iteration (ResetDistanceParameters + processPlannerFeatures, :847-852,:336-341)
-        int n_ok = 0;
-        for (int k = 0; k < 9; ++k) { st->hist_obs[k] = __ldcg(&bv.hist[s * 16 + k]); }
-        for (int k = 0; k < 7; ++k) { st->hist_rej[k] = __ldcg(&bv.hist[s * 16 + 9 + k]); }
-        n_ok = st->hist_rej[0];
+        for (int k = 0; k < 9; ++k) st->hist_obs[k] = __ldcg(&bv.hist[s * 16 + k]);
+        for (int k = 0; k < 7; ++k) st->hist_rej[k] = __ldcg(&bv.hist[s * 16 + 9 + k]);
+        const int n_ok = st->hist_rej[0];
         for (int k = 0; k < 16; ++k) bv.hist[s * 16 + k] = 0;
         if (st->max_icp_iters < 0) {          // stage mode (so_correspond): stop here
             for (int k = 0; k < 21; ++k) st->H[k] = s_sum[k];
@@ -561,7 +646,8 @@ __global__ void __launch_bounds__(kThreads) k_correspond(MapView m, BatchView bv
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_evaluate: robustified normal equations at the candidate pose over the stored correspondences
+// k_evaluate: robustified normal equations at the candidate pose over the stored correspondences.
+// kEvalPts points per thread (strided by the CTA width, so loads stay coalesced) before the one warp/CTA reduction.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_evaluate(BatchView bv, CorrBuf cb) {
     const int s = blockIdx.y;
@@ -575,22 +661,26 @@ __global__ void __launch_bounds__(kThreads) k_evaluate(BatchView bv, CorrBuf cb)
     if (threadIdx.x == 0) qtoR(s_pose + 3, s_R);
     __syncthreads();
     const uint32_t n = uint32_t(st->n_points);
-    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-    const size_t gi = size_t(bv.offset[s]) + i;
+    const size_t base = size_t(bv.offset[s]);
     double acc[kAcc];
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
-    if (i < n) {
-        const double w = cb.w[gi];
-        if (w != 0.0) {
-            const double4 nd = cb.nd[gi];
-            const float4 sp = __ldg(&bv.scan[gi]);
-            const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
-            double pw[3];
-            qrot(s_pose + 3, pin, pw);
-            pw[0] += s_pose[0]; pw[1] += s_pose[1]; pw[2] += s_pose[2];
-            const double nn[3] = {nd.x, nd.y, nd.z};
-            accumulate(acc, nn, nd.w, w, pin, pw, s_R, bv.tukey_a2);
+#pragma unroll 1
+    for (int r = 0; r < kEvalPts; ++r) {
+        const uint32_t i = (blockIdx.x * kEvalPts + r) * kThreads + threadIdx.x;
+        if (i < n) {
+            const size_t gi = base + i;
+            const double w = cb.w[gi];
+            if (w != 0.0) {
+                const double4 nd = cb.nd[gi];
+                const float4 sp = __ldg(&bv.scan[gi]);
+                const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+                double pw[3];
+                qrot(s_pose + 3, pin, pw);
+                pw[0] += s_pose[0]; pw[1] += s_pose[1]; pw[2] += s_pose[2];
+                const double nn[3] = {nd.x, nd.y, nd.z};
+                accumulate(acc, nn, nd.w, w, pin, pw, s_R, bv.tukey_a2);
+            }
         }
     }
     if (!reduce_and_elect(acc, bv, s, s_sum)) return;
@@ -649,11 +739,19 @@ __global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __res
 // ------------------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------------------
-void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
-    k_correspond<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, cb);
+void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+    k_scan_keys<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, keys, vals);
+}
+void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st) {
+    k_scan_gather<<<uint32_t((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(in, vals, keys, offset, total, out);
+}
+void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+    k_knn_scan<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, nb);
+    k_fit<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
 }
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
-    k_evaluate<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(bv, cb);
+    const uint32_t gx = (grid_x + kEvalPts - 1) / kEvalPts;
+    k_evaluate<<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb);
 }
 int launch_knn(const MapView& m, const float4* q, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st) {
     const uint32_t grid = uint32_t((nq + kThreads - 1) / kThreads);

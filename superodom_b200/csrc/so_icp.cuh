@@ -22,7 +22,18 @@ struct BatchView {
     double tukey_a2;          // a^2, a = double(sqrtf(3*planeRes_))  (LidarSlam.cpp:271)
 };
 
-void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
+// neighbour hand-off between k_knn_scan and k_fit
+struct NnBuf {
+    uint32_t* pos;       // [5][cap] positions of the 5 neighbours in the sorted map (0xFFFFFFFF = none)
+    unsigned char* pre;  // [cap] SO_MATCH_SKIPPED / NOT_ENOUGH_NEIGHBORS / NEIGHBORS_TOO_FAR / SUCCESS (= has 5 neighbours)
+    size_t cap;
+};
+
+constexpr int kEvalPts = 4;     // points per thread in k_evaluate
+
+void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
+void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st);
+void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 int launch_knn(const MapView& m, const float4* q, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st);
 

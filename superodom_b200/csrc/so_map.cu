@@ -193,4 +193,21 @@ int map_rebuild(Ctx* c) {
     return SO_OK;
 }
 
+int scan_sort_alloc(Ctx* c) {
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, c->d_skeys, c->d_skeys_out, c->d_svals, c->d_svals_out, int(c->scan_cap), 0, 64);
+    c->sort_tmp_bytes = need + 256;
+    SO_CUDA_TRY(cudaMalloc(&c->d_sort_tmp, c->sort_tmp_bytes));
+    return SO_OK;
+}
+
+int scan_sort(Ctx* c, size_t n, int n_scans) {
+    int bits = 32;
+    while ((1 << (bits - 32)) < n_scans) ++bits;
+    size_t tmp = c->sort_tmp_bytes;
+    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_skeys, c->d_skeys_out, c->d_svals, c->d_svals_out, int(n), 0, bits, c->stream));
+    c->launches += 5;
+    return SO_OK;
+}
+
 }  // namespace so
