@@ -151,7 +151,7 @@ static int upload_cloud(Ctx* c, const void* src, size_t n, size_t stride, size_t
 // ---------------------------------------------------------------------------------------------- ICP schedule
 static BatchView batch_view(const Ctx* c, const float4* scan) {
     BatchView bv;
-    bv.scan = scan; bv.offset = c->d_offset; bv.st = c->d_state; bv.partials = c->d_partials; bv.counters = c->d_counters; bv.hist = c->d_hist;
+    bv.scan = scan; bv.offset = c->d_offset; bv.st = c->d_state; bv.partials = c->d_partials; bv.partial_stride = c->grid_x_cap; bv.hist = c->d_hist;
     const double a = double(std::sqrt(3 * c->plane_res));     // float sqrt of a float product (LidarSlam.cpp:271)
     bv.tukey_a2 = a * a;
     return bv;
@@ -194,7 +194,7 @@ static int run_schedule(Ctx* c, uint32_t grid_x, uint32_t n_scans, int iters, in
     const BatchView bv = batch_view(c, d_scan);
     CorrBuf cb = c->corr;
     if (!with_nn) { cb.nn = nullptr; cb.nn_d2 = nullptr; }
-    const uint64_t kernels = uint64_t(iters) * (2 + lm);
+    const uint64_t kernels = uint64_t(iters) * (3 + 2 * lm);
     if (c->profiling || with_nn) {
         // profiling mode: one launch at a time, timed with events, and only launches that have work (the host peeks
         // at the phases) so that the per-class average is the duration of a kernel that actually ran
@@ -206,9 +206,9 @@ static int run_schedule(Ctx* c, uint32_t grid_x, uint32_t n_scans, int iters, in
             return false;
         };
         for (int it = 0; it < iters; ++it) {
-            if (any_in(PH_CORR)) { timed_launch_begin(c); launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream); c->launches++; timed_launch_end(c, 0); }
+            if (any_in(PH_CORR)) { timed_launch_begin(c); launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream); c->launches += 2; timed_launch_end(c, 0); }
             for (int k = 0; k < lm; ++k)
-                if (any_in(PH_EVAL)) { timed_launch_begin(c); launch_evaluate(bv, cb, grid_x, n_scans, c->stream); timed_launch_end(c, 1); }
+                if (any_in(PH_EVAL)) { timed_launch_begin(c); launch_evaluate(bv, cb, grid_x, n_scans, c->stream); c->launches++; timed_launch_end(c, 1); }
         }
         SO_CUDA_TRY(cudaGetLastError());
         return SO_OK;
@@ -563,7 +563,7 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     if (rc) return rc;
     const MapView mv = map_view(c);
     const BatchView bv = batch_view(c, c->d_scan_sorted);
-    timed_launch_begin(c); launch_correspond(mv, bv, c->corr, c->nn, grid_x, 1, c->stream); c->launches++; timed_launch_end(c, 0);
+    timed_launch_begin(c); launch_correspond(mv, bv, c->corr, c->nn, grid_x, 1, c->stream); c->launches += 2; timed_launch_end(c, 0);
     SO_CUDA_TRY(cudaGetLastError());
     std::vector<double4> nd(n); std::vector<double> w(n); std::vector<uchar4> fl(n); std::vector<uint32_t> nn(n * 5); std::vector<float> d2(n * 5);
     std::vector<float4> sorted(n);
@@ -601,7 +601,7 @@ int so_evaluate(so_ctx* ctx, const double pose[7], double H[36], double g[6], do
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
     const uint32_t grid_x = (n + kThreads - 1) / kThreads;
     const BatchView bv = batch_view(c, c->d_scan_sorted);
-    timed_launch_begin(c); launch_evaluate(bv, c->corr, grid_x, 1, c->stream); timed_launch_end(c, 1);
+    timed_launch_begin(c); launch_evaluate(bv, c->corr, grid_x, 1, c->stream); c->launches++; timed_launch_end(c, 1);
     SO_CUDA_TRY(cudaGetLastError());
     SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
     SO_CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -7,7 +7,7 @@
 //                  warp/CTA-reduced in FP64 (21+6+1 accumulators).                                  [K3+K4+K5]
 //   k_evaluate   : per correspondence -- residual, 1x6 Jacobian, Tukey/Scaled robust weight at the LM candidate pose,
 //                  same reduction.                                                          [K5]
-//   last CTA of either kernel: fixed-order final reduction, then ONE thread advances the device-resident state
+//   k_lm_step    : fixed-order cross-CTA reduction, then ONE thread per scan advances the device-resident state
 //                  machine: Ceres' trust-region LM (step solve by 6x6 Cholesky, accept/reject, tolerances), the outer
 //                  ICP convergence rule, and at the end the covariance pseudo-inverse + 3x3 eigen analysis. [K6+K7]
 //   k_knn        : stand-alone k-NN (so_knn*), radius-bounded or exact with ring expansion.
@@ -109,56 +109,63 @@ __device__ __forceinline__ void scan_range(const MapView& m, uint32_t beg, uint3
     for (; t < end; ++t) offer_candidate<K>(__ldg(&m.pts[t]), t, qx, qy, qz, tk);
 }
 
-// Cube of cells [c-R, c+R]^3 clipped to the block, as (2R+1)^2 contiguous x-rows.  For R == 1 rows are visited
-// nearest-first and pruned against the current k-th distance (exact for all neighbours with d2 <= bound <= cs^2).
+// Pruned walk over the (2R+1)^2 x-rows of the search cube around the query's cell, nearest rows first (MapView::row_*).
+// A row / an x-cell is skipped when its distance lower bound already exceeds the current k-th distance.  Exact for
+// every neighbour with d2 <= min(bound, (R*cs)^2); stays inside the query's block (LocalMap.h:488-507).
 template <int K>
-__device__ __forceinline__ void knn_ring(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, int R, TopK<K>& tk) {
-    const int nb = m.nb;
+__device__ __forceinline__ void knn_rows(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, TopK<K>& tk) {
+    const int nb = m.nb, R = m.R;
     const uint32_t base = uint32_t(qc.slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
     const float cs = m.cs;
     const float fx = qc.f[0], fy = qc.f[1], fz = qc.f[2];
-    if (R == 1) {
-        // row order: centre, 4 edge neighbours, 4 corners; 2-bit codes 0 -> 0, 1 -> -1, 2 -> +1
-        constexpr uint32_t DY = 0u | 1u << 2 | 2u << 4 | 0u << 6 | 0u << 8 | 1u << 10 | 2u << 12 | 1u << 14 | 2u << 16;
-        constexpr uint32_t DZ = 0u | 0u << 2 | 0u << 4 | 1u << 6 | 2u << 8 | 1u << 10 | 1u << 12 | 2u << 14 | 2u << 16;
 #pragma unroll 1
-        for (int r = 0; r < 9; ++r) {
-            const int cy = (DY >> (2 * r)) & 3, cz = (DZ >> (2 * r)) & 3;
-            const int oy = cy == 0 ? 0 : (cy == 1 ? -1 : 1);
-            const int oz = cz == 0 ? 0 : (cz == 1 ? -1 : 1);
-            const int yy = qc.c[1] + oy, zz = qc.c[2] + oz;
-            if (yy < 0 || yy >= nb || zz < 0 || zz >= nb) continue;   // stay inside the query's block (LocalMap.h:488-507)
-            const float ly = oy < 0 ? fy : (oy > 0 ? cs - fy : 0.f);
-            const float lz = oz < 0 ? fz : (oz > 0 ? cs - fz : 0.f);
-            const float lb = ly * ly + lz * lz;
-            const float w = tk.worst();
-            if (lb * 0.9999f > w) continue;
-            int xlo = qc.c[0], xhi = qc.c[0];
-            if (xlo > 0 && (lb + fx * fx) * 0.9999f <= w) xlo--;
-            if (xhi < nb - 1 && (lb + (cs - fx) * (cs - fx)) * 0.9999f <= w) xhi++;
-            const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
-            const uint32_t beg = __ldg(&m.cell_start[row + xlo]);
-            const uint32_t end = __ldg(&m.cell_start[row + xhi + 1]);
-            scan_range<K>(m, beg, end, qx, qy, qz, tk);
+    for (int r = 0; r < m.n_rows; ++r) {
+        const int oy = m.row_dy[r], oz = m.row_dz[r];
+        const int yy = qc.c[1] + oy, zz = qc.c[2] + oz;
+        if (yy < 0 || yy >= nb || zz < 0 || zz >= nb) continue;
+        const float ly = oy < 0 ? fy + float(-oy - 1) * cs : (oy > 0 ? (cs - fy) + float(oy - 1) * cs : 0.f);
+        const float lz = oz < 0 ? fz + float(-oz - 1) * cs : (oz > 0 ? (cs - fz) + float(oz - 1) * cs : 0.f);
+        const float lb = ly * ly + lz * lz;
+        const float w = tk.worst();
+        if (lb * 0.9999f > w) continue;
+        int xlo = qc.c[0], xhi = qc.c[0];
+        for (int k = 1; k <= R; ++k) {
+            const float lx = fx + float(k - 1) * cs;
+            if (qc.c[0] - k < 0 || (lb + lx * lx) * 0.9999f > w) break;
+            xlo = qc.c[0] - k;
         }
-    } else {
-        const int xlo = max(qc.c[0] - R, 0), xhi = min(qc.c[0] + R, nb - 1);
-        for (int zz = max(qc.c[2] - R, 0); zz <= min(qc.c[2] + R, nb - 1); ++zz)
-            for (int yy = max(qc.c[1] - R, 0); yy <= min(qc.c[1] + R, nb - 1); ++yy) {
-                const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
-                scan_range<K>(m, __ldg(&m.cell_start[row + xlo]), __ldg(&m.cell_start[row + xhi + 1]), qx, qy, qz, tk);
-            }
+        for (int k = 1; k <= R; ++k) {
+            const float lx = (cs - fx) + float(k - 1) * cs;
+            if (qc.c[0] + k > nb - 1 || (lb + lx * lx) * 0.9999f > w) break;
+            xhi = qc.c[0] + k;
+        }
+        const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
+        const uint32_t beg = __ldg(&m.cell_start[row + xlo]);
+        const uint32_t end = __ldg(&m.cell_start[row + xhi + 1]);
+        scan_range<K>(m, beg, end, qx, qy, qz, tk);
     }
 }
 
+// Unpruned cube [c-R, c+R]^3 clipped to the block (fallback rings of the exact, unbounded search).
+template <int K>
+__device__ __forceinline__ void knn_cube(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, int R, TopK<K>& tk) {
+    const int nb = m.nb;
+    const uint32_t base = uint32_t(qc.slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
+    const int xlo = max(qc.c[0] - R, 0), xhi = min(qc.c[0] + R, nb - 1);
+    for (int zz = max(qc.c[2] - R, 0); zz <= min(qc.c[2] + R, nb - 1); ++zz)
+        for (int yy = max(qc.c[1] - R, 0); yy <= min(qc.c[1] + R, nb - 1); ++yy) {
+            const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
+            scan_range<K>(m, __ldg(&m.cell_start[row + xlo]), __ldg(&m.cell_start[row + xhi + 1]), qx, qy, qz, tk);
+        }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-// CTA reduction of kAcc doubles per thread + "last CTA" hand-off.
-// Returns true in exactly one CTA per scan (the last to arrive), with the fully reduced sums in s_out[kAcc]
-// (valid for thread 0).  Fixed thread->point mapping + fixed reduction trees => run-to-run deterministic sums.
+// CTA reduction of kAcc doubles per thread into partials[scan][cta][kAcc].  Fixed thread->point mapping and fixed
+// reduction trees => run-to-run deterministic sums.  The cross-CTA sum and the optimiser step run in k_lm_step
+// (keeping that scalar FP64 code out of the per-point kernels saves ~70 registers per thread in them).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool reduce_and_elect(double acc[kAcc], const BatchView& bv, int s, double* s_out) {
+__device__ __forceinline__ void reduce_to_partials(double acc[kAcc], const BatchView& bv, int s) {
     __shared__ double s_red[kThreads / 32][kAcc];
-    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) {
@@ -168,41 +175,12 @@ __device__ __forceinline__ bool reduce_and_elect(double acc[kAcc], const BatchVi
         if (lane == 0) s_red[warp][k] = v;
     }
     __syncthreads();
-    double* part = bv.partials + (size_t(s) * gridDim.x + blockIdx.x) * kAcc;
     if (threadIdx.x < kAcc) {
         double v = 0.0;
 #pragma unroll
         for (int wv = 0; wv < kThreads / 32; ++wv) v += s_red[wv][threadIdx.x];
-        part[threadIdx.x] = v;
+        bv.partials[(size_t(s) * bv.partial_stride + blockIdx.x) * kAcc + threadIdx.x] = v;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t prev = atomicAdd(&bv.counters[s], 1u);
-        s_last = (prev == gridDim.x - 1);
-        if (s_last) bv.counters[s] = 0;          // self-reset for the next kernel
-    }
-    __syncthreads();
-    if (!s_last) return false;
-    __threadfence();
-    // final reduction over CTAs: thread t sums component (t & 31) over CTAs t>>5, t>>5 + 8, ...
-    const int comp = threadIdx.x & 31, sub = threadIdx.x >> 5;
-    double v = 0.0;
-    if (comp < kAcc) {
-        const double* base = bv.partials + size_t(s) * gridDim.x * kAcc;
-        for (uint32_t b = sub; b < gridDim.x; b += kThreads / 32) v += __ldcg(&base[size_t(b) * kAcc + comp]);
-    }
-    __syncthreads();
-    if (comp < kAcc) s_red[sub][comp] = v;
-    __syncthreads();
-    if (threadIdx.x < kAcc) {
-        double t = 0.0;
-#pragma unroll
-        for (int wv = 0; wv < kThreads / 32; ++wv) t += s_red[wv][threadIdx.x];
-        s_out[threadIdx.x] = t;
-    }
-    __syncthreads();
-    return true;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -468,7 +446,7 @@ __global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, 
         locate(m, qx, qy, qz, qc);
         if (qc.slot < 0 || qc.nblock < 5) pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
         else {
-            knn_ring<5>(m, qc, qx, qy, qz, 1, tk);
+            knn_rows<5>(m, qc, qx, qy, qz, tk);
             pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
         }
     }
@@ -482,14 +460,13 @@ __global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, 
 // five neighbours -- PCA, plane fit, gates, observability -- plus the first residual/Jacobian evaluation of the
 // following ceres::Solve and the histogram / normal-equation reductions.  FP64 throughout.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_fit(MapView m, BatchView bv, CorrBuf cb, NnBuf nb) {
+__global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, CorrBuf cb, NnBuf nb) {
     const int s = blockIdx.y;
     IcpState* st = bv.st + s;
     if (st->phase != PH_CORR) return;
     __shared__ double s_pose[7];
     __shared__ double s_R[9];
     __shared__ int s_hist[16];
-    __shared__ double s_sum[kAcc];
     if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
     if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
     __syncthreads();
@@ -630,32 +607,19 @@ __global__ void __launch_bounds__(kThreads) k_fit(MapView m, BatchView bv, CorrB
     __syncthreads();
     if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&bv.hist[s * 16 + threadIdx.x], s_hist[threadIdx.x]);
 
-    if (!reduce_and_elect(acc, bv, s, s_sum)) return;
-    if (threadIdx.x == 0) {
-        // histograms of this ICP iteration (ResetDistanceParameters + processPlannerFeatures, :847-852,:336-341)
-        for (int k = 0; k < 9; ++k) st->hist_obs[k] = __ldcg(&bv.hist[s * 16 + k]);
-        for (int k = 0; k < 7; ++k) st->hist_rej[k] = __ldcg(&bv.hist[s * 16 + 9 + k]);
-        const int n_ok = st->hist_rej[0];
-        for (int k = 0; k < 16; ++k) bv.hist[s * 16 + k] = 0;
-        if (st->max_icp_iters < 0) {          // stage mode (so_correspond): stop here
-            for (int k = 0; k < 21; ++k) st->H[k] = s_sum[k];
-            for (int k = 0; k < 6; ++k) st->g[k] = s_sum[21 + k];
-            st->cost = s_sum[27]; st->n_ok = n_ok; st->phase = PH_DONE;
-        } else lm_begin_solve(*st, s_sum, n_ok);
-    }
+    reduce_to_partials(acc, bv, s);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_evaluate: robustified normal equations at the candidate pose over the stored correspondences.
 // kEvalPts points per thread (strided by the CTA width, so loads stay coalesced) before the one warp/CTA reduction.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_evaluate(BatchView bv, CorrBuf cb) {
+__global__ void __launch_bounds__(kThreads, 2) k_evaluate(BatchView bv, CorrBuf cb) {
     const int s = blockIdx.y;
     IcpState* st = bv.st + s;
     if (st->phase != PH_EVAL) return;
     __shared__ double s_pose[7];
     __shared__ double s_R[9];
-    __shared__ double s_sum[kAcc];
     if (threadIdx.x < 7) s_pose[threadIdx.x] = st->cand[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) qtoR(s_pose + 3, s_R);
@@ -683,8 +647,45 @@ __global__ void __launch_bounds__(kThreads) k_evaluate(BatchView bv, CorrBuf cb)
             }
         }
     }
-    if (!reduce_and_elect(acc, bv, s, s_sum)) return;
-    if (threadIdx.x == 0) {
+    reduce_to_partials(acc, bv, s);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_lm_step: one CTA per scan.  Sums the per-CTA partials of the preceding k_fit (AFTER == PH_CORR) or k_evaluate
+// (AFTER == PH_EVAL) in a fixed order, then one thread advances the optimiser / ICP state machine.
+// ------------------------------------------------------------------------------------------------------------------
+template <int AFTER>
+__global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partials) {
+    const int s = blockIdx.x;
+    IcpState* st = bv.st + s;
+    if (st->phase != AFTER) return;
+    __shared__ double s_red[4][kAcc];
+    __shared__ double s_sum[kAcc];
+    const int comp = threadIdx.x & 31, sub = threadIdx.x >> 5;
+    double v = 0.0;
+    if (comp < kAcc) {
+        const double* base = bv.partials + size_t(s) * bv.partial_stride * kAcc;
+        const uint32_t np = (AFTER == PH_CORR) ? (uint32_t(st->n_points) + kThreads - 1) / kThreads
+                                               : (uint32_t(st->n_points) + kThreads * kEvalPts - 1) / (kThreads * kEvalPts);
+        for (uint32_t b = sub; b < np && b < n_partials; b += 4) v += base[size_t(b) * kAcc + comp];
+        s_red[sub][comp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kAcc) s_sum[threadIdx.x] = (s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + (s_red[2][threadIdx.x] + s_red[3][threadIdx.x]);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (AFTER == PH_CORR) {
+        // histograms of this ICP iteration (ResetDistanceParameters + processPlannerFeatures, :847-852,:336-341)
+        for (int k = 0; k < 9; ++k) st->hist_obs[k] = bv.hist[s * 16 + k];
+        for (int k = 0; k < 7; ++k) st->hist_rej[k] = bv.hist[s * 16 + 9 + k];
+        const int n_ok = st->hist_rej[0];
+        for (int k = 0; k < 16; ++k) bv.hist[s * 16 + k] = 0;
+        if (st->max_icp_iters < 0) {          // stage mode (so_correspond): stop here
+            for (int k = 0; k < 21; ++k) st->H[k] = s_sum[k];
+            for (int k = 0; k < 6; ++k) st->g[k] = s_sum[21 + k];
+            st->cost = s_sum[27]; st->n_ok = n_ok; st->phase = PH_DONE;
+        } else lm_begin_solve(*st, s_sum, n_ok);
+    } else {
         if (st->max_icp_iters < 0) {          // stage mode (so_evaluate): report and stop
             for (int k = 0; k < 21; ++k) st->H[k] = s_sum[k];
             for (int k = 0; k < 6; ++k) st->g[k] = s_sum[21 + k];
@@ -708,14 +709,19 @@ __global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __res
     QueryCell qc;
     locate(m, p.x, p.y, p.z, qc);
     if (qc.slot >= 0) {
-        // rings needed so that a bounded search is complete: R * cs >= sqrt(max_d2)
-        int R = 1;
-        if (bounded) { const float r = sqrtf(max_d2); while (float(R) * m.cs < r && R < m.nb) ++R; }
-        for (;;) {
-            if (R > 1 || !bounded) tk.init(bounded ? max_d2 : FLT_MAX);
-            knn_ring<K>(m, qc, p.x, p.y, p.z, R, tk);
+        // the pruned ring walk is complete up to min(bound, (R*cs)^2); wider / unbounded searches grow an unpruned cube
+        int R = m.R;
+        const float ring_d2 = float(R) * m.cs * float(R) * m.cs;
+        bool done = false;
+        if (bounded && max_d2 <= ring_d2) { knn_rows<K>(m, qc, p.x, p.y, p.z, tk); done = true; }
+        else if (!bounded) {
+            knn_rows<K>(m, qc, p.x, p.y, p.z, tk);
+            done = tk.count() == K && tk.worst() < ring_d2 * 0.999f;     // k-th neighbour inside the guaranteed-complete radius
+        } else { const float r = sqrtf(max_d2); while (float(R) * m.cs < r && R < m.nb) ++R; }
+        while (!done) {
+            tk.init(bounded ? max_d2 : FLT_MAX);
+            knn_cube<K>(m, qc, p.x, p.y, p.z, R, tk);
             if (bounded) break;
-            // exact: done when the k-th distance is inside the guaranteed-complete radius, or the cube covers the block
             float reach = FLT_MAX;
             bool covers = true;
 #pragma unroll
@@ -748,10 +754,12 @@ void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* 
 void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
     k_knn_scan<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, nb);
     k_fit<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
+    k_lm_step<PH_CORR><<<n_scans, 128, 0, st>>>(bv, grid_x);
 }
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
     const uint32_t gx = (grid_x + kEvalPts - 1) / kEvalPts;
     k_evaluate<<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb);
+    k_lm_step<PH_EVAL><<<n_scans, 128, 0, st>>>(bv, gx);
 }
 int launch_knn(const MapView& m, const float4* q, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st) {
     const uint32_t grid = uint32_t((nq + kThreads - 1) / kThreads);

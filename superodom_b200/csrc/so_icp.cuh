@@ -16,8 +16,8 @@ struct BatchView {
     const float4* scan;       // all scans back to back
     const uint32_t* offset;   // [n_scans] first point of each scan
     IcpState* st;             // [n_scans]
-    double* partials;         // [n_scans][grid.x][kAcc]
-    uint32_t* counters;       // [n_scans] CTA arrival counters (self-resetting)
+    double* partials;         // [n_scans][partial_stride][kAcc] per-CTA sums of the last per-point kernel
+    uint32_t partial_stride;  // CTAs per scan the partials buffer is laid out for
     int32_t* hist;            // [n_scans][16] histogram accumulators (self-resetting): 9 obs + 7 rejection causes
     double tukey_a2;          // a^2, a = double(sqrtf(3*planeRes_))  (LidarSlam.cpp:271)
 };

@@ -31,6 +31,9 @@ struct MapView {
     float cs;                   // cell edge (m)
     float bound_d2;             // float(3 * planeRes_)  -- the NEIGHBORS_TOO_FAR gate doubles as search radius^2
     float plane_res;
+    int32_t R;                  // search rings: R * cs >= sqrt(bound_d2)
+    int32_t n_rows;             // (2R+1)^2 (y,z) row offsets, nearest first
+    int8_t row_dy[49], row_dz[49];
 };
 
 // Per-scan device state: the Ceres trust-region minimiser + the outer ICP loop, advanced by the last CTA of every
@@ -110,7 +113,7 @@ __host__ __device__ inline void rel_motion(const double a[7], const double b[7],
 // v (row-major) the eigenvectors in columns; then sorted ascending.  With N a compile-time constant and full
 // unrolling every index is static, so for N=3 the whole thing lives in registers.
 template <int N, int SWEEPS>
-__host__ __device__ inline void jacobi_eig(double* a, double* v, double* w) {
+__device__ inline void jacobi_eig(double* a, double* v, double* w) {
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -131,9 +134,12 @@ __host__ __device__ inline void jacobi_eig(double* a, double* v, double* w) {
             for (int q = p + 1; q < N; ++q) {
                 const double apq = a[p * N + q];
                 if (apq != 0.0) {
-                    const double theta = (a[q * N + q] - a[p * N + p]) / (2.0 * apq);
-                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                    // tan of the rotation angle: t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq),
+                    // rearranged to one sqrt + one divide + one rsqrt (FP64 divides/sqrts dominate this routine's cost)
+                    const double dlt = a[q * N + q] - a[p * N + p], b2 = 2.0 * apq;
+                    double t = b2 / (fabs(dlt) + sqrt(dlt * dlt + b2 * b2));
+                    if (dlt < 0.0) t = -t;
+                    const double c = rsqrt(t * t + 1.0), s = t * c;
                     a[p * N + p] -= t * apq; a[q * N + q] += t * apq; a[p * N + q] = 0.0; a[q * N + p] = 0.0;
 #pragma unroll
                     for (int r = 0; r < N; ++r) {

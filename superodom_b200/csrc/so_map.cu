@@ -5,19 +5,32 @@
 // built by histogram + exclusive scan.  Cells have edge cs = 50/nb >= sqrt(3*planeRes): every neighbour that can
 // pass the NEIGHBORS_TOO_FAR gate lies in the 27 cells around the query's cell, and because nb divides the 50 m
 // block exactly, "same block" (LocalMap.h:488-507) is "same slot".
+#include <algorithm>
+#include <cmath>
+
 #include <cub/cub.cuh>
 
 #include "so_ctx.cuh"
 
 namespace so {
 
+// Cells per 50 m block axis: cell edge cs = 50/nb is about half the search radius sqrt(3*planeRes) (so the pruned
+// walk over (2R+1)^2 rows visits few points beyond the true k-NN ball), capped at 128 (8 MB cell table per block).
 int map_cells_per_block(float plane_res) {
     const float bound = 3 * plane_res;                               // float product, as LidarSlam.cpp:526
     const double r = std::sqrt(double(bound)) * (1.0 + 1e-4);
-    int nb = int(kBlock / r);
+    int nb = int(2.0 * kBlock / r);
     if (nb < 1) nb = 1;
     if (nb > 128) nb = 128;
     return nb;
+}
+
+static int map_rings(float plane_res, int nb) {
+    const float bound = 3 * plane_res;
+    const double r = std::sqrt(double(bound)) * (1.0 + 1e-4);
+    const double cs = kBlock / double(nb);
+    int R = int(std::ceil(r / cs));
+    return R < 1 ? 1 : R;
 }
 
 __device__ __forceinline__ int block_coord(double v, int origin) {   // LocalMap.h:594-605
@@ -120,6 +133,16 @@ MapView map_view(const Ctx* c) {
     m.nb = c->nb; m.inv_cs = double(c->nb) / kBlock; m.cs = float(kBlock / double(c->nb));
     m.bound_d2 = 3 * c->plane_res;        // float product (LidarSlam.cpp:526)
     m.plane_res = c->plane_res;
+    // (y,z) row offsets of the search cube, nearest rows first, so the k-th distance shrinks early and prunes the rest
+    m.R = map_rings(c->plane_res, c->nb);
+    if (m.R > 3) m.R = 3;            // nb cap can only force this for planeRes > 1.8 m; so_map_set_resolution rejects those
+    struct RowOff { int d2, dy, dz; };
+    RowOff rows[49];
+    int n = 0;
+    for (int dz = -m.R; dz <= m.R; ++dz) for (int dy = -m.R; dy <= m.R; ++dy) rows[n++] = RowOff{dy * dy + dz * dz, dy, dz};
+    std::stable_sort(rows, rows + n, [](const RowOff& a, const RowOff& b) { return a.d2 < b.d2; });
+    m.n_rows = n;
+    for (int i = 0; i < n; ++i) { m.row_dy[i] = int8_t(rows[i].dy); m.row_dz[i] = int8_t(rows[i].dz); }
     return m;
 }
 
