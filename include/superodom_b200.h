@@ -143,6 +143,9 @@ int so_map_set_points(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_byt
 /* replaces: LocalMap::addSurfPointCloud (LocalMap.h:591-645): bin world-frame points into blocks, voxel-centroid
  * filter every touched block at leaf planeRes (pcl::VoxelGrid semantics), rebuild the neighbour index. */
 int so_map_add_surf(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset);
+/* replaces: LidarSLAM::transformAndAddToMap(cloud, world_cloud, false) (LidarSlam.cpp:60-80): transform the
+ * sensor-frame scan by pose (utils::TransformPoint: double math, float store) on the device, then so_map_add_surf. */
+int so_map_add_scan(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset, const double pose[7]);
 /* replaces: LocalMap::get5x5LocalMapFeatureSize (LocalMap.h:291-318) */
 int so_map_counts_5x5(so_ctx* ctx, const int32_t ijk[3], int32_t* n_edge, int32_t* n_surf);
 /* replaces: LocalMap::getAllLocalMap (mode 0, LocalMap.h:647-658) / get5x5LocalMap(pos) (mode 1, :660-687).

@@ -79,6 +79,7 @@ def lib():
     L.orc_map_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
     L.orc_map_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_map_get_origin.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_map_set_origin.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_map_counts_5x5.restype = C.c_int32
     L.orc_map_counts_5x5.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -134,6 +135,11 @@ class OracleMap:
         if ref_octree is None:
             ref_octree = has_ref_octree()
         return int(self.L.orc_map_set_points(self.h, _p(xyzi), xyzi.shape[0], xyzi.shape[1], int(ref_octree)))
+
+    def set_origin(self, o):
+        """Set LocalMap::origin_ directly (call before set_points: binning uses it)."""
+        o = np.ascontiguousarray(o, dtype=np.int32)
+        self.L.orc_map_set_origin(self.h, _p(o))
 
     def origin(self):
         o = np.zeros(3, np.int32)
@@ -246,3 +252,49 @@ def lidar_uncertainty(hist9):
     u = np.zeros(6)
     lib().orc_lidar_uncertainty(_p(h), _p(u))
     return u
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# numpy restatements of the map-insert path (integer / float32 element-wise work)
+# ---------------------------------------------------------------------------------------------------------------
+def transform_scan_numpy(scan_xyzi, pose7):
+    """utils::TransformPoint (superodom_utils.h:116-127) for every point: double math, float32 store; intensity kept.
+    Rotation = v + 2w(q x v) + 2 q x (q x v), the expression Eigen evaluates for quaternion * vector."""
+    s = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
+    p = s[:, :3].astype(np.float64)
+    x, y, z, w = [float(v) for v in pose7[3:]]
+    ux = y * p[:, 2] - z * p[:, 1]
+    uy = z * p[:, 0] - x * p[:, 2]
+    uz = x * p[:, 1] - y * p[:, 0]
+    ux = ux + ux
+    uy = uy + uy
+    uz = uz + uz
+    ox = p[:, 0] + w * ux + (y * uz - z * uy)
+    oy = p[:, 1] + w * uy + (z * ux - x * uz)
+    oz = p[:, 2] + w * uz + (x * uy - y * ux)
+    out = s.copy()
+    out[:, 0] = (ox + float(pose7[0])).astype(np.float32)
+    out[:, 1] = (oy + float(pose7[1])).astype(np.float32)
+    out[:, 2] = (oz + float(pose7[2])).astype(np.float32)
+    return out
+
+
+def map_insert_numpy(old_xyzi, new_xyzi, leaf, origin=(10, 10, 5)):
+    """LocalMap::addSurfPointCloud (LocalMap.h:591-645): bin the new world-frame points to blocks (off-grid dropped);
+    every TOUCHED block is voxel-filtered as a whole (old block cloud followed by the new points; pcl::VoxelGrid
+    semantics as in superodom_b200.synth.voxel_filter_blocks); untouched blocks are kept as they are.
+    Returns the new map: untouched points in their old order, then the filtered blocks in (block, voxel) order."""
+    from superodom_b200 import synth
+    old = np.ascontiguousarray(old_xyzi, dtype=np.float32).reshape(-1, 4)
+    new = np.ascontiguousarray(new_xyzi, dtype=np.float32).reshape(-1, 4)
+    lin_old = synth.block_linear(synth.block_of(old[:, :3], origin))
+    lin_new = synth.block_linear(synth.block_of(new[:, :3], origin))
+    fin = np.isfinite(new[:, :3]).all(1)
+    new, lin_new = new[(lin_new >= 0) & fin], lin_new[(lin_new >= 0) & fin]
+    old, lin_old = old[lin_old >= 0], lin_old[lin_old >= 0]
+    touched = np.zeros(21 * 21 * 11, dtype=bool)
+    touched[lin_new] = True
+    keep = old[~touched[lin_old]]
+    work = np.concatenate([old[touched[lin_old]], new], 0)
+    filt = synth.voxel_filter_blocks(work, leaf, origin) if len(work) else np.zeros((0, 4), np.float32)
+    return np.concatenate([keep, filt], 0)

@@ -862,6 +862,7 @@ size_t orc_sizeof_result(void) { return sizeof(orc_result); }
 
 void* orc_map_create(void) { return new orc::Map(); }
 void orc_map_destroy(void* m) { delete static_cast<orc::Map*>(m); }
+void orc_map_set_origin(void* m, const int32_t o[3]) { auto* M = static_cast<orc::Map*>(m); M->origin[0] = o[0]; M->origin[1] = o[1]; M->origin[2] = o[2]; }
 void orc_map_get_origin(void* m, int32_t o[3]) { auto* M = static_cast<orc::Map*>(m); o[0] = M->origin[0]; o[1] = M->origin[1]; o[2] = M->origin[2]; }
 
 // Replace the map's surf points with xyzi (world frame), binned by LocalMap.h:594-612 under the current origin.

@@ -453,8 +453,33 @@ int so_map_set_points(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, si
 }
 
 int so_map_add_surf(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff) {
-    (void)ctx; (void)xyzi; (void)n; (void)stride; (void)ioff;
-    return fail(SO_ERR_ARG, "so_map_add_surf: voxel-filter insert not built yet (SURVEY 8f row 1)");
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || (!xyzi && n) || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (size_t(c->map_n) + n > c->cfg.max_map_points) return fail(SO_ERR_CAPACITY, "map + new points exceed so_config.max_map_points");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return SO_OK;
+    int rc = upload_cloud(c, xyzi, n, stride, ioff, c->d_map_xyzi + c->map_n);
+    if (rc) return rc;
+    timed_launch_begin(c);
+    rc = map_add_surf(c, uint32_t(n));
+    timed_launch_end(c, 3);
+    return rc;
+}
+
+int so_map_add_scan(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff, const double pose[7]) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || (!xyzi && n) || stride < 12 || !pose) return fail(SO_ERR_ARG, "bad args");
+    if (size_t(c->map_n) + n > c->cfg.max_map_points) return fail(SO_ERR_CAPACITY, "map + new points exceed so_config.max_map_points");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return SO_OK;
+    int rc = upload_cloud(c, xyzi, n, stride, ioff, c->d_map_xyzi + c->map_n);
+    if (rc) return rc;
+    rc = map_transform_tail(c, uint32_t(n), pose);
+    if (rc) return rc;
+    timed_launch_begin(c);
+    rc = map_add_surf(c, uint32_t(n));
+    timed_launch_end(c, 3);
+    return rc;
 }
 
 int so_map_counts_5x5(so_ctx* ctx, const int32_t ijk[3], int32_t* n_edge, int32_t* n_surf) {

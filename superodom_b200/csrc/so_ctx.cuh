@@ -88,6 +88,8 @@ struct Ctx {
 // so_map.cu
 int map_alloc(Ctx* c);
 void map_free(Ctx* c);
+int map_add_surf(Ctx* c, uint32_t n_new);   // d_map_xyzi[map_n .. map_n+n_new) holds the new points: voxel-filter touched blocks, rebuild
+int map_transform_tail(Ctx* c, uint32_t n_new, const double pose[7]);   // sensor-frame tail points -> world frame
 int map_rebuild(Ctx* c);                 // (re)bin, drop off-grid points, sort, build cell table
 MapView map_view(const Ctx* c);
 int map_cells_per_block(float plane_res);

@@ -233,4 +233,128 @@ int scan_sort(Ctx* c, size_t n, int n_scans) {
     return SO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Map insert: LocalMap::addSurfPointCloud (LocalMap.h:591-645).  New world-frame points are appended, every block they
+// touch is re-filtered as a whole by a voxel-centroid filter of leaf planeRes_ (pcl::VoxelGrid semantics: voxel =
+// floor(coord * (1.0f/leaf)) in float32, centroid of all four fields accumulated in float32 and divided by
+// float(count), output ordered by voxel index (k, j, i)), untouched blocks keep their clouds.  PCL leaves the in-voxel
+// accumulation order unspecified (std::sort on the voxel index); here it is ascending cloud order (old points, then
+// new points in input order), the order the stable radix sort preserves.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_mark_touched(const int32_t* __restrict__ block_of_point, uint32_t first_new, uint32_t n, uint8_t* __restrict__ touched) {
+    const uint32_t i = first_new + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && block_of_point[i] >= 0) touched[block_of_point[i]] = 1;
+}
+
+__global__ void k_voxel_keys(const float4* __restrict__ raw, const int32_t* __restrict__ block_of_point, const uint8_t* __restrict__ touched,
+                             uint32_t n, float inv_leaf, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t b = block_of_point[i];
+    uint64_t key;
+    if (b < 0) key = ~uint64_t(0);                                  // off-grid: dropped
+    else if (!touched[b]) key = 0;                                  // untouched block: keep, in place (stable sort)
+    else {
+        const float4 p = raw[i];
+        const int64_t vi = int64_t(floorf(__fmul_rn(p.x, inv_leaf))) + 65536;
+        const int64_t vj = int64_t(floorf(__fmul_rn(p.y, inv_leaf))) + 65536;
+        const int64_t vk = int64_t(floorf(__fmul_rn(p.z, inv_leaf))) + 65536;
+        key = (uint64_t(1) << 63) | (uint64_t(b) << 51) | (uint64_t(vk & 0x1FFFF) << 34) | (uint64_t(vj & 0x1FFFF) << 17) | uint64_t(vi & 0x1FFFF);
+    }
+    keys[i] = key;
+    vals[i] = i;
+}
+
+__global__ void k_voxel_heads(const uint64_t* __restrict__ keys, uint32_t begin, uint32_t end, uint32_t* __restrict__ head) {
+    const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < end) head[i - begin] = (i == begin || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+__global__ void k_voxel_centroid(const float4* __restrict__ raw, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                 const uint32_t* __restrict__ rank, uint32_t begin, uint32_t end, float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < begin) { out[i] = raw[vals[i]]; return; }               // untouched blocks: copied through in order
+    if (i >= end) return;
+    if (!(i == begin || keys[i] != keys[i - 1])) return;             // not a voxel head
+    const uint64_t key = keys[i];
+    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+    uint32_t cnt = 0;
+    for (uint32_t j = i; j < end && keys[j] == key; ++j) {           // pcl::CentroidPoint: float accumulators, cloud order
+        const float4 p = raw[vals[j]];
+        ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z); aw = __fadd_rn(aw, p.w);
+        ++cnt;
+    }
+    const float nf = float(cnt);
+    out[begin + rank[i - begin]] = make_float4(__fdiv_rn(ax, nf), __fdiv_rn(ay, nf), __fdiv_rn(az, nf), __fdiv_rn(aw, nf));
+}
+
+__global__ void k_transform_points(float4* __restrict__ pts, uint32_t n, const double* __restrict__ pose) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pts[i];
+    const double v[3] = {double(p.x), double(p.y), double(p.z)};
+    double o[3];
+    qrot(pose + 3, v, o);                              // utils::TransformPoint (superodom_utils.h:116-127): double math, float store
+    p.x = float(o[0] + pose[0]); p.y = float(o[1] + pose[1]); p.z = float(o[2] + pose[2]);
+    pts[i] = p;
+}
+
+int map_transform_tail(Ctx* c, uint32_t n_new, const double pose[7]) {
+    double* d_pose = reinterpret_cast<double*>(c->d_keys_out);               // scratch
+    SO_CUDA_TRY(cudaMemcpyAsync(d_pose, pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_transform_points<<<(n_new + 255) / 256, 256, 0, c->stream>>>(c->d_map_xyzi + c->map_n, n_new, d_pose);
+    c->launches++;
+    SO_CUDA_TRY(cudaStreamSynchronize(c->stream));                           // `pose` is caller memory
+    return SO_OK;
+}
+
+int map_add_surf(Ctx* c, uint32_t n_new) {
+    cudaStream_t st = c->stream;
+    const uint32_t total = c->map_n + n_new;
+    if (n_new == 0) return SO_OK;
+    const int3 origin = make_int3(c->origin[0], c->origin[1], c->origin[2]);
+    const uint32_t grid = (total + 255) / 256;
+    uint8_t* d_touched = reinterpret_cast<uint8_t*>(c->d_vals_out);          // scratch: 4851 bytes
+    SO_CUDA_TRY(cudaMemsetAsync(c->d_block_count, 0, kNumBlocks * sizeof(int32_t), st));
+    SO_CUDA_TRY(cudaMemsetAsync(d_touched, 0, kNumBlocks, st));
+    k_block_of<<<grid, 256, 0, st>>>(c->d_map_xyzi, total, origin, c->d_block_of_point, c->d_block_count);
+    k_mark_touched<<<(n_new + 255) / 256, 256, 0, st>>>(c->d_block_of_point, c->map_n, total, d_touched);
+    std::vector<uint8_t> h_touched(kNumBlocks);
+    SO_CUDA_TRY(cudaMemcpyAsync(c->h_block_count.data(), c->d_block_count, kNumBlocks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SO_CUDA_TRY(cudaMemcpyAsync(h_touched.data(), d_touched, kNumBlocks, cudaMemcpyDeviceToHost, st));
+    SO_CUDA_TRY(cudaStreamSynchronize(st));
+    uint64_t n_untouched = 0, n_touched = 0;
+    for (int b = 0; b < kNumBlocks; ++b) (h_touched[b] ? n_touched : n_untouched) += uint64_t(c->h_block_count[b]);
+    // keys need the touched flags: keep them in a scratch that the sort does not use
+    uint8_t* d_touched2 = reinterpret_cast<uint8_t*>(c->d_cub_tmp);
+    SO_CUDA_TRY(cudaMemcpyAsync(d_touched2, h_touched.data(), kNumBlocks, cudaMemcpyHostToDevice, st));
+    const float inv_leaf = 1.0f / c->plane_res;                               // Eigen::Array4f::Ones() / leaf_size_
+    k_voxel_keys<<<grid, 256, 0, st>>>(c->d_map_xyzi, c->d_block_of_point, d_touched2, total, inv_leaf, c->d_keys, c->d_vals);
+    SO_CUDA_TRY(cudaStreamSynchronize(st));                                   // d_cub_tmp is reused by the sort next
+    size_t tmp = c->cub_tmp_bytes;
+    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, tmp, c->d_keys, c->d_keys_out, c->d_vals, c->d_vals_out, int(total), 0, 64, st));
+    const uint32_t begin = uint32_t(n_untouched), end = uint32_t(n_untouched + n_touched);
+    uint32_t n_vox = 0;
+    uint32_t* d_head = reinterpret_cast<uint32_t*>(c->d_keys);               // keys_in is free after the sort
+    if (n_touched) {
+        k_voxel_heads<<<(uint32_t(n_touched) + 255) / 256, 256, 0, st>>>(c->d_keys_out, begin, end, d_head);
+        uint32_t last_flag = 0, last_rank = 0;
+        tmp = c->cub_tmp_bytes;
+        uint32_t* d_rank = d_head + n_touched;                                // second half of the same scratch (8 B/pt available)
+        SO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, tmp, d_head, d_rank, int(n_touched), st));
+        SO_CUDA_TRY(cudaMemcpyAsync(&last_flag, d_head + n_touched - 1, 4, cudaMemcpyDeviceToHost, st));
+        SO_CUDA_TRY(cudaMemcpyAsync(&last_rank, d_rank + n_touched - 1, 4, cudaMemcpyDeviceToHost, st));
+        SO_CUDA_TRY(cudaStreamSynchronize(st));
+        n_vox = last_rank + last_flag;
+        k_voxel_centroid<<<(end + 255) / 256, 256, 0, st>>>(c->d_map_xyzi, c->d_keys_out, c->d_vals_out, d_rank, begin, end, c->d_map_sorted);
+    } else if (begin) {
+        k_voxel_centroid<<<(begin + 255) / 256, 256, 0, st>>>(c->d_map_xyzi, c->d_keys_out, c->d_vals_out, nullptr, begin, begin, c->d_map_sorted);
+    }
+    c->map_n = begin + n_vox;
+    if (c->map_n) SO_CUDA_TRY(cudaMemcpyAsync(c->d_map_xyzi, c->d_map_sorted, size_t(c->map_n) * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    c->launches += 12;
+    SO_CUDA_TRY(cudaGetLastError());
+    return map_rebuild(c);
+}
+
 }  // namespace so

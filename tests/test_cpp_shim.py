@@ -1,0 +1,81 @@
+"""The C++ shim (include/superodom_b200/LidarSlam.hpp) keeps the reference's LidarSLAM/LocalMap member names; a small
+C++ program drives it the way laserMapping does.  CPU: it must compile and link against the in-tree library.
+GPU: its poses must equal the same sequence driven through the C ABI from Python, and the oracle's."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import get_case, quat_angle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(tmp_path):
+    from superodom_b200 import build
+    lib = build.build()
+    exe = str(tmp_path / "shim_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "shim_test.cpp"), "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)])
+    return exe
+
+
+def test_shim_compiles_and_links(tmp_path):
+    assert os.path.exists(_build(tmp_path))
+
+
+def _sequence(n_scans=4):
+    from superodom_b200 import synth
+    c0 = get_case("tiny", 0)
+    scans, priors = [], []
+    for i in range(n_scans):
+        c = get_case("tiny", i)
+        scans.append(c["scan_xyzi"][::3].copy())
+        priors.append(c["pose_true"] if i == 0 else c["pose_prior"])     # first scan: pose taken as is (map init)
+    return c0, scans, priors
+
+
+@pytest.mark.gpu
+def test_shim_sequence_matches_abi_and_oracle(tmp_path, gpu_api, oracle_mod):
+    exe = _build(tmp_path)
+    c0, scans, priors = _sequence()
+    path = tmp_path / "case.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iiif", len(scans), 5, 0, 0.2))
+        for s, p in zip(scans, priors):
+            f.write(struct.pack("<i", len(s)))
+            f.write(np.asarray(p, np.float64).tobytes())
+            f.write(np.ascontiguousarray(s, np.float32).tobytes())
+    out = subprocess.run([exe, str(path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    rows = [list(map(float, ln.split())) for ln in lines[:-1]]
+    # same sequence through the C ABI from Python: setOrigin -> add_scan -> (register -> add_scan)*
+    ctx = gpu_api.Context(max_map_points=1 << 21, max_scan_points=1 << 17, plane_res=0.2, line_res=0.1)
+    ctx.map_set_origin(priors[0][:3])
+    ctx.map_add_scan(scans[0], priors[0])
+    om_points = oracle_mod.map_insert_numpy(np.zeros((0, 4), np.float32), oracle_mod.transform_scan_numpy(scans[0], priors[0]), 0.2,
+                                            origin=tuple(ctx.map_origin()))
+    assert np.array_equal(ctx.map_download(0), om_points)
+    assert np.allclose(rows[0][1:8], priors[0])
+    for i in range(1, len(scans)):
+        r = ctx.register(scans[i], priors[i], 5, 0)
+        assert np.array_equal(np.array(r.pose), np.array(rows[i][1:8]))              # shim == ABI, bit for bit
+        assert int(rows[i][8]) == r.n_iterations and int(rows[i][9]) == r.map_surf_5x5
+        # oracle on the same (device-built) map
+        om = oracle_mod.OracleMap()
+        om.set_origin(ctx.map_origin())             # the origin shiftMap left behind inside so_register
+        om.set_points(om_points)
+        ro = om.register(scans[i], priors[i], 0.2, 5, 0, knn_mode=0, skip_map_checks=True)
+        assert np.abs(np.array(r.pose)[:3] - np.array(ro.pose)[:3]).max() < 1e-4 and quat_angle(np.array(r.pose)[3:], np.array(ro.pose)[3:]) < 1e-4
+        ctx.map_add_scan(scans[i], np.array(r.pose))
+        om_points = oracle_mod.map_insert_numpy(om_points, oracle_mod.transform_scan_numpy(scans[i], np.array(r.pose)), 0.2,
+                                                origin=tuple(ctx.map_origin()))
+        assert np.array_equal(ctx.map_download(0), om_points)                         # voxel-filter insert: bit-exact vs the restatement
+        assert int(rows[i][10]) == len(om_points)
+        assert np.linalg.norm(np.array(r.pose)[:3] - get_case("tiny", i)["pose_true"][:3]) < 0.03
+    n_all, n_near = map(int, lines[-1].split()[1:])
+    assert n_all == len(om_points) and 0 < n_near <= n_all
+    ctx.close()
