@@ -140,7 +140,9 @@ def run_ours(args):
     flat = np.ascontiguousarray(np.concatenate(scans, 0))
 
     ctx = api.Context(device=local, max_map_points=len(map_xyzi) + 1024, max_scan_points=int(n_points.max()), max_batch=B, plane_res=0.2)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream(device=dev)             # a real (non-legacy) stream shared by torch events and the library
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     ctx.map_set_points(map_xyzi)
     d_scans = torch.from_numpy(flat).to(dev)
     h_pinned = torch.from_numpy(flat).pin_memory()

@@ -42,7 +42,9 @@ nq = len(q)
 q4 = np.concatenate([q, np.zeros((nq, 1), np.float32)], 1)
 print(f"[rank {rank}] map {M} pts, {nq} queries, gen {time.time() - t0:.1f}s", file=sys.stderr)
 ctx = api.Context(device=local, max_map_points=M + 1024, max_scan_points=1024, plane_res=0.1)
-ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+stream = torch.cuda.Stream()                           # a real (non-legacy) stream shared by torch events and the library
+torch.cuda.set_stream(stream)
+ctx.set_stream(stream.cuda_stream)
 ctx.map_set_points(map_xyzi)
 dq = torch.from_numpy(q4).cuda()
 didx = torch.empty((nq, 5), dtype=torch.int32, device="cuda")
