@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -217,21 +218,54 @@ static int run_schedule(Ctx* c, uint32_t grid_x, uint32_t n_scans, int iters, in
                      c->graph_scan_ptr == d_scan && c->graph_map_epoch == c->map_epoch;
     if (!hit) {
         if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
-        cudaGraph_t g = nullptr;
-        SO_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        for (int it = 0; it < iters; ++it) {
-            launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream);
-            for (int k = 0; k < lm; ++k) launch_evaluate(bv, cb, grid_x, n_scans, c->stream);
+        // Preferred form: a WHILE conditional node whose body is ONE ICP iteration; k_loop_cond ends the loop as soon as
+        // every scan of the batch is done, so converged batches do not pay for the remaining (no-op) iterations.
+        c->graph_is_loop = false;
+        if (!c->no_cond_graph) {
+            cudaGraph_t g = nullptr;
+            cudaGraphConditionalHandle handle;
+            bool ok = cudaGraphCreate(&g, 0) == cudaSuccess &&
+                      cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+            cudaGraphNodeParams p = {cudaGraphNodeTypeConditional};
+            cudaGraphNode_t node;
+            if (ok) {
+                p.type = cudaGraphNodeTypeConditional;
+                p.conditional.handle = handle; p.conditional.type = cudaGraphCondTypeWhile; p.conditional.size = 1;
+                ok = cudaGraphAddNode(&node, g, nullptr, 0, &p) == cudaSuccess;
+            }
+            if (ok) {
+                cudaGraph_t body = p.conditional.phGraph_out[0];
+                ok = cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream);
+                    for (int k = 0; k < lm; ++k) launch_evaluate(bv, cb, grid_x, n_scans, c->stream);
+                    launch_loop_cond(bv, n_scans, handle, c->stream);
+                    cudaGraph_t dummy = nullptr;
+                    ok = cudaStreamEndCapture(c->stream, &dummy) == cudaSuccess;
+                }
+            }
+            if (ok) ok = cudaGraphInstantiate(&c->graph, g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            if (ok) c->graph_is_loop = true;
+            else { cudaGetLastError(); c->graph = nullptr; c->no_cond_graph = true; }       // fall back to the unrolled schedule
         }
-        SO_CUDA_TRY(cudaStreamEndCapture(c->stream, &g));
-        cudaError_t e = cudaGraphInstantiate(&c->graph, g, 0);
-        cudaGraphDestroy(g);
-        if (e != cudaSuccess) return fail(SO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        if (!c->graph) {
+            cudaGraph_t g = nullptr;
+            SO_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            for (int it = 0; it < iters; ++it) {
+                launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream);
+                for (int k = 0; k < lm; ++k) launch_evaluate(bv, cb, grid_x, n_scans, c->stream);
+            }
+            SO_CUDA_TRY(cudaStreamEndCapture(c->stream, &g));
+            cudaError_t e = cudaGraphInstantiate(&c->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(SO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        }
         c->graph_grid_x = grid_x; c->graph_n_scans = n_scans; c->graph_iters = iters; c->graph_lm = lm; c->graph_scan_ptr = d_scan;
         c->graph_map_epoch = c->map_epoch;
     }
     SO_CUDA_TRY(cudaGraphLaunch(c->graph, c->stream));
-    c->launches += kernels;
+    if (!c->graph_is_loop) c->launches += kernels;      // loop form: counted after the results are back (iterations executed)
     return SO_OK;
 }
 
@@ -323,6 +357,11 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        if (c->graph_is_loop && !c->profiling) {
+            int max_it = 0;
+            for (size_t s = 0; s < n_scans; ++s) max_it = std::max(max_it, int(c->h_state[s].n_iterations));
+            c->launches += uint64_t(max_it) * uint64_t(4 + 2 * o.lm_max_iterations);
+        }
         for (size_t s = 0; s < n_scans; ++s) {
             if (results[s].status == SO_STATUS_NOT_ENOUGH_FEATURES || n_points[s] == 0) continue;
             fill_result(c, c->h_state[s], poses + 7 * s, o, results + s);
@@ -366,6 +405,7 @@ so_ctx* so_create(const so_config* cfg_in) {
     c->cfg = cfg;
     if (cfg.plane_res > 0) c->plane_res = cfg.plane_res;
     if (cfg.line_res > 0) c->line_res = cfg.line_res;
+    if (std::getenv("SO_NO_COND_GRAPH")) c->no_cond_graph = true;      // profiling aid: ncu cannot see inside conditional-node bodies
     if (ctx_alloc(c) != SO_OK) { ctx_free(c); return nullptr; }
     return reinterpret_cast<so_ctx*>(c);
 }

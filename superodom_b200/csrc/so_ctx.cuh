@@ -76,6 +76,8 @@ struct Ctx {
     cudaGraphExec_t graph = nullptr;
     uint32_t graph_grid_x = 0, graph_n_scans = 0; int graph_iters = 0, graph_lm = 0; const void* graph_scan_ptr = nullptr;
     uint64_t graph_map_epoch = 0, map_epoch = 1;
+    bool graph_is_loop = false;                    // graph is a WHILE conditional node around one ICP iteration
+    bool no_cond_graph = false;                    // conditional nodes unavailable: use the unrolled schedule
 
     // ---- instrumentation ----------------------------------------------------------------------------------------
     uint64_t launches = 0;

@@ -30,18 +30,25 @@ struct TopK {
         for (int j = 0; j < K; ++j) { d2[j] = bound; id[j] = 0xFFFFFFFFu; pos[j] = 0; }
     }
     __device__ __forceinline__ float worst() const { return d2[K - 1]; }
+    // Insert (d, i, p) if it precedes the current last entry in (d2, id) order.  The shift is a branch-free select
+    // network: in a warp some lane inserts at almost every candidate step, so this path runs ~once per step at low lane
+    // occupancy and its length, not its frequency, is what matters.
     __device__ __forceinline__ void offer(float d, uint32_t i, uint32_t p) {
         if (d < d2[K - 1] || (d == d2[K - 1] && i < id[K - 1])) {
-            d2[K - 1] = d; id[K - 1] = i; pos[K - 1] = p;
+            bool lt[K];                     // lt[j]: candidate precedes slot j
+#pragma unroll
+            for (int j = 0; j < K - 1; ++j) lt[j] = d < d2[j] || (d == d2[j] && i < id[j]);
+            lt[K - 1] = true;
 #pragma unroll
             for (int j = K - 1; j > 0; --j) {
-                const bool lt = d2[j] < d2[j - 1] || (d2[j] == d2[j - 1] && id[j] < id[j - 1]);
-                if (lt) {
-                    const float td = d2[j]; d2[j] = d2[j - 1]; d2[j - 1] = td;
-                    const uint32_t ti = id[j]; id[j] = id[j - 1]; id[j - 1] = ti;
-                    const uint32_t tp = pos[j]; pos[j] = pos[j - 1]; pos[j - 1] = tp;
-                }
+                // slot j takes slot j-1 when the candidate precedes slot j-1, the candidate when it lands exactly here
+                d2[j] = lt[j - 1] ? d2[j - 1] : (lt[j] ? d : d2[j]);
+                id[j] = lt[j - 1] ? id[j - 1] : (lt[j] ? i : id[j]);
+                pos[j] = lt[j - 1] ? pos[j - 1] : (lt[j] ? p : pos[j]);
             }
+            d2[0] = lt[0] ? d : d2[0];
+            id[0] = lt[0] ? i : id[0];
+            pos[0] = lt[0] ? p : pos[0];
         }
     }
     __device__ __forceinline__ int count() const {
@@ -446,6 +453,19 @@ __global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, 
         locate(m, qx, qy, qz, qc);
         if (qc.slot < 0 || qc.nblock < 5) pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
         else {
+            if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) {
+                // ICP iterations after the first: the previous iteration's five neighbours still exist, so the largest
+                // of their (exact) distances to the moved query bounds the new 5th-neighbour distance.  Starting the walk
+                // with that bound prunes rows from the first step; the result is unchanged (all true neighbours lie within it).
+                float u = 0.f;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float4 c = __ldg(&m.pts[nb.pos[size_t(j) * nb.cap + gi]]);
+                    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+                    u = fmaxf(u, float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)));
+                }
+                if (u < m.bound_d2) tk.init(u);
+            }
             knn_rows<5>(m, qc, qx, qy, qz, tk);
             pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
         }
@@ -473,13 +493,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, Co
     if (threadIdx.x == 0) qtoR(s_pose + 3, s_R);
     __syncthreads();
     const uint32_t n = uint32_t(st->n_points);
-    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-    const size_t gi = size_t(bv.offset[s]) + i;
 
     double acc[kAcc];
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
 
+#pragma unroll 1
+    for (int rr = 0; rr < kFitPts; ++rr) {          // kFitPts points per thread before the one CTA reduction
+    const uint32_t i = (blockIdx.x * kFitPts + rr) * kThreads + threadIdx.x;
+    const size_t gi = size_t(bv.offset[s]) + i;
     if (i < n) {
         int status = nb.pre[gi];
         int o0 = 0, o1 = 0, o2 = 0;
@@ -604,6 +626,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, Co
         cb.w[gi] = wq;
         cb.flags[gi] = make_uchar4((unsigned char)status, (unsigned char)o0, (unsigned char)o1, (unsigned char)o2);
     }
+    }
     __syncthreads();
     if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&bv.hist[s * 16 + threadIdx.x], s_hist[threadIdx.x]);
 
@@ -665,7 +688,7 @@ __global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partia
     double v = 0.0;
     if (comp < kAcc) {
         const double* base = bv.partials + size_t(s) * bv.partial_stride * kAcc;
-        const uint32_t np = (AFTER == PH_CORR) ? (uint32_t(st->n_points) + kThreads - 1) / kThreads
+        const uint32_t np = (AFTER == PH_CORR) ? (uint32_t(st->n_points) + kThreads * kFitPts - 1) / (kThreads * kFitPts)
                                                : (uint32_t(st->n_points) + kThreads * kEvalPts - 1) / (kThreads * kEvalPts);
         for (uint32_t b = sub; b < np && b < n_partials; b += 4) v += base[size_t(b) * kAcc + comp];
         s_red[sub][comp] = v;
@@ -692,6 +715,15 @@ __global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partia
             st->cost = s_sum[27]; st->phase = PH_DONE;
         } else lm_after_eval(*st, s_sum);
     }
+}
+
+// Loop condition of the CUDA-graph WHILE node that wraps one ICP iteration: keep iterating while any scan of the
+// batch is still registering (LidarSlam.cpp:119-148 runs this loop on the host, one scan at a time).
+__global__ void k_loop_cond(const IcpState* __restrict__ st, uint32_t n_scans, cudaGraphConditionalHandle handle) {
+    int active = 0;
+    for (uint32_t s = threadIdx.x; s < n_scans; s += 32) active |= (st[s].phase != PH_DONE);
+    active = __any_sync(0xffffffffu, active);
+    if (threadIdx.x == 0) cudaGraphSetConditional(handle, active ? 1u : 0u);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -753,13 +785,17 @@ void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* 
 }
 void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
     k_knn_scan<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, nb);
-    k_fit<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
-    k_lm_step<PH_CORR><<<n_scans, 128, 0, st>>>(bv, grid_x);
+    const uint32_t gf = (grid_x + kFitPts - 1) / kFitPts;
+    k_fit<<<dim3(gf, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
+    k_lm_step<PH_CORR><<<n_scans, 128, 0, st>>>(bv, gf);
 }
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
     const uint32_t gx = (grid_x + kEvalPts - 1) / kEvalPts;
     k_evaluate<<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb);
     k_lm_step<PH_EVAL><<<n_scans, 128, 0, st>>>(bv, gx);
+}
+void launch_loop_cond(const BatchView& bv, uint32_t n_scans, cudaGraphConditionalHandle handle, cudaStream_t st) {
+    k_loop_cond<<<1, 32, 0, st>>>(bv.st, n_scans, handle);
 }
 int launch_knn(const MapView& m, const float4* q, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st) {
     const uint32_t grid = uint32_t((nq + kThreads - 1) / kThreads);

@@ -30,11 +30,13 @@ struct NnBuf {
 };
 
 constexpr int kEvalPts = 4;     // points per thread in k_evaluate
+constexpr int kFitPts = 2;      // points per thread in k_fit
 
 void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st);
 void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
+void launch_loop_cond(const BatchView& bv, uint32_t n_scans, cudaGraphConditionalHandle handle, cudaStream_t st);
 int launch_knn(const MapView& m, const float4* q, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st);
 
 }  // namespace so
