@@ -199,7 +199,8 @@ uint64_t so_kernel_launches(so_ctx* ctx, int reset);
  * last reset (bench.py e2e accounting). */
 int so_bytes_copied(so_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);
 /* Accumulated device time (ms, CUDA events on the context stream) and launch count of a kernel class since the last
- * reset; classes: 0 correspond (k-NN + fit + first evaluation), 1 evaluate (LM step), 2 k-NN only (so_knn), 3 map build.
+ * reset; classes: 0 k_knn_scan (scan k-NN), 1 k_evaluate + k_lm_step (LM step), 2 k_knn (so_knn*), 3 scan ordering / map
+ * build / map insert, 4 k_fit + k_lm_step (plane fit + first evaluation).
  * Profiling mode serialises kernels; enable only for roofline runs. */
 int so_profile_enable(so_ctx* ctx, int on);
 int so_profile_get(so_ctx* ctx, int kernel_class, double* ms, uint64_t* launches, int reset);

@@ -75,6 +75,7 @@ static int ctx_alloc(Ctx* c) {
     SO_CUDA_TRY(cudaMalloc(&c->d_svals, c->scan_cap * sizeof(uint32_t)));
     SO_CUDA_TRY(cudaMalloc(&c->d_svals_out, c->scan_cap * sizeof(uint32_t)));
     SO_CUDA_TRY(cudaMalloc(&c->nn.pos, c->scan_cap * 5 * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->nn.pts, c->scan_cap * 5 * sizeof(float4)));
     SO_CUDA_TRY(cudaMalloc(&c->nn.pre, c->scan_cap));
     c->nn.cap = c->scan_cap;
     { int rc2 = scan_sort_alloc(c); if (rc2) return rc2; }
@@ -102,7 +103,7 @@ static void ctx_free(Ctx* c) {
     if (c->graph) cudaGraphExecDestroy(c->graph);
     map_free(c);
     cudaFree(c->d_scan_sorted); cudaFree(c->d_skeys); cudaFree(c->d_skeys_out); cudaFree(c->d_svals); cudaFree(c->d_svals_out);
-    cudaFree(c->d_sort_tmp); cudaFree(c->nn.pos); cudaFree(c->nn.pre);
+    cudaFree(c->d_sort_tmp); cudaFree(c->nn.pos); cudaFree(c->nn.pts); cudaFree(c->nn.pre);
     cudaFree(c->d_scan); cudaFree(c->d_offset); cudaFree(c->d_state); cudaFreeHost(c->h_state); cudaFreeHost(c->h_offset);
     cudaFree(c->d_partials); cudaFree(c->d_counters); cudaFree(c->d_hist);
     cudaFree(c->corr.nd); cudaFree(c->corr.w); cudaFree(c->corr.flags); cudaFree(c->corr.nn); cudaFree(c->corr.nn_d2);
@@ -207,7 +208,10 @@ static int run_schedule(Ctx* c, uint32_t grid_x, uint32_t n_scans, int iters, in
             return false;
         };
         for (int it = 0; it < iters; ++it) {
-            if (any_in(PH_CORR)) { timed_launch_begin(c); launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream); c->launches += 2; timed_launch_end(c, 0); }
+            if (any_in(PH_CORR)) {
+                timed_launch_begin(c); launch_knn_scan(mv, bv, c->nn, grid_x, n_scans, c->stream); timed_launch_end(c, 0);
+                timed_launch_begin(c); launch_fit(mv, bv, cb, c->nn, grid_x, n_scans, c->stream); c->launches++; timed_launch_end(c, 4);
+            }
             for (int k = 0; k < lm; ++k)
                 if (any_in(PH_EVAL)) { timed_launch_begin(c); launch_evaluate(bv, cb, grid_x, n_scans, c->stream); c->launches++; timed_launch_end(c, 1); }
         }
@@ -739,7 +743,7 @@ int so_profile_enable(so_ctx* ctx, int on) {
 
 int so_profile_get(so_ctx* ctx, int cls, double* ms, uint64_t* launches, int reset) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (!c || cls < 0 || cls > 3) return fail(SO_ERR_ARG, "bad args");
+    if (!c || cls < 0 || cls > 4) return fail(SO_ERR_ARG, "bad args");
     if (ms) *ms = c->prof[cls].ms;
     if (launches) *launches = c->prof[cls].launches;
     if (reset) c->prof[cls] = ProfileSlot{};

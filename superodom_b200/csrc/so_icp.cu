@@ -153,6 +153,101 @@ __device__ __forceinline__ void knn_rows(const MapView& m, const QueryCell& qc, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// 5-NN for the ICP kernel in three warp-friendly rounds (all loops do the same kind of work in every lane):
+//   1. bound : a value-only min/max selection network over the 27 cells around the query gives U, an upper bound on the
+//              5th-neighbour distance (skipped when the previous ICP iteration's neighbours already provide one);
+//   2. gather: pruned walk of the search cube with the fixed bound U; the few candidates with approx d2 <= U are only
+//              recorded (position into a per-lane shared-memory list) -- no divergent insertion in the hot loop;
+//   3. refine: the recorded candidates get the reference's exact d2 rounding and are ordered by (d2, id).
+// The result is identical to an exhaustive in-block search with the same ordering: every true neighbour has
+// approx d2 <= U (U carries a 4e-6 relative margin over the FP32 evaluation error of 4e-7).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kBufCap = 24;
+
+template <class F>
+__device__ __forceinline__ void walk_cube(const MapView& m, const QueryCell& qc, float U, int R, F&& f) {
+    const int nb = m.nb;
+    const uint32_t base = uint32_t(qc.slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
+    const float cs = m.cs;
+    const float fx = qc.f[0], fy = qc.f[1], fz = qc.f[2];
+#pragma unroll 1
+    for (int zi = 0; zi <= 2 * R; ++zi) {                    // offsets 0,-1,+1,-2,+2: nearest slabs first
+        const int oz = (zi & 1) ? -((zi + 1) >> 1) : (zi >> 1);
+        const int zz = qc.c[2] + oz;
+        if (zz < 0 || zz >= nb) continue;                    // stay inside the query's block (LocalMap.h:488-507)
+        const float lz = oz < 0 ? fz + float(-oz - 1) * cs : (oz > 0 ? (cs - fz) + float(oz - 1) * cs : 0.f);
+        const float lz2 = lz * lz;
+        if (lz2 * 0.9999f > U) continue;
+#pragma unroll 1
+        for (int yi = 0; yi <= 2 * R; ++yi) {
+            const int oy = (yi & 1) ? -((yi + 1) >> 1) : (yi >> 1);
+            const int yy = qc.c[1] + oy;
+            if (yy < 0 || yy >= nb) continue;
+            const float ly = oy < 0 ? fy + float(-oy - 1) * cs : (oy > 0 ? (cs - fy) + float(oy - 1) * cs : 0.f);
+            const float lb = ly * ly + lz2;
+            if (lb * 0.9999f > U) continue;
+            int xlo = qc.c[0], xhi = qc.c[0];
+            for (int k = 1; k <= R; ++k) {
+                const float lx = fx + float(k - 1) * cs;
+                if (qc.c[0] - k < 0 || (lb + lx * lx) * 0.9999f > U) break;
+                xlo = qc.c[0] - k;
+            }
+            for (int k = 1; k <= R; ++k) {
+                const float lx = (cs - fx) + float(k - 1) * cs;
+                if (qc.c[0] + k > nb - 1 || (lb + lx * lx) * 0.9999f > U) break;
+                xhi = qc.c[0] + k;
+            }
+            const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
+            uint32_t t = __ldg(&m.cell_start[row + xlo]);
+            const uint32_t end = __ldg(&m.cell_start[row + xhi + 1]);
+            for (; t + 4 <= end; t += 4) {                   // four independent 16-byte loads in flight per lane
+                const float4 c0 = __ldg(&m.pts[t]), c1 = __ldg(&m.pts[t + 1]), c2 = __ldg(&m.pts[t + 2]), c3 = __ldg(&m.pts[t + 3]);
+                f(c0, t); f(c1, t + 1); f(c2, t + 2); f(c3, t + 3);
+            }
+            for (; t < end; ++t) f(__ldg(&m.pts[t]), t);
+        }
+    }
+}
+
+__device__ __forceinline__ float approx_d2(const float4 c, float qx, float qy, float qz) {
+    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+
+// s_buf: [kBufCap][kThreads] positions, column = this thread.  u_seed < 0: no seed.
+__device__ __forceinline__ void knn5_select(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, float u_seed,
+                                            uint32_t* s_buf, TopK<5>& tk) {
+    float U;
+    if (u_seed >= 0.f) U = u_seed * 1.000004f;
+    else {
+        float a0 = m.bound_d2, a1 = a0, a2 = a0, a3 = a0, a4 = a0;             // five smallest approx d2 so far, ascending
+        walk_cube(m, qc, m.bound_d2, 1, [&](const float4 c, uint32_t) {
+            const float d = approx_d2(c, qx, qy, qz);
+            a4 = fminf(a4, fmaxf(a3, d)); a3 = fminf(a3, fmaxf(a2, d)); a2 = fminf(a2, fmaxf(a1, d)); a1 = fminf(a1, fmaxf(a0, d)); a0 = fminf(a0, d);
+        });
+        U = a4 * 1.000004f;
+    }
+    U = fminf(U, m.bound_d2 * 1.000004f);
+    int cnt = 0;
+    walk_cube(m, qc, U, m.R, [&](const float4 c, uint32_t t) {
+        const float d = approx_d2(c, qx, qy, qz);
+        if (d <= U) {
+            if (cnt < kBufCap) { s_buf[cnt * kThreads + threadIdx.x] = t; ++cnt; }
+            else {                                                             // overflow (dense cluster inside U): insert directly
+                const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+                tk.offer(float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)), __float_as_uint(c.w), t);
+            }
+        }
+    });
+    for (int e = 0; e < cnt; ++e) {
+        const uint32_t t = s_buf[e * kThreads + threadIdx.x];
+        const float4 c = __ldg(&m.pts[t]);
+        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+        tk.offer(float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)), __float_as_uint(c.w), t);
+    }
+}
+
 // Unpruned cube [c-R, c+R]^3 clipped to the block (fallback rings of the exact, unbounded search).
 template <int K>
 __device__ __forceinline__ void knn_cube(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, int R, TopK<K>& tk) {
@@ -434,6 +529,7 @@ __global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, 
     const IcpState* st = bv.st + s;
     if (st->phase != PH_CORR) return;
     __shared__ double s_pose[7];
+    __shared__ uint32_t s_buf[kBufCap * kThreads];
     if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
     __syncthreads();
     const uint32_t n = uint32_t(st->n_points);
@@ -453,10 +549,10 @@ __global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, 
         locate(m, qx, qy, qz, qc);
         if (qc.slot < 0 || qc.nblock < 5) pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
         else {
+            float u_seed = -1.f;
             if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) {
                 // ICP iterations after the first: the previous iteration's five neighbours still exist, so the largest
-                // of their (exact) distances to the moved query bounds the new 5th-neighbour distance.  Starting the walk
-                // with that bound prunes rows from the first step; the result is unchanged (all true neighbours lie within it).
+                // of their (exact) distances to the moved query bounds the new 5th-neighbour distance.
                 float u = 0.f;
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
@@ -464,15 +560,20 @@ __global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, 
                     const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
                     u = fmaxf(u, float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)));
                 }
-                if (u < m.bound_d2) tk.init(u);
+                u_seed = u;
             }
-            knn_rows<5>(m, qc, qx, qy, qz, tk);
+            knn5_select(m, qc, qx, qy, qz, u_seed, s_buf, tk);
             pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
         }
     }
     nb.pre[gi] = (unsigned char)pre;
 #pragma unroll
-    for (int j = 0; j < 5; ++j) nb.pos[size_t(j) * nb.cap + gi] = tk.id[j] != 0xFFFFFFFFu ? tk.pos[j] : 0xFFFFFFFFu;
+    for (int j = 0; j < 5; ++j) {
+        const bool ok = tk.id[j] != 0xFFFFFFFFu;
+        nb.pos[size_t(j) * nb.cap + gi] = ok ? tk.pos[j] : 0xFFFFFFFFu;
+        // the five points are L1-hot here; handing them on as coalesced 16-byte stores saves k_fit five scattered gathers
+        if (pre == SO_MATCH_SUCCESS) nb.pts[size_t(j) * nb.cap + gi] = __ldg(&m.pts[tk.pos[j]]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -519,8 +620,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, Co
             double mean[3] = {0, 0, 0};
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-                const uint32_t pos = nb.pos[size_t(j) * nb.cap + gi];
-                const float4 c = __ldg(&m.pts[pos]);
+                const float4 c = nb.pts[size_t(j) * nb.cap + gi];
                 mm[j][0] = double(c.x); mm[j][1] = double(c.y); mm[j][2] = double(c.z);
                 mean[0] += mm[j][0]; mean[1] += mm[j][1]; mean[2] += mm[j][2];
                 if (cb.nn) {
@@ -783,11 +883,17 @@ void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uin
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st) {
     k_scan_gather<<<uint32_t((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(in, vals, keys, offset, total, out);
 }
-void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+void launch_knn_scan(const MapView& m, const BatchView& bv, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
     k_knn_scan<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, nb);
+}
+void launch_fit(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
     const uint32_t gf = (grid_x + kFitPts - 1) / kFitPts;
     k_fit<<<dim3(gf, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
     k_lm_step<PH_CORR><<<n_scans, 128, 0, st>>>(bv, gf);
+}
+void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+    launch_knn_scan(m, bv, nb, grid_x, n_scans, st);
+    launch_fit(m, bv, cb, nb, grid_x, n_scans, st);
 }
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
     const uint32_t gx = (grid_x + kEvalPts - 1) / kEvalPts;

@@ -24,16 +24,22 @@ struct BatchView {
 
 // neighbour hand-off between k_knn_scan and k_fit
 struct NnBuf {
-    uint32_t* pos;       // [5][cap] positions of the 5 neighbours in the sorted map (0xFFFFFFFF = none)
+    uint32_t* pos;       // [5][cap] positions of the 5 neighbours in the sorted map (0xFFFFFFFF = none); seeds the next iteration
+    float4* pts;         // [5][cap] the neighbours themselves {x,y,z,bitcast(id)}: k_fit streams them instead of gathering
     unsigned char* pre;  // [cap] SO_MATCH_SKIPPED / NOT_ENOUGH_NEIGHBORS / NEIGHBORS_TOO_FAR / SUCCESS (= has 5 neighbours)
     size_t cap;
 };
 
 constexpr int kEvalPts = 4;     // points per thread in k_evaluate
-constexpr int kFitPts = 2;      // points per thread in k_fit
+#ifndef SO_FIT_PTS
+#define SO_FIT_PTS 2
+#endif
+constexpr int kFitPts = SO_FIT_PTS;      // points per thread in k_fit
 
 void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st);
+void launch_knn_scan(const MapView& m, const BatchView& bv, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
+void launch_fit(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 void launch_loop_cond(const BatchView& bv, uint32_t n_scans, cudaGraphConditionalHandle handle, cudaStream_t st);

@@ -325,3 +325,54 @@ def test_cfg3_mid360_with_covariance(gpu_api, oracle_mod):
         assert abs(getattr(r, f) - getattr(ro, f)) <= 1e-6 * abs(getattr(ro, f))
     assert np.linalg.norm(np.array(r.pose)[:3] - case["pose_true"][:3]) < 0.01
     ctx.close()
+
+
+def test_map_insert_voxel_filter_bit_exact(gpu_api, oracle_mod):
+    """LocalMap::addSurfPointCloud (LocalMap.h:591-645) on the device vs the numpy restatement: fresh map, a second insert
+    that touches only some blocks (untouched blocks must stay as they are, even after planeRes changed), off-grid points."""
+    from superodom_b200 import synth
+    rng = np.random.default_rng(9)
+    ctx = gpu_api.Context(max_map_points=1 << 21, max_scan_points=65536, plane_res=0.2)
+    a = np.concatenate([rng.uniform(-60, 60, size=(200000, 2)), rng.uniform(-2, 6, size=(200000, 1)), rng.uniform(0, 255, size=(200000, 1))], 1).astype(np.float32)
+    a[:100, 0] += 5000.0                                     # off-grid: dropped
+    ctx.map_add_surf(a)
+    ref = oracle_mod.map_insert_numpy(np.zeros((0, 4), np.float32), a, 0.2)
+    got = ctx.map_download(0)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    # second insert, coarser leaf (auto_voxel_size switches planeRes per scan, laserMapping.cpp:624-633), one block only
+    ctx.map_set_resolution(0.2, 0.4)
+    b = np.concatenate([rng.uniform(-20, 20, size=(50000, 2)), rng.uniform(-2, 6, size=(50000, 1)), rng.uniform(0, 255, size=(50000, 1))], 1).astype(np.float32)
+    ctx.map_add_surf(b)
+    ref2 = oracle_mod.map_insert_numpy(ref, b, 0.4)
+    got2 = ctx.map_download(0)
+    assert got2.shape == ref2.shape and np.array_equal(got2, ref2)
+    lin = synth.block_linear(synth.block_of(got2[:, :3]))
+    centre = 10 + 21 * 10 + 21 * 21 * 5
+    assert (lin == centre).sum() < (synth.block_linear(synth.block_of(ref[:, :3])) == centre).sum()      # centre block got coarser
+    # the index over the new map answers k-NN exactly
+    om = oracle_mod.OracleMap(ref2)
+    q = ref2[::50, :3] + rng.normal(0, 0.05, size=ref2[::50, :3].shape).astype(np.float32)
+    gi, gd = ctx.knn(q, 5, 0.0)
+    oi, od, of = om.knn(q, 5, 0)
+    assert np.array_equal(_gi(gi)[of], oi[of]) and np.array_equal(gd[of], od[of])
+    # 5x5x3 download is a subset in the same order
+    near = ctx.map_download(1, [10, 10, 5])
+    assert len(near) == len(got2)                             # everything lies within +-2 blocks of the centre here
+    ctx.close()
+
+
+def test_resolution_change_rebuilds_index(gpu_api, oracle_mod):
+    """planeRes drives the gates AND the search radius; switching it (adjustVoxelSize, laserMapping.cpp:600-651) must keep parity."""
+    case = get_case("tiny")
+    ctx = _ctx(gpu_api, case)
+    om = oracle_mod.OracleMap(case["map_xyzi"])
+    for pr in (0.4, 0.1, 0.2):
+        ctx.map_set_resolution(0.1, pr)
+        gc, gho, ghr = ctx.correspond(case["scan_xyzi"], case["pose_prior"], 0)
+        oc, oho, ohr = om.correspond(case["scan_xyzi"], case["pose_prior"], pr, 0, 0)
+        assert np.array_equal(gho, oho) and np.array_equal(ghr, ohr), pr
+        r = ctx.register(case["scan_xyzi"], case["pose_prior"], 5)
+        ro = om.register(case["scan_xyzi"], case["pose_prior"], pr, 5)
+        _assert_pose_close(np.array(r.pose), np.array(ro.pose))
+        assert r.n_iterations == ro.n_iterations
+    ctx.close()
