@@ -63,6 +63,8 @@ static int ctx_alloc(Ctx* c) {
     SO_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SO_CUDA_TRY(cudaEventCreate(&c->ev0)); SO_CUDA_TRY(cudaEventCreate(&c->ev1));
     SO_CUDA_TRY(cudaEventCreate(&c->evp0)); SO_CUDA_TRY(cudaEventCreate(&c->evp1));
+    SO_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev_copy) SO_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int rc = map_alloc(c);
     if (rc) return rc;
     c->max_batch = c->cfg.max_batch;
@@ -76,6 +78,7 @@ static int ctx_alloc(Ctx* c) {
     SO_CUDA_TRY(cudaMalloc(&c->d_svals_out, c->scan_cap * sizeof(uint32_t)));
     SO_CUDA_TRY(cudaMalloc(&c->nn.pos, c->scan_cap * 5 * sizeof(uint32_t)));
     SO_CUDA_TRY(cudaMalloc(&c->nn.pts, c->scan_cap * 5 * sizeof(float4)));
+    SO_CUDA_TRY(cudaMalloc(&c->nn.d5, c->scan_cap * sizeof(float)));
     SO_CUDA_TRY(cudaMalloc(&c->nn.pre, c->scan_cap));
     c->nn.cap = c->scan_cap;
     { int rc2 = scan_sort_alloc(c); if (rc2) return rc2; }
@@ -100,10 +103,12 @@ static void ctx_free(Ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->graph) cudaGraphExecDestroy(c->graph);
+    for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto& e : c->ev_copy) if (e) cudaEventDestroy(e);
     map_free(c);
     cudaFree(c->d_scan_sorted); cudaFree(c->d_skeys); cudaFree(c->d_skeys_out); cudaFree(c->d_svals); cudaFree(c->d_svals_out);
-    cudaFree(c->d_sort_tmp); cudaFree(c->nn.pos); cudaFree(c->nn.pts); cudaFree(c->nn.pre);
+    cudaFree(c->d_sort_tmp); cudaFree(c->nn.pos); cudaFree(c->nn.pts); cudaFree(c->nn.d5); cudaFree(c->nn.pre);
     cudaFree(c->d_scan); cudaFree(c->d_offset); cudaFree(c->d_state); cudaFreeHost(c->h_state); cudaFreeHost(c->h_offset);
     cudaFree(c->d_partials); cudaFree(c->d_counters); cudaFree(c->d_hist);
     cudaFree(c->corr.nd); cudaFree(c->corr.w); cudaFree(c->corr.flags); cudaFree(c->corr.nn); cudaFree(c->corr.nn_d2);
@@ -151,9 +156,10 @@ static int upload_cloud(Ctx* c, const void* src, size_t n, size_t stride, size_t
 }
 
 // ---------------------------------------------------------------------------------------------- ICP schedule
-static BatchView batch_view(const Ctx* c, const float4* scan) {
+static BatchView batch_view(const Ctx* c, const float4* scan, uint32_t first = 0) {
     BatchView bv;
-    bv.scan = scan; bv.offset = c->d_offset; bv.st = c->d_state; bv.partials = c->d_partials; bv.partial_stride = c->grid_x_cap; bv.hist = c->d_hist;
+    bv.scan = scan; bv.offset = c->d_offset + first; bv.st = c->d_state + first;
+    bv.partials = c->d_partials + size_t(first) * c->grid_x_cap * kAcc; bv.partial_stride = c->grid_x_cap; bv.hist = c->d_hist + size_t(first) * 16;
     const double a = double(std::sqrt(3 * c->plane_res));     // float sqrt of a float product (LidarSlam.cpp:271)
     bv.tukey_a2 = a * a;
     return bv;
@@ -173,36 +179,43 @@ static void timed_launch_end(Ctx* c, int cls) {
     c->prof[cls].ms += ms; c->prof[cls].launches++;
 }
 
-// [k_correspond, k_evaluate x lm] x icp iterations; every kernel exits at once when its scan is not in the
-// matching phase, so the fixed schedule follows whatever path the device-side state machine takes.
+// A contiguous run of scans of the batch that is uploaded, ordered and registered together.
+struct Chunk { uint32_t first, count, pt_first, pt_count, grid_x; };
+
 // Once per registration: order every scan by map cell at its prior pose (k_scan_keys -> radix sort -> k_scan_gather).
-static int prepare_scans(Ctx* c, const float4* d_scan_in, uint32_t grid_x, uint32_t n_scans, size_t total) {
+static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch) {
     const MapView mv = map_view(c);
-    const BatchView bv = batch_view(c, d_scan_in);
+    const BatchView bv = batch_view(c, d_scan_in, ch.first);
     timed_launch_begin(c);
-    launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, grid_x, n_scans, c->stream);
-    int rc = scan_sort(c, total, int(n_scans));
+    launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, ch.grid_x, ch.count, c->stream);
+    int rc = scan_sort(c, ch.pt_first, ch.pt_count, int(ch.count));
     if (rc) return rc;
-    launch_scan_gather(d_scan_in, c->d_svals_out, c->d_skeys_out, c->d_offset, total, c->d_scan_sorted, c->stream);
+    launch_scan_gather(d_scan_in, c->d_svals_out + ch.pt_first, c->d_skeys_out + ch.pt_first, c->d_offset + ch.first, ch.pt_count,
+                       c->d_scan_sorted + ch.pt_first, c->stream);
     c->launches++;
     timed_launch_end(c, 3);
     SO_CUDA_TRY(cudaGetLastError());
     return SO_OK;
 }
 
-static int run_schedule(Ctx* c, uint32_t grid_x, uint32_t n_scans, int iters, int lm, bool with_nn) {
+// [k_knn_scan, k_fit, k_lm_step, (k_evaluate, k_lm_step) x lm] per ICP iteration; every kernel exits at once when its
+// scan is not in the matching phase, so a fixed schedule follows whatever path the device-side state machine takes.
+// Preferred form: a CUDA-graph WHILE node around ONE iteration (k_loop_cond ends the loop when every scan of the chunk
+// is done); fallback: the schedule unrolled max_icp_iters times.  Returns whether the loop form ran.
+static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn, bool* was_loop) {
     const float4* d_scan = c->d_scan_sorted;
     const MapView mv = map_view(c);
-    const BatchView bv = batch_view(c, d_scan);
+    const BatchView bv = batch_view(c, d_scan, ch.first);
     CorrBuf cb = c->corr;
     if (!with_nn) { cb.nn = nullptr; cb.nn_d2 = nullptr; }
-    const uint64_t kernels = uint64_t(iters) * (3 + 2 * lm);
+    const uint32_t grid_x = ch.grid_x, n_scans = ch.count;
+    *was_loop = false;
     if (c->profiling || with_nn) {
         // profiling mode: one launch at a time, timed with events, and only launches that have work (the host peeks
         // at the phases) so that the per-class average is the duration of a kernel that actually ran
         std::vector<IcpState> peek(n_scans);
         auto any_in = [&](int ph) -> bool {
-            cudaMemcpyAsync(peek.data(), c->d_state, n_scans * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(peek.data(), c->d_state + ch.first, n_scans * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream);
             cudaStreamSynchronize(c->stream);
             for (uint32_t s = 0; s < n_scans; ++s) if (peek[s].phase == ph) return true;
             return false;
@@ -218,13 +231,14 @@ static int run_schedule(Ctx* c, uint32_t grid_x, uint32_t n_scans, int iters, in
         SO_CUDA_TRY(cudaGetLastError());
         return SO_OK;
     }
-    const bool hit = c->graph && c->graph_grid_x == grid_x && c->graph_n_scans == n_scans && c->graph_iters == iters && c->graph_lm == lm &&
-                     c->graph_scan_ptr == d_scan && c->graph_map_epoch == c->map_epoch;
-    if (!hit) {
-        if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
-        // Preferred form: a WHILE conditional node whose body is ONE ICP iteration; k_loop_cond ends the loop as soon as
-        // every scan of the batch is done, so converged batches do not pay for the remaining (no-op) iterations.
-        c->graph_is_loop = false;
+    Ctx::GraphSlot* slot = nullptr;
+    for (auto& g : c->graphs)
+        if (g.exec && g.first == ch.first && g.count == n_scans && g.grid_x == grid_x && g.iters == iters && g.lm == lm && g.epoch == c->map_epoch) slot = &g;
+    if (!slot) {
+        slot = &c->graphs[0];
+        for (auto& g : c->graphs) { if (!g.exec) { slot = &g; break; } if (g.used < slot->used) slot = &g; }
+        if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+        slot->is_loop = false;
         if (!c->no_cond_graph) {
             cudaGraph_t g = nullptr;
             cudaGraphConditionalHandle handle;
@@ -233,7 +247,6 @@ static int run_schedule(Ctx* c, uint32_t grid_x, uint32_t n_scans, int iters, in
             cudaGraphNodeParams p = {cudaGraphNodeTypeConditional};
             cudaGraphNode_t node;
             if (ok) {
-                p.type = cudaGraphNodeTypeConditional;
                 p.conditional.handle = handle; p.conditional.type = cudaGraphCondTypeWhile; p.conditional.size = 1;
                 ok = cudaGraphAddNode(&node, g, nullptr, 0, &p) == cudaSuccess;
             }
@@ -248,12 +261,12 @@ static int run_schedule(Ctx* c, uint32_t grid_x, uint32_t n_scans, int iters, in
                     ok = cudaStreamEndCapture(c->stream, &dummy) == cudaSuccess;
                 }
             }
-            if (ok) ok = cudaGraphInstantiate(&c->graph, g, 0) == cudaSuccess;
+            if (ok) ok = cudaGraphInstantiate(&slot->exec, g, 0) == cudaSuccess;
             if (g) cudaGraphDestroy(g);
-            if (ok) c->graph_is_loop = true;
-            else { cudaGetLastError(); c->graph = nullptr; c->no_cond_graph = true; }       // fall back to the unrolled schedule
+            if (ok) slot->is_loop = true;
+            else { cudaGetLastError(); slot->exec = nullptr; c->no_cond_graph = true; }      // fall back to the unrolled schedule
         }
-        if (!c->graph) {
+        if (!slot->exec) {
             cudaGraph_t g = nullptr;
             SO_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             for (int it = 0; it < iters; ++it) {
@@ -261,15 +274,16 @@ static int run_schedule(Ctx* c, uint32_t grid_x, uint32_t n_scans, int iters, in
                 for (int k = 0; k < lm; ++k) launch_evaluate(bv, cb, grid_x, n_scans, c->stream);
             }
             SO_CUDA_TRY(cudaStreamEndCapture(c->stream, &g));
-            cudaError_t e = cudaGraphInstantiate(&c->graph, g, 0);
+            cudaError_t e = cudaGraphInstantiate(&slot->exec, g, 0);
             cudaGraphDestroy(g);
-            if (e != cudaSuccess) return fail(SO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+            if (e != cudaSuccess) { slot->exec = nullptr; return fail(SO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
         }
-        c->graph_grid_x = grid_x; c->graph_n_scans = n_scans; c->graph_iters = iters; c->graph_lm = lm; c->graph_scan_ptr = d_scan;
-        c->graph_map_epoch = c->map_epoch;
+        slot->first = ch.first; slot->count = n_scans; slot->grid_x = grid_x; slot->iters = iters; slot->lm = lm; slot->epoch = c->map_epoch;
     }
-    SO_CUDA_TRY(cudaGraphLaunch(c->graph, c->stream));
-    if (!c->graph_is_loop) c->launches += kernels;      // loop form: counted after the results are back (iterations executed)
+    slot->used = ++c->graph_clock;
+    SO_CUDA_TRY(cudaGraphLaunch(slot->exec, c->stream));
+    *was_loop = slot->is_loop;
+    if (!slot->is_loop) c->launches += uint64_t(iters) * (3 + 2 * lm);      // loop form: counted from the iterations executed
     return SO_OK;
 }
 
@@ -312,8 +326,10 @@ static void fill_result(const Ctx* c, const IcpState& s, const double pose_in[7]
 }
 
 // Shared tail of so_register / so_register_batch*: scans are on the device at d_scan (packed, back to back).
+// d_scan: device scans (packed, back to back).  host_src != nullptr: the scans are still on the host (packed float4); this
+// function uploads them into d_scan chunk by chunk on the copy stream.
 static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points, size_t n_scans, const double* poses,
-                         const so_icp_opts* opts_in, so_icp_result* results, bool allow_shift) {
+                         const so_icp_opts* opts_in, so_icp_result* results, bool allow_shift, const void* host_src = nullptr) {
     so_icp_opts o = *opts_in;
     if (o.lm_max_iterations <= 0) o.lm_max_iterations = 4;
     if (o.max_icp_iters <= 0 || o.max_icp_iters > SO_MAX_ICP_ITERS) return fail(SO_ERR_ARG, "max_icp_iters must be in [1,32]");
@@ -349,21 +365,53 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, n_scans * sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
         SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, n_scans * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
         count_h2d(c, n_scans * (sizeof(IcpState) + sizeof(uint32_t)));
-        const uint32_t grid_x = (max_n + kThreads - 1) / kThreads;
+        // Chunk the batch: with host input the H2D of chunk k+1 (copy stream) overlaps the kernels of chunk k.
+        const size_t n_chunks = (host_src && n_scans >= 8 && !c->profiling) ? 4 : 1;
+        std::vector<Chunk> chunks;
+        for (size_t k = 0; k < n_chunks; ++k) {
+            const uint32_t f = uint32_t(k * n_scans / n_chunks), e = uint32_t((k + 1) * n_scans / n_chunks);
+            if (e == f) continue;
+            Chunk ch{f, e - f, c->h_offset[f], (e < n_scans ? c->h_offset[e] : off) - c->h_offset[f], 0};
+            uint32_t mx = 0;
+            for (uint32_t s = f; s < e; ++s) if (c->h_state[s].phase == PH_CORR) mx = std::max(mx, n_points[s]);
+            ch.grid_x = (mx + kThreads - 1) / kThreads;
+            chunks.push_back(ch);
+        }
         SO_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-        int rc = prepare_scans(c, d_scan, grid_x, uint32_t(n_scans), size_t(off));
-        if (rc) return rc;
-        rc = run_schedule(c, grid_x, uint32_t(n_scans), o.max_icp_iters, o.lm_max_iterations, false);
-        if (rc) return rc;
+        if (host_src) {
+            SO_CUDA_TRY(cudaEventRecord(c->ev_copy[7], c->stream));                 // copies must not overtake earlier work on d_scan
+            SO_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[7], 0));
+            for (size_t k = 0; k < chunks.size(); ++k) {
+                const Chunk& ch = chunks[k];
+                if (ch.pt_count)
+                    SO_CUDA_TRY(cudaMemcpyAsync(c->d_scan + ch.pt_first, static_cast<const float4*>(host_src) + ch.pt_first,
+                                                size_t(ch.pt_count) * sizeof(float4), cudaMemcpyHostToDevice, c->copy_stream));
+                count_h2d(c, size_t(ch.pt_count) * sizeof(float4));
+                SO_CUDA_TRY(cudaEventRecord(c->ev_copy[k], c->copy_stream));
+            }
+        }
+        std::vector<char> loop_flags(chunks.size(), 0);
+        for (size_t k = 0; k < chunks.size(); ++k) {
+            const Chunk& ch = chunks[k];
+            if (host_src) SO_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copy[k], 0));
+            if (ch.grid_x == 0) continue;
+            int rc = prepare_scans(c, d_scan, ch);
+            if (rc) return rc;
+            bool was_loop = false;
+            rc = run_schedule(c, ch, o.max_icp_iters, o.lm_max_iterations, false, &was_loop);
+            if (rc) return rc;
+            loop_flags[k] = was_loop;
+        }
         SO_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, n_scans * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
         count_d2h(c, n_scans * sizeof(IcpState));
         SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-        if (c->graph_is_loop && !c->profiling) {
+        for (size_t k = 0; k < chunks.size(); ++k) {
+            if (!loop_flags[k]) continue;
             int max_it = 0;
-            for (size_t s = 0; s < n_scans; ++s) max_it = std::max(max_it, int(c->h_state[s].n_iterations));
+            for (uint32_t s = chunks[k].first; s < chunks[k].first + chunks[k].count; ++s) max_it = std::max(max_it, int(c->h_state[s].n_iterations));
             c->launches += uint64_t(max_it) * uint64_t(4 + 2 * o.lm_max_iterations);
         }
         for (size_t s = 0; s < n_scans; ++s) {
@@ -421,7 +469,7 @@ int so_set_stream(so_ctx* ctx, void* cuda_stream) {
     if (!c) return fail(SO_ERR_ARG, "null ctx");
     SO_CUDA_TRY(cudaSetDevice(c->device));
     SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+    for (auto& g : c->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     if (cuda_stream) {
         if (c->own_stream) cudaStreamDestroy(c->stream);
         c->stream = static_cast<cudaStream_t>(cuda_stream); c->own_stream = false;
@@ -588,9 +636,14 @@ int so_register_batch(so_ctx* ctx, const void* surf, const uint32_t* n_points, s
     for (size_t s = 0; s < n_scans; ++s) { if (n_points[s] > c->cfg.max_scan_points) return fail(SO_ERR_CAPACITY, "scan too large"); total += n_points[s]; }
     SO_CUDA_TRY(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
-    int rc = upload_cloud(c, surf, total, stride, ioff, c->d_scan);
-    if (rc) return rc;
-    rc = register_core(c, c->d_scan, n_points, n_scans, poses_in, opts, results, false);
+    int rc;
+    if (stride == 16 && ioff == 12) {
+        rc = register_core(c, c->d_scan, n_points, n_scans, poses_in, opts, results, false, surf);      // chunked, overlapped upload
+    } else {
+        rc = upload_cloud(c, surf, total, stride, ioff, c->d_scan);
+        if (rc) return rc;
+        rc = register_core(c, c->d_scan, n_points, n_scans, poses_in, opts, results, false);
+    }
     if (rc) return rc;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     for (size_t s = 0; s < n_scans; ++s) results[s].time_total_ms = ms;
@@ -628,7 +681,8 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     const uint32_t grid_x = (uint32_t(n) + kThreads - 1) / kThreads;
-    rc = prepare_scans(c, c->d_scan, grid_x, 1, n);
+    const Chunk ch{0, 1, 0, uint32_t(n), grid_x};
+    rc = prepare_scans(c, c->d_scan, ch);
     if (rc) return rc;
     const MapView mv = map_view(c);
     const BatchView bv = batch_view(c, c->d_scan_sorted);

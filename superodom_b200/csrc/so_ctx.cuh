@@ -72,12 +72,17 @@ struct Ctx {
     // ---- k-NN scratch -------------------------------------------------------------------------------------------
     float4* d_q = nullptr; uint32_t* d_knn_idx = nullptr; float* d_knn_d2 = nullptr; size_t knn_cap = 0;
 
-    // ---- CUDA graph cache for the ICP schedule ------------------------------------------------------------------
-    cudaGraphExec_t graph = nullptr;
-    uint32_t graph_grid_x = 0, graph_n_scans = 0; int graph_iters = 0, graph_lm = 0; const void* graph_scan_ptr = nullptr;
-    uint64_t graph_map_epoch = 0, map_epoch = 1;
-    bool graph_is_loop = false;                    // graph is a WHILE conditional node around one ICP iteration
-    bool no_cond_graph = false;                    // conditional nodes unavailable: use the unrolled schedule
+    // ---- CUDA graph cache for the ICP schedule (one entry per batch chunk shape) ------------------------------------
+    struct GraphSlot {
+        cudaGraphExec_t exec = nullptr;
+        uint32_t first = 0, count = 0, grid_x = 0; int iters = 0, lm = 0; uint64_t epoch = 0; bool is_loop = false; uint64_t used = 0;
+    };
+    GraphSlot graphs[8];
+    uint64_t graph_clock = 0;
+    uint64_t map_epoch = 1;
+    bool no_cond_graph = false;                    // conditional nodes unavailable (or SO_NO_COND_GRAPH): unrolled schedule
+    cudaStream_t copy_stream = nullptr;            // H2D of batch chunks overlaps the previous chunk's kernels
+    cudaEvent_t ev_copy[8] = {};
 
     // ---- instrumentation ----------------------------------------------------------------------------------------
     uint64_t launches = 0;
@@ -96,6 +101,6 @@ int map_rebuild(Ctx* c);                 // (re)bin, drop off-grid points, sort,
 MapView map_view(const Ctx* c);
 int map_cells_per_block(float plane_res);
 int scan_sort_alloc(Ctx* c);             // temp storage for the per-registration scan sort
-int scan_sort(Ctx* c, size_t n, int n_scans);   // d_skeys/d_svals -> d_skeys_out/d_svals_out
+int scan_sort(Ctx* c, size_t first, size_t n, int n_scans);   // d_skeys/d_svals[first..first+n) -> *_out
 
 }  // namespace so

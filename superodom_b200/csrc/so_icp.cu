@@ -560,13 +560,16 @@ __global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, 
                     const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
                     u = fmaxf(u, float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)));
                 }
-                u_seed = u;
+                // use it only while it is about as tight as a freshly estimated bound would be (small pose update);
+                // after a large update the 27-cell estimate of round 1 prunes better than a loose seed
+                if (u <= 1.3f * nb.d5[gi]) u_seed = u;
             }
             knn5_select(m, qc, qx, qy, qz, u_seed, s_buf, tk);
             pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
         }
     }
     nb.pre[gi] = (unsigned char)pre;
+    nb.d5[gi] = tk.d2[4];
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const bool ok = tk.id[j] != 0xFFFFFFFFu;

@@ -224,11 +224,12 @@ int scan_sort_alloc(Ctx* c) {
     return SO_OK;
 }
 
-int scan_sort(Ctx* c, size_t n, int n_scans) {
+int scan_sort(Ctx* c, size_t first, size_t n, int n_scans) {
     int bits = 32;
     while ((1 << (bits - 32)) < n_scans) ++bits;
     size_t tmp = c->sort_tmp_bytes;
-    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_skeys, c->d_skeys_out, c->d_svals, c->d_svals_out, int(n), 0, bits, c->stream));
+    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_skeys + first, c->d_skeys_out + first, c->d_svals + first,
+                                                c->d_svals_out + first, int(n), 0, bits, c->stream));
     c->launches += 5;
     return SO_OK;
 }
