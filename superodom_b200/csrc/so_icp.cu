@@ -116,47 +116,10 @@ __device__ __forceinline__ void scan_range(const MapView& m, uint32_t beg, uint3
     for (; t < end; ++t) offer_candidate<K>(__ldg(&m.pts[t]), t, qx, qy, qz, tk);
 }
 
-// Pruned walk over the (2R+1)^2 x-rows of the search cube around the query's cell, nearest rows first (MapView::row_*).
-// A row / an x-cell is skipped when its distance lower bound already exceeds the current k-th distance.  Exact for
-// every neighbour with d2 <= min(bound, (R*cs)^2); stays inside the query's block (LocalMap.h:488-507).
-template <int K>
-__device__ __forceinline__ void knn_rows(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, TopK<K>& tk) {
-    const int nb = m.nb, R = m.R;
-    const uint32_t base = uint32_t(qc.slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
-    const float cs = m.cs;
-    const float fx = qc.f[0], fy = qc.f[1], fz = qc.f[2];
-#pragma unroll 1
-    for (int r = 0; r < m.n_rows; ++r) {
-        const int oy = m.row_dy[r], oz = m.row_dz[r];
-        const int yy = qc.c[1] + oy, zz = qc.c[2] + oz;
-        if (yy < 0 || yy >= nb || zz < 0 || zz >= nb) continue;
-        const float ly = oy < 0 ? fy + float(-oy - 1) * cs : (oy > 0 ? (cs - fy) + float(oy - 1) * cs : 0.f);
-        const float lz = oz < 0 ? fz + float(-oz - 1) * cs : (oz > 0 ? (cs - fz) + float(oz - 1) * cs : 0.f);
-        const float lb = ly * ly + lz * lz;
-        const float w = tk.worst();
-        if (lb * 0.9999f > w) continue;
-        int xlo = qc.c[0], xhi = qc.c[0];
-        for (int k = 1; k <= R; ++k) {
-            const float lx = fx + float(k - 1) * cs;
-            if (qc.c[0] - k < 0 || (lb + lx * lx) * 0.9999f > w) break;
-            xlo = qc.c[0] - k;
-        }
-        for (int k = 1; k <= R; ++k) {
-            const float lx = (cs - fx) + float(k - 1) * cs;
-            if (qc.c[0] + k > nb - 1 || (lb + lx * lx) * 0.9999f > w) break;
-            xhi = qc.c[0] + k;
-        }
-        const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
-        const uint32_t beg = __ldg(&m.cell_start[row + xlo]);
-        const uint32_t end = __ldg(&m.cell_start[row + xhi + 1]);
-        scan_range<K>(m, beg, end, qx, qy, qz, tk);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
-// 5-NN for the ICP kernel in three warp-friendly rounds (all loops do the same kind of work in every lane):
+// k-NN in three warp-friendly rounds (all loops do the same kind of work in every lane):
 //   1. bound : a value-only min/max selection network over the 27 cells around the query gives U, an upper bound on the
-//              5th-neighbour distance (skipped when the previous ICP iteration's neighbours already provide one);
+//              k-th-neighbour distance (skipped when the previous ICP iteration's neighbours already provide one);
 //   2. gather: pruned walk of the search cube with the fixed bound U; the few candidates with approx d2 <= U are only
 //              recorded (position into a per-lane shared-memory list) -- no divergent insertion in the hot loop;
 //   3. refine: the recorded candidates get the reference's exact d2 rounding and are ordered by (d2, id).
@@ -215,20 +178,26 @@ __device__ __forceinline__ float approx_d2(const float4 c, float qx, float qy, f
     return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
 }
 
-// s_buf: [kBufCap][kThreads] positions, column = this thread.  u_seed < 0: no seed.
-__device__ __forceinline__ void knn5_select(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, float u_seed,
-                                            uint32_t* s_buf, TopK<5>& tk) {
+// s_buf: [kBufCap][kThreads] positions, column = this thread.  u_seed < 0: no seed.  `bound`: neighbours farther than this
+// (squared) are not wanted; tk must have been initialised with it.  Complete for d2 <= min(bound, (R*cs)^2).
+template <int K>
+__device__ __forceinline__ void knn_select(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, float u_seed, float bound,
+                                           uint32_t* s_buf, TopK<K>& tk) {
     float U;
     if (u_seed >= 0.f) U = u_seed * 1.000004f;
     else {
-        float a0 = m.bound_d2, a1 = a0, a2 = a0, a3 = a0, a4 = a0;             // five smallest approx d2 so far, ascending
-        walk_cube(m, qc, m.bound_d2, 1, [&](const float4 c, uint32_t) {
+        float a[K];                                                            // K smallest approx d2 so far, ascending
+#pragma unroll
+        for (int j = 0; j < K; ++j) a[j] = bound;
+        walk_cube(m, qc, bound, 1, [&](const float4 c, uint32_t) {
             const float d = approx_d2(c, qx, qy, qz);
-            a4 = fminf(a4, fmaxf(a3, d)); a3 = fminf(a3, fmaxf(a2, d)); a2 = fminf(a2, fmaxf(a1, d)); a1 = fminf(a1, fmaxf(a0, d)); a0 = fminf(a0, d);
+#pragma unroll
+            for (int j = K - 1; j > 0; --j) a[j] = fminf(a[j], fmaxf(a[j - 1], d));
+            a[0] = fminf(a[0], d);
         });
-        U = a4 * 1.000004f;
+        U = a[K - 1] * 1.000004f;
     }
-    U = fminf(U, m.bound_d2 * 1.000004f);
+    U = fminf(U, bound * 1.000004f);
     int cnt = 0;
     walk_cube(m, qc, U, m.R, [&](const float4 c, uint32_t t) {
         const float d = approx_d2(c, qx, qy, qz);
@@ -564,7 +533,7 @@ __global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, 
                 // after a large update the 27-cell estimate of round 1 prunes better than a loose seed
                 if (u <= 1.3f * nb.d5[gi]) u_seed = u;
             }
-            knn5_select(m, qc, qx, qy, qz, u_seed, s_buf, tk);
+            knn_select<5>(m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
             pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
         }
     }
@@ -835,6 +804,7 @@ __global__ void k_loop_cond(const IcpState* __restrict__ st, uint32_t n_scans, c
 template <int K>
 __global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __restrict__ q, size_t nq, float max_d2,
                                                   uint32_t* __restrict__ idx, float* __restrict__ d2) {
+    __shared__ uint32_t s_buf[kBufCap * kThreads];
     const size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
     if (i >= nq) return;
     const float4 p = __ldg(&q[i]);
@@ -844,14 +814,15 @@ __global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __res
     QueryCell qc;
     locate(m, p.x, p.y, p.z, qc);
     if (qc.slot >= 0) {
-        // the pruned ring walk is complete up to min(bound, (R*cs)^2); wider / unbounded searches grow an unpruned cube
+        // the select walk is complete up to min(bound, (R*cs)^2); wider / unbounded searches then grow an unpruned cube
         int R = m.R;
         const float ring_d2 = float(R) * m.cs * float(R) * m.cs;
         bool done = false;
-        if (bounded && max_d2 <= ring_d2) { knn_rows<K>(m, qc, p.x, p.y, p.z, tk); done = true; }
+        if (bounded && max_d2 <= ring_d2) { knn_select<K>(m, qc, p.x, p.y, p.z, -1.f, max_d2, s_buf, tk); done = true; }
         else if (!bounded) {
-            knn_rows<K>(m, qc, p.x, p.y, p.z, tk);
-            done = tk.count() == K && tk.worst() < ring_d2 * 0.999f;     // k-th neighbour inside the guaranteed-complete radius
+            tk.init(ring_d2 * 0.999f);
+            knn_select<K>(m, qc, p.x, p.y, p.z, -1.f, ring_d2 * 0.999f, s_buf, tk);
+            done = tk.count() == K;                                      // K neighbours inside the guaranteed-complete radius
         } else { const float r = sqrtf(max_d2); while (float(R) * m.cs < r && R < m.nb) ++R; }
         while (!done) {
             tk.init(bounded ? max_d2 : FLT_MAX);

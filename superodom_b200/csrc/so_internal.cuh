@@ -32,8 +32,6 @@ struct MapView {
     float bound_d2;             // float(3 * planeRes_)  -- the NEIGHBORS_TOO_FAR gate doubles as search radius^2
     float plane_res;
     int32_t R;                  // search rings: R * cs >= sqrt(bound_d2)
-    int32_t n_rows;             // (2R+1)^2 (y,z) row offsets, nearest first
-    int8_t row_dy[49], row_dz[49];
 };
 
 // Per-scan device state: the Ceres trust-region minimiser + the outer ICP loop, advanced by the last CTA of every

@@ -133,16 +133,7 @@ MapView map_view(const Ctx* c) {
     m.nb = c->nb; m.inv_cs = double(c->nb) / kBlock; m.cs = float(kBlock / double(c->nb));
     m.bound_d2 = 3 * c->plane_res;        // float product (LidarSlam.cpp:526)
     m.plane_res = c->plane_res;
-    // (y,z) row offsets of the search cube, nearest rows first, so the k-th distance shrinks early and prunes the rest
     m.R = map_rings(c->plane_res, c->nb);
-    if (m.R > 3) m.R = 3;            // nb cap can only force this for planeRes > 1.8 m; so_map_set_resolution rejects those
-    struct RowOff { int d2, dy, dz; };
-    RowOff rows[49];
-    int n = 0;
-    for (int dz = -m.R; dz <= m.R; ++dz) for (int dy = -m.R; dy <= m.R; ++dy) rows[n++] = RowOff{dy * dy + dz * dz, dy, dz};
-    std::stable_sort(rows, rows + n, [](const RowOff& a, const RowOff& b) { return a.d2 < b.d2; });
-    m.n_rows = n;
-    for (int i = 0; i < n; ++i) { m.row_dy[i] = int8_t(rows[i].dy); m.row_dz[i] = int8_t(rows[i].dz); }
     return m;
 }
 
