@@ -113,6 +113,7 @@ static void ctx_free(Ctx* c) {
     cudaFree(c->d_partials); cudaFree(c->d_counters); cudaFree(c->d_hist);
     cudaFree(c->corr.nd); cudaFree(c->corr.w); cudaFree(c->corr.flags); cudaFree(c->corr.nn); cudaFree(c->corr.nn_d2);
     cudaFree(c->d_q); cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2);
+    cudaFree(c->d_qkeys); cudaFree(c->d_qkeys_out); cudaFree(c->d_qvals); cudaFree(c->d_qvals_out); cudaFree(c->d_qsort_tmp);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -366,7 +367,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, n_scans * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
         count_h2d(c, n_scans * (sizeof(IcpState) + sizeof(uint32_t)));
         // Chunk the batch: with host input the H2D of chunk k+1 (copy stream) overlaps the kernels of chunk k.
-        const size_t n_chunks = (host_src && n_scans >= 8 && !c->profiling) ? 4 : 1;
+        const size_t n_chunks = (!host_src || c->profiling) ? 1 : (n_scans >= 32 ? 4 : (n_scans >= 16 ? 2 : 1));     // keep chunks >= 8 scans
         std::vector<Chunk> chunks;
         for (size_t k = 0; k < n_chunks; ++k) {
             const uint32_t f = uint32_t(k * n_scans / n_chunks), e = uint32_t((k + 1) * n_scans / n_chunks);
@@ -741,8 +742,21 @@ int so_knn_device(so_ctx* ctx, const void* d_q, size_t nq, int k, float max_d2, 
     SO_CUDA_TRY(cudaSetDevice(c->device));
     if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
     if (nq == 0) return SO_OK;
+    // Large query sets are first ordered by map cell (cell key -> radix sort); threads then take queries in that order and
+    // write their answers at the caller's positions.  Small sets skip the ordering.
+    const uint32_t* order = nullptr;
+    const MapView mv = map_view(c);
     timed_launch_begin(c);
-    if (launch_knn(map_view(c), static_cast<const float4*>(d_q), nq, k, max_d2, d_idx, d_d2, c->stream)) return fail(SO_ERR_ARG, "bad k");
+    if (nq >= 32768 && nq < (size_t(1) << 31)) {
+        int rc = query_sort_reserve(c, nq);
+        if (rc) return rc;
+        launch_query_keys(mv, static_cast<const float4*>(d_q), nq, c->d_qkeys, c->d_qvals, c->stream);
+        rc = query_sort(c, nq);
+        if (rc) return rc;
+        order = c->d_qvals_out;
+        c->launches++;
+    }
+    if (launch_knn(mv, static_cast<const float4*>(d_q), order, nq, k, max_d2, d_idx, d_d2, c->stream)) return fail(SO_ERR_ARG, "bad k");
     timed_launch_end(c, 2);
     SO_CUDA_TRY(cudaGetLastError());
     return SO_OK;

@@ -71,6 +71,8 @@ struct Ctx {
 
     // ---- k-NN scratch -------------------------------------------------------------------------------------------
     float4* d_q = nullptr; uint32_t* d_knn_idx = nullptr; float* d_knn_d2 = nullptr; size_t knn_cap = 0;
+    uint32_t* d_qkeys = nullptr; uint32_t* d_qkeys_out = nullptr; uint32_t* d_qvals = nullptr; uint32_t* d_qvals_out = nullptr;
+    void* d_qsort_tmp = nullptr; size_t qsort_tmp_bytes = 0; size_t qsort_cap = 0;      // cell ordering of so_knn* queries
 
     // ---- CUDA graph cache for the ICP schedule (one entry per batch chunk shape) ------------------------------------
     struct GraphSlot {
@@ -101,6 +103,8 @@ int map_rebuild(Ctx* c);                 // (re)bin, drop off-grid points, sort,
 MapView map_view(const Ctx* c);
 int map_cells_per_block(float plane_res);
 int scan_sort_alloc(Ctx* c);             // temp storage for the per-registration scan sort
+int query_sort(Ctx* c, size_t n);         // d_qkeys/d_qvals -> *_out (allocates on growth)
+int query_sort_reserve(Ctx* c, size_t n);
 int scan_sort(Ctx* c, size_t first, size_t n, int n_scans);   // d_skeys/d_svals[first..first+n) -> *_out
 
 }  // namespace so

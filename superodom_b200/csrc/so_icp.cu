@@ -801,12 +801,25 @@ __global__ void k_loop_cond(const IcpState* __restrict__ st, uint32_t n_scans, c
 // ------------------------------------------------------------------------------------------------------------------
 // k_knn: LocalMap::nearestKSearchSurf for a batch of world-frame queries (so_knn / so_knn_device)
 // ------------------------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __restrict__ q, size_t nq, float max_d2,
-                                                  uint32_t* __restrict__ idx, float* __restrict__ d2) {
-    __shared__ uint32_t s_buf[kBufCap * kThreads];
+// cell key of every query (so_knn* orders large query sets by map cell first, for the same reason scans are ordered)
+__global__ void __launch_bounds__(kThreads) k_query_keys(MapView m, const float4* __restrict__ q, size_t nq, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ vals) {
     const size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
     if (i >= nq) return;
+    const float4 p = __ldg(&q[i]);
+    QueryCell qc;
+    locate(m, p.x, p.y, p.z, qc);
+    keys[i] = qc.slot >= 0 ? uint32_t(qc.slot) * uint32_t(m.nb * m.nb * m.nb) + uint32_t((qc.c[2] * m.nb + qc.c[1]) * m.nb + qc.c[0]) : 0xFFFFFFFFu;
+    vals[i] = uint32_t(i);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __restrict__ q, const uint32_t* __restrict__ order, size_t nq,
+                                                  float max_d2, uint32_t* __restrict__ idx, float* __restrict__ d2) {
+    __shared__ uint32_t s_buf[kBufCap * kThreads];
+    const size_t j = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    if (j >= nq) return;
+    const size_t i = order ? size_t(order[j]) : j;        // thread j handles the j-th query in cell order, answers in caller order
     const float4 p = __ldg(&q[i]);
     TopK<K> tk;
     const bool bounded = max_d2 > 0.f;
@@ -877,17 +890,20 @@ void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, ui
 void launch_loop_cond(const BatchView& bv, uint32_t n_scans, cudaGraphConditionalHandle handle, cudaStream_t st) {
     k_loop_cond<<<1, 32, 0, st>>>(bv.st, n_scans, handle);
 }
-int launch_knn(const MapView& m, const float4* q, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st) {
+void launch_query_keys(const MapView& m, const float4* q, size_t nq, uint32_t* keys, uint32_t* vals, cudaStream_t st) {
+    k_query_keys<<<uint32_t((nq + kThreads - 1) / kThreads), kThreads, 0, st>>>(m, q, nq, keys, vals);
+}
+int launch_knn(const MapView& m, const float4* q, const uint32_t* order, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st) {
     const uint32_t grid = uint32_t((nq + kThreads - 1) / kThreads);
     switch (k) {
-        case 1: k_knn<1><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
-        case 2: k_knn<2><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
-        case 3: k_knn<3><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
-        case 4: k_knn<4><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
-        case 5: k_knn<5><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
-        case 6: k_knn<6><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
-        case 7: k_knn<7><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
-        case 8: k_knn<8><<<grid, kThreads, 0, st>>>(m, q, nq, max_d2, idx, d2); break;
+        case 1: k_knn<1><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
+        case 2: k_knn<2><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
+        case 3: k_knn<3><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
+        case 4: k_knn<4><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
+        case 5: k_knn<5><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
+        case 6: k_knn<6><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
+        case 7: k_knn<7><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
+        case 8: k_knn<8><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
         default: return -1;
     }
     return 0;

@@ -215,6 +215,29 @@ int scan_sort_alloc(Ctx* c) {
     return SO_OK;
 }
 
+int query_sort_reserve(Ctx* c, size_t n) {
+    if (n <= c->qsort_cap) return SO_OK;
+    cudaFree(c->d_qkeys); cudaFree(c->d_qkeys_out); cudaFree(c->d_qvals); cudaFree(c->d_qvals_out); cudaFree(c->d_qsort_tmp);
+    c->d_qkeys = c->d_qkeys_out = c->d_qvals = c->d_qvals_out = nullptr; c->d_qsort_tmp = nullptr; c->qsort_cap = 0;
+    SO_CUDA_TRY(cudaMalloc(&c->d_qkeys, n * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_qkeys_out, n * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_qvals, n * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_qvals_out, n * sizeof(uint32_t)));
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, c->d_qkeys, c->d_qkeys_out, c->d_qvals, c->d_qvals_out, int(n), 0, 32);
+    c->qsort_tmp_bytes = need + 256;
+    SO_CUDA_TRY(cudaMalloc(&c->d_qsort_tmp, c->qsort_tmp_bytes));
+    c->qsort_cap = n;
+    return SO_OK;
+}
+
+int query_sort(Ctx* c, size_t n) {
+    size_t tmp = c->qsort_tmp_bytes;
+    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_qsort_tmp, tmp, c->d_qkeys, c->d_qkeys_out, c->d_qvals, c->d_qvals_out, int(n), 0, 32, c->stream));
+    c->launches += 5;
+    return SO_OK;
+}
+
 int scan_sort(Ctx* c, size_t first, size_t n, int n_scans) {
     int bits = 32;
     while ((1 << (bits - 32)) < n_scans) ++bits;
