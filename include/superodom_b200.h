@@ -71,7 +71,12 @@ typedef struct {
     int32_t lm_max_iterations;    /* ceres options.max_num_iterations = 4 (LidarSlam.cpp:232); 0 -> 4 */
     float yaw_ratio;              /* OptSet.yaw_ratio (LidarSlam.cpp:905) */
     int32_t skip_map_checks;      /* 1: do not run shiftMap / hasEnoughFeatures (replay against a frozen map) */
-    int32_t reserved[3];
+    /* SE3AbsolutatePoseFactor on T_w_initial_guess (LidarSlam.cpp:281-298): set when shouldAddAbsolutePoseConstraints()
+     * holds, i.e. predictodom == VIO_ODOM && isDegenerate && Visual_confidence_factor != 0 (dormant in the shipped node:
+     * isDegenerate is never set, LidarSlam.cpp:976-985). */
+    int32_t use_pose_prior;
+    float visual_confidence_factor;   /* LidarSLAM::Visual_confidence_factor */
+    float prior_uncertainty[3];       /* lidarOdomUncer.uncertainty_{x,y,z} (EstimateLidarUncertainty, LidarSlam.cpp:915-964) */
 } so_icp_opts;
 
 /* Everything the reference leaves in LidarSLAM members after Localization():
@@ -99,7 +104,7 @@ typedef struct {
     double total_translation, total_rotation, translation_from_last, rotation_from_last; /* stats.* (LidarSlam.cpp:198-210) */
     int32_t map_surf_5x5, map_edge_5x5, scan_surf_num, scan_edge_num; /* stats.laser_cloud_* (LidarSlam.cpp:371-377) */
     int32_t pos_in_localmap[3];   /* LidarSLAM::pos_in_localmap (shiftMap return) */
-    int32_t pad_;
+    int32_t prediction_source;    /* stats.prediction_source: 1 when the pose prior rows were added (LidarSlam.cpp:278,297) */
     double time_ms;               /* stats.time_elapsed: the ICP loop, device time measured with CUDA events */
     double time_total_ms;         /* whole so_register call incl. H2D / D2H (host clock) */
 } so_icp_result;

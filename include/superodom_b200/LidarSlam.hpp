@@ -245,7 +245,6 @@ public:
     template <class CloudPtr>
     void Localization(bool initialization, PredictionSource predictodom, const Transformd& position, const CloudPtr& edge_point,
                       const CloudPtr& planner_point, double timeLaserOdometry) {
-        (void)predictodom;
         T_w_lidar = position; T_w_initial_guess = position; last_T_w_lidar = position;          // initializeState (:53-57)
         localMap.sync_resolution();
         size_t stride, ioff;
@@ -266,6 +265,14 @@ public:
         o.max_surface_features = OptSet.max_surface_features;
         o.lm_max_iterations = 4;
         o.yaw_ratio = OptSet.yaw_ratio;
+        // shouldAddAbsolutePoseConstraints (LidarSlam.cpp:281-283)
+        if (predictodom == PredictionSource::VIO_ODOM && isDegenerate && Visual_confidence_factor != 0) {
+            o.use_pose_prior = 1;
+            o.visual_confidence_factor = Visual_confidence_factor;
+            o.prior_uncertainty[0] = float(lidarOdomUncer.uncertainty_x);
+            o.prior_uncertainty[1] = float(lidarOdomUncer.uncertainty_y);
+            o.prior_uncertainty[2] = float(lidarOdomUncer.uncertainty_z);
+        }
         position.to_pose7(pose);
         const int rc = so_register(context.h, surf, planner_point->size(), edge_point ? (const void*)edge_point->points.data() : nullptr,
                                    edge_point ? edge_point->size() : 0, stride, ioff, pose, &o, &last_result);
@@ -282,7 +289,7 @@ public:
             it.translation_norm = r.iter_dtrans[i]; it.rotation_norm = r.iter_drot[i];
             stats.iterations.push_back(it);
         }
-        stats.prediction_source = 0;                                                             // addFeatureConstraints (:278)
+        stats.prediction_source = r.prediction_source;                                            // (:278,297)
         for (int i = 0; i < 9; ++i) PlaneFeatureHistogramObs[i] = r.hist_obs[i];
         for (int i = 0; i < 7; ++i) { MatchRejectionHistogramPlane[i] = r.hist_reject_plane[i]; MatchRejectionHistogramLine[i] = r.hist_reject_line[i]; }
         LocalizationUncertainty.PositionError = r.pos_err; LocalizationUncertainty.PosInverseConditionNum = r.pos_inv_cond;

@@ -24,7 +24,8 @@ STATUS_NAMES = ["SUCCESS", "NOT_ENOUGH_NEIGHBORS", "NEIGHBORS_TOO_FAR", "BAD_PCA
 class Opts(C.Structure):
     _fields_ = [("plane_res", C.c_float), ("max_icp_iters", C.c_int32), ("max_surface_features", C.c_int32),
                 ("lm_max_iterations", C.c_int32), ("knn_mode", C.c_int32), ("n_threads", C.c_int32),
-                ("yaw_ratio", C.c_float), ("skip_map_checks", C.c_int32)]
+                ("yaw_ratio", C.c_float), ("skip_map_checks", C.c_int32), ("use_pose_prior", C.c_int32),
+                ("visual_confidence_factor", C.c_float), ("prior_uncertainty", C.c_float * 3)]
 
 
 class Result(C.Structure):
@@ -177,10 +178,16 @@ class OracleMap:
         return corr, ho, hr
 
     def register(self, scan_xyzi, pose7, plane_res, max_icp_iters, max_surface_features=0, knn_mode=0, n_threads=1,
-                 lm_max_iterations=4, yaw_ratio=0.0, skip_map_checks=False) -> Result:
+                 lm_max_iterations=4, yaw_ratio=0.0, skip_map_checks=False, pose_prior=None) -> Result:
+        """pose_prior = (visual_confidence_factor, (ux, uy, uz)) enables the SE3AbsolutatePoseFactor rows."""
         s = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
         pose = np.ascontiguousarray(pose7, dtype=np.float64)
-        o = Opts(plane_res, max_icp_iters, max_surface_features, lm_max_iterations, knn_mode, n_threads, yaw_ratio, int(skip_map_checks))
+        o = Opts(plane_res, max_icp_iters, max_surface_features, lm_max_iterations, knn_mode, n_threads, yaw_ratio, int(skip_map_checks),
+                 0, 0.0, (C.c_float * 3)(0, 0, 0))
+        if pose_prior is not None:
+            o.use_pose_prior = 1
+            o.visual_confidence_factor = float(pose_prior[0])
+            o.prior_uncertainty = (C.c_float * 3)(*[float(v) for v in pose_prior[1]])
         r = Result()
         self.L.orc_register(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.byref(o), C.byref(r))
         return r

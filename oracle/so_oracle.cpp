@@ -625,8 +625,40 @@ static void correspond_all(const Map& M, const float* scan, size_t n, size_t str
 }
 
 // ----------------------------------------------------------------------------- residual / loss (Ceres 2.0.0 semantics)
+// SE3AbsolutatePoseFactor (factor/SE3AbsolutatePoseFactor.{h,cpp}) as added by addAbsolutePoseConstraints
+// (LidarSlam.cpp:285-298): 6 residuals [p - p_meas ; 2 vec(q_meas^* q)] premultiplied by sqrt_information, no loss function.
+// The information matrix is diagonal; sqrt_information = LLT(information).matrixL().transpose() -- Eigen's unblocked LLT
+// stops at the first non-positive pivot and leaves that and all later diagonal entries as they were (NOT square-rooted).
+struct PosePrior {
+    bool on = false;
+    double meas[7];
+    double sqrt_info[6];
+    void set_information(const double info[6]) {
+        bool failed = false;
+        for (int k = 0; k < 6; ++k) {
+            if (!failed && info[k] <= 0.0) failed = true;
+            sqrt_info[k] = failed ? info[k] : std::sqrt(info[k]);
+        }
+    }
+    // residual (6) and local Jacobian (6x6, row-major) at pose x
+    void eval(const double x[7], double r[6], double J[36]) const {
+        const Quat qm{meas[3], meas[4], meas[5], meas[6]}, q{x[3], x[4], x[5], x[6]};
+        const Quat e = qmul(qconj(qm), q);
+        r[0] = x[0] - meas[0]; r[1] = x[1] - meas[1]; r[2] = x[2] - meas[2];
+        r[3] = 2.0 * e.x; r[4] = 2.0 * e.y; r[5] = 2.0 * e.z;
+        for (int i = 0; i < 36; ++i) J[i] = 0.0;
+        J[0] = J[7] = J[14] = 1.0;
+        // Utility::Qleft(q_meas^* q).bottomRightCorner<3,3>() = w I + [v]x   (utils/utility.h:47-55)
+        J[3 * 6 + 3] = e.w;  J[3 * 6 + 4] = -e.z; J[3 * 6 + 5] = e.y;
+        J[4 * 6 + 3] = e.z;  J[4 * 6 + 4] = e.w;  J[4 * 6 + 5] = -e.x;
+        J[5 * 6 + 3] = -e.y; J[5 * 6 + 4] = e.x;  J[5 * 6 + 5] = e.w;
+        for (int i = 0; i < 6; ++i) { r[i] *= sqrt_info[i]; for (int j = 0; j < 6; ++j) J[i * 6 + j] *= sqrt_info[i]; }
+    }
+};
+
 struct Evaluator {
     std::vector<const Corr*> blocks;    // accepted correspondences in scan order
+    PosePrior prior;                    // optional 6 extra residual rows (after the plane blocks, as the reference adds it)
     double a2;                          // Tukey a^2, a = double(sqrtf(3*planeRes)) (LidarSlam.cpp:271)
     // TukeyLoss::Evaluate (ceres 2.0.0 loss_function.cc) wrapped by ScaledLoss(w)
     inline void rho(double s, double w, double r[3]) const {
@@ -645,18 +677,27 @@ struct Evaluator {
     double cost(const double x[7]) const {
         double c = 0.0;
         for (const Corr* b : blocks) { double r = residual(*b, x), rr[3]; rho(r * r, b->w, rr); c += 0.5 * rr[0]; }
+        if (prior.on) { double r[6], J[36]; prior.eval(x, r, J); double sq = 0; for (int i = 0; i < 6; ++i) sq += r[i] * r[i]; c += 0.5 * sq; }
         return c;
     }
     // full: corrected residuals, corrected local Jacobian (column-major n x 6), gradient, cost.
     // Tukey has rho'' <= 0 everywhere => Corrector takes the "rho[2] <= 0" branch: both r and J scaled by sqrt(rho') (corrector.cc).
     void full(const double x[7], double* cost_out, std::vector<double>& res, std::vector<double>& J, double g[6]) const {
-        const size_t n = blocks.size();
+        const size_t np = blocks.size();
+        const size_t n = np + (prior.on ? 6 : 0);          // rows
         res.resize(n); J.resize(n * 6);
         Quat q{x[3], x[4], x[5], x[6]};
         double R[9]; qtoR(q, R);
         double c = 0.0;
         for (int j = 0; j < 6; ++j) g[j] = 0.0;
-        for (size_t i = 0; i < n; ++i) {
+        if (prior.on) {
+            double r[6], Jp[36]; prior.eval(x, r, Jp);
+            for (int i = 0; i < 6; ++i) {
+                res[np + i] = r[i]; c += 0.5 * r[i] * r[i];
+                for (int j = 0; j < 6; ++j) { J[size_t(j) * n + np + i] = Jp[i * 6 + j]; g[j] += Jp[i * 6 + j] * r[i]; }
+            }
+        }
+        for (size_t i = 0; i < np; ++i) {
             const Corr& b = *blocks[i];
             double r = residual(b, x);
             // J = [ n^T , -n^T R [p]x ] ; -a^T[p]x = p x a with a = R^T n
@@ -680,8 +721,8 @@ struct SolveSummary { int num_successful_steps = 0, num_unsuccessful_steps = 0, 
 // TrustRegionMinimizer::Minimize + LevenbergMarquardtStrategy + TrustRegionStepEvaluator(monotonic).
 static SolveSummary ceres_solve(const Evaluator& E, double params[7], int max_num_iterations = 4) {
     SolveSummary S;
-    const size_t n = E.blocks.size();
-    if (n == 0) { S.termination = 6; return S; }
+    if (E.blocks.empty() && !E.prior.on) { S.termination = 6; return S; }
+    const size_t n = E.blocks.size() + (E.prior.on ? 6 : 0);      // residual rows
     const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
     const double min_relative_decrease = 1e-3, min_lm_diagonal = 1e-6, max_lm_diagonal = 1e32;
     const double max_radius = 1e16, min_radius = 1e-32;
@@ -765,7 +806,7 @@ static SolveSummary ceres_solve(const Evaluator& E, double params[7], int max_nu
 // ceres::Covariance{apply_loss_function, DENSE_SVD, null_space_rank=-1} in tangent space (LidarSlam.cpp:854-871;
 // covariance_impl.cc ComputeCovarianceValuesUsingDenseSVD): V diag(1/s^2) V^T with s_i/s_0 < sqrt(1e-14) truncated.
 static void ceres_covariance(const Evaluator& E, const double x[7], double cov[36]) {
-    const size_t n = E.blocks.size();
+    const size_t n = E.blocks.size() + (E.prior.on ? 6 : 0);
     std::vector<double> res, J; double g[6], c;
     E.full(x, &c, res, J, g);
     double R[36]; householder_ls(int(n), 6, J.data(), nullptr, nullptr, R);
@@ -819,6 +860,9 @@ typedef struct {
     int32_t n_threads;          // threads for the per-point loop (1 = faithful to the reference)
     float yaw_ratio;            // OptSet.yaw_ratio (0 in all shipped calibrations)
     int32_t skip_map_checks;    // 0: shiftMap + hasEnoughFeatures as the reference does
+    int32_t use_pose_prior;     // shouldAddAbsolutePoseConstraints(): VIO_ODOM && isDegenerate && Visual_confidence_factor != 0
+    float visual_confidence_factor;
+    float prior_uncertainty[3]; // lidarOdomUncer.uncertainty_{x,y,z} (from the previous scan's histogram)
 } orc_opts;
 
 typedef struct {
@@ -1012,6 +1056,18 @@ int orc_register(void* m, const float* scan_xyzi, size_t n, size_t stride_floats
         knn_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk).count();
         E.blocks.clear();
         for (size_t i = 0; i < n; ++i) if (corr[i].status == SUCCESS) E.blocks.push_back(&corr[i]);
+        E.prior.on = false;
+        if (opt->use_pose_prior) {                                // addAbsolutePoseConstraints (:285-298), position = T_w_initial_guess
+            const int good = int(E.blocks.size());
+            const double vcf = double(opt->visual_confidence_factor);
+            double info[6];
+            for (int a = 0; a < 3; ++a) info[a] = (1 - double(opt->prior_uncertainty[a])) * std::max(50, int(good * 0.1)) * vcf;
+            info[3] = info[4] = std::max(10, int(good * 0.01)) * vcf;
+            info[5] = std::max(5, int(good * 0.001)) * 0;
+            E.prior.on = true;
+            std::memcpy(E.prior.meas, T0, sizeof(T0));
+            E.prior.set_information(info);
+        }
         double prev[7]; std::memcpy(prev, T, sizeof(T));
         double params[7]; std::memcpy(params, T, sizeof(T));     // pose_parameters were set in prepareOptimizationState and by the previous solve
         SolveSummary S = ceres_solve(E, params, opt->lm_max_iterations);

@@ -32,7 +32,8 @@ class Config(C.Structure):
 
 class IcpOpts(C.Structure):
     _fields_ = [("max_icp_iters", C.c_int32), ("max_surface_features", C.c_int32), ("lm_max_iterations", C.c_int32),
-                ("yaw_ratio", C.c_float), ("skip_map_checks", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("yaw_ratio", C.c_float), ("skip_map_checks", C.c_int32), ("use_pose_prior", C.c_int32),
+                ("visual_confidence_factor", C.c_float), ("prior_uncertainty", C.c_float * 3)]
 
 
 class IcpResult(C.Structure):
@@ -48,7 +49,7 @@ class IcpResult(C.Structure):
                 ("total_translation", C.c_double), ("total_rotation", C.c_double),
                 ("translation_from_last", C.c_double), ("rotation_from_last", C.c_double),
                 ("map_surf_5x5", C.c_int32), ("map_edge_5x5", C.c_int32), ("scan_surf_num", C.c_int32), ("scan_edge_num", C.c_int32),
-                ("pos_in_localmap", C.c_int32 * 3), ("pad_", C.c_int32),
+                ("pos_in_localmap", C.c_int32 * 3), ("prediction_source", C.c_int32),
                 ("time_ms", C.c_double), ("time_total_ms", C.c_double)]
 
 
@@ -221,8 +222,14 @@ class Context:
 
     # ---- registration
     @staticmethod
-    def _opts(max_icp_iters, max_surface_features=0, lm_max_iterations=4, yaw_ratio=0.0, skip_map_checks=False):
-        return IcpOpts(max_icp_iters, max_surface_features, lm_max_iterations, yaw_ratio, int(skip_map_checks), (C.c_int32 * 3)())
+    def _opts(max_icp_iters, max_surface_features=0, lm_max_iterations=4, yaw_ratio=0.0, skip_map_checks=False, pose_prior=None):
+        """pose_prior = (visual_confidence_factor, (ux, uy, uz)) enables the SE3AbsolutatePoseFactor rows."""
+        o = IcpOpts(max_icp_iters, max_surface_features, lm_max_iterations, yaw_ratio, int(skip_map_checks), 0, 0.0, (C.c_float * 3)(0, 0, 0))
+        if pose_prior is not None:
+            o.use_pose_prior = 1
+            o.visual_confidence_factor = float(pose_prior[0])
+            o.prior_uncertainty = (C.c_float * 3)(*[float(v) for v in pose_prior[1]])
+        return o
 
     def register(self, scan_xyzi: np.ndarray, pose7, max_icp_iters: int, max_surface_features: int = 0, **kw) -> IcpResult:
         s = np.ascontiguousarray(scan_xyzi, dtype=np.float32)

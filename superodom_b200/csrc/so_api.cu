@@ -298,6 +298,9 @@ static void init_state(IcpState& s, const double pose[7], uint32_t n, const so_i
     s.lm_max_iterations = o.lm_max_iterations;
     // calculateSamplingRate (LidarSlam.cpp:346-351)
     s.sampling_rate = (o.max_surface_features > 0 && n > uint32_t(o.max_surface_features)) ? 1.0 * o.max_surface_features / double(n) : -1.0;
+    s.use_prior = o.use_pose_prior ? 1 : 0;
+    s.prior_vcf = o.visual_confidence_factor;
+    for (int a = 0; a < 3; ++a) s.prior_unc[a] = o.prior_uncertainty[a];
     s.phase = PH_CORR;
 }
 
@@ -315,6 +318,7 @@ static void fill_result(const Ctx* c, const IcpState& s, const double pose_in[7]
     r->pos_err = s.pos_err; r->pos_inv_cond = s.pos_inv_cond; r->ori_err_deg = s.ori_err_deg; r->ori_inv_cond = s.ori_inv_cond;
     for (int i = 0; i < 3; ++i) { r->pos_dir[i] = s.pos_dir[i]; r->ori_dir[i] = s.ori_dir[i]; }
     if (s.status) r->status = s.status;
+    r->prediction_source = s.use_prior ? 1 : 0;
     double T[7];
     std::memcpy(T, s.x, sizeof(T));
     std::memcpy(r->pose_opt, T, sizeof(T));

@@ -310,7 +310,7 @@ __device__ __noinline__ void end_solve(IcpState& st) {
     st.iter_lm_termination[it] = st.termination;
     st.iter_cost[it] = st.cost;
     st.n_iterations = it + 1;
-    if (st.n_ok == 0) {          // reference: ceres::Covariance CHECK-fails on an empty problem; we stop with a status
+    if (st.n_ok == 0 && !st.use_prior) {          // reference: ceres::Covariance CHECK-fails on an empty problem; we stop with a status
         st.status = SO_STATUS_NO_CORRESPONDENCES; st.phase = PH_DONE; return;
     }
     if (st.num_successful == 1 || it == st.max_icp_iters - 1) {      // (:141)
@@ -367,15 +367,55 @@ __device__ __noinline__ void lm_continue(IcpState& st, bool step_successful) {
     }
 }
 
-// IterationZero of a new solve, fed by k_correspond's reduction.
-__device__ __noinline__ void lm_begin_solve(IcpState& st, const double* acc, int n_ok) {
+// SE3AbsolutatePoseFactor (factor/SE3AbsolutatePoseFactor.cpp:9-51) added by addAbsolutePoseConstraints (LidarSlam.cpp:285-298):
+// residual [p - p_meas ; 2 vec(q_meas^* q)] times sqrt_information (diagonal here), no loss function; local Jacobian
+// [I 0; 0 (w I + [v]x)] of q_e = q_meas^* q (Utility::Qleft bottom-right block), T_meas = T_w_initial_guess.
+// Adds its J^T J, J^T r and 1/2 r^T r to the 28 reduced sums at pose x.
+__device__ __noinline__ void add_pose_prior(const IcpState& st, const double x[7], double a[kAcc]) {
+    const double qm[4] = {-st.x0[3], -st.x0[4], -st.x0[5], st.x0[6]};
+    double e[4];
+    qmul(qm, x + 3, e);
+    double r[6] = {x[0] - st.x0[0], x[1] - st.x0[1], x[2] - st.x0[2], 2.0 * e[0], 2.0 * e[1], 2.0 * e[2]};
+    double J[36];
+    for (int i = 0; i < 36; ++i) J[i] = 0.0;
+    J[0] = J[7] = J[14] = 1.0;
+    J[3 * 6 + 3] = e[3];  J[3 * 6 + 4] = -e[2]; J[3 * 6 + 5] = e[1];
+    J[4 * 6 + 3] = e[2];  J[4 * 6 + 4] = e[3];  J[4 * 6 + 5] = -e[0];
+    J[5 * 6 + 3] = -e[1]; J[5 * 6 + 4] = e[0];  J[5 * 6 + 5] = e[3];
+    for (int i = 0; i < 6; ++i) { r[i] *= st.prior_sqrt_info[i]; for (int j = 0; j < 6; ++j) J[i * 6 + j] *= st.prior_sqrt_info[i]; }
+    for (int i = 0; i < 6; ++i) {
+        for (int j = i; j < 6; ++j) { double t = 0.0; for (int k = 0; k < 6; ++k) t += J[k * 6 + i] * J[k * 6 + j]; a[tri(i, j)] += t; }
+        double t = 0.0; for (int k = 0; k < 6; ++k) t += J[k * 6 + i] * r[k];
+        a[21 + i] += t;
+    }
+    double sq = 0.0; for (int k = 0; k < 6; ++k) sq += r[k] * r[k];
+    a[27] += 0.5 * sq;
+}
+
+// IterationZero of a new solve, fed by k_fit's reduction.
+__device__ __noinline__ void lm_begin_solve(IcpState& st, const double* acc_in, int n_ok) {
+    double acc[kAcc];
+    for (int k = 0; k < kAcc; ++k) acc[k] = acc_in[k];
+    if (st.use_prior) {
+        // information diagonal (LidarSlam.cpp:287-294); sqrt by Eigen's unblocked LLT: the first non-positive pivot and
+        // everything after it stay un-square-rooted
+        const double vcf = double(st.prior_vcf);
+        double info[6];
+        const int m1 = max(50, int(n_ok * 0.1)), m2 = max(10, int(n_ok * 0.01));
+        for (int a = 0; a < 3; ++a) info[a] = (1 - double(st.prior_unc[a])) * m1 * vcf;
+        info[3] = info[4] = m2 * vcf;
+        info[5] = max(5, int(n_ok * 0.001)) * 0;
+        bool failed = false;
+        for (int k = 0; k < 6; ++k) { if (!failed && info[k] <= 0.0) failed = true; st.prior_sqrt_info[k] = failed ? info[k] : sqrt(info[k]); }
+        add_pose_prior(st, st.x, acc);
+    }
     for (int k = 0; k < 21; ++k) st.H[k] = acc[k];
     for (int k = 0; k < 6; ++k) st.g[k] = acc[21 + k];
     st.cost = acc[27];
     st.n_ok = n_ok;
     for (int i = 0; i < 7; ++i) st.x_iter_start[i] = st.x[i];
     st.lm_iter = 0; st.num_successful = 0; st.num_unsuccessful = 0; st.consecutive_invalid = 0; st.termination = 0;
-    if (n_ok == 0) { st.termination = 6; end_solve(st); return; }
+    if (n_ok == 0 && !st.use_prior) { st.termination = 6; end_solve(st); return; }
     for (int j = 0; j < 6; ++j) st.scale[j] = 1.0 / (1.0 + sqrt(st.H[tri(j, j)]));      // jacobi_scaling at iteration 0
     double xn = 0.0; for (int i = 0; i < 7; ++i) xn += st.x[i] * st.x[i];
     st.x_norm = sqrt(xn);
@@ -385,7 +425,10 @@ __device__ __noinline__ void lm_begin_solve(IcpState& st, const double* acc, int
 }
 
 // After the cost (and H, g) at the candidate are known.
-__device__ __noinline__ void lm_after_eval(IcpState& st, const double* acc) {
+__device__ __noinline__ void lm_after_eval(IcpState& st, const double* acc_in) {
+    double acc[kAcc];
+    for (int k = 0; k < kAcc; ++k) acc[k] = acc_in[k];
+    if (st.use_prior) add_pose_prior(st, st.cand, acc);
     const double cand_cost = acc[27];
     // ParameterToleranceReached
     double sn = 0.0; for (int i = 0; i < 7; ++i) { const double d = st.x[i] - st.cand[i]; sn += d * d; }

@@ -42,6 +42,9 @@ struct IcpState {
     int32_t n_points;
     int32_t max_icp_iters, lm_max_iterations;
     double sampling_rate;  // calculateSamplingRate(): <0 = keep all
+    int32_t use_prior;     // addAbsolutePoseConstraints rows active (LidarSlam.cpp:281-298)
+    float prior_vcf, prior_unc[3];   // Visual_confidence_factor, lidarOdomUncer.uncertainty_{x,y,z}
+    double prior_sqrt_info[6];       // set when a solve begins (depends on the number of accepted correspondences)
     // --- minimiser state (one ceres::Solve)
     double x[7];           // last accepted iterate (parameters_)
     double cand[7];        // candidate being evaluated

@@ -15,13 +15,13 @@
 namespace so {
 
 // Cells per 50 m block axis: cell edge cs = 50/nb is about half the search radius sqrt(3*planeRes) (so the pruned
-// walk over (2R+1)^2 rows visits few points beyond the true k-NN ball), capped at 128 (8 MB cell table per block).
+// walk over (2R+1)^2 rows visits few points beyond the true k-NN ball), capped at 192 (28 MB cell table per block).
 int map_cells_per_block(float plane_res) {
     const float bound = 3 * plane_res;                               // float product, as LidarSlam.cpp:526
     const double r = std::sqrt(double(bound)) * (1.0 + 1e-4);
     int nb = int(2.0 * kBlock / r);
     if (nb < 1) nb = 1;
-    if (nb > 128) nb = 128;
+    if (nb > 192) nb = 192;
     return nb;
 }
 

@@ -378,3 +378,28 @@ def test_resolution_change_rebuilds_index(gpu_api, oracle_mod):
         _assert_pose_close(np.array(r.pose), np.array(ro.pose))
         assert r.n_iterations == ro.n_iterations
     ctx.close()
+
+
+@pytest.mark.parametrize("prior", [(1.0, (0.2, 0.5, 0.9)), (100.0, (0.0, 0.0, 0.0)), (2.0, (1.0, 0.3, 0.3)), (0.5, (0.3, 1.0, 0.2))])
+def test_absolute_pose_prior_factor(gpu_api, oracle_mod, prior):
+    """SE3AbsolutatePoseFactor rows (LidarSlam.cpp:281-298; dormant upstream because isDegenerate is never set): the 6 extra
+    residuals, their sqrt-information (including Eigen's LLT quirk when an uncertainty saturates at 1 -> information 0)."""
+    case = get_case("tiny")
+    ctx = _ctx(gpu_api, case)
+    om = oracle_mod.OracleMap(case["map_xyzi"])
+    r = ctx.register(case["scan_xyzi"], case["pose_prior"], 5, 0, pose_prior=prior)
+    ro = om.register(case["scan_xyzi"], case["pose_prior"], 0.2, 5, 0, knn_mode=0, pose_prior=prior)
+    r0 = ctx.register(case["scan_xyzi"], case["pose_prior"], 5, 0)
+    _assert_pose_close(np.array(r.pose), np.array(ro.pose))
+    n = ro.n_iterations
+    assert r.n_iterations == n and list(r.iter_lm_steps[:n]) == list(ro.iter_lm_steps[:n])
+    assert list(r.iter_lm_successful[:n]) == list(ro.iter_lm_successful[:n])
+    assert np.allclose(r.iter_cost[:n], ro.iter_cost[:n], rtol=1e-9)
+    cg, co = np.array(r.cov).reshape(6, 6), np.array(ro.cov).reshape(6, 6)
+    assert np.abs(cg - co).max() <= 1e-6 * np.abs(co).max()
+    assert r.prediction_source == 1 and r0.prediction_source == 0
+    # the prior pulls towards the initial guess
+    d_with = np.linalg.norm(np.array(r.pose)[:3] - case["pose_prior"][:3])
+    d_without = np.linalg.norm(np.array(r0.pose)[:3] - case["pose_prior"][:3])
+    assert d_with <= d_without + 1e-9
+    ctx.close()
