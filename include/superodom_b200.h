@@ -158,6 +158,15 @@ int so_map_counts_5x5(so_ctx* ctx, const int32_t ijk[3], int32_t* n_edge, int32_
 int so_map_download(so_ctx* ctx, int mode, const int32_t ijk[3], float* out_xyzi, size_t cap_points, size_t* n_out);
 size_t so_map_size(so_ctx* ctx);
 
+/* ---- scan pre-filter (the step right before the path) ------------------------------------------ */
+/* replaces: laserMapping::adjustVoxelSize (src/LaserMapping/laserMapping.cpp:600-651) for the surf cloud: with
+ * auto_voxel_size, pick config_.lineRes/planeRes from the scan statistics (mean|x| * mean|y| * mean|z| < 25 -> 0.1/0.2,
+ * > 65 -> 0.4/0.8, else unchanged), then pcl::VoxelGrid(planeRes) on the sensor-frame cloud, then push the resolutions
+ * into the map (slam.localMap.lineRes_/planeRes_ = config_, :648-649).  line_res/plane_res are in/out.  Writes up to cap
+ * packed float4 {x,y,z,intensity} points ordered by voxel index; *n_out = points produced. */
+int so_scan_prefilter(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset, int auto_voxel_size,
+                      float* line_res, float* plane_res, float* out_xyzi, size_t cap_points, size_t* n_out, double* average_distance);
+
 /* ---- registration (LidarSLAM) --------------------------------------------------------------------- */
 /* replaces: LidarSLAM::Localization(true, predictodom, position, edge, planner, t) -> performLocalizationAndMapping
  * (LidarSlam.cpp:30-51,107-171), excluding the map insert at its end (call so_map_add_surf with the

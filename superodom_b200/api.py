@@ -20,7 +20,7 @@ EXPORTS = [
     "so_create", "so_destroy", "so_last_error", "so_device_available", "so_set_stream",
     "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
     "so_map_add_surf", "so_map_add_scan", "so_map_counts_5x5", "so_map_download", "so_map_size",
-    "so_register", "so_register_batch", "so_register_batch_device", "so_correspond", "so_evaluate",
+    "so_scan_prefilter", "so_register", "so_register_batch", "so_register_batch_device", "so_correspond", "so_evaluate",
     "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_profile_enable", "so_profile_get",
 ]
 
@@ -83,6 +83,8 @@ def load_library():
     L.so_map_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.so_map_size.restype = C.c_size_t
     L.so_map_size.argtypes = [C.c_void_p]
+    L.so_scan_prefilter.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.so_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                               C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_register_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
@@ -219,6 +221,19 @@ class Context:
         ij = np.ascontiguousarray(ijk if ijk is not None else [0, 0, 0], dtype=np.int32)
         self._chk(self.L.so_map_download(self.h, mode, _p(ij), _p(out), cap, C.byref(n)), "so_map_download")
         return out[: n.value]
+
+    # ---- scan pre-filter
+    def scan_prefilter(self, scan_xyzi: np.ndarray, line_res: float, plane_res: float, auto_voxel_size: bool = True):
+        """-> (filtered float32 [m,4], line_res, plane_res, average_distance)"""
+        a = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
+        lr, pr = C.c_float(line_res), C.c_float(plane_res)
+        out = np.zeros((max(len(a), 1), 4), np.float32)
+        n = C.c_size_t()
+        avg = C.c_double(0.0)
+        stride = a.shape[1] * 4
+        self._chk(self.L.so_scan_prefilter(self.h, _p(a), a.shape[0], stride, 12 if a.shape[1] >= 4 else stride, int(auto_voxel_size),
+                                           C.byref(lr), C.byref(pr), _p(out), len(out), C.byref(n), C.byref(avg)), "so_scan_prefilter")
+        return out[: n.value], lr.value, pr.value, avg.value
 
     # ---- registration
     @staticmethod

@@ -613,6 +613,52 @@ int so_map_download(so_ctx* ctx, int mode, const int32_t ijk[3], float* out, siz
     return SO_OK;
 }
 
+// ---- scan pre-filter ---------------------------------------------------------------------------------------------
+int so_scan_prefilter(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff, int auto_voxel_size, float* line_res,
+                      float* plane_res, float* out_xyzi, size_t cap, size_t* n_out, double* average_distance) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || (!xyzi && n) || stride < 12 || !line_res || !plane_res || !n_out || (!out_xyzi && cap)) return fail(SO_ERR_ARG, "bad args");
+    if (n > c->scan_cap) return fail(SO_ERR_CAPACITY, "cloud larger than the scan buffers");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    *n_out = 0;
+    if (auto_voxel_size && n) {
+        // laserMapping::adjustVoxelSize (laserMapping.cpp:603-636): float accumulators in cloud order, exactly as written there
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        int far_points = 0;
+        const unsigned char* p = static_cast<const unsigned char*>(xyzi);
+        for (size_t i = 0; i < n; ++i, p += stride) {
+            float v[3];
+            std::memcpy(v, p, 12);
+            a0 += std::fabs(v[0]); a1 += std::fabs(v[1]); a2 += std::fabs(v[2]);
+            if (v[0] * v[0] + v[1] * v[1] + v[2] * v[2] > 9) far_points++;
+        }
+        (void)far_points;                                          // increase_blind_radius is computed and never used upstream
+        const float sz = float(n);
+        a0 /= sz; a1 /= sz; a2 /= sz;
+        const double avg = double(a0 * a1 * a2);                   // float product stored into a float64 field
+        if (average_distance) *average_distance = avg;
+        if (avg < 25) { *line_res = 0.1f; *plane_res = 0.2f; }
+        else if (avg > 65) { *line_res = 0.4f; *plane_res = 0.8f; }
+    }
+    int rc = so_map_set_resolution(ctx, *line_res, *plane_res);   // slam.localMap.lineRes_/planeRes_ = config_ (:648-649)
+    if (rc) return rc;
+    rc = upload_cloud(c, xyzi, n, stride, ioff, c->d_scan);
+    if (rc) return rc;
+    uint32_t m = 0;
+    timed_launch_begin(c);
+    rc = scan_voxel_filter(c, uint32_t(n), *plane_res, &m);
+    timed_launch_end(c, 3);
+    if (rc) return rc;
+    *n_out = m;
+    const size_t ncopy = std::min<size_t>(m, cap);
+    if (ncopy) {
+        SO_CUDA_TRY(cudaMemcpyAsync(out_xyzi, c->d_scan_sorted, ncopy * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+        count_d2h(c, ncopy * sizeof(float4));
+        SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return SO_OK;
+}
+
 // ---- registration ----------------------------------------------------------------------------------------------
 int so_register(so_ctx* ctx, const void* surf, size_t n_surf, const void* edge, size_t n_edge, size_t stride, size_t ioff,
                 const double pose_in[7], const so_icp_opts* opts, so_icp_result* out) {

@@ -99,6 +99,7 @@ int map_alloc(Ctx* c);
 void map_free(Ctx* c);
 int map_add_surf(Ctx* c, uint32_t n_new);   // d_map_xyzi[map_n .. map_n+n_new) holds the new points: voxel-filter touched blocks, rebuild
 int map_transform_tail(Ctx* c, uint32_t n_new, const double pose[7]);   // sensor-frame tail points -> world frame
+int scan_voxel_filter(Ctx* c, uint32_t n, float leaf, uint32_t* n_out);   // d_scan -> d_scan_sorted (VoxelGrid on a scan)
 int map_rebuild(Ctx* c);                 // (re)bin, drop off-grid points, sort, build cell table
 MapView map_view(const Ctx* c);
 int map_cells_per_block(float plane_res);
