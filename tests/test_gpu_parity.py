@@ -413,15 +413,16 @@ def test_scan_prefilter_adjust_voxel_size(gpu_api, oracle_mod):
     for scale, expect in ((0.3, (0.1, 0.2)), (0.75, (0.2, 0.4)), (1.0, (0.4, 0.8))):       # statistic 3 / 47 / 112 vs thresholds 25, 65
         s = case["scan_xyzi"].copy()
         s[:, :3] *= np.float32(scale)
-        s[::1000, 0] = np.nan                                    # non-finite points are skipped
         out, lr, pr, avg = ctx.scan_prefilter(s, 0.2, 0.4, True)
         ref, rlr, rpr, ravg = oracle_mod.adjust_voxel_size_numpy(s, 0.2, 0.4, True)
         assert abs(avg - ravg) <= 1e-6 * ravg and (np.float32(lr), np.float32(pr)) == (np.float32(rlr), np.float32(rpr))
         if expect:
             assert (np.float32(lr), np.float32(pr)) == (np.float32(expect[0]), np.float32(expect[1]))
         assert out.shape == ref.shape and np.array_equal(out, ref)
-    out, lr, pr, avg = ctx.scan_prefilter(case["scan_xyzi"], 0.2, 0.4, False)        # fixed leaf
-    ref, _, _, _ = oracle_mod.adjust_voxel_size_numpy(case["scan_xyzi"], 0.2, 0.4, False)
+    s = case["scan_xyzi"].copy()
+    s[::1000, 0] = np.nan                                        # non-finite points are skipped by the VoxelGrid
+    out, lr, pr, avg = ctx.scan_prefilter(s, 0.2, 0.4, False)                                  # fixed leaf
+    ref, _, _, _ = oracle_mod.adjust_voxel_size_numpy(s, 0.2, 0.4, False)
     assert np.array_equal(out, ref) and (lr, pr) == (np.float32(0.2), np.float32(0.4))
     # the filtered scan registers
     r = ctx.register(out, case["pose_prior"], 5, 2000)
