@@ -88,7 +88,7 @@ typedef struct {
     int32_t status;       /* SO_OK / SO_STATUS_* */
     int32_t n_iterations; /* ICP iterations executed (stats.iterations.size()) */
     int32_t iter_n_surf[SO_MAX_ICP_ITERS];        /* IterationStats.num_surf_from_scan */
-    int32_t iter_n_edge[SO_MAX_ICP_ITERS];        /* IterationStats.num_corner_from_scan (edge path dormant: 0) */
+    int32_t iter_n_edge[SO_MAX_ICP_ITERS];        /* IterationStats.num_corner_from_scan */
     double iter_dtrans[SO_MAX_ICP_ITERS];         /* IterationStats.translation_norm */
     double iter_drot[SO_MAX_ICP_ITERS];           /* IterationStats.rotation_norm */
     int32_t iter_lm_steps[SO_MAX_ICP_ITERS];      /* ceres summary: iterations of this solve (diagnostic) */
@@ -97,7 +97,7 @@ typedef struct {
     double iter_cost[SO_MAX_ICP_ITERS];           /* final cost of this solve */
     int32_t hist_obs[9];          /* PlaneFeatureHistogramObs of the last ICP iteration */
     int32_t hist_reject_plane[7]; /* MatchRejectionHistogramPlane of the last ICP iteration */
-    int32_t hist_reject_line[7];  /* MatchRejectionHistogramLine (edge path dormant: 0) */
+    int32_t hist_reject_line[7];  /* MatchRejectionHistogramLine of the last ICP iteration (all 0 without an edge cloud) */
     double cov[36];               /* RegistrationError::Covariance, row-major, order x,y,z,rx,ry,rz */
     double pos_err, pos_dir[3], pos_inv_cond;     /* PositionError, PositionErrorDirection, PosInverseConditionNum */
     double ori_err_deg, ori_dir[3], ori_inv_cond; /* OrientationError (degrees), ...Direction, OriInverseConditionNum */
@@ -122,6 +122,17 @@ typedef struct {
     uint8_t pad_[4];
 } so_corr;
 
+/* One edge / line correspondence (stage-level parity of the dormant edge branch, LidarSlam.cpp:402-493). */
+typedef struct {
+    double a[3], b[3];      /* corres: mean +- 0.1 * line direction */
+    double w;               /* residualCoefficient */
+    uint32_t nn[10];        /* the 10 nearest edge-map points (ids as given to so_map_set_edge_points / insert output order) */
+    uint32_t selected_mask; /* bit j: nn[j] kept by nearestKSearchSpecificEdgePoint's best-line selection (bit 0 always) */
+    uint8_t status;         /* so_match_result */
+    uint8_t n_selected;
+    uint8_t pad_[2];
+} so_edge_corr;
+
 /* ---- lifetime ------------------------------------------------------------------------------------ */
 /* replaces: LidarSLAM::LidarSLAM() + LocalMap::LocalMap() (LidarSlam.cpp:14-19, LocalMap.h:141-144) */
 so_ctx* so_create(const so_config* cfg);
@@ -145,12 +156,18 @@ int so_map_shift(so_ctx* ctx, const double t_w_cur[3], int32_t out_ijk[3]);
 /* Load an ALREADY voxel-filtered world-frame surf cloud as the whole map (no filtering): replay / localization
  * mode with a prebuilt map.  Point ids (so_corr.nn) are indices into this array. */
 int so_map_set_points(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset);
+/* Same for the edge clouds (MapBlock::pedge_pc_): an already lineRes-filtered world-frame edge cloud as the whole edge map. */
+int so_map_set_edge_points(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset);
 /* replaces: LocalMap::addSurfPointCloud (LocalMap.h:591-645): bin world-frame points into blocks, voxel-centroid
  * filter every touched block at leaf planeRes (pcl::VoxelGrid semantics), rebuild the neighbour index. */
 int so_map_add_surf(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset);
+/* replaces: LocalMap::addEdgePointCloud (LocalMap.h:529-589): the same insert at leaf lineRes into the edge clouds. */
+int so_map_add_edge(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset);
 /* replaces: LidarSLAM::transformAndAddToMap(cloud, world_cloud, false) (LidarSlam.cpp:60-80): transform the
  * sensor-frame scan by pose (utils::TransformPoint: double math, float store) on the device, then so_map_add_surf. */
 int so_map_add_scan(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset, const double pose[7]);
+/* ... and transformAndAddToMap(cloud, world_cloud, true) for the edge cloud. */
+int so_map_add_scan_edge(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset, const double pose[7]);
 /* replaces: LocalMap::get5x5LocalMapFeatureSize (LocalMap.h:291-318) */
 int so_map_counts_5x5(so_ctx* ctx, const int32_t ijk[3], int32_t* n_edge, int32_t* n_surf);
 /* replaces: LocalMap::getAllLocalMap (mode 0, LocalMap.h:647-658) / get5x5LocalMap(pos) (mode 1, :660-687).
@@ -171,8 +188,9 @@ int so_scan_prefilter(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_byt
 /* replaces: LidarSLAM::Localization(true, predictodom, position, edge, planner, t) -> performLocalizationAndMapping
  * (LidarSlam.cpp:30-51,107-171), excluding the map insert at its end (call so_map_add_surf with the
  * transformed scan, as transformAndAddToMap does, LidarSlam.cpp:60-80).
- * edge cloud: accepted and ignored exactly as the reference does today (featureExtraction emits an empty edge
- * cloud, featureExtraction.cpp:429-436; processEdgeFeatures returns at LidarSlam.cpp:311). */
+ * edge cloud: processed by the edge / line branch (processEdgeFeatures, LidarSlam.cpp:310-321 -> ComputeLineDistanceParameters
+ * :402-493, EdgeAnalyticCostFunction lidarOptimization.cpp:12-47) against the edge map; empty in the shipped pipeline
+ * (featureExtraction.cpp:429-436), in which case the branch is idle exactly as upstream (LidarSlam.cpp:311). */
 int so_register(so_ctx* ctx,
                 const void* surf_xyzi, size_t n_surf, const void* edge_xyzi, size_t n_edge,
                 size_t stride_bytes, size_t intensity_offset,
@@ -193,6 +211,9 @@ int so_register_batch_device(so_ctx* ctx, const void* d_scans_xyzi, const uint32
 /* processPlannerFeatures at a fixed pose (LidarSlam.cpp:323-344): fills corr[n], hist_obs[9], hist_rej[7]. */
 int so_correspond(so_ctx* ctx, const void* surf_xyzi, size_t n, size_t stride_bytes, size_t intensity_offset,
                   const double pose[7], int32_t max_surface_features, so_corr* corr, int32_t hist_obs[9], int32_t hist_rej[7]);
+/* processEdgeFeatures at a fixed pose (LidarSlam.cpp:310-321): fills corr[n], hist_rej_line[7]. */
+int so_correspond_edge(so_ctx* ctx, const void* edge_xyzi, size_t n, size_t stride_bytes, size_t intensity_offset, const double pose[7],
+                       so_edge_corr* corr, int32_t hist_rej_line[7]);
 /* Robustified normal equations at `pose` over the correspondences of the last so_correspond call:
  * H = sum rho' J^T J (row-major 6x6), g = sum rho' J^T r, cost = 1/2 sum rho (lidarOptimization.cpp:55-80 + Ceres corrector). */
 int so_evaluate(so_ctx* ctx, const double pose[7], double H[36], double g[6], double* cost);

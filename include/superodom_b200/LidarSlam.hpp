@@ -163,7 +163,13 @@ public:
         point_layout<typename std::decay<decltype(laserCloudSurfStack.points[0])>::type>(&stride, &ioff);
         check(so_map_add_surf(ctx_->h, laserCloudSurfStack.points.data(), laserCloudSurfStack.size(), stride, ioff), "so_map_add_surf");
     }
-    template <class Cloud> void addEdgePointCloud(Cloud&) {}                        // edge map dormant (featureExtraction.cpp:429-436)
+    template <class Cloud> void addEdgePointCloud(Cloud& laserCloudEdgeStack) {     // LocalMap.h:529-589 (world-frame points)
+        sync_resolution();
+        if (laserCloudEdgeStack.size() == 0) return;
+        size_t stride, ioff;
+        point_layout<typename std::decay<decltype(laserCloudEdgeStack.points[0])>::type>(&stride, &ioff);
+        check(so_map_add_edge(ctx_->h, laserCloudEdgeStack.points.data(), laserCloudEdgeStack.size(), stride, ioff), "so_map_add_edge");
+    }
     // getAllLocalMap / get5x5LocalMap (LocalMap.h:647-687) fill a caller cloud type (resize + x,y,z,intensity)
     template <class Cloud> Cloud getAllLocalMap() { return download<Cloud>(0, nullptr); }
     template <class Cloud> Cloud get5x5LocalMap(const Vector3i& position) { return download<Cloud>(1, position.v); }
@@ -255,6 +261,7 @@ public:
         if (!initialization) {                                                                   // initializeMapping (:83-94)
             localMap.setOrigin(T_w_lidar.pos);
             T_w_lidar.to_pose7(pose);
+            if (edge_point && edge_point->size()) check(so_map_add_scan_edge(context.h, edge_point->points.data(), edge_point->size(), stride, ioff, pose), "so_map_add_scan_edge");
             if (planner_point->size()) check(so_map_add_scan(context.h, surf, planner_point->size(), stride, ioff, pose), "so_map_add_scan");
             lasttimeLaserOdometry = timeLaserOdometry;
             return;
@@ -304,6 +311,7 @@ public:
         stats.n_iterations = r.n_iterations;
         last_T_w_lidar = T_w_lidar;
         // checkMotionThresholds always accepts (:193) -> transformAndAddToMap (:163-167)
+        if (edge_point && edge_point->size()) check(so_map_add_scan_edge(context.h, edge_point->points.data(), edge_point->size(), stride, ioff, r.pose), "so_map_add_scan_edge");
         if (planner_point->size()) check(so_map_add_scan(context.h, surf, planner_point->size(), stride, ioff, r.pose), "so_map_add_scan");
         lasttimeLaserOdometry = timeLaserOdometry;
     }

@@ -25,7 +25,7 @@ class Opts(C.Structure):
     _fields_ = [("plane_res", C.c_float), ("max_icp_iters", C.c_int32), ("max_surface_features", C.c_int32),
                 ("lm_max_iterations", C.c_int32), ("knn_mode", C.c_int32), ("n_threads", C.c_int32),
                 ("yaw_ratio", C.c_float), ("skip_map_checks", C.c_int32), ("use_pose_prior", C.c_int32),
-                ("visual_confidence_factor", C.c_float), ("prior_uncertainty", C.c_float * 3)]
+                ("visual_confidence_factor", C.c_float), ("prior_uncertainty", C.c_float * 3), ("line_res", C.c_float)]
 
 
 class Result(C.Structure):
@@ -48,6 +48,10 @@ class Result(C.Structure):
 CORR_DTYPE = np.dtype([("p", "<f8", 3), ("n", "<f8", 3), ("d", "<f8"), ("w", "<f8"), ("eigval", "<f8", 3),
                        ("mean_dist", "<f8"), ("nn", "<i8", 5), ("nn_d2", "<f4", 5), ("status", "<i4"), ("obs", "<i4", 3)],
                       align=True)
+
+
+EDGE_CORR_DTYPE = np.dtype([("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3), ("w", "<f8"), ("nn", "<i8", 10), ("sel", "<i4", 10),
+                            ("n_sel", "<i4"), ("status", "<i4")], align=True)
 
 
 def build(force: bool = False) -> None:
@@ -90,6 +94,11 @@ def lib():
     L.orc_solve.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_covariance.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_float, C.c_void_p]
     L.orc_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_register_full.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_map_set_edge_points.restype = C.c_int64
+    L.orc_map_set_edge_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    L.orc_correspond_edge.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_sizeof_edge_corr.restype = C.c_size_t
     L.orc_sym_eig.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_colpiv_qr_solve.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_pose_plus.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -99,6 +108,7 @@ def lib():
     L.orc_sizeof_result.restype = C.c_size_t
     assert L.orc_sizeof_corr() == CORR_DTYPE.itemsize, (L.orc_sizeof_corr(), CORR_DTYPE.itemsize)
     assert L.orc_sizeof_result() == C.sizeof(Result), (L.orc_sizeof_result(), C.sizeof(Result))
+    assert L.orc_sizeof_edge_corr() == EDGE_CORR_DTYPE.itemsize, (L.orc_sizeof_edge_corr(), EDGE_CORR_DTYPE.itemsize)
     L._path = path
     _lib = L
     return L
@@ -142,6 +152,19 @@ class OracleMap:
         o = np.ascontiguousarray(o, dtype=np.int32)
         self.L.orc_map_set_origin(self.h, _p(o))
 
+    def set_edge_points(self, xyzi: np.ndarray) -> int:
+        xyzi = np.ascontiguousarray(xyzi, dtype=np.float32)
+        self.edge_xyzi = xyzi
+        return int(self.L.orc_map_set_edge_points(self.h, _p(xyzi), xyzi.shape[0], xyzi.shape[1]))
+
+    def correspond_edge(self, edge_scan_xyzi, pose7, line_res, knn_mode=0):
+        s = np.ascontiguousarray(edge_scan_xyzi, dtype=np.float32)
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        corr = np.zeros(s.shape[0], EDGE_CORR_DTYPE)
+        hr = np.zeros(7, np.int32)
+        self.L.orc_correspond_edge(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.c_float(line_res), knn_mode, _p(corr), _p(hr))
+        return corr, hr
+
     def origin(self):
         o = np.zeros(3, np.int32)
         self.L.orc_map_get_origin(self.h, _p(o))
@@ -178,18 +201,23 @@ class OracleMap:
         return corr, ho, hr
 
     def register(self, scan_xyzi, pose7, plane_res, max_icp_iters, max_surface_features=0, knn_mode=0, n_threads=1,
-                 lm_max_iterations=4, yaw_ratio=0.0, skip_map_checks=False, pose_prior=None) -> Result:
+                 lm_max_iterations=4, yaw_ratio=0.0, skip_map_checks=False, pose_prior=None, edge_xyzi=None, line_res=0.1) -> Result:
         """pose_prior = (visual_confidence_factor, (ux, uy, uz)) enables the SE3AbsolutatePoseFactor rows."""
         s = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
         pose = np.ascontiguousarray(pose7, dtype=np.float64)
         o = Opts(plane_res, max_icp_iters, max_surface_features, lm_max_iterations, knn_mode, n_threads, yaw_ratio, int(skip_map_checks),
-                 0, 0.0, (C.c_float * 3)(0, 0, 0))
+                 0, 0.0, (C.c_float * 3)(0, 0, 0), float(line_res))
         if pose_prior is not None:
             o.use_pose_prior = 1
             o.visual_confidence_factor = float(pose_prior[0])
             o.prior_uncertainty = (C.c_float * 3)(*[float(v) for v in pose_prior[1]])
         r = Result()
-        self.L.orc_register(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.byref(o), C.byref(r))
+        if edge_xyzi is not None and len(edge_xyzi):
+            e = np.ascontiguousarray(edge_xyzi, dtype=np.float32)
+            assert e.shape[1] == s.shape[1]
+            self.L.orc_register_full(self.h, _p(s), s.shape[0], _p(e), e.shape[0], s.shape[1], _p(pose), C.byref(o), C.byref(r))
+        else:
+            self.L.orc_register(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.byref(o), C.byref(r))
         return r
 
 

@@ -412,8 +412,9 @@ struct BlockData {
 
 struct Map {
     int origin[3] = {kW / 2, kH / 2, kD / 2};     // LocalMap() ctor: (10,10,5)
-    std::vector<std::unique_ptr<BlockData>> blocks;   // kNumBlocks entries, null if empty
-    Map() : blocks(kNumBlocks) {}
+    std::vector<std::unique_ptr<BlockData>> blocks;   // surf clouds: kNumBlocks entries, null if empty
+    std::vector<std::unique_ptr<BlockData>> eblocks;  // edge clouds (pedge_pc_ / pkdtree_edge_from_block_)
+    Map() : blocks(kNumBlocks), eblocks(kNumBlocks) {}
 };
 
 // Exact k-NN inside one block with tie-break (d2, index) ascending == brute force scanning the block
@@ -590,6 +591,125 @@ static void plane_correspondence(const Map& M, const float* sp, const double pos
     out.status = SUCCESS;
 }
 
+// ----------------------------------------------------------------------------- edge / line branch (dormant upstream: the edge cloud is always empty)
+struct EdgeCorr {
+    double p[3];        // Xvalue = pInit
+    double a[3], b[3];  // corres = (mean + 0.1 dir, mean - 0.1 dir)
+    double w;           // residualCoefficient
+    int64_t nn[10];     // the 10 nearest edge points (caller's input index)
+    int32_t sel[10];    // positions in nn[] of the points kept by the best-line selection (closest first), -1 padded
+    int32_t n_sel;
+    int32_t status;
+};
+
+// LocalMap::nearestKSearchSpecificEdgePoint (LocalMap.h:377-474) + ComputeLineDistanceParameters (LidarSlam.cpp:402-435)
+// + processLineResults (:438-493).
+static void line_correspondence(const Map& M, const float* sp, const double pose[7], float lineRes, int knn_mode, EdgeCorr& out) {
+    std::memset(&out, 0, sizeof(out));
+    for (int j = 0; j < 10; ++j) { out.nn[j] = -1; out.sel[j] = -1; }
+    const Quat q{pose[3], pose[4], pose[5], pose[6]};
+    const double pin[3] = {double(sp[0]), double(sp[1]), double(sp[2])};
+    double pf[3]; qrot(q, pin, pf); pf[0] += pose[0]; pf[1] += pose[1]; pf[2] += pose[2];
+    out.p[0] = pin[0]; out.p[1] = pin[1]; out.p[2] = pin[2];
+    const Pt qf{float(pf[0]), float(pf[1]), float(pf[2])};
+    const int bl = block_of(qf.x, qf.y, qf.z, M.origin);
+    const BlockData* B = bl >= 0 ? M.eblocks[bl].get() : nullptr;
+    // "<k points in the block": the reference indexes with size_t(-1) (UB, LocalMap.h:404-419); treated as NOT_ENOUGH_NEIGHBORS
+    if (!B || B->pts.size() < 10) { out.status = NOT_ENOUGH_NEIGHBORS; return; }
+    int64_t idx[10]; float d2[10];
+    if (knn_mode == 1) knn_brute(*B, qf, 10, idx, d2); else knn_exact(*B, qf, 10, idx, d2);
+    for (int j = 0; j < 10; ++j) out.nn[j] = B->gid[idx[j]];
+    // best line through the closest point by inlier count (float arithmetic, Eigen's evaluation order)
+    const Pt& P1 = B->pts[idx[0]];
+    const float thr = 0.2f * 0.2f;                       // LocalizationLineMaxDistInlier^2 (LidarSlam.h:280), static_cast<float>
+    int best = -1; size_t best_n = 0; bool best_in[10] = {false};
+    for (int pi = 1; pi < 10; ++pi) {
+        const Pt& P2 = B->pts[idx[pi]];
+        float dx = P2.x - P1.x, dy = P2.y - P1.y, dz = P2.z - P1.z;
+        const float z2 = dx * dx + (dy * dy + dz * dz);                        // Vector3f::squaredNorm
+        if (z2 > 0.f) { const float s = std::sqrt(z2); dx /= s; dy /= s; dz /= s; }   // normalized(): zero vector stays zero
+        bool in[10] = {false}; size_t cnt = 0;
+        for (int ci = 1; ci < 10; ++ci) {
+            bool ok;
+            if (ci == pi) ok = true;
+            else {
+                const Pt& Pc = B->pts[idx[ci]];
+                const float vx = Pc.x - P1.x, vy = Pc.y - P1.y, vz = Pc.z - P1.z;
+                const float cx = vy * dz - vz * dy, cy = vz * dx - vx * dz, cz = vx * dy - vy * dx;
+                ok = (cx * cx + (cy * cy + cz * cz)) < thr;
+            }
+            in[ci] = ok; cnt += ok;
+        }
+        if (cnt > best_n) { best_n = cnt; best = pi; for (int ci = 0; ci < 10; ++ci) best_in[ci] = in[ci]; }
+    }
+    (void)best;
+    int sel[10], ns = 0;
+    sel[ns++] = 0;
+    for (int ci = 1; ci < 10; ++ci) if (best_in[ci]) sel[ns++] = ci;
+    out.n_sel = ns;
+    for (int j = 0; j < ns; ++j) out.sel[j] = sel[j];
+    // validateNeighborSearch (:495-512)
+    if (ns < 4) { out.status = NOT_ENOUGH_NEIGHBORS; return; }
+    if (d2[sel[ns - 1]] > 3 * lineRes) { out.status = NEIGHBORS_TOO_FAR; return; }      // float compare
+    // computePCAForFeature, EdgeFeature branch (:749-790)
+    double m[10][3], mean[3] = {0, 0, 0};
+    for (int j = 0; j < ns; ++j) { const Pt& a = B->pts[idx[sel[j]]]; m[j][0] = a.x; m[j][1] = a.y; m[j][2] = a.z; }
+    for (int j = 0; j < ns; ++j) for (int a = 0; a < 3; ++a) mean[a] += m[j][a];
+    for (int a = 0; a < 3; ++a) mean[a] /= double(ns);
+    double S[9] = {0};
+    for (int j = 0; j < ns; ++j) {
+        const double c[3] = {m[j][0] - mean[0], m[j][1] - mean[1], m[j][2] - mean[2]};
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) S[a * 3 + b] += c[a] * c[b];
+    }
+    double ev[3], V[9];
+    sym_eig(3, S, ev, V);
+    if (!(std::isfinite(ev[0]) && std::isfinite(ev[1]) && std::isfinite(ev[2]))) { out.status = INVALID_NUMERICAL; return; }
+    if (ev[2] < 4.0 * ev[1]) { out.status = BAD_PCA_STRUCTURE; return; }                 // LocalizationMinmumLineNeighborRejection * ev1
+    // processLineResults (:438-493)
+    double dir[3] = {V[2], V[5], V[8]};
+    const double dn = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    dir[0] /= dn; dir[1] /= dn; dir[2] /= dn;
+    double A[9];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) A[a * 3 + b] = (a == b ? 1.0 : 0.0) - dir[a] * dir[b];
+    for (int i = 0; i < 9; ++i) if (!std::isfinite(A[i])) { out.status = INVALID_NUMERICAL; return; }
+    double msd = 0.0;
+    const double lim = double(3 * lineRes);
+    for (int j = 0; j < ns; ++j) {
+        const double c[3] = {m[j][0] - mean[0], m[j][1] - mean[1], m[j][2] - mean[2]};
+        double Ac[3]; for (int a = 0; a < 3; ++a) Ac[a] = A[a * 3] * c[0] + A[a * 3 + 1] * c[1] + A[a * 3 + 2] * c[2];
+        const double sd = c[0] * Ac[0] + c[1] * Ac[1] + c[2] * Ac[2];
+        if (sd > lim) { out.status = MSE_TOO_LARGE; return; }
+        msd += sd;
+    }
+    msd /= double(ns);
+    out.w = 1.0 - std::sqrt(msd / lim);
+    for (int a = 0; a < 3; ++a) { out.a[a] = 0.1 * dir[a] + mean[a]; out.b[a] = -0.1 * dir[a] + mean[a]; }
+    out.status = SUCCESS;
+}
+
+// EdgeAnalyticCostFunction::Evaluate (lidarOptimization.cpp:12-47): r = ((lp-a) x (lp-b)) / |a-b|, J = skew(b-a) [I, -R [p]x] / |a-b|
+static inline void edge_residual(const EdgeCorr& c, const double x[7], const double R[9], double r[3], double J[18]) {
+    Quat q{x[3], x[4], x[5], x[6]};
+    double lp[3]; qrot(q, c.p, lp); lp[0] += x[0]; lp[1] += x[1]; lp[2] += x[2];
+    const double u[3] = {lp[0] - c.a[0], lp[1] - c.a[1], lp[2] - c.a[2]}, v[3] = {lp[0] - c.b[0], lp[1] - c.b[1], lp[2] - c.b[2]};
+    const double de[3] = {c.a[0] - c.b[0], c.a[1] - c.b[1], c.a[2] - c.b[2]};
+    const double den = std::sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+    r[0] = (u[1] * v[2] - u[2] * v[1]) / den; r[1] = (u[2] * v[0] - u[0] * v[2]) / den; r[2] = (u[0] * v[1] - u[1] * v[0]) / den;
+    if (!J) return;
+    const double re[3] = {-de[0], -de[1], -de[2]};      // b - a
+    const double K[9] = {0, -re[2], re[1], re[2], 0, -re[0], -re[1], re[0], 0};     // skew(re)
+    // dp_by_so3 = [I, -R skew(p)]
+    const double* p = c.p;
+    const double Sp[9] = {0, -p[2], p[1], p[2], 0, -p[0], -p[1], p[0], 0};
+    double RS[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double t = 0; for (int k = 0; k < 3; ++k) t += R[i * 3 + k] * Sp[k * 3 + j]; RS[i * 3 + j] = -t; }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        J[i * 6 + j] = K[i * 3 + j] / den;
+        double t = 0; for (int k = 0; k < 3; ++k) t += K[i * 3 + k] * RS[k * 3 + j];
+        J[i * 6 + 3 + j] = t / den;
+    }
+}
+
 // shouldProcessPoint (LidarSlam.cpp:346-359)
 static inline bool should_process(size_t i, double rate) {
     if (rate < 0.0) return true;
@@ -657,11 +777,14 @@ struct PosePrior {
 };
 
 struct Evaluator {
+    std::vector<const EdgeCorr*> edges; // accepted edge correspondences (added BEFORE the planes, LidarSlam.cpp:304-307)
+    double a2_line = 0;                 // Tukey a^2 for edges, a = double(sqrtf(3*lineRes)) (LidarSlam.cpp:263)
     std::vector<const Corr*> blocks;    // accepted correspondences in scan order
     PosePrior prior;                    // optional 6 extra residual rows (after the plane blocks, as the reference adds it)
     double a2;                          // Tukey a^2, a = double(sqrtf(3*planeRes)) (LidarSlam.cpp:271)
     // TukeyLoss::Evaluate (ceres 2.0.0 loss_function.cc) wrapped by ScaledLoss(w)
-    inline void rho(double s, double w, double r[3]) const {
+    inline void rho(double s, double w, double r[3]) const { rho_a(s, w, a2, r); }
+    static inline void rho_a(double s, double w, double a2, double r[3]) {
         if (s <= a2) { const double v = 1.0 - s / a2, v2 = v * v; r[0] = a2 / 6.0 * (1.0 - v2 * v); r[1] = 0.5 * v2; r[2] = -1.0 / a2 * v; }
         else { r[0] = a2 / 6.0; r[1] = 0.0; r[2] = 0.0; }
         r[0] *= w; r[1] *= w; r[2] *= w;
@@ -677,14 +800,15 @@ struct Evaluator {
     double cost(const double x[7]) const {
         double c = 0.0;
         for (const Corr* b : blocks) { double r = residual(*b, x), rr[3]; rho(r * r, b->w, rr); c += 0.5 * rr[0]; }
+        for (const EdgeCorr* e : edges) { double r[3], rr[3]; edge_residual(*e, x, nullptr, r, nullptr); rho_a(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], e->w, a2_line, rr); c += 0.5 * rr[0]; }
         if (prior.on) { double r[6], J[36]; prior.eval(x, r, J); double sq = 0; for (int i = 0; i < 6; ++i) sq += r[i] * r[i]; c += 0.5 * sq; }
         return c;
     }
     // full: corrected residuals, corrected local Jacobian (column-major n x 6), gradient, cost.
     // Tukey has rho'' <= 0 everywhere => Corrector takes the "rho[2] <= 0" branch: both r and J scaled by sqrt(rho') (corrector.cc).
     void full(const double x[7], double* cost_out, std::vector<double>& res, std::vector<double>& J, double g[6]) const {
-        const size_t np = blocks.size();
-        const size_t n = np + (prior.on ? 6 : 0);          // rows
+        const size_t np = blocks.size(), ne = edges.size();
+        const size_t n = np + 3 * ne + (prior.on ? 6 : 0);          // rows: planes, then 3 per edge, then the prior (order is immaterial to the sums)
         res.resize(n); J.resize(n * 6);
         Quat q{x[3], x[4], x[5], x[6]};
         double R[9]; qtoR(q, R);
@@ -693,8 +817,20 @@ struct Evaluator {
         if (prior.on) {
             double r[6], Jp[36]; prior.eval(x, r, Jp);
             for (int i = 0; i < 6; ++i) {
-                res[np + i] = r[i]; c += 0.5 * r[i] * r[i];
-                for (int j = 0; j < 6; ++j) { J[size_t(j) * n + np + i] = Jp[i * 6 + j]; g[j] += Jp[i * 6 + j] * r[i]; }
+                res[np + 3 * ne + i] = r[i]; c += 0.5 * r[i] * r[i];
+                for (int j = 0; j < 6; ++j) { J[size_t(j) * n + np + 3 * ne + i] = Jp[i * 6 + j]; g[j] += Jp[i * 6 + j] * r[i]; }
+            }
+        }
+        for (size_t e = 0; e < ne; ++e) {
+            double r[3], Je[18], rr[3];
+            edge_residual(*edges[e], x, R, r, Je);
+            rho_a(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], edges[e]->w, a2_line, rr);
+            c += 0.5 * rr[0];
+            const double sc = std::sqrt(rr[1]);
+            for (int i = 0; i < 3; ++i) {
+                r[i] *= sc;
+                for (int j = 0; j < 6; ++j) { Je[i * 6 + j] *= sc; J[size_t(j) * n + np + 3 * e + i] = Je[i * 6 + j]; g[j] += Je[i * 6 + j] * r[i]; }
+                res[np + 3 * e + i] = r[i];
             }
         }
         for (size_t i = 0; i < np; ++i) {
@@ -721,8 +857,8 @@ struct SolveSummary { int num_successful_steps = 0, num_unsuccessful_steps = 0, 
 // TrustRegionMinimizer::Minimize + LevenbergMarquardtStrategy + TrustRegionStepEvaluator(monotonic).
 static SolveSummary ceres_solve(const Evaluator& E, double params[7], int max_num_iterations = 4) {
     SolveSummary S;
-    if (E.blocks.empty() && !E.prior.on) { S.termination = 6; return S; }
-    const size_t n = E.blocks.size() + (E.prior.on ? 6 : 0);      // residual rows
+    if (E.blocks.empty() && E.edges.empty() && !E.prior.on) { S.termination = 6; return S; }
+    const size_t n = E.blocks.size() + 3 * E.edges.size() + (E.prior.on ? 6 : 0);      // residual rows
     const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
     const double min_relative_decrease = 1e-3, min_lm_diagonal = 1e-6, max_lm_diagonal = 1e32;
     const double max_radius = 1e16, min_radius = 1e-32;
@@ -806,7 +942,7 @@ static SolveSummary ceres_solve(const Evaluator& E, double params[7], int max_nu
 // ceres::Covariance{apply_loss_function, DENSE_SVD, null_space_rank=-1} in tangent space (LidarSlam.cpp:854-871;
 // covariance_impl.cc ComputeCovarianceValuesUsingDenseSVD): V diag(1/s^2) V^T with s_i/s_0 < sqrt(1e-14) truncated.
 static void ceres_covariance(const Evaluator& E, const double x[7], double cov[36]) {
-    const size_t n = E.blocks.size() + (E.prior.on ? 6 : 0);
+    const size_t n = E.blocks.size() + 3 * E.edges.size() + (E.prior.on ? 6 : 0);
     std::vector<double> res, J; double g[6], c;
     E.full(x, &c, res, J, g);
     double R[36]; householder_ls(int(n), 6, J.data(), nullptr, nullptr, R);
@@ -863,6 +999,7 @@ typedef struct {
     int32_t use_pose_prior;     // shouldAddAbsolutePoseConstraints(): VIO_ODOM && isDegenerate && Visual_confidence_factor != 0
     float visual_confidence_factor;
     float prior_uncertainty[3]; // lidarOdomUncer.uncertainty_{x,y,z} (from the previous scan's histogram)
+    float line_res;             // localMap.lineRes_ (edge branch)
 } orc_opts;
 
 typedef struct {
@@ -893,6 +1030,7 @@ typedef struct {
 } orc_result;
 
 typedef orc::Corr orc_corr;
+typedef orc::EdgeCorr orc_edge_corr;
 
 int orc_has_ref_octree(void) {
 #ifdef SO_ORACLE_WITH_REF_OCTREE
@@ -903,6 +1041,7 @@ int orc_has_ref_octree(void) {
 }
 size_t orc_sizeof_corr(void) { return sizeof(orc_corr); }
 size_t orc_sizeof_result(void) { return sizeof(orc_result); }
+size_t orc_sizeof_edge_corr(void) { return sizeof(orc_edge_corr); }
 
 void* orc_map_create(void) { return new orc::Map(); }
 void orc_map_destroy(void* m) { delete static_cast<orc::Map*>(m); }
@@ -934,6 +1073,32 @@ int64_t orc_map_set_points(void* m, const float* xyzi, size_t n, size_t stride_f
     return kept;
 }
 
+// Same for the edge clouds (pedge_pc_): already line-res filtered points, binned under the current origin.
+int64_t orc_map_set_edge_points(void* m, const float* xyzi, size_t n, size_t stride_floats) {
+    auto* M = static_cast<orc::Map*>(m);
+    for (auto& b : M->eblocks) b.reset();
+    int64_t kept = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = xyzi + i * stride_floats;
+        int b = orc::block_of(p[0], p[1], p[2], M->origin);
+        if (b < 0) continue;
+        if (!M->eblocks[b]) M->eblocks[b].reset(new orc::BlockData());
+        M->eblocks[b]->pts.push_back(orc::Pt{p[0], p[1], p[2]});
+        M->eblocks[b]->gid.push_back(int64_t(i));
+        ++kept;
+    }
+    for (auto& b : M->eblocks) if (b) b->build_grid();
+    return kept;
+}
+
+int orc_correspond_edge(void* m, const float* scan_xyzi, size_t n, size_t stride_floats, const double pose[7], float line_res, int knn_mode,
+                        orc_edge_corr* out, int32_t hist_rej_line[7]) {
+    auto* M = static_cast<orc::Map*>(m);
+    for (int i = 0; i < 7; ++i) hist_rej_line[i] = 0;
+    for (size_t i = 0; i < n; ++i) { orc::line_correspondence(*M, scan_xyzi + i * stride_floats, pose, line_res, knn_mode, out[i]); hist_rej_line[out[i].status]++; }
+    return 0;
+}
+
 // LocalMap::shiftMap (LocalMap.h:169-287): returns the sensor block; origin may change, blocks that roll off are dropped.
 // Because block membership is a pure function of (world coordinate, origin), rolling == re-binning under the new origin.
 void orc_map_shift(void* m, const double t[3], int32_t out_ijk[3]) {
@@ -954,6 +1119,13 @@ void orc_map_shift(void* m, const double t[3], int32_t out_ijk[3]) {
             nb[ni + orc::kW * nj + orc::kW * orc::kH * nk] = std::move(M->blocks[i + orc::kW * j + orc::kW * orc::kH * k]);
         }
         M->blocks.swap(nb);
+        std::vector<std::unique_ptr<orc::BlockData>> ne(orc::kNumBlocks);
+        for (int k = 0; k < orc::kD; ++k) for (int j = 0; j < orc::kH; ++j) for (int i = 0; i < orc::kW; ++i) {
+            int ni = i + shift[0], nj = j + shift[1], nk = k + shift[2];
+            if (ni < 0 || ni >= orc::kW || nj < 0 || nj >= orc::kH || nk < 0 || nk >= orc::kD) continue;
+            ne[ni + orc::kW * nj + orc::kW * orc::kH * nk] = std::move(M->eblocks[i + orc::kW * j + orc::kW * orc::kH * k]);
+        }
+        M->eblocks.swap(ne);
         for (int a = 0; a < 3; ++a) M->origin[a] += shift[a];
     }
     out_ijk[0] = c[0]; out_ijk[1] = c[1]; out_ijk[2] = c[2];
@@ -965,6 +1137,14 @@ int32_t orc_map_counts_5x5(void* m, const int32_t ijk[3]) {
     int n = 0;
     for (int i = ijk[0] - 2; i <= ijk[0] + 2; ++i) for (int j = ijk[1] - 2; j <= ijk[1] + 2; ++j) for (int k = ijk[2] - 1; k <= ijk[2] + 1; ++k)
         if (i >= 0 && i < orc::kW && j >= 0 && j < orc::kH && k >= 0 && k < orc::kD) { auto& b = M->blocks[i + orc::kW * j + orc::kW * orc::kH * k]; if (b) n += int(b->pts.size()); }
+    return n;
+}
+
+int32_t orc_map_edge_counts_5x5(void* m, const int32_t ijk[3]) {
+    auto* M = static_cast<orc::Map*>(m);
+    int n = 0;
+    for (int i = ijk[0] - 2; i <= ijk[0] + 2; ++i) for (int j = ijk[1] - 2; j <= ijk[1] + 2; ++j) for (int k = ijk[2] - 1; k <= ijk[2] + 1; ++k)
+        if (i >= 0 && i < orc::kW && j >= 0 && j < orc::kH && k >= 0 && k < orc::kD) { auto& b = M->eblocks[i + orc::kW * j + orc::kW * orc::kH * k]; if (b) n += int(b->pts.size()); }
     return n;
 }
 
@@ -1029,36 +1209,47 @@ void orc_yaw_round_trip(const double last[7], double T[7], double yaw_ratio) { o
 
 // LidarSLAM::Localization, initialization==true branch -> performLocalizationAndMapping (LidarSlam.cpp:30-51,107-171),
 // without the map insert at the end (transformAndAddToMap is a "next" row; use orc_voxel_filter + orc_map_set_points).
-int orc_register(void* m, const float* scan_xyzi, size_t n, size_t stride_floats, const double pose_in[7], const orc_opts* opt, orc_result* out) {
+int orc_register_full(void* m, const float* scan_xyzi, size_t n, const float* edge_xyzi, size_t n_edge, size_t stride_floats,
+                      const double pose_in[7], const orc_opts* opt, orc_result* out) {
     using namespace orc;
     auto* M = static_cast<Map*>(m);
     std::memset(out, 0, sizeof(*out));
     double T[7], T0[7], last_T[7];
     std::memcpy(T, pose_in, sizeof(T)); std::memcpy(T0, pose_in, sizeof(T)); std::memcpy(last_T, pose_in, sizeof(T));   // initializeState (:53-57)
     std::memcpy(out->pose, T, sizeof(T)); std::memcpy(out->pose_opt, T, sizeof(T));
-    out->scan_surf_num = int32_t(n);
+    out->scan_surf_num = int32_t(n); out->scan_edge_num = int32_t(n_edge);
     // prepareOptimizationState (:361-369)
     int32_t ijk[3];
     if (!opt->skip_map_checks) orc_map_shift(m, T, ijk);
     else for (int a = 0; a < 3; ++a) ijk[a] = block_coord(T[a] + kHalfBlock, M->origin[a]);
     out->pos_in_localmap[0] = ijk[0]; out->pos_in_localmap[1] = ijk[1]; out->pos_in_localmap[2] = ijk[2];
     out->map_surf_5x5 = orc_map_counts_5x5(m, ijk);
+    out->map_edge_5x5 = orc_map_edge_counts_5x5(m, ijk);
     if (!(out->map_surf_5x5 > 50)) { out->status = 1; return 1; }       // hasEnoughFeatures (:379-381)
     const int max_iters = std::min<int>(opt->max_icp_iters, ORC_MAX_ICP_ITERS);
     std::vector<Corr> corr(n);
-    Evaluator E; { const double a = double(std::sqrt(3 * opt->plane_res)); E.a2 = a * a; }   // TukeyLoss(std::sqrt(3*planeRes_)) float sqrt (:271)
+    std::vector<EdgeCorr> ecorr(n_edge);
+    Evaluator E; { const double a = double(std::sqrt(3 * opt->plane_res)); E.a2 = a * a; const double al = double(std::sqrt(3 * opt->line_res)); E.a2_line = al * al; }   // TukeyLoss(std::sqrt(3*planeRes_)) float sqrt (:271)
     auto t0 = std::chrono::steady_clock::now();
     double knn_ms = 0;
     bool have_cov = false;
     for (int it = 0; it < max_iters; ++it) {
         auto tk = std::chrono::steady_clock::now();
+        // processEdgeFeatures (:310-321): every edge point, no decimation
+        for (int k = 0; k < 7; ++k) out->hist_reject_line[k] = 0;
+        E.edges.clear();
+        for (size_t i = 0; i < n_edge; ++i) {
+            line_correspondence(*M, edge_xyzi + i * stride_floats, T, opt->line_res, opt->knn_mode == 1 ? 1 : 0, ecorr[i]);
+            out->hist_reject_line[ecorr[i].status]++;
+            if (ecorr[i].status == SUCCESS) E.edges.push_back(&ecorr[i]);
+        }
         correspond_all(*M, scan_xyzi, n, stride_floats, T, opt->plane_res, opt->max_surface_features, opt->knn_mode, opt->n_threads, corr.data(), out->hist_obs, out->hist_reject_plane);
         knn_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk).count();
         E.blocks.clear();
         for (size_t i = 0; i < n; ++i) if (corr[i].status == SUCCESS) E.blocks.push_back(&corr[i]);
         E.prior.on = false;
         if (opt->use_pose_prior) {                                // addAbsolutePoseConstraints (:285-298), position = T_w_initial_guess
-            const int good = int(E.blocks.size());
+            const int good = int(E.blocks.size() + E.edges.size());      // features_corres.size()
             const double vcf = double(opt->visual_confidence_factor);
             double info[6];
             for (int a = 0; a < 3; ++a) info[a] = (1 - double(opt->prior_uncertainty[a])) * std::max(50, int(good * 0.1)) * vcf;
@@ -1072,12 +1263,12 @@ int orc_register(void* m, const float* scan_xyzi, size_t n, size_t stride_floats
         double params[7]; std::memcpy(params, T, sizeof(T));     // pose_parameters were set in prepareOptimizationState and by the previous solve
         SolveSummary S = ceres_solve(E, params, opt->lm_max_iterations);
         std::memcpy(T, params, sizeof(T));                       // T_w_lidar <- T_w_curr/Q_w_curr (:135-136)
-        out->iter_n_surf[it] = int32_t(E.blocks.size()); out->iter_n_edge[it] = 0;
+        out->iter_n_surf[it] = int32_t(E.blocks.size()); out->iter_n_edge[it] = int32_t(E.edges.size());
         rel_motion(prev, T, &out->iter_dtrans[it], &out->iter_drot[it]);
         out->iter_lm_steps[it] = S.iterations; out->iter_lm_successful[it] = S.num_successful_steps; out->iter_lm_termination[it] = S.termination; out->iter_cost[it] = S.final_cost;
         out->n_iterations = it + 1;
         if (S.num_successful_steps == 1 || it == max_iters - 1) {     // (:141-146)
-            if (!E.blocks.empty()) {
+            if (!E.blocks.empty() || !E.edges.empty()) {
                 ceres_covariance(E, T, out->cov); have_cov = true;
             }
             break;
@@ -1092,7 +1283,7 @@ int orc_register(void* m, const float* scan_xyzi, size_t n, size_t stride_floats
         sym_eig(3, O, w, V);
         out->ori_err_deg = std::sqrt(w[2]) / M_PI * 180.; out->ori_dir[0] = V[2]; out->ori_dir[1] = V[5]; out->ori_dir[2] = V[8];
         out->ori_inv_cond = std::sqrt(w[0]) / std::sqrt(w[2]);
-    } else if (out->n_iterations > 0 && out->iter_n_surf[out->n_iterations - 1] == 0) out->status = 2;
+    } else if (out->n_iterations > 0 && out->iter_n_surf[out->n_iterations - 1] == 0 && out->iter_n_edge[out->n_iterations - 1] == 0) out->status = 2;
     std::memcpy(out->pose_opt, T, sizeof(T));
     // performPostOptimizationProcessing (:155-171)
     manual_yaw_correction(last_T, T, double(opt->yaw_ratio));
@@ -1102,6 +1293,10 @@ int orc_register(void* m, const float* scan_xyzi, size_t n, size_t stride_floats
     rel_motion(last_T, T, &out->translation_from_last, &out->rotation_from_last);
     std::memcpy(out->pose, T, sizeof(T));
     return out->status;
+}
+
+int orc_register(void* m, const float* scan_xyzi, size_t n, size_t stride_floats, const double pose_in[7], const orc_opts* opt, orc_result* out) {
+    return orc_register_full(m, scan_xyzi, n, nullptr, 0, stride_floats, pose_in, opt, out);
 }
 
 // EstimateLidarUncertainty (LidarSlam.cpp:915-964) from a 9-bin observability histogram

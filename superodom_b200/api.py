@@ -19,8 +19,8 @@ MAX_ICP_ITERS = 32
 EXPORTS = [
     "so_create", "so_destroy", "so_last_error", "so_device_available", "so_set_stream",
     "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
-    "so_map_add_surf", "so_map_add_scan", "so_map_counts_5x5", "so_map_download", "so_map_size",
-    "so_scan_prefilter", "so_register", "so_register_batch", "so_register_batch_device", "so_correspond", "so_evaluate",
+    "so_map_set_edge_points", "so_map_add_surf", "so_map_add_edge", "so_map_add_scan", "so_map_add_scan_edge", "so_map_counts_5x5", "so_map_download", "so_map_size",
+    "so_scan_prefilter", "so_register", "so_register_batch", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
     "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_profile_enable", "so_profile_get",
 ]
 
@@ -56,6 +56,9 @@ class IcpResult(C.Structure):
 CORR_DTYPE = np.dtype([("n", "<f8", 3), ("d", "<f8"), ("w", "<f8"), ("nn", "<u4", 5), ("nn_d2", "<f4", 5),
                        ("status", "u1"), ("obs", "u1", 3), ("pad_", "u1", 4)], align=True)
 
+EDGE_CORR_DTYPE = np.dtype([("a", "<f8", 3), ("b", "<f8", 3), ("w", "<f8"), ("nn", "<u4", 10), ("selected_mask", "<u4"),
+                            ("status", "u1"), ("n_selected", "u1"), ("pad_", "u1", 2)], align=True)
+
 _lib = None
 
 
@@ -79,6 +82,10 @@ def load_library():
     L.so_map_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
     L.so_map_add_surf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
     L.so_map_add_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    L.so_map_add_scan_edge.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    L.so_map_set_edge_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
+    L.so_map_add_edge.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
+    L.so_correspond_edge.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_map_counts_5x5.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_map_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.so_map_size.restype = C.c_size_t
@@ -177,6 +184,22 @@ class Context:
         ioff = 12 if a.shape[1] >= 4 else stride
         self._chk(self.L.so_map_set_points(self.h, _p(a), a.shape[0], stride, ioff), "so_map_set_points")
 
+    def map_set_edge_points(self, xyzi: np.ndarray):
+        a = np.ascontiguousarray(xyzi, dtype=np.float32)
+        stride = a.shape[1] * 4
+        self._chk(self.L.so_map_set_edge_points(self.h, _p(a), a.shape[0], stride, 12 if a.shape[1] >= 4 else stride), "so_map_set_edge_points")
+
+    def map_add_edge(self, xyzi: np.ndarray):
+        a = np.ascontiguousarray(xyzi, dtype=np.float32)
+        stride = a.shape[1] * 4
+        self._chk(self.L.so_map_add_edge(self.h, _p(a), a.shape[0], stride, 12 if a.shape[1] >= 4 else stride), "so_map_add_edge")
+
+    def map_add_scan_edge(self, scan_xyzi: np.ndarray, pose7):
+        a = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        stride = a.shape[1] * 4
+        self._chk(self.L.so_map_add_scan_edge(self.h, _p(a), a.shape[0], stride, 12 if a.shape[1] >= 4 else stride, _p(pose)), "so_map_add_scan_edge")
+
     def map_add_surf(self, xyzi: np.ndarray):
         a = np.ascontiguousarray(xyzi, dtype=np.float32)
         stride = a.shape[1] * 4
@@ -205,11 +228,11 @@ class Context:
         self._chk(self.L.so_map_shift(self.h, _p(t), _p(o)), "so_map_shift")
         return o
 
-    def map_counts_5x5(self, ijk) -> int:
+    def map_counts_5x5(self, ijk, with_edge: bool = False):
         ijk = np.ascontiguousarray(ijk, dtype=np.int32)
         ne, ns = C.c_int32(), C.c_int32()
         self._chk(self.L.so_map_counts_5x5(self.h, _p(ijk), C.byref(ne), C.byref(ns)), "so_map_counts_5x5")
-        return ns.value
+        return (ne.value, ns.value) if with_edge else ns.value
 
     def map_size(self) -> int:
         return int(self.L.so_map_size(self.h))
@@ -246,15 +269,30 @@ class Context:
             o.prior_uncertainty = (C.c_float * 3)(*[float(v) for v in pose_prior[1]])
         return o
 
-    def register(self, scan_xyzi: np.ndarray, pose7, max_icp_iters: int, max_surface_features: int = 0, **kw) -> IcpResult:
+    def register(self, scan_xyzi: np.ndarray, pose7, max_icp_iters: int, max_surface_features: int = 0, edge_xyzi=None, **kw) -> IcpResult:
         s = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
         pose = np.ascontiguousarray(pose7, dtype=np.float64)
         o = self._opts(max_icp_iters, max_surface_features, **kw)
         r = IcpResult()
         stride = s.shape[1] * 4
-        self._chk(self.L.so_register(self.h, _p(s), s.shape[0], None, 0, stride, 12 if s.shape[1] >= 4 else stride,
+        e, ne = None, 0
+        if edge_xyzi is not None and len(edge_xyzi):
+            ea = np.ascontiguousarray(edge_xyzi, dtype=np.float32)
+            assert ea.shape[1] == s.shape[1]
+            e, ne = _p(ea), ea.shape[0]
+        self._chk(self.L.so_register(self.h, _p(s), s.shape[0], e, ne, stride, 12 if s.shape[1] >= 4 else stride,
                                      _p(pose), C.byref(o), C.byref(r)), "so_register")
         return r
+
+    def correspond_edge(self, edge_xyzi: np.ndarray, pose7):
+        e = np.ascontiguousarray(edge_xyzi, dtype=np.float32)
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        corr = np.zeros(e.shape[0], EDGE_CORR_DTYPE)
+        hr = np.zeros(7, np.int32)
+        stride = e.shape[1] * 4
+        self._chk(self.L.so_correspond_edge(self.h, _p(e), e.shape[0], stride, 12 if e.shape[1] >= 4 else stride, _p(pose), _p(corr), _p(hr)),
+                  "so_correspond_edge")
+        return corr, hr
 
     def register_batch(self, scans_xyzi: np.ndarray, n_points, poses, max_icp_iters: int, max_surface_features: int = 0, **kw):
         """scans_xyzi: float32 [sum(n_points), 4] host array (pinned or pageable)."""

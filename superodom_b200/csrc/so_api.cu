@@ -48,13 +48,20 @@ static void manual_yaw_correction(const double last[7], double T[7], double yaw_
 static inline int block_coord_h(double v, int origin) { int c = int(v / kBlock); if (v < 0) c--; return c + origin; }
 
 // LocalMap::get5x5LocalMapFeatureSize (LocalMap.h:291-318) on the host mirror of the block counts
-static int counts_5x5(const Ctx* c, const int32_t ijk[3]) {
+static int counts_5x5(const Ctx* c, const MapStore& ms, const int32_t ijk[3]) {
+    (void)c;
     int n = 0;
     for (int i = ijk[0] - 2; i <= ijk[0] + 2; ++i)
         for (int j = ijk[1] - 2; j <= ijk[1] + 2; ++j)
             for (int k = ijk[2] - 1; k <= ijk[2] + 1; ++k)
-                if (i >= 0 && i < kW && j >= 0 && j < kH && k >= 0 && k < kD) n += c->h_block_count[i + kW * j + kW * kH * k];
+                if (i >= 0 && i < kW && j >= 0 && j < kH && k >= 0 && k < kD) n += ms.h_block_count[i + kW * j + kW * kH * k];
     return n;
+}
+
+static int ensure_maps(Ctx* c) {
+    if (c->surf.dirty) { int rc = map_rebuild(c, c->surf); if (rc) return rc; }
+    if (c->edge.dirty) { int rc = map_rebuild(c, c->edge); if (rc) return rc; }
+    return SO_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- allocation
@@ -86,11 +93,22 @@ static int ctx_alloc(Ctx* c) {
     SO_CUDA_TRY(cudaMalloc(&c->d_state, c->max_batch * sizeof(IcpState)));
     SO_CUDA_TRY(cudaMallocHost(&c->h_state, c->max_batch * sizeof(IcpState)));
     SO_CUDA_TRY(cudaMallocHost(&c->h_offset, c->max_batch * sizeof(uint32_t)));
-    SO_CUDA_TRY(cudaMalloc(&c->d_partials, size_t(c->max_batch) * c->grid_x_cap * kAcc * sizeof(double)));
+    c->edge_cap = c->cfg.max_scan_points;
+    c->edge_grid_cap = uint32_t((c->edge_cap + kThreads - 1) / kThreads);
+    SO_CUDA_TRY(cudaMalloc(&c->d_partials, size_t(c->max_batch) * (c->grid_x_cap + c->edge_grid_cap) * kAcc * sizeof(double)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_escan, c->edge_cap * sizeof(float4)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_eoffset, c->max_batch * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMemset(c->d_eoffset, 0, c->max_batch * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->ebuf.a, c->edge_cap * sizeof(double4)));
+    SO_CUDA_TRY(cudaMalloc(&c->ebuf.b, c->edge_cap * sizeof(double4)));
+    SO_CUDA_TRY(cudaMalloc(&c->ebuf.flags, c->edge_cap * sizeof(uchar4)));
+    SO_CUDA_TRY(cudaMalloc(&c->ebuf.nn, c->edge_cap * 10 * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->ebuf.selmask, c->edge_cap * sizeof(uint32_t)));
+    c->ebuf.scan = c->d_escan; c->ebuf.offset = c->d_eoffset;
     SO_CUDA_TRY(cudaMalloc(&c->d_counters, c->max_batch * sizeof(uint32_t)));
-    SO_CUDA_TRY(cudaMalloc(&c->d_hist, c->max_batch * 16 * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_hist, c->max_batch * kHistStride * sizeof(int32_t)));
     SO_CUDA_TRY(cudaMemset(c->d_counters, 0, c->max_batch * sizeof(uint32_t)));
-    SO_CUDA_TRY(cudaMemset(c->d_hist, 0, c->max_batch * 16 * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMemset(c->d_hist, 0, c->max_batch * kHistStride * sizeof(int32_t)));
     SO_CUDA_TRY(cudaMalloc(&c->corr.nd, c->scan_cap * sizeof(double4)));
     SO_CUDA_TRY(cudaMalloc(&c->corr.w, c->scan_cap * sizeof(double)));
     SO_CUDA_TRY(cudaMalloc(&c->corr.flags, c->scan_cap * sizeof(uchar4)));
@@ -111,6 +129,7 @@ static void ctx_free(Ctx* c) {
     cudaFree(c->d_sort_tmp); cudaFree(c->nn.pos); cudaFree(c->nn.pts); cudaFree(c->nn.d5); cudaFree(c->nn.pre);
     cudaFree(c->d_scan); cudaFree(c->d_offset); cudaFree(c->d_state); cudaFreeHost(c->h_state); cudaFreeHost(c->h_offset);
     cudaFree(c->d_partials); cudaFree(c->d_counters); cudaFree(c->d_hist);
+    cudaFree(c->d_escan); cudaFree(c->d_eoffset); cudaFree(c->ebuf.a); cudaFree(c->ebuf.b); cudaFree(c->ebuf.flags); cudaFree(c->ebuf.nn); cudaFree(c->ebuf.selmask);
     cudaFree(c->corr.nd); cudaFree(c->corr.w); cudaFree(c->corr.flags); cudaFree(c->corr.nn); cudaFree(c->corr.nn_d2);
     cudaFree(c->d_q); cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2);
     cudaFree(c->d_qkeys); cudaFree(c->d_qkeys_out); cudaFree(c->d_qvals); cudaFree(c->d_qvals_out); cudaFree(c->d_qsort_tmp);
@@ -160,9 +179,12 @@ static int upload_cloud(Ctx* c, const void* src, size_t n, size_t stride, size_t
 static BatchView batch_view(const Ctx* c, const float4* scan, uint32_t first = 0) {
     BatchView bv;
     bv.scan = scan; bv.offset = c->d_offset + first; bv.st = c->d_state + first;
-    bv.partials = c->d_partials + size_t(first) * c->grid_x_cap * kAcc; bv.partial_stride = c->grid_x_cap; bv.hist = c->d_hist + size_t(first) * 16;
-    const double a = double(std::sqrt(3 * c->plane_res));     // float sqrt of a float product (LidarSlam.cpp:271)
+    bv.partial_stride = c->grid_x_cap + c->edge_grid_cap; bv.edge_partial_offset = c->grid_x_cap;
+    bv.partials = c->d_partials + size_t(first) * bv.partial_stride * kAcc; bv.hist = c->d_hist + size_t(first) * kHistStride;
+    const double a = double(std::sqrt(3 * c->surf.res));     // float sqrt of a float product (LidarSlam.cpp:271)
     bv.tukey_a2 = a * a;
+    const double al = double(std::sqrt(3 * c->edge.res));     // TukeyLoss(std::sqrt(3*lineRes_)) (LidarSlam.cpp:263)
+    bv.tukey_a2_line = al * al;
     return bv;
 }
 
@@ -181,11 +203,11 @@ static void timed_launch_end(Ctx* c, int cls) {
 }
 
 // A contiguous run of scans of the batch that is uploaded, ordered and registered together.
-struct Chunk { uint32_t first, count, pt_first, pt_count, grid_x; };
+struct Chunk { uint32_t first, count, pt_first, pt_count, grid_x, grid_e = 0; };
 
 // Once per registration: order every scan by map cell at its prior pose (k_scan_keys -> radix sort -> k_scan_gather).
 static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch) {
-    const MapView mv = map_view(c);
+    const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, d_scan_in, ch.first);
     timed_launch_begin(c);
     launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, ch.grid_x, ch.count, c->stream);
@@ -205,11 +227,14 @@ static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch) {
 // is done); fallback: the schedule unrolled max_icp_iters times.  Returns whether the loop form ran.
 static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn, bool* was_loop) {
     const float4* d_scan = c->d_scan_sorted;
-    const MapView mv = map_view(c);
+    const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, d_scan, ch.first);
     CorrBuf cb = c->corr;
     if (!with_nn) { cb.nn = nullptr; cb.nn_d2 = nullptr; }
-    const uint32_t grid_x = ch.grid_x, n_scans = ch.count;
+    const uint32_t grid_x = ch.grid_x, n_scans = ch.count, grid_e = ch.grid_e;
+    const MapView me = map_view(c, c->edge);
+    EdgeBuf eb = c->ebuf;
+    if (!with_nn) { eb.nn = nullptr; eb.selmask = nullptr; }
     *was_loop = false;
     if (c->profiling || with_nn) {
         // profiling mode: one launch at a time, timed with events, and only launches that have work (the host peeks
@@ -224,17 +249,17 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
         for (int it = 0; it < iters; ++it) {
             if (any_in(PH_CORR)) {
                 timed_launch_begin(c); launch_knn_scan(mv, bv, c->nn, grid_x, n_scans, c->stream); timed_launch_end(c, 0);
-                timed_launch_begin(c); launch_fit(mv, bv, cb, c->nn, grid_x, n_scans, c->stream); c->launches++; timed_launch_end(c, 4);
+                timed_launch_begin(c); launch_fit(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, &me, &eb, grid_e); c->launches += 1 + (grid_e ? 1 : 0); timed_launch_end(c, 4);
             }
             for (int k = 0; k < lm; ++k)
-                if (any_in(PH_EVAL)) { timed_launch_begin(c); launch_evaluate(bv, cb, grid_x, n_scans, c->stream); c->launches++; timed_launch_end(c, 1); }
+                if (any_in(PH_EVAL)) { timed_launch_begin(c); launch_evaluate(bv, cb, grid_x, n_scans, c->stream, &eb, grid_e); c->launches += 1 + (grid_e ? 1 : 0); timed_launch_end(c, 1); }
         }
         SO_CUDA_TRY(cudaGetLastError());
         return SO_OK;
     }
     Ctx::GraphSlot* slot = nullptr;
     for (auto& g : c->graphs)
-        if (g.exec && g.first == ch.first && g.count == n_scans && g.grid_x == grid_x && g.iters == iters && g.lm == lm && g.epoch == c->map_epoch) slot = &g;
+        if (g.exec && g.first == ch.first && g.count == n_scans && g.grid_x == grid_x && g.grid_e == grid_e && g.iters == iters && g.lm == lm && g.epoch == c->map_epoch) slot = &g;
     if (!slot) {
         slot = &c->graphs[0];
         for (auto& g : c->graphs) { if (!g.exec) { slot = &g; break; } if (g.used < slot->used) slot = &g; }
@@ -255,8 +280,8 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
                 cudaGraph_t body = p.conditional.phGraph_out[0];
                 ok = cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
                 if (ok) {
-                    launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream);
-                    for (int k = 0; k < lm; ++k) launch_evaluate(bv, cb, grid_x, n_scans, c->stream);
+                    launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, &me, &eb, grid_e);
+                    for (int k = 0; k < lm; ++k) launch_evaluate(bv, cb, grid_x, n_scans, c->stream, &eb, grid_e);
                     launch_loop_cond(bv, n_scans, handle, c->stream);
                     cudaGraph_t dummy = nullptr;
                     ok = cudaStreamEndCapture(c->stream, &dummy) == cudaSuccess;
@@ -271,29 +296,30 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
             cudaGraph_t g = nullptr;
             SO_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             for (int it = 0; it < iters; ++it) {
-                launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream);
-                for (int k = 0; k < lm; ++k) launch_evaluate(bv, cb, grid_x, n_scans, c->stream);
+                launch_correspond(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, &me, &eb, grid_e);
+                for (int k = 0; k < lm; ++k) launch_evaluate(bv, cb, grid_x, n_scans, c->stream, &eb, grid_e);
             }
             SO_CUDA_TRY(cudaStreamEndCapture(c->stream, &g));
             cudaError_t e = cudaGraphInstantiate(&slot->exec, g, 0);
             cudaGraphDestroy(g);
             if (e != cudaSuccess) { slot->exec = nullptr; return fail(SO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
         }
-        slot->first = ch.first; slot->count = n_scans; slot->grid_x = grid_x; slot->iters = iters; slot->lm = lm; slot->epoch = c->map_epoch;
+        slot->first = ch.first; slot->count = n_scans; slot->grid_x = grid_x; slot->grid_e = grid_e; slot->iters = iters; slot->lm = lm; slot->epoch = c->map_epoch;
     }
     slot->used = ++c->graph_clock;
     SO_CUDA_TRY(cudaGraphLaunch(slot->exec, c->stream));
     *was_loop = slot->is_loop;
-    if (!slot->is_loop) c->launches += uint64_t(iters) * (3 + 2 * lm);      // loop form: counted from the iterations executed
+    if (!slot->is_loop) c->launches += uint64_t(iters) * (3 + 2 * lm + (grid_e ? 1 + lm : 0));      // loop form: counted from the iterations executed
     return SO_OK;
 }
 
-static void init_state(IcpState& s, const double pose[7], uint32_t n, const so_icp_opts& o) {
+static void init_state(IcpState& s, const double pose[7], uint32_t n, const so_icp_opts& o, uint32_t n_edge = 0) {
     std::memset(&s, 0, sizeof(s));
     std::memcpy(s.x0, pose, 7 * sizeof(double));
     std::memcpy(s.x, pose, 7 * sizeof(double));
     std::memcpy(s.cand, pose, 7 * sizeof(double));
     s.n_points = int32_t(n);
+    s.n_edge = int32_t(n_edge);
     s.max_icp_iters = o.max_icp_iters;
     s.lm_max_iterations = o.lm_max_iterations;
     // calculateSamplingRate (LidarSlam.cpp:346-351)
@@ -307,13 +333,13 @@ static void init_state(IcpState& s, const double pose[7], uint32_t n, const so_i
 static void fill_result(const Ctx* c, const IcpState& s, const double pose_in[7], const so_icp_opts& o, so_icp_result* r) {
     r->n_iterations = s.n_iterations;
     for (int i = 0; i < SO_MAX_ICP_ITERS; ++i) {
-        r->iter_n_surf[i] = s.iter_n_surf[i]; r->iter_n_edge[i] = 0; r->iter_dtrans[i] = s.iter_dtrans[i]; r->iter_drot[i] = s.iter_drot[i];
+        r->iter_n_surf[i] = s.iter_n_surf[i]; r->iter_n_edge[i] = s.iter_n_edge[i]; r->iter_dtrans[i] = s.iter_dtrans[i]; r->iter_drot[i] = s.iter_drot[i];
         r->iter_lm_steps[i] = s.iter_lm_steps[i]; r->iter_lm_successful[i] = s.iter_lm_successful[i];
         r->iter_lm_termination[i] = s.iter_lm_termination[i]; r->iter_cost[i] = s.iter_cost[i];
     }
     std::memcpy(r->hist_obs, s.hist_obs, sizeof(r->hist_obs));
     std::memcpy(r->hist_reject_plane, s.hist_rej, sizeof(r->hist_reject_plane));
-    std::memset(r->hist_reject_line, 0, sizeof(r->hist_reject_line));
+    std::memcpy(r->hist_reject_line, s.hist_rej_line, sizeof(r->hist_reject_line));
     std::memcpy(r->cov, s.cov, sizeof(r->cov));
     r->pos_err = s.pos_err; r->pos_inv_cond = s.pos_inv_cond; r->ori_err_deg = s.ori_err_deg; r->ori_inv_cond = s.ori_inv_cond;
     for (int i = 0; i < 3; ++i) { r->pos_dir[i] = s.pos_dir[i]; r->ori_dir[i] = s.ori_dir[i]; }
@@ -334,12 +360,13 @@ static void fill_result(const Ctx* c, const IcpState& s, const double pose_in[7]
 // d_scan: device scans (packed, back to back).  host_src != nullptr: the scans are still on the host (packed float4); this
 // function uploads them into d_scan chunk by chunk on the copy stream.
 static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points, size_t n_scans, const double* poses,
-                         const so_icp_opts* opts_in, so_icp_result* results, bool allow_shift, const void* host_src = nullptr) {
+                         const so_icp_opts* opts_in, so_icp_result* results, bool allow_shift, const void* host_src = nullptr,
+                         uint32_t n_edge0 = 0) {
     so_icp_opts o = *opts_in;
     if (o.lm_max_iterations <= 0) o.lm_max_iterations = 4;
     if (o.max_icp_iters <= 0 || o.max_icp_iters > SO_MAX_ICP_ITERS) return fail(SO_ERR_ARG, "max_icp_iters must be in [1,32]");
     if (o.lm_max_iterations > 16) return fail(SO_ERR_ARG, "lm_max_iterations must be <= 16");
-    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
+    { int rc = ensure_maps(c); if (rc) return rc; }
     uint32_t max_n = 0, off = 0;
     bool any = false;
     for (size_t s = 0; s < n_scans; ++s) {
@@ -354,8 +381,9 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         if (allow_shift && !o.skip_map_checks) { int rc = so_map_shift(reinterpret_cast<so_ctx*>(c), pose, ijk); if (rc < 0) return rc; }
         else for (int a = 0; a < 3; ++a) ijk[a] = block_coord_h(pose[a] + kHalfBlock, c->origin[a]);
         for (int a = 0; a < 3; ++a) r->pos_in_localmap[a] = ijk[a];
-        r->map_surf_5x5 = counts_5x5(c, ijk);
-        init_state(c->h_state[s], pose, n_points[s], o);
+        r->map_surf_5x5 = counts_5x5(c, c->surf, ijk);
+        r->map_edge_5x5 = counts_5x5(c, c->edge, ijk);
+        init_state(c->h_state[s], pose, n_points[s], o, s == 0 ? n_edge0 : 0);
         c->h_offset[s] = off;
         off += n_points[s];
         if (!o.skip_map_checks && !(r->map_surf_5x5 > 50)) {       // hasEnoughFeatures (:379-381): pose stays the prior
@@ -380,6 +408,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             uint32_t mx = 0;
             for (uint32_t s = f; s < e; ++s) if (c->h_state[s].phase == PH_CORR) mx = std::max(mx, n_points[s]);
             ch.grid_x = (mx + kThreads - 1) / kThreads;
+            if (f == 0 && n_edge0 && c->h_state[0].phase == PH_CORR) ch.grid_e = (n_edge0 + kThreads - 1) / kThreads;
             chunks.push_back(ch);
         }
         SO_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
@@ -417,7 +446,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             if (!loop_flags[k]) continue;
             int max_it = 0;
             for (uint32_t s = chunks[k].first; s < chunks[k].first + chunks[k].count; ++s) max_it = std::max(max_it, int(c->h_state[s].n_iterations));
-            c->launches += uint64_t(max_it) * uint64_t(4 + 2 * o.lm_max_iterations);
+            c->launches += uint64_t(max_it) * uint64_t(4 + 2 * o.lm_max_iterations + (chunks[k].grid_e ? 1 + o.lm_max_iterations : 0));
         }
         for (size_t s = 0; s < n_scans; ++s) {
             if (results[s].status == SO_STATUS_NOT_ENOUGH_FEATURES || n_points[s] == 0) continue;
@@ -460,8 +489,8 @@ so_ctx* so_create(const so_config* cfg_in) {
     Ctx* c = new Ctx();
     c->device = cfg.device;
     c->cfg = cfg;
-    if (cfg.plane_res > 0) c->plane_res = cfg.plane_res;
-    if (cfg.line_res > 0) c->line_res = cfg.line_res;
+    if (cfg.plane_res > 0) c->surf.res = cfg.plane_res;
+    if (cfg.line_res > 0) c->edge.res = cfg.line_res;
     if (std::getenv("SO_NO_COND_GRAPH")) c->no_cond_graph = true;      // profiling aid: ncu cannot see inside conditional-node bodies
     if (ctx_alloc(c) != SO_OK) { ctx_free(c); return nullptr; }
     return reinterpret_cast<so_ctx*>(c);
@@ -488,12 +517,17 @@ int so_set_stream(so_ctx* ctx, void* cuda_stream) {
 int so_map_set_resolution(so_ctx* ctx, float line_res, float plane_res) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !(plane_res > 0)) return fail(SO_ERR_ARG, "bad args");
-    if (line_res > 0) c->line_res = line_res;
-    if (plane_res != c->plane_res) {
-        const int nb_old = c->nb;
-        c->plane_res = plane_res;
+    if (line_res > 0 && line_res != c->edge.res) {
+        const int nb_old = c->edge.nb;
+        c->edge.res = line_res;
+        c->map_epoch++;
+        if (map_cells_per_block(line_res) != nb_old) c->edge.dirty = true;
+    }
+    if (plane_res != c->surf.res) {
+        const int nb_old = c->surf.nb;
+        c->surf.res = plane_res;
         c->map_epoch++;                                     // bound_d2 / plane_res live in the captured MapView
-        if (map_cells_per_block(plane_res) != nb_old) c->map_dirty = true;
+        if (map_cells_per_block(plane_res) != nb_old) c->surf.dirty = true;
     }
     return SO_OK;
 }
@@ -507,7 +541,7 @@ int so_map_set_origin(so_ctx* ctx, const double t[3], int32_t out_origin[3]) {
         c->origin[a] = -cc;
         if (out_origin) out_origin[a] = c->origin[a];
     }
-    c->map_dirty = true;
+    c->surf.dirty = true; c->edge.dirty = true;
     return SO_OK;
 }
 
@@ -531,82 +565,106 @@ int so_map_shift(so_ctx* ctx, const double t[3], int32_t out_ijk[3]) {
     }
     if (shift[0] || shift[1] || shift[2]) {
         for (int a = 0; a < 3; ++a) c->origin[a] += shift[a];
-        c->map_dirty = true;
+        c->surf.dirty = true; c->edge.dirty = true;
     }
-    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
+    { int rc = ensure_maps(c); if (rc) return rc; }
     for (int a = 0; a < 3; ++a) out_ijk[a] = cc[a];
     return SO_OK;
 }
 
-int so_map_set_points(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff) {
-    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+static int store_set_points(Ctx* c, MapStore& ms, const void* xyzi, size_t n, size_t stride, size_t ioff) {
     if (!c || (!xyzi && n) || stride < 12) return fail(SO_ERR_ARG, "bad args");
     if (n > c->cfg.max_map_points) return fail(SO_ERR_CAPACITY, "map larger than so_config.max_map_points");
     SO_CUDA_TRY(cudaSetDevice(c->device));
-    int rc = upload_cloud(c, xyzi, n, stride, ioff, c->d_map_xyzi);
+    int rc = upload_cloud(c, xyzi, n, stride, ioff, ms.d_xyzi);
     if (rc) return rc;
-    c->map_n = uint32_t(n);
-    return map_rebuild(c);
+    ms.n = uint32_t(n);
+    return map_rebuild(c, ms);
+}
+static int store_add(Ctx* c, MapStore& ms, const void* xyzi, size_t n, size_t stride, size_t ioff, const double* pose) {
+    if (!c || (!xyzi && n) || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (size_t(ms.n) + n > c->cfg.max_map_points) return fail(SO_ERR_CAPACITY, "map + new points exceed so_config.max_map_points");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return SO_OK;
+    int rc = upload_cloud(c, xyzi, n, stride, ioff, ms.d_xyzi + ms.n);
+    if (rc) return rc;
+    if (pose) { rc = map_transform_tail(c, ms, uint32_t(n), pose); if (rc) return rc; }
+    timed_launch_begin(c);
+    rc = map_add_points(c, ms, uint32_t(n));
+    timed_launch_end(c, 3);
+    return rc;
 }
 
+int so_map_set_points(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    return c ? store_set_points(c, c->surf, xyzi, n, stride, ioff) : fail(SO_ERR_ARG, "null ctx");
+}
+int so_map_set_edge_points(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    return c ? store_set_points(c, c->edge, xyzi, n, stride, ioff) : fail(SO_ERR_ARG, "null ctx");
+}
 int so_map_add_surf(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (!c || (!xyzi && n) || stride < 12) return fail(SO_ERR_ARG, "bad args");
-    if (size_t(c->map_n) + n > c->cfg.max_map_points) return fail(SO_ERR_CAPACITY, "map + new points exceed so_config.max_map_points");
-    SO_CUDA_TRY(cudaSetDevice(c->device));
-    if (n == 0) return SO_OK;
-    int rc = upload_cloud(c, xyzi, n, stride, ioff, c->d_map_xyzi + c->map_n);
-    if (rc) return rc;
-    timed_launch_begin(c);
-    rc = map_add_surf(c, uint32_t(n));
-    timed_launch_end(c, 3);
-    return rc;
+    return c ? store_add(c, c->surf, xyzi, n, stride, ioff, nullptr) : fail(SO_ERR_ARG, "null ctx");
 }
-
+int so_map_add_edge(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    return c ? store_add(c, c->edge, xyzi, n, stride, ioff, nullptr) : fail(SO_ERR_ARG, "null ctx");
+}
 int so_map_add_scan(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff, const double pose[7]) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (!c || (!xyzi && n) || stride < 12 || !pose) return fail(SO_ERR_ARG, "bad args");
-    if (size_t(c->map_n) + n > c->cfg.max_map_points) return fail(SO_ERR_CAPACITY, "map + new points exceed so_config.max_map_points");
-    SO_CUDA_TRY(cudaSetDevice(c->device));
-    if (n == 0) return SO_OK;
-    int rc = upload_cloud(c, xyzi, n, stride, ioff, c->d_map_xyzi + c->map_n);
-    if (rc) return rc;
-    rc = map_transform_tail(c, uint32_t(n), pose);
-    if (rc) return rc;
-    timed_launch_begin(c);
-    rc = map_add_surf(c, uint32_t(n));
-    timed_launch_end(c, 3);
-    return rc;
+    if (!pose) return fail(SO_ERR_ARG, "bad args");
+    return c ? store_add(c, c->surf, xyzi, n, stride, ioff, pose) : fail(SO_ERR_ARG, "null ctx");
+}
+int so_map_add_scan_edge(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff, const double pose[7]) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!pose) return fail(SO_ERR_ARG, "bad args");
+    return c ? store_add(c, c->edge, xyzi, n, stride, ioff, pose) : fail(SO_ERR_ARG, "null ctx");
 }
 
 int so_map_counts_5x5(so_ctx* ctx, const int32_t ijk[3], int32_t* n_edge, int32_t* n_surf) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !ijk) return fail(SO_ERR_ARG, "bad args");
-    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
-    if (n_edge) *n_edge = 0;
-    if (n_surf) *n_surf = counts_5x5(c, ijk);
+    { int rc = ensure_maps(c); if (rc) return rc; }
+    if (n_edge) *n_edge = counts_5x5(c, c->edge, ijk);
+    if (n_surf) *n_surf = counts_5x5(c, c->surf, ijk);
     return SO_OK;
 }
 
-size_t so_map_size(so_ctx* ctx) { Ctx* c = reinterpret_cast<Ctx*>(ctx); return c ? c->map_n : 0; }
+size_t so_map_size(so_ctx* ctx) { Ctx* c = reinterpret_cast<Ctx*>(ctx); return c ? size_t(c->surf.n) + size_t(c->edge.n) : 0; }
 
 int so_map_download(so_ctx* ctx, int mode, const int32_t ijk[3], float* out, size_t cap, size_t* n_out) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !n_out) return fail(SO_ERR_ARG, "bad args");
+    if (mode == 1 && !ijk) return fail(SO_ERR_ARG, "mode 1 needs ijk");
     SO_CUDA_TRY(cudaSetDevice(c->device));
-    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
-    // raw order is (block, point id) already for set_points / add_surf output, so mode 0 is a plain copy
-    std::vector<float4> h(c->map_n);
-    if (c->map_n) SO_CUDA_TRY(cudaMemcpy(h.data(), c->d_map_xyzi, size_t(c->map_n) * sizeof(float4), cudaMemcpyDeviceToHost));
-    size_t k = 0;
-    for (uint32_t i = 0; i < c->map_n; ++i) {
-        if (mode == 1) {
-            if (!ijk) return fail(SO_ERR_ARG, "mode 1 needs ijk");
+    { int rc = ensure_maps(c); if (rc) return rc; }
+    // LocalMap::getAllLocalMap / get5x5LocalMap (LocalMap.h:647-687): cubes in index order, each cube's edge cloud then its surf cloud
+    std::vector<float4> he(c->edge.n), hs(c->surf.n);
+    if (c->edge.n) SO_CUDA_TRY(cudaMemcpy(he.data(), c->edge.d_xyzi, size_t(c->edge.n) * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (c->surf.n) SO_CUDA_TRY(cudaMemcpy(hs.data(), c->surf.d_xyzi, size_t(c->surf.n) * sizeof(float4), cudaMemcpyDeviceToHost));
+    struct Ref { int32_t lin; uint8_t kind; uint32_t idx; };
+    std::vector<Ref> refs;
+    refs.reserve(he.size() + hs.size());
+    auto push = [&](const std::vector<float4>& h, uint8_t kind) {
+        for (uint32_t i = 0; i < h.size(); ++i) {
             int g[3]; const float q[3] = {h[i].x, h[i].y, h[i].z};
             for (int a = 0; a < 3; ++a) g[a] = block_coord_h(double(q[a]) + kHalfBlock, c->origin[a]);
-            if (std::abs(g[0] - ijk[0]) > 2 || std::abs(g[1] - ijk[1]) > 2 || std::abs(g[2] - ijk[2]) > 1) continue;
+            if (mode == 1 && (std::abs(g[0] - ijk[0]) > 2 || std::abs(g[1] - ijk[1]) > 2 || std::abs(g[2] - ijk[2]) > 1)) continue;
+            refs.push_back(Ref{g[0] + kW * g[1] + kW * kH * g[2], kind, i});
         }
-        if (out && k < cap) std::memcpy(out + 4 * k, &h[i], sizeof(float4));
+    };
+    push(he, 0); push(hs, 1);
+    if (mode == 1) {    // get5x5LocalMap loops i (x) outermost, then j, then k: order by (i, j, k), not by the linear cube index
+        std::stable_sort(refs.begin(), refs.end(), [](const Ref& a, const Ref& b) {
+            const int ai = a.lin % kW, aj = (a.lin / kW) % kH, ak = a.lin / (kW * kH), bi = b.lin % kW, bj = (b.lin / kW) % kH, bk = b.lin / (kW * kH);
+            if (ai != bi) return ai < bi; if (aj != bj) return aj < bj; if (ak != bk) return ak < bk; return a.kind < b.kind; });
+    } else {
+        std::stable_sort(refs.begin(), refs.end(), [](const Ref& a, const Ref& b) { return a.lin != b.lin ? a.lin < b.lin : a.kind < b.kind; });
+    }
+    size_t k = 0;
+    for (const Ref& r : refs) {
+        if (out && k < cap) std::memcpy(out + 4 * k, r.kind ? &hs[r.idx] : &he[r.idx], sizeof(float4));
         ++k;
     }
     *n_out = k;
@@ -663,15 +721,17 @@ int so_scan_prefilter(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, si
 int so_register(so_ctx* ctx, const void* surf, size_t n_surf, const void* edge, size_t n_edge, size_t stride, size_t ioff,
                 const double pose_in[7], const so_icp_opts* opts, so_icp_result* out) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    (void)edge;
-    if (!c || !pose_in || !opts || !out || (!surf && n_surf) || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (!c || !pose_in || !opts || !out || (!surf && n_surf) || (!edge && n_edge) || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (n_edge > c->edge_cap) return fail(SO_ERR_CAPACITY, "edge cloud larger than so_config.max_scan_points");
     if (n_surf > c->cfg.max_scan_points) return fail(SO_ERR_CAPACITY, "scan larger than so_config.max_scan_points");
     SO_CUDA_TRY(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
     int rc = upload_cloud(c, surf, n_surf, stride, ioff, c->d_scan);
     if (rc) return rc;
     const uint32_t n = uint32_t(n_surf);
-    rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true);
+    rc = upload_cloud(c, edge, n_edge, stride, ioff, c->d_escan);       // edge branch input (empty upstream: featureExtraction.cpp:429-436)
+    if (rc) return rc;
+    rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true, nullptr, uint32_t(n_edge));
     if (rc) return rc;
     out->scan_edge_num = int32_t(n_edge);
     out->time_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -723,7 +783,7 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     if (!c || !surf || !pose || !corr || n == 0 || stride < 12) return fail(SO_ERR_ARG, "bad args");
     if (n > c->cfg.max_scan_points) return fail(SO_ERR_CAPACITY, "scan larger than so_config.max_scan_points");
     SO_CUDA_TRY(cudaSetDevice(c->device));
-    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
+    { int rc0 = ensure_maps(c); if (rc0) return rc0; }
     int rc = upload_cloud(c, surf, n, stride, ioff, c->d_scan);
     if (rc) return rc;
     so_icp_opts o{}; o.max_icp_iters = -1; o.lm_max_iterations = 4; o.max_surface_features = max_surface_features;
@@ -735,7 +795,7 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     const Chunk ch{0, 1, 0, uint32_t(n), grid_x};
     rc = prepare_scans(c, c->d_scan, ch);
     if (rc) return rc;
-    const MapView mv = map_view(c);
+    const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, c->d_scan_sorted);
     timed_launch_begin(c); launch_correspond(mv, bv, c->corr, c->nn, grid_x, 1, c->stream); c->launches += 2; timed_launch_end(c, 0);
     SO_CUDA_TRY(cudaGetLastError());
@@ -763,19 +823,61 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     return SO_OK;
 }
 
+int so_correspond_edge(so_ctx* ctx, const void* edge, size_t n, size_t stride, size_t ioff, const double pose[7], so_edge_corr* corr,
+                       int32_t hist_rej_line[7]) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !edge || !pose || !corr || n == 0 || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (n > c->edge_cap) return fail(SO_ERR_CAPACITY, "edge cloud larger than so_config.max_scan_points");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    { int rc0 = ensure_maps(c); if (rc0) return rc0; }
+    int rc = upload_cloud(c, edge, n, stride, ioff, c->d_escan);
+    if (rc) return rc;
+    so_icp_opts o{}; o.max_icp_iters = -1; o.lm_max_iterations = 4;
+    init_state(c->h_state[0], pose, 0, o, uint32_t(n));
+    c->h_offset[0] = 0;
+    SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    const uint32_t grid_e = (uint32_t(n) + kThreads - 1) / kThreads;
+    const MapView mv = map_view(c, c->surf), me = map_view(c, c->edge);
+    const BatchView bv = batch_view(c, c->d_scan_sorted);
+    timed_launch_begin(c);
+    launch_fit(mv, bv, c->corr, c->nn, 0, 1, c->stream, &me, &c->ebuf, grid_e);     // 0 plane CTAs: only the edge kernel + k_lm_step have work
+    c->launches += 2;
+    timed_launch_end(c, 4);
+    SO_CUDA_TRY(cudaGetLastError());
+    std::vector<double4> a(n), b(n); std::vector<uchar4> fl(n); std::vector<uint32_t> nn(n * 10), sel(n);
+    SO_CUDA_TRY(cudaMemcpyAsync(a.data(), c->ebuf.a, n * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(b.data(), c->ebuf.b, n * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(fl.data(), c->ebuf.flags, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(nn.data(), c->ebuf.nn, n * 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(sel.data(), c->ebuf.selmask, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; ++i) {
+        so_edge_corr& r = corr[i];
+        std::memset(&r, 0, sizeof(r));
+        r.a[0] = a[i].x; r.a[1] = a[i].y; r.a[2] = a[i].z; r.w = a[i].w; r.b[0] = b[i].x; r.b[1] = b[i].y; r.b[2] = b[i].z;
+        for (int k = 0; k < 10; ++k) r.nn[k] = nn[i * 10 + k];
+        r.selected_mask = sel[i]; r.status = fl[i].x; r.n_selected = fl[i].y;
+    }
+    if (hist_rej_line) std::memcpy(hist_rej_line, c->h_state[0].hist_rej_line, 7 * sizeof(int32_t));
+    return SO_OK;
+}
+
 int so_evaluate(so_ctx* ctx, const double pose[7], double H[36], double g[6], double* cost) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !pose) return fail(SO_ERR_ARG, "bad args");
     SO_CUDA_TRY(cudaSetDevice(c->device));
     IcpState& s = c->h_state[0];
     const uint32_t n = uint32_t(s.n_points);
-    if (n == 0) return fail(SO_ERR_ARG, "so_evaluate needs a preceding so_correspond");
+    const uint32_t grid_e = (uint32_t(s.n_edge) + kThreads - 1) / kThreads;
+    if (n == 0 && grid_e == 0) return fail(SO_ERR_ARG, "so_evaluate needs a preceding so_correspond / so_correspond_edge");
     std::memcpy(s.cand, pose, 7 * sizeof(double));
     s.phase = PH_EVAL; s.max_icp_iters = -1;
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
     const uint32_t grid_x = (n + kThreads - 1) / kThreads;
     const BatchView bv = batch_view(c, c->d_scan_sorted);
-    timed_launch_begin(c); launch_evaluate(bv, c->corr, grid_x, 1, c->stream); c->launches++; timed_launch_end(c, 1);
+    timed_launch_begin(c); launch_evaluate(bv, c->corr, grid_x, 1, c->stream, &c->ebuf, grid_e); c->launches++; timed_launch_end(c, 1);
     SO_CUDA_TRY(cudaGetLastError());
     SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
     SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -790,12 +892,12 @@ int so_knn_device(so_ctx* ctx, const void* d_q, size_t nq, int k, float max_d2, 
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !d_q || !d_idx || !d_d2 || k < 1 || k > 8) return fail(SO_ERR_ARG, "bad args");
     SO_CUDA_TRY(cudaSetDevice(c->device));
-    if (c->map_dirty) { int rc = map_rebuild(c); if (rc) return rc; }
+    { int rc0 = ensure_maps(c); if (rc0) return rc0; }
     if (nq == 0) return SO_OK;
     // Large query sets are first ordered by map cell (cell key -> radix sort); threads then take queries in that order and
     // write their answers at the caller's positions.  Small sets skip the ordering.
     const uint32_t* order = nullptr;
-    const MapView mv = map_view(c);
+    const MapView mv = map_view(c, c->surf);
     timed_launch_begin(c);
     if (nq >= 32768 && nq < (size_t(1) << 31)) {
         int rc = query_sort_reserve(c, nq);

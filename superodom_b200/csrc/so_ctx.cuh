@@ -20,33 +20,39 @@ void set_error(const std::string& s);
 
 struct ProfileSlot { double ms = 0.0; uint64_t launches = 0; };
 
+// One per-block cloud family of the LocalMap (surf or edge): points in id order, the sorted hash grid, block tables.
+struct MapStore {
+    float res = 0.4f;                              // planeRes_ (surf) / lineRes_ (edge): voxel leaf and gate / search radius
+    uint32_t n = 0;                                // points held (on-grid)
+    float4* d_xyzi = nullptr;                      // [max_map] id order, w = intensity
+    float4* d_sorted = nullptr;                    // [max_map] sorted by (slot, cell), w = bitcast(id)
+    int32_t* d_block_slot = nullptr;               // [4851]
+    int32_t* d_block_count = nullptr;              // [4851]
+    uint32_t* d_cell_start = nullptr;              // [cell_cap]
+    size_t cell_cap = 0;
+    std::vector<int32_t> h_block_count, h_block_slot;   // host mirrors
+    int n_slots = 0;
+    int nb = 64;                                   // cells per block axis
+    bool dirty = true;
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     so_config cfg{};
-    float plane_res = 0.4f, line_res = 0.2f;       // LocalMap defaults (LocalMap.h:761-762)
 
-    // ---- map: raw (id order) + sorted hash grid --------------------------------------------------------------
+    // ---- maps: raw (id order) + sorted hash grid; one store for surf points, one for edge points -------------------
     int32_t origin[3] = {kW / 2, kH / 2, kD / 2};  // LocalMap() ctor (LocalMap.h:141-144)
-    uint32_t map_n = 0;                            // points held (on-grid)
-    float4* d_map_xyzi = nullptr;                  // [max_map] id order, w = intensity
-    float4* d_map_sorted = nullptr;                // [max_map] sorted by (slot, cell), w = bitcast(id)
+    MapStore surf, edge;                           // psurf_pc_ / pedge_pc_ of every MapBlock
+    // scratch shared by both stores (builds are sequential on the context stream)
     uint64_t* d_keys = nullptr;                    // [max_map] sort keys (in)
     uint64_t* d_keys_out = nullptr;                // [max_map]
     uint32_t* d_vals = nullptr;                    // [max_map] ids (in)
     uint32_t* d_vals_out = nullptr;                // [max_map]
     int32_t* d_block_of_point = nullptr;           // [max_map] grid block of each raw point or -1
-    int32_t* d_block_slot = nullptr;               // [4851]
-    int32_t* d_block_count = nullptr;              // [4851]
-    uint32_t* d_cell_start = nullptr;              // [cell_cap + 1]
-    size_t cell_cap = 0;
     void* d_cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
-    std::vector<int32_t> h_block_count, h_block_slot;   // host mirrors
-    int n_slots = 0;
-    int nb = 64;                                   // cells per block axis
-    bool map_dirty = true;
 
     // ---- scans / correspondences / optimiser state -------------------------------------------------------------
     uint32_t max_batch = 1;
@@ -65,6 +71,9 @@ struct Ctx {
     uint32_t* d_counters = nullptr;
     int32_t* d_hist = nullptr;
     CorrBuf corr{};
+    // edge / line branch (single-scan so_register only)
+    size_t edge_cap = 0; uint32_t edge_grid_cap = 0;
+    float4* d_escan = nullptr; uint32_t* d_eoffset = nullptr; EdgeBuf ebuf{};
     uint32_t grid_x_cap = 0;
     void* h_stage = nullptr;                       // pinned staging for strided host clouds
     size_t h_stage_bytes = 0;
@@ -77,7 +86,7 @@ struct Ctx {
     // ---- CUDA graph cache for the ICP schedule (one entry per batch chunk shape) ------------------------------------
     struct GraphSlot {
         cudaGraphExec_t exec = nullptr;
-        uint32_t first = 0, count = 0, grid_x = 0; int iters = 0, lm = 0; uint64_t epoch = 0; bool is_loop = false; uint64_t used = 0;
+        uint32_t first = 0, count = 0, grid_x = 0, grid_e = 0; int iters = 0, lm = 0; uint64_t epoch = 0; bool is_loop = false; uint64_t used = 0;
     };
     GraphSlot graphs[8];
     uint64_t graph_clock = 0;
@@ -97,11 +106,11 @@ struct Ctx {
 // so_map.cu
 int map_alloc(Ctx* c);
 void map_free(Ctx* c);
-int map_add_surf(Ctx* c, uint32_t n_new);   // d_map_xyzi[map_n .. map_n+n_new) holds the new points: voxel-filter touched blocks, rebuild
-int map_transform_tail(Ctx* c, uint32_t n_new, const double pose[7]);   // sensor-frame tail points -> world frame
+int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new);   // ms.d_xyzi[n .. n+n_new) holds the new points: voxel-filter touched blocks, rebuild
+int map_transform_tail(Ctx* c, MapStore& ms, uint32_t n_new, const double pose[7]);   // sensor-frame tail points -> world frame
 int scan_voxel_filter(Ctx* c, uint32_t n, float leaf, uint32_t* n_out);   // d_scan -> d_scan_sorted (VoxelGrid on a scan)
-int map_rebuild(Ctx* c);                 // (re)bin, drop off-grid points, sort, build cell table
-MapView map_view(const Ctx* c);
+int map_rebuild(Ctx* c, MapStore& ms);    // (re)bin, drop off-grid points, sort, build cell table
+MapView map_view(const Ctx* c, const MapStore& ms);
 int map_cells_per_block(float plane_res);
 int scan_sort_alloc(Ctx* c);             // temp storage for the per-registration scan sort
 int query_sort(Ctx* c, size_t n);         // d_qkeys/d_qvals -> *_out (allocates on growth)

@@ -230,12 +230,44 @@ __device__ __forceinline__ void knn_cube(const MapView& m, const QueryCell& qc, 
         }
 }
 
+// In-block k-NN, radius-bounded (max_d2 > 0) or exact (max_d2 <= 0).  The select walk is complete up to
+// min(bound, (R*cs)^2); wider / unbounded searches then grow an unpruned cube until the k-th distance is provably final.
+template <int K>
+__device__ __forceinline__ void knn_search(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, float max_d2,
+                                           uint32_t* s_buf, TopK<K>& tk) {
+    const bool bounded = max_d2 > 0.f;
+    int R = m.R;
+    const float ring_d2 = float(R) * m.cs * float(R) * m.cs;
+    bool done = false;
+    if (bounded && max_d2 <= ring_d2) { tk.init(max_d2); knn_select<K>(m, qc, qx, qy, qz, -1.f, max_d2, s_buf, tk); done = true; }
+    else if (!bounded) {
+        tk.init(ring_d2 * 0.999f);
+        knn_select<K>(m, qc, qx, qy, qz, -1.f, ring_d2 * 0.999f, s_buf, tk);
+        done = tk.count() == K;                                      // K neighbours inside the guaranteed-complete radius
+    } else { const float r = sqrtf(max_d2); while (float(R) * m.cs < r && R < m.nb) ++R; }
+    while (!done) {
+        tk.init(bounded ? max_d2 : FLT_MAX);
+        knn_cube<K>(m, qc, qx, qy, qz, R, tk);
+        if (bounded) break;
+        float reach = FLT_MAX;
+        bool covers = true;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (qc.c[a] - R > 0) { covers = false; reach = fminf(reach, qc.f[a] + float(R) * m.cs); }
+            if (qc.c[a] + R < m.nb - 1) { covers = false; reach = fminf(reach, (m.cs - qc.f[a]) + float(R) * m.cs); }
+        }
+        if (covers) break;
+        if (tk.count() == K && tk.worst() < reach * reach * 0.999f) break;
+        R = (R < 4) ? R + 1 : R * 2;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // CTA reduction of kAcc doubles per thread into partials[scan][cta][kAcc].  Fixed thread->point mapping and fixed
 // reduction trees => run-to-run deterministic sums.  The cross-CTA sum and the optimiser step run in k_lm_step
 // (keeping that scalar FP64 code out of the per-point kernels saves ~70 registers per thread in them).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void reduce_to_partials(double acc[kAcc], const BatchView& bv, int s) {
+__device__ __forceinline__ void reduce_to_partials(double acc[kAcc], const BatchView& bv, int s, uint32_t slot_offset = 0) {
     __shared__ double s_red[kThreads / 32][kAcc];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -250,7 +282,7 @@ __device__ __forceinline__ void reduce_to_partials(double acc[kAcc], const Batch
         double v = 0.0;
 #pragma unroll
         for (int wv = 0; wv < kThreads / 32; ++wv) v += s_red[wv][threadIdx.x];
-        bv.partials[(size_t(s) * bv.partial_stride + blockIdx.x) * kAcc + threadIdx.x] = v;
+        bv.partials[(size_t(s) * bv.partial_stride + slot_offset + blockIdx.x) * kAcc + threadIdx.x] = v;
     }
 }
 
@@ -303,7 +335,8 @@ __device__ __noinline__ void covariance_and_errors(IcpState& st) {
 // End of one ceres::Solve == end of one ICP iteration (LidarSlam.cpp:134-146).
 __device__ __noinline__ void end_solve(IcpState& st) {
     const int it = st.icp_iter;
-    st.iter_n_surf[it] = st.n_ok;
+    st.iter_n_surf[it] = st.n_ok - st.n_ok_edge;
+    st.iter_n_edge[it] = st.n_ok_edge;
     rel_motion(st.x_iter_start, st.x, &st.iter_dtrans[it], &st.iter_drot[it]);      // recordIterationStats (:242-251)
     st.iter_lm_steps[it] = st.lm_iter;
     st.iter_lm_successful[it] = st.num_successful;
@@ -743,7 +776,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, Co
     }
     }
     __syncthreads();
-    if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&bv.hist[s * 16 + threadIdx.x], s_hist[threadIdx.x]);
+    if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&bv.hist[s * kHistStride + threadIdx.x], s_hist[threadIdx.x]);
 
     reduce_to_partials(acc, bv, s);
 }
@@ -789,11 +822,206 @@ __global__ void __launch_bounds__(kThreads, 2) k_evaluate(BatchView bv, CorrBuf 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Edge / line branch (a19; dormant upstream because featureExtraction emits an empty edge cloud, featureExtraction.cpp:429-436).
+// k_edge_fit: LidarSLAM::ComputeLineDistanceParameters (LidarSlam.cpp:402-435) for every edge point -- exact 10-NN in the
+// point's block of the EDGE map, LocalMap::nearestKSearchSpecificEdgePoint's best-line-by-inliers selection in float
+// (LocalMap.h:377-474), PCA of the selected points, the line gates and processLineResults (:438-493) -- plus the first
+// evaluation of EdgeAnalyticCostFunction (lidarOptimization.cpp:12-47) for the following solve.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void accumulate_edge(double acc[kAcc], const double a[3], const double b[3], double w, const double p[3],
+                                                const double lp[3], const double R[9], double a2_line) {
+    const double u[3] = {lp[0] - a[0], lp[1] - a[1], lp[2] - a[2]}, v[3] = {lp[0] - b[0], lp[1] - b[1], lp[2] - b[2]};
+    const double de[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+    const double den = sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+    const double r[3] = {(u[1] * v[2] - u[2] * v[1]) / den, (u[2] * v[0] - u[0] * v[2]) / den, (u[0] * v[1] - u[1] * v[0]) / den};
+    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double rho0, rho1;
+    if (s <= a2_line) { const double t = 1.0 - s / a2_line, t2 = t * t; rho0 = a2_line / 6.0 * (1.0 - t2 * t); rho1 = 0.5 * t2; }
+    else { rho0 = a2_line / 6.0; rho1 = 0.0; }
+    rho0 *= w; rho1 *= w;
+    // J = skew(b - a) [I, -R [p]x] / |a - b|
+    const double re[3] = {-de[0], -de[1], -de[2]};
+    const double K[9] = {0, -re[2], re[1], re[2], 0, -re[0], -re[1], re[0], 0};
+    const double Sp[9] = {0, -p[2], p[1], p[2], 0, -p[0], -p[1], p[0], 0};
+    double J[18];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        J[i * 6 + j] = K[i * 3 + j] / den;
+        double t = 0.0;
+        for (int k = 0; k < 3; ++k) { double rs = 0.0; for (int l = 0; l < 3; ++l) rs += R[k * 3 + l] * Sp[l * 3 + j]; t += K[i * 3 + k] * (-rs); }
+        J[i * 6 + 3 + j] = t / den;
+    }
+    int kk = 0;
+    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { acc[kk++] += rho1 * (J[i] * J[j] + J[6 + i] * J[6 + j] + J[12 + i] * J[12 + j]); }
+    for (int i = 0; i < 6; ++i) acc[21 + i] += rho1 * (J[i] * r[0] + J[6 + i] * r[1] + J[12 + i] * r[2]);
+    acc[27] += 0.5 * rho0;
+}
+
+__global__ void __launch_bounds__(kThreads) k_edge_fit(MapView m, BatchView bv, EdgeBuf eb, uint32_t partial_offset) {
+    const int s = blockIdx.y;
+    IcpState* st = bv.st + s;
+    if (st->phase != PH_CORR || st->n_edge == 0) return;
+    __shared__ double s_pose[7];
+    __shared__ double s_R[9];
+    __shared__ int s_hist[8];
+    __shared__ uint32_t s_buf[kBufCap * kThreads];
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
+    if (threadIdx.x < 8) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) qtoR(s_pose + 3, s_R);
+    __syncthreads();
+    const uint32_t n = uint32_t(st->n_edge);
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    double acc[kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+    if (i < n) {
+        const size_t gi = size_t(eb.offset[s]) + i;
+        const float4 sp = __ldg(&eb.scan[gi]);
+        const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+        double pf[3];
+        qrot(s_pose + 3, pin, pf);
+        pf[0] += s_pose[0]; pf[1] += s_pose[1]; pf[2] += s_pose[2];
+        const float qx = float(pf[0]), qy = float(pf[1]), qz = float(pf[2]);
+        int status = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
+        double ea[3] = {0, 0, 0}, ebb[3] = {0, 0, 0}, wq = 0.0;
+        int nsel = 0;
+        uint32_t selmask = 0;
+        TopK<10> tk;
+        tk.init(FLT_MAX);
+        QueryCell qc;
+        locate(m, qx, qy, qz, qc);
+        // "<10 points in the block": the reference indexes with size_t(-1) (LocalMap.h:404-419); treated as NOT_ENOUGH_NEIGHBORS
+        if (qc.slot >= 0 && qc.nblock >= 10) {
+            knn_search<10>(m, qc, qx, qy, qz, 0.f, s_buf, tk);
+            float P[10][3];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { const float4 c = __ldg(&m.pts[tk.pos[j]]); P[j][0] = c.x; P[j][1] = c.y; P[j][2] = c.z; }
+            // best line through the closest point by inlier count: float arithmetic in Eigen's evaluation order, no FMA contraction
+            const float thr = __fmul_rn(0.2f, 0.2f);
+            int best_n = 0;
+            for (int pi = 1; pi < 10; ++pi) {
+                float dx = __fsub_rn(P[pi][0], P[0][0]), dy = __fsub_rn(P[pi][1], P[0][1]), dz = __fsub_rn(P[pi][2], P[0][2]);
+                const float z2 = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
+                if (z2 > 0.f) { const float sq = __fsqrt_rn(z2); dx = __fdiv_rn(dx, sq); dy = __fdiv_rn(dy, sq); dz = __fdiv_rn(dz, sq); }
+                uint32_t mask = 0; int cnt = 0;
+                for (int ci = 1; ci < 10; ++ci) {
+                    bool ok;
+                    if (ci == pi) ok = true;
+                    else {
+                        const float vx = __fsub_rn(P[ci][0], P[0][0]), vy = __fsub_rn(P[ci][1], P[0][1]), vz = __fsub_rn(P[ci][2], P[0][2]);
+                        const float cx = __fsub_rn(__fmul_rn(vy, dz), __fmul_rn(vz, dy)), cy = __fsub_rn(__fmul_rn(vz, dx), __fmul_rn(vx, dz)),
+                                    cz = __fsub_rn(__fmul_rn(vx, dy), __fmul_rn(vy, dx));
+                        ok = __fadd_rn(__fmul_rn(cx, cx), __fadd_rn(__fmul_rn(cy, cy), __fmul_rn(cz, cz))) < thr;
+                    }
+                    if (ok) { mask |= 1u << ci; ++cnt; }
+                }
+                if (cnt > best_n) { best_n = cnt; selmask = mask; }
+            }
+            selmask |= 1u;                                               // the closest point is always kept, first
+            nsel = __popc(selmask);
+            const int last = 31 - __clz(selmask);
+            if (nsel < 4) status = SO_MATCH_NOT_ENOUGH_NEIGHBORS;                                 // validateNeighborSearch (:495-512)
+            else if (tk.d2[last] > __fmul_rn(3.f, m.plane_res)) status = SO_MATCH_NEIGHBORS_TOO_FAR;   // MapView::plane_res holds lineRes_ for the edge map
+            else {
+                // PCA of the selected points (computePCAForFeature, EdgeFeature branch, :749-790)
+                double mean[3] = {0, 0, 0};
+                for (int j = 0; j < 10; ++j) if (selmask >> j & 1) { mean[0] += double(P[j][0]); mean[1] += double(P[j][1]); mean[2] += double(P[j][2]); }
+                mean[0] /= double(nsel); mean[1] /= double(nsel); mean[2] /= double(nsel);
+                double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int j = 0; j < 10; ++j) if (selmask >> j & 1) {
+                    const double c0 = double(P[j][0]) - mean[0], c1 = double(P[j][1]) - mean[1], c2 = double(P[j][2]) - mean[2];
+                    S[0] += c0 * c0; S[1] += c0 * c1; S[2] += c0 * c2; S[4] += c1 * c1; S[5] += c1 * c2; S[8] += c2 * c2;
+                }
+                S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
+                double V[9], ev[3];
+                jacobi_eig<3, 12>(S, V, ev);
+                if (!(isfinite(ev[0]) && isfinite(ev[1]) && isfinite(ev[2]))) status = SO_MATCH_INVALID_NUMERICAL;
+                else if (ev[2] < 4.0 * ev[1]) status = SO_MATCH_BAD_PCA_STRUCTURE;
+                else {
+                    double dir[3] = {V[2], V[5], V[8]};                     // processLineResults (:438-493)
+                    const double dn = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+                    dir[0] /= dn; dir[1] /= dn; dir[2] /= dn;
+                    const double lim = double(__fmul_rn(3.f, m.plane_res));
+                    double msd = 0.0;
+                    bool ok = isfinite(dir[0]) && isfinite(dir[1]) && isfinite(dir[2]);
+                    if (!ok) status = SO_MATCH_INVALID_NUMERICAL;
+                    else {
+                        for (int j = 0; j < 10; ++j) if (selmask >> j & 1) {
+                            const double c[3] = {double(P[j][0]) - mean[0], double(P[j][1]) - mean[1], double(P[j][2]) - mean[2]};
+                            double sd = 0.0;
+                            for (int a2 = 0; a2 < 3; ++a2) {
+                                double Ac = 0.0;
+                                for (int b2 = 0; b2 < 3; ++b2) Ac += ((a2 == b2 ? 1.0 : 0.0) - dir[a2] * dir[b2]) * c[b2];
+                                sd += c[a2] * Ac;
+                            }
+                            if (ok && sd > lim) ok = false;
+                            msd += sd;
+                        }
+                        if (!ok) status = SO_MATCH_MSE_TOO_LARGE;
+                        else {
+                            msd /= double(nsel);
+                            wq = 1.0 - sqrt(msd / lim);
+                            for (int a2 = 0; a2 < 3; ++a2) { ea[a2] = 0.1 * dir[a2] + mean[a2]; ebb[a2] = -0.1 * dir[a2] + mean[a2]; }
+                            status = SO_MATCH_SUCCESS;
+                            accumulate_edge(acc, ea, ebb, wq, pin, pf, s_R, bv.tukey_a2_line);
+                        }
+                    }
+                }
+            }
+        }
+        atomicAdd(&s_hist[status], 1);
+        eb.a[gi] = make_double4(ea[0], ea[1], ea[2], wq);
+        eb.b[gi] = make_double4(ebb[0], ebb[1], ebb[2], 0.0);
+        eb.flags[gi] = make_uchar4((unsigned char)status, (unsigned char)nsel, 0, 0);
+        if (eb.nn) {
+#pragma unroll
+            for (int j = 0; j < 10; ++j) eb.nn[gi * 10 + j] = tk.id[j];
+            eb.selmask[gi] = selmask;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 7 && s_hist[threadIdx.x]) atomicAdd(&bv.hist[s * kHistStride + 16 + threadIdx.x], s_hist[threadIdx.x]);
+    reduce_to_partials(acc, bv, s, partial_offset);
+}
+
+__global__ void __launch_bounds__(kThreads) k_edge_evaluate(BatchView bv, EdgeBuf eb, uint32_t partial_offset) {
+    const int s = blockIdx.y;
+    IcpState* st = bv.st + s;
+    if (st->phase != PH_EVAL || st->n_edge == 0) return;
+    __shared__ double s_pose[7];
+    __shared__ double s_R[9];
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = st->cand[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) qtoR(s_pose + 3, s_R);
+    __syncthreads();
+    const uint32_t n = uint32_t(st->n_edge);
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    double acc[kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+    if (i < n) {
+        const size_t gi = size_t(eb.offset[s]) + i;
+        const double4 a = eb.a[gi];
+        if (a.w != 0.0) {
+            const double4 b = eb.b[gi];
+            const float4 sp = __ldg(&eb.scan[gi]);
+            const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+            double lp[3];
+            qrot(s_pose + 3, pin, lp);
+            lp[0] += s_pose[0]; lp[1] += s_pose[1]; lp[2] += s_pose[2];
+            const double aa[3] = {a.x, a.y, a.z}, bb[3] = {b.x, b.y, b.z};
+            accumulate_edge(acc, aa, bb, a.w, pin, lp, s_R, bv.tukey_a2_line);
+        }
+    }
+    reduce_to_partials(acc, bv, s, partial_offset);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // k_lm_step: one CTA per scan.  Sums the per-CTA partials of the preceding k_fit (AFTER == PH_CORR) or k_evaluate
 // (AFTER == PH_EVAL) in a fixed order, then one thread advances the optimiser / ICP state machine.
 // ------------------------------------------------------------------------------------------------------------------
 template <int AFTER>
-__global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partials) {
+__global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partials, uint32_t edge_partial_offset) {
     const int s = blockIdx.x;
     IcpState* st = bv.st + s;
     if (st->phase != AFTER) return;
@@ -806,6 +1034,8 @@ __global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partia
         const uint32_t np = (AFTER == PH_CORR) ? (uint32_t(st->n_points) + kThreads * kFitPts - 1) / (kThreads * kFitPts)
                                                : (uint32_t(st->n_points) + kThreads * kEvalPts - 1) / (kThreads * kEvalPts);
         for (uint32_t b = sub; b < np && b < n_partials; b += 4) v += base[size_t(b) * kAcc + comp];
+        const uint32_t ne = (uint32_t(st->n_edge) + kThreads - 1) / kThreads;          // edge branch partials (0 when no edge cloud)
+        for (uint32_t b = sub; b < ne; b += 4) v += base[size_t(edge_partial_offset + b) * kAcc + comp];
         s_red[sub][comp] = v;
     }
     __syncthreads();
@@ -814,10 +1044,12 @@ __global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partia
     if (threadIdx.x != 0) return;
     if (AFTER == PH_CORR) {
         // histograms of this ICP iteration (ResetDistanceParameters + processPlannerFeatures, :847-852,:336-341)
-        for (int k = 0; k < 9; ++k) st->hist_obs[k] = bv.hist[s * 16 + k];
-        for (int k = 0; k < 7; ++k) st->hist_rej[k] = bv.hist[s * 16 + 9 + k];
-        const int n_ok = st->hist_rej[0];
-        for (int k = 0; k < 16; ++k) bv.hist[s * 16 + k] = 0;
+        for (int k = 0; k < 9; ++k) st->hist_obs[k] = bv.hist[s * kHistStride + k];
+        for (int k = 0; k < 7; ++k) st->hist_rej[k] = bv.hist[s * kHistStride + 9 + k];
+        for (int k = 0; k < 7; ++k) st->hist_rej_line[k] = bv.hist[s * kHistStride + 16 + k];
+        st->n_ok_edge = st->hist_rej_line[0];
+        const int n_ok = st->hist_rej[0] + st->n_ok_edge;       // features_corres.size(): edges + planes
+        for (int k = 0; k < kHistStride; ++k) bv.hist[s * kHistStride + k] = 0;
         if (st->max_icp_iters < 0) {          // stage mode (so_correspond): stop here
             for (int k = 0; k < 21; ++k) st->H[k] = s_sum[k];
             for (int k = 0; k < 6; ++k) st->g[k] = s_sum[21 + k];
@@ -865,37 +1097,10 @@ __global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __res
     const size_t i = order ? size_t(order[j]) : j;        // thread j handles the j-th query in cell order, answers in caller order
     const float4 p = __ldg(&q[i]);
     TopK<K> tk;
-    const bool bounded = max_d2 > 0.f;
-    tk.init(bounded ? max_d2 : FLT_MAX);
+    tk.init(max_d2 > 0.f ? max_d2 : FLT_MAX);
     QueryCell qc;
     locate(m, p.x, p.y, p.z, qc);
-    if (qc.slot >= 0) {
-        // the select walk is complete up to min(bound, (R*cs)^2); wider / unbounded searches then grow an unpruned cube
-        int R = m.R;
-        const float ring_d2 = float(R) * m.cs * float(R) * m.cs;
-        bool done = false;
-        if (bounded && max_d2 <= ring_d2) { knn_select<K>(m, qc, p.x, p.y, p.z, -1.f, max_d2, s_buf, tk); done = true; }
-        else if (!bounded) {
-            tk.init(ring_d2 * 0.999f);
-            knn_select<K>(m, qc, p.x, p.y, p.z, -1.f, ring_d2 * 0.999f, s_buf, tk);
-            done = tk.count() == K;                                      // K neighbours inside the guaranteed-complete radius
-        } else { const float r = sqrtf(max_d2); while (float(R) * m.cs < r && R < m.nb) ++R; }
-        while (!done) {
-            tk.init(bounded ? max_d2 : FLT_MAX);
-            knn_cube<K>(m, qc, p.x, p.y, p.z, R, tk);
-            if (bounded) break;
-            float reach = FLT_MAX;
-            bool covers = true;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                if (qc.c[a] - R > 0) { covers = false; reach = fminf(reach, qc.f[a] + float(R) * m.cs); }
-                if (qc.c[a] + R < m.nb - 1) { covers = false; reach = fminf(reach, (m.cs - qc.f[a]) + float(R) * m.cs); }
-            }
-            if (covers) break;
-            if (tk.count() == K && tk.worst() < reach * reach * 0.999f) break;
-            R = (R < 4) ? R + 1 : R * 2;
-        }
-    }
+    if (qc.slot >= 0) knn_search<K>(m, qc, p.x, p.y, p.z, max_d2, s_buf, tk);
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         const bool ok = tk.id[j] != 0xFFFFFFFFu;
@@ -916,19 +1121,25 @@ void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* 
 void launch_knn_scan(const MapView& m, const BatchView& bv, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
     k_knn_scan<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, nb);
 }
-void launch_fit(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+// medge / eb / grid_e: edge branch (grid_e == 0: idle).  The edge kernel runs between the plane kernel and k_lm_step, which
+// sums the partials of both.
+void launch_fit(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st,
+                const MapView* medge, const EdgeBuf* eb, uint32_t grid_e) {
     const uint32_t gf = (grid_x + kFitPts - 1) / kFitPts;
-    k_fit<<<dim3(gf, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
-    k_lm_step<PH_CORR><<<n_scans, 128, 0, st>>>(bv, gf);
+    if (gf) k_fit<<<dim3(gf, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
+    if (grid_e) k_edge_fit<<<dim3(grid_e, n_scans), kThreads, 0, st>>>(*medge, bv, *eb, bv.edge_partial_offset);
+    k_lm_step<PH_CORR><<<n_scans, 128, 0, st>>>(bv, gf, bv.edge_partial_offset);
 }
-void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st,
+                       const MapView* medge, const EdgeBuf* eb, uint32_t grid_e) {
     launch_knn_scan(m, bv, nb, grid_x, n_scans, st);
-    launch_fit(m, bv, cb, nb, grid_x, n_scans, st);
+    launch_fit(m, bv, cb, nb, grid_x, n_scans, st, medge, eb, grid_e);
 }
-void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const EdgeBuf* eb, uint32_t grid_e) {
     const uint32_t gx = (grid_x + kEvalPts - 1) / kEvalPts;
-    k_evaluate<<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb);
-    k_lm_step<PH_EVAL><<<n_scans, 128, 0, st>>>(bv, gx);
+    if (gx) k_evaluate<<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb);
+    if (grid_e) k_edge_evaluate<<<dim3(grid_e, n_scans), kThreads, 0, st>>>(bv, *eb, bv.edge_partial_offset);
+    k_lm_step<PH_EVAL><<<n_scans, 128, 0, st>>>(bv, gx, bv.edge_partial_offset);
 }
 void launch_loop_cond(const BatchView& bv, uint32_t n_scans, cudaGraphConditionalHandle handle, cudaStream_t st) {
     k_loop_cond<<<1, 32, 0, st>>>(bv.st, n_scans, handle);

@@ -12,13 +12,28 @@ struct CorrBuf {
     float* nn_d2;       // optional [5 per point]
 };
 
+constexpr int kHistStride = 24;
+
+// edge / line branch buffers (single-scan registration only; batches carry no edge clouds)
+struct EdgeBuf {
+    const float4* scan;       // edge points, sensor frame
+    const uint32_t* offset;   // [n_scans] first edge point of each scan
+    double4* a;               // {point_a, residualCoefficient}; w == 0 for rejected points
+    double4* b;               // {point_b, 0}
+    uchar4* flags;            // {status, n_selected, 0, 0}
+    uint32_t* nn;             // optional [10 per point] neighbour ids (stage tests)
+    uint32_t* selmask;        // optional: bit j set = j-th neighbour kept by the best-line selection
+};
+
 struct BatchView {
     const float4* scan;       // all scans back to back
     const uint32_t* offset;   // [n_scans] first point of each scan
     IcpState* st;             // [n_scans]
     double* partials;         // [n_scans][partial_stride][kAcc] per-CTA sums of the last per-point kernel
     uint32_t partial_stride;  // CTAs per scan the partials buffer is laid out for
-    int32_t* hist;            // [n_scans][16] histogram accumulators (self-resetting): 9 obs + 7 rejection causes
+    int32_t* hist;            // [n_scans][kHistStride] histogram accumulators (self-resetting): 9 obs + 7 plane + 7 line rejection causes
+    uint32_t edge_partial_offset;   // first partial slot of the edge kernels
+    double tukey_a2_line;     // a^2 for edges, a = double(sqrtf(3*lineRes_))  (LidarSlam.cpp:263)
     double tukey_a2;          // a^2, a = double(sqrtf(3*planeRes_))  (LidarSlam.cpp:271)
 };
 
@@ -40,9 +55,11 @@ constexpr int kFitPts = SO_FIT_PTS;      // points per thread in k_fit
 void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st);
 void launch_knn_scan(const MapView& m, const BatchView& bv, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
-void launch_fit(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
-void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
-void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
+void launch_fit(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st,
+                const MapView* medge = nullptr, const EdgeBuf* eb = nullptr, uint32_t grid_e = 0);
+void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st,
+                       const MapView* medge = nullptr, const EdgeBuf* eb = nullptr, uint32_t grid_e = 0);
+void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const EdgeBuf* eb = nullptr, uint32_t grid_e = 0);
 void launch_loop_cond(const BatchView& bv, uint32_t n_scans, cudaGraphConditionalHandle handle, cudaStream_t st);
 void launch_query_keys(const MapView& m, const float4* q, size_t nq, uint32_t* keys, uint32_t* vals, cudaStream_t st);
 int launch_knn(const MapView& m, const float4* q, const uint32_t* order, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st);

@@ -40,6 +40,7 @@ struct IcpState {
     // --- inputs
     double x0[7];          // T_w_initial_guess
     int32_t n_points;
+    int32_t n_edge;        // edge points of this scan (0: edge branch idle, as upstream)
     int32_t max_icp_iters, lm_max_iterations;
     double sampling_rate;  // calculateSamplingRate(): <0 = keep all
     int32_t use_prior;     // addAbsolutePoseConstraints rows active (LidarSlam.cpp:281-298)
@@ -55,13 +56,14 @@ struct IcpState {
     int32_t phase, icp_iter, lm_iter, num_successful, num_unsuccessful, reuse_diagonal, consecutive_invalid, termination;
     // --- per-ICP-iteration bookkeeping
     double x_iter_start[7];
-    int32_t n_ok;
+    int32_t n_ok;          // accepted correspondences, edges + planes (features_corres.size())
+    int32_t n_ok_edge;
     // --- outputs
     int32_t status, n_iterations;
-    int32_t iter_n_surf[SO_MAX_ICP_ITERS];
+    int32_t iter_n_surf[SO_MAX_ICP_ITERS], iter_n_edge[SO_MAX_ICP_ITERS];
     double iter_dtrans[SO_MAX_ICP_ITERS], iter_drot[SO_MAX_ICP_ITERS], iter_cost[SO_MAX_ICP_ITERS];
     int32_t iter_lm_steps[SO_MAX_ICP_ITERS], iter_lm_successful[SO_MAX_ICP_ITERS], iter_lm_termination[SO_MAX_ICP_ITERS];
-    int32_t hist_obs[9], hist_rej[7];
+    int32_t hist_obs[9], hist_rej[7], hist_rej_line[7];
     double cov[36];
     double pos_err, pos_dir[3], pos_inv_cond, ori_err_deg, ori_dir[3], ori_inv_cond;
 };

@@ -94,25 +94,34 @@ __global__ void k_gather(const float4* __restrict__ raw, const uint32_t* __restr
     sorted[i] = make_float4(p.x, p.y, p.z, __uint_as_float(id));
 }
 
+static int store_alloc(Ctx* c, MapStore& ms) {
+    const size_t M = c->cfg.max_map_points;
+    SO_CUDA_TRY(cudaMalloc(&ms.d_xyzi, M * sizeof(float4)));
+    SO_CUDA_TRY(cudaMalloc(&ms.d_sorted, M * sizeof(float4)));
+    SO_CUDA_TRY(cudaMalloc(&ms.d_block_slot, kNumBlocks * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMalloc(&ms.d_block_count, kNumBlocks * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMemset(ms.d_block_slot, 0xFF, kNumBlocks * sizeof(int32_t)));
+    SO_CUDA_TRY(cudaMemset(ms.d_block_count, 0, kNumBlocks * sizeof(int32_t)));
+    ms.h_block_count.assign(kNumBlocks, 0);
+    ms.h_block_slot.assign(kNumBlocks, -1);
+    return SO_OK;
+}
+
 int map_alloc(Ctx* c) {
     const size_t M = c->cfg.max_map_points;
-    SO_CUDA_TRY(cudaMalloc(&c->d_map_xyzi, M * sizeof(float4)));
-    SO_CUDA_TRY(cudaMalloc(&c->d_map_sorted, M * sizeof(float4)));
+    int rc = store_alloc(c, c->surf);
+    if (rc) return rc;
+    rc = store_alloc(c, c->edge);
+    if (rc) return rc;
     SO_CUDA_TRY(cudaMalloc(&c->d_keys, M * sizeof(uint64_t)));
     SO_CUDA_TRY(cudaMalloc(&c->d_keys_out, M * sizeof(uint64_t)));
     SO_CUDA_TRY(cudaMalloc(&c->d_vals, M * sizeof(uint32_t)));
     SO_CUDA_TRY(cudaMalloc(&c->d_vals_out, M * sizeof(uint32_t)));
     SO_CUDA_TRY(cudaMalloc(&c->d_block_of_point, M * sizeof(int32_t)));
-    SO_CUDA_TRY(cudaMalloc(&c->d_block_slot, kNumBlocks * sizeof(int32_t)));
-    SO_CUDA_TRY(cudaMalloc(&c->d_block_count, kNumBlocks * sizeof(int32_t)));
-    SO_CUDA_TRY(cudaMemset(c->d_block_slot, 0xFF, kNumBlocks * sizeof(int32_t)));
-    SO_CUDA_TRY(cudaMemset(c->d_block_count, 0, kNumBlocks * sizeof(int32_t)));
-    c->h_block_count.assign(kNumBlocks, 0);
-    c->h_block_slot.assign(kNumBlocks, -1);
     // cub temp: the larger of sort / scan / select requirements at full capacity
     size_t a = 0, b = 0, d = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, c->d_keys, c->d_keys_out, c->d_vals, c->d_vals_out, int(M), 0, 64);
-    cub::DeviceSelect::Flagged(nullptr, d, c->d_map_xyzi, (uint8_t*)nullptr, c->d_map_sorted, (uint32_t*)nullptr, int(M));
+    cub::DeviceSelect::Flagged(nullptr, d, c->surf.d_xyzi, (uint8_t*)nullptr, c->surf.d_sorted, (uint32_t*)nullptr, int(M));
     const size_t max_cells = size_t(64) * 128 * 128 * 128 + 1;     // scan temp is tiny; size for a generous table
     cub::DeviceScan::ExclusiveSum(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, int(std::min<size_t>(max_cells, size_t(1) << 30)));
     c->cub_tmp_bytes = std::max(a, std::max(b, d)) + 256;
@@ -121,86 +130,87 @@ int map_alloc(Ctx* c) {
 }
 
 void map_free(Ctx* c) {
-    cudaFree(c->d_map_xyzi); cudaFree(c->d_map_sorted); cudaFree(c->d_keys); cudaFree(c->d_keys_out);
-    cudaFree(c->d_vals); cudaFree(c->d_vals_out); cudaFree(c->d_block_of_point); cudaFree(c->d_block_slot);
-    cudaFree(c->d_block_count); cudaFree(c->d_cell_start); cudaFree(c->d_cub_tmp);
+    for (MapStore* ms : {&c->surf, &c->edge}) {
+        cudaFree(ms->d_xyzi); cudaFree(ms->d_sorted); cudaFree(ms->d_block_slot); cudaFree(ms->d_block_count); cudaFree(ms->d_cell_start);
+    }
+    cudaFree(c->d_keys); cudaFree(c->d_keys_out); cudaFree(c->d_vals); cudaFree(c->d_vals_out); cudaFree(c->d_block_of_point); cudaFree(c->d_cub_tmp);
 }
 
-MapView map_view(const Ctx* c) {
+MapView map_view(const Ctx* c, const MapStore& ms) {
     MapView m;
-    m.pts = c->d_map_sorted; m.block_slot = c->d_block_slot; m.block_count = c->d_block_count; m.cell_start = c->d_cell_start;
+    m.pts = ms.d_sorted; m.block_slot = ms.d_block_slot; m.block_count = ms.d_block_count; m.cell_start = ms.d_cell_start;
     m.origin[0] = c->origin[0]; m.origin[1] = c->origin[1]; m.origin[2] = c->origin[2];
-    m.nb = c->nb; m.inv_cs = double(c->nb) / kBlock; m.cs = float(kBlock / double(c->nb));
-    m.bound_d2 = 3 * c->plane_res;        // float product (LidarSlam.cpp:526)
-    m.plane_res = c->plane_res;
-    m.R = map_rings(c->plane_res, c->nb);
+    m.nb = ms.nb; m.inv_cs = double(ms.nb) / kBlock; m.cs = float(kBlock / double(ms.nb));
+    m.bound_d2 = 3 * ms.res;        // float product (LidarSlam.cpp:526)
+    m.plane_res = ms.res;
+    m.R = map_rings(ms.res, ms.nb);
     return m;
 }
 
 // (Re)build the index from d_map_xyzi[0..map_n): bin to blocks under the current origin, drop off-grid points
 // (what LocalMap::shiftMap does to blocks rolled off the grid, LocalMap.h:169-287), sort, build the cell table.
-int map_rebuild(Ctx* c) {
+int map_rebuild(Ctx* c, MapStore& ms) {
     cudaStream_t st = c->stream;
-    c->nb = map_cells_per_block(c->plane_res);
+    ms.nb = map_cells_per_block(ms.res);
     c->map_epoch++;
-    c->map_dirty = false;
+    ms.dirty = false;
     const int3 origin = make_int3(c->origin[0], c->origin[1], c->origin[2]);
-    SO_CUDA_TRY(cudaMemsetAsync(c->d_block_count, 0, kNumBlocks * sizeof(int32_t), st));
-    std::fill(c->h_block_count.begin(), c->h_block_count.end(), 0);
-    std::fill(c->h_block_slot.begin(), c->h_block_slot.end(), -1);
-    c->n_slots = 0;
-    if (c->map_n == 0) {
-        SO_CUDA_TRY(cudaMemsetAsync(c->d_block_slot, 0xFF, kNumBlocks * sizeof(int32_t), st));
+    SO_CUDA_TRY(cudaMemsetAsync(ms.d_block_count, 0, kNumBlocks * sizeof(int32_t), st));
+    std::fill(ms.h_block_count.begin(), ms.h_block_count.end(), 0);
+    std::fill(ms.h_block_slot.begin(), ms.h_block_slot.end(), -1);
+    ms.n_slots = 0;
+    if (ms.n == 0) {
+        SO_CUDA_TRY(cudaMemsetAsync(ms.d_block_slot, 0xFF, kNumBlocks * sizeof(int32_t), st));
         SO_CUDA_TRY(cudaStreamSynchronize(st));
         return SO_OK;
     }
-    const uint32_t n = c->map_n;
+    const uint32_t n = ms.n;
     const uint32_t grid = (n + 255) / 256;
-    k_block_of<<<grid, 256, 0, st>>>(c->d_map_xyzi, n, origin, c->d_block_of_point, c->d_block_count);
+    k_block_of<<<grid, 256, 0, st>>>(ms.d_xyzi, n, origin, c->d_block_of_point, ms.d_block_count);
     c->launches++;
-    SO_CUDA_TRY(cudaMemcpyAsync(c->h_block_count.data(), c->d_block_count, kNumBlocks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SO_CUDA_TRY(cudaMemcpyAsync(ms.h_block_count.data(), ms.d_block_count, kNumBlocks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SO_CUDA_TRY(cudaStreamSynchronize(st));
     uint64_t kept = 0;
-    for (int b = 0; b < kNumBlocks; ++b) if (c->h_block_count[b] > 0) { c->h_block_slot[b] = c->n_slots++; kept += uint64_t(c->h_block_count[b]); }
-    SO_CUDA_TRY(cudaMemcpyAsync(c->d_block_slot, c->h_block_slot.data(), kNumBlocks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    for (int b = 0; b < kNumBlocks; ++b) if (ms.h_block_count[b] > 0) { ms.h_block_slot[b] = ms.n_slots++; kept += uint64_t(ms.h_block_count[b]); }
+    SO_CUDA_TRY(cudaMemcpyAsync(ms.d_block_slot, ms.h_block_slot.data(), kNumBlocks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (kept < n) {
         // compact away the points whose block rolled off the grid, preserving order (ids are ranks in this order)
         uint8_t* flags = reinterpret_cast<uint8_t*>(c->d_vals_out);
         uint32_t* d_num = reinterpret_cast<uint32_t*>(c->d_keys_out);
         k_flags<<<grid, 256, 0, st>>>(c->d_block_of_point, n, flags);
         size_t tmp = c->cub_tmp_bytes;
-        SO_CUDA_TRY(cub::DeviceSelect::Flagged(c->d_cub_tmp, tmp, c->d_map_xyzi, flags, c->d_map_sorted, d_num, int(n), st));
-        SO_CUDA_TRY(cudaMemcpyAsync(c->d_map_xyzi, c->d_map_sorted, kept * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        SO_CUDA_TRY(cub::DeviceSelect::Flagged(c->d_cub_tmp, tmp, ms.d_xyzi, flags, ms.d_sorted, d_num, int(n), st));
+        SO_CUDA_TRY(cudaMemcpyAsync(ms.d_xyzi, ms.d_sorted, kept * sizeof(float4), cudaMemcpyDeviceToDevice, st));
         c->launches += 3;
-        c->map_n = uint32_t(kept);
+        ms.n = uint32_t(kept);
     }
     if (kept == 0) { SO_CUDA_TRY(cudaStreamSynchronize(st)); return SO_OK; }
-    const uint32_t m = c->map_n;
-    const size_t cells = size_t(c->n_slots) * c->nb * c->nb * c->nb;
-    if (cells + 1 > c->cell_cap) {
+    const uint32_t m = ms.n;
+    const size_t cells = size_t(ms.n_slots) * ms.nb * ms.nb * ms.nb;
+    if (cells + 1 > ms.cell_cap) {
         SO_CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(c->d_cell_start);
-        c->d_cell_start = nullptr;
-        c->cell_cap = cells + 1 + cells / 4;
-        SO_CUDA_TRY(cudaMalloc(&c->d_cell_start, c->cell_cap * sizeof(uint32_t)));
+        cudaFree(ms.d_cell_start);
+        ms.d_cell_start = nullptr;
+        ms.cell_cap = cells + 1 + cells / 4;
+        SO_CUDA_TRY(cudaMalloc(&ms.d_cell_start, ms.cell_cap * sizeof(uint32_t)));
         size_t need = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, need, c->d_cell_start, c->d_cell_start, int(c->cell_cap));
+        cub::DeviceScan::ExclusiveSum(nullptr, need, ms.d_cell_start, ms.d_cell_start, int(ms.cell_cap));
         if (need > c->cub_tmp_bytes) {
             cudaFree(c->d_cub_tmp);
             c->cub_tmp_bytes = need + 256;
             SO_CUDA_TRY(cudaMalloc(&c->d_cub_tmp, c->cub_tmp_bytes));
         }
     }
-    SO_CUDA_TRY(cudaMemsetAsync(c->d_cell_start, 0, (cells + 1) * sizeof(uint32_t), st));
+    SO_CUDA_TRY(cudaMemsetAsync(ms.d_cell_start, 0, (cells + 1) * sizeof(uint32_t), st));
     const uint32_t g2 = (m + 255) / 256;
-    k_keys<<<g2, 256, 0, st>>>(c->d_map_xyzi, m, origin, c->d_block_slot, c->nb, double(c->nb) / kBlock, c->d_keys, c->d_vals, c->d_cell_start);
+    k_keys<<<g2, 256, 0, st>>>(ms.d_xyzi, m, origin, ms.d_block_slot, ms.nb, double(ms.nb) / kBlock, c->d_keys, c->d_vals, ms.d_cell_start);
     int bits = 1;
     while ((uint64_t(1) << bits) < uint64_t(cells)) ++bits;
     size_t tmp = c->cub_tmp_bytes;
     SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, tmp, c->d_keys, c->d_keys_out, c->d_vals, c->d_vals_out, int(m), 0, bits, st));
-    k_gather<<<g2, 256, 0, st>>>(c->d_map_xyzi, c->d_vals_out, m, c->d_map_sorted);
+    k_gather<<<g2, 256, 0, st>>>(ms.d_xyzi, c->d_vals_out, m, ms.d_sorted);
     tmp = c->cub_tmp_bytes;
-    SO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, tmp, c->d_cell_start, c->d_cell_start, int(cells + 1), st));
+    SO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, tmp, ms.d_cell_start, ms.d_cell_start, int(cells + 1), st));
     c->launches += 8;
     SO_CUDA_TRY(cudaGetLastError());
     SO_CUDA_TRY(cudaStreamSynchronize(st));
@@ -314,37 +324,37 @@ __global__ void k_transform_points(float4* __restrict__ pts, uint32_t n, const d
     pts[i] = p;
 }
 
-int map_transform_tail(Ctx* c, uint32_t n_new, const double pose[7]) {
+int map_transform_tail(Ctx* c, MapStore& ms, uint32_t n_new, const double pose[7]) {
     double* d_pose = reinterpret_cast<double*>(c->d_keys_out);               // scratch
     SO_CUDA_TRY(cudaMemcpyAsync(d_pose, pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_transform_points<<<(n_new + 255) / 256, 256, 0, c->stream>>>(c->d_map_xyzi + c->map_n, n_new, d_pose);
+    k_transform_points<<<(n_new + 255) / 256, 256, 0, c->stream>>>(ms.d_xyzi + ms.n, n_new, d_pose);
     c->launches++;
     SO_CUDA_TRY(cudaStreamSynchronize(c->stream));                           // `pose` is caller memory
     return SO_OK;
 }
 
-int map_add_surf(Ctx* c, uint32_t n_new) {
+int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new) {
     cudaStream_t st = c->stream;
-    const uint32_t total = c->map_n + n_new;
+    const uint32_t total = ms.n + n_new;
     if (n_new == 0) return SO_OK;
     const int3 origin = make_int3(c->origin[0], c->origin[1], c->origin[2]);
     const uint32_t grid = (total + 255) / 256;
     uint8_t* d_touched = reinterpret_cast<uint8_t*>(c->d_vals_out);          // scratch: 4851 bytes
-    SO_CUDA_TRY(cudaMemsetAsync(c->d_block_count, 0, kNumBlocks * sizeof(int32_t), st));
+    SO_CUDA_TRY(cudaMemsetAsync(ms.d_block_count, 0, kNumBlocks * sizeof(int32_t), st));
     SO_CUDA_TRY(cudaMemsetAsync(d_touched, 0, kNumBlocks, st));
-    k_block_of<<<grid, 256, 0, st>>>(c->d_map_xyzi, total, origin, c->d_block_of_point, c->d_block_count);
-    k_mark_touched<<<(n_new + 255) / 256, 256, 0, st>>>(c->d_block_of_point, c->map_n, total, d_touched);
+    k_block_of<<<grid, 256, 0, st>>>(ms.d_xyzi, total, origin, c->d_block_of_point, ms.d_block_count);
+    k_mark_touched<<<(n_new + 255) / 256, 256, 0, st>>>(c->d_block_of_point, ms.n, total, d_touched);
     std::vector<uint8_t> h_touched(kNumBlocks);
-    SO_CUDA_TRY(cudaMemcpyAsync(c->h_block_count.data(), c->d_block_count, kNumBlocks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SO_CUDA_TRY(cudaMemcpyAsync(ms.h_block_count.data(), ms.d_block_count, kNumBlocks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SO_CUDA_TRY(cudaMemcpyAsync(h_touched.data(), d_touched, kNumBlocks, cudaMemcpyDeviceToHost, st));
     SO_CUDA_TRY(cudaStreamSynchronize(st));
     uint64_t n_untouched = 0, n_touched = 0;
-    for (int b = 0; b < kNumBlocks; ++b) (h_touched[b] ? n_touched : n_untouched) += uint64_t(c->h_block_count[b]);
+    for (int b = 0; b < kNumBlocks; ++b) (h_touched[b] ? n_touched : n_untouched) += uint64_t(ms.h_block_count[b]);
     // keys need the touched flags: keep them in a scratch that the sort does not use
     uint8_t* d_touched2 = reinterpret_cast<uint8_t*>(c->d_cub_tmp);
     SO_CUDA_TRY(cudaMemcpyAsync(d_touched2, h_touched.data(), kNumBlocks, cudaMemcpyHostToDevice, st));
-    const float inv_leaf = 1.0f / c->plane_res;                               // Eigen::Array4f::Ones() / leaf_size_
-    k_voxel_keys<<<grid, 256, 0, st>>>(c->d_map_xyzi, c->d_block_of_point, d_touched2, total, inv_leaf, c->d_keys, c->d_vals);
+    const float inv_leaf = 1.0f / ms.res;                               // Eigen::Array4f::Ones() / leaf_size_
+    k_voxel_keys<<<grid, 256, 0, st>>>(ms.d_xyzi, c->d_block_of_point, d_touched2, total, inv_leaf, c->d_keys, c->d_vals);
     SO_CUDA_TRY(cudaStreamSynchronize(st));                                   // d_cub_tmp is reused by the sort next
     size_t tmp = c->cub_tmp_bytes;
     SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, tmp, c->d_keys, c->d_keys_out, c->d_vals, c->d_vals_out, int(total), 0, 64, st));
@@ -361,15 +371,15 @@ int map_add_surf(Ctx* c, uint32_t n_new) {
         SO_CUDA_TRY(cudaMemcpyAsync(&last_rank, d_rank + n_touched - 1, 4, cudaMemcpyDeviceToHost, st));
         SO_CUDA_TRY(cudaStreamSynchronize(st));
         n_vox = last_rank + last_flag;
-        k_voxel_centroid<<<(end + 255) / 256, 256, 0, st>>>(c->d_map_xyzi, c->d_keys_out, c->d_vals_out, d_rank, begin, end, c->d_map_sorted);
+        k_voxel_centroid<<<(end + 255) / 256, 256, 0, st>>>(ms.d_xyzi, c->d_keys_out, c->d_vals_out, d_rank, begin, end, ms.d_sorted);
     } else if (begin) {
-        k_voxel_centroid<<<(begin + 255) / 256, 256, 0, st>>>(c->d_map_xyzi, c->d_keys_out, c->d_vals_out, nullptr, begin, begin, c->d_map_sorted);
+        k_voxel_centroid<<<(begin + 255) / 256, 256, 0, st>>>(ms.d_xyzi, c->d_keys_out, c->d_vals_out, nullptr, begin, begin, ms.d_sorted);
     }
-    c->map_n = begin + n_vox;
-    if (c->map_n) SO_CUDA_TRY(cudaMemcpyAsync(c->d_map_xyzi, c->d_map_sorted, size_t(c->map_n) * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    ms.n = begin + n_vox;
+    if (ms.n) SO_CUDA_TRY(cudaMemcpyAsync(ms.d_xyzi, ms.d_sorted, size_t(ms.n) * sizeof(float4), cudaMemcpyDeviceToDevice, st));
     c->launches += 12;
     SO_CUDA_TRY(cudaGetLastError());
-    return map_rebuild(c);
+    return map_rebuild(c, ms);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

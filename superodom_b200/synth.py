@@ -169,6 +169,47 @@ def sample_surfaces(scene: Scene, pitch: float, seed: int = 1234, noise: float =
     return pts.astype(np.float32)
 
 
+def sample_edges(scene: Scene, pitch: float, seed: int = 4321, noise: float = 0.01) -> np.ndarray:
+    """Points along the 12 edges of every box (the line features a curvature-based extractor would emit), float32 [M,3]."""
+    rng = np.random.default_rng(seed)
+    chunks = []
+    for b in scene.boxes:
+        x0, x1, y0, y1, z0, z1 = b
+        for (ax, lo, hi, others) in ((0, x0, x1, [(y, z) for y in (y0, y1) for z in (z0, z1)]),
+                                     (1, y0, y1, [(x, z) for x in (x0, x1) for z in (z0, z1)]),
+                                     (2, z0, z1, [(x, y) for x in (x0, x1) for y in (y0, y1)])):
+            n = max(2, int((hi - lo) / pitch))
+            t = lo + (np.arange(n) + 0.5) * (hi - lo) / n
+            for (u, v) in others:
+                p = np.zeros((n, 3))
+                p[:, ax] = t
+                oth = [a for a in range(3) if a != ax]
+                p[:, oth[0]] = u
+                p[:, oth[1]] = v
+                chunks.append(p)
+    pts = np.concatenate(chunks, 0) + rng.normal(0.0, noise, size=(sum(len(c) for c in chunks), 3))
+    return pts.astype(np.float32)
+
+
+def make_edge_map(scene: Scene, line_res: float) -> np.ndarray:
+    raw = sample_edges(scene, line_res)
+    xyzi = np.concatenate([raw, np.ones((len(raw), 1), np.float32)], 1)
+    return voxel_filter_blocks(xyzi, line_res)
+
+
+def make_edge_scan(edge_map_xyzi: np.ndarray, pose7: np.ndarray, seed: int, max_range: float = 30.0, keep_every: int = 3,
+                   noise: float = 0.01) -> np.ndarray:
+    """Edge points as the sensor would see them: nearby edge-map points, perturbed, expressed in the SENSOR frame."""
+    rng = np.random.default_rng(seed)
+    P = edge_map_xyzi[:, :3].astype(np.float64)
+    d = np.linalg.norm(P - pose7[:3], axis=1)
+    P = P[d < max_range][::keep_every]
+    P = P + rng.normal(0.0, noise, size=P.shape)
+    R = quat_to_R(pose7[3:])
+    local = (P - pose7[:3]) @ R                      # R^T (p - t)
+    return np.concatenate([local, np.ones((len(local), 1))], 1).astype(np.float32)
+
+
 # --------------------------------------------------------------------------
 # block binning + voxel-centroid filter (restates LocalMap.h:591-645 + pcl::VoxelGrid)
 # --------------------------------------------------------------------------

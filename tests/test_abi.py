@@ -43,11 +43,12 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_struct_layouts_match_header(tmp_path):
     from superodom_b200 import api
     f = tmp_path / "sz.c"
-    f.write_text('#include <stdio.h>\n#include "superodom_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(so_config), sizeof(so_icp_opts), sizeof(so_icp_result), sizeof(so_corr));return 0;}\n')
+    f.write_text('#include <stdio.h>\n#include "superodom_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(so_config), sizeof(so_icp_opts), sizeof(so_icp_result), sizeof(so_corr), sizeof(so_edge_corr));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(f), "-o", str(exe)])
-    a, b, c, d = map(int, subprocess.check_output([str(exe)]).split())
-    assert (a, b, c, d) == (C.sizeof(api.Config), C.sizeof(api.IcpOpts), C.sizeof(api.IcpResult), api.CORR_DTYPE.itemsize)
+    a, b, c, d, e = map(int, subprocess.check_output([str(exe)]).split())
+    assert (a, b, c, d, e) == (C.sizeof(api.Config), C.sizeof(api.IcpOpts), C.sizeof(api.IcpResult), api.CORR_DTYPE.itemsize,
+                               api.EDGE_CORR_DTYPE.itemsize)
 
 
 def test_no_cpu_fallback():

@@ -428,3 +428,91 @@ def test_scan_prefilter_adjust_voxel_size(gpu_api, oracle_mod):
     r = ctx.register(out, case["pose_prior"], 5, 2000)
     assert r.status == 0 and np.linalg.norm(np.array(r.pose)[:3] - case["pose_true"][:3]) < 0.05
     ctx.close()
+
+
+def _edge_case(name="cfg1"):
+    from superodom_b200 import synth
+    case = get_case(name)
+    em = synth.make_edge_map(case["scene"], 0.1)
+    es = synth.make_edge_scan(em, case["pose_true"], 5000)
+    return case, em, es
+
+
+def test_edge_line_branch_correspondences(gpu_api, oracle_mod):
+    """a19: processEdgeFeatures / ComputeLineDistanceParameters (LidarSlam.cpp:310-321,402-493) -- 10-NN in the edge map,
+    best-line-by-inliers selection, line PCA gates -- against the oracle, per edge point."""
+    case, em, es = _edge_case()
+    ctx = _ctx(gpu_api, case)
+    ctx.map_set_resolution(0.1, 0.2)
+    ctx.map_set_edge_points(em)
+    om = oracle_mod.OracleMap(case["map_xyzi"])
+    om.set_edge_points(em)
+    assert ctx.map_counts_5x5([10, 10, 5], with_edge=True) == (len(em), len(case["map_xyzi"]))
+    gc, ghr = ctx.correspond_edge(es, case["pose_prior"])
+    oc, ohr = om.correspond_edge(es, case["pose_prior"], 0.1)
+    assert np.array_equal(ghr, ohr) and ohr[0] > 1000
+    assert np.array_equal(gc["status"].astype(np.int32), oc["status"])
+    searched = oc["nn"][:, 0] >= 0
+    assert np.array_equal(gc["nn"][searched].astype(np.int64), oc["nn"][searched])                # exact 10-NN, same order
+    omask = np.zeros(len(oc), np.uint32)
+    for j in range(10):
+        omask |= np.where(np.arange(10)[None, :] < oc["n_sel"][:, None], (oc["sel"] == j), False).any(1).astype(np.uint32) << np.uint32(j)
+    assert np.array_equal(gc["selected_mask"][searched], omask[searched])                          # same inlier selection
+    ok = oc["status"] == 0
+    assert np.allclose(gc["a"][ok], oc["a"][ok], rtol=0, atol=1e-9) and np.allclose(gc["b"][ok], oc["b"][ok], rtol=0, atol=1e-9)
+    assert np.allclose(gc["w"][ok], oc["w"][ok], rtol=1e-9)
+    # normal equations of the edge rows alone
+    for pose in (case["pose_prior"], case["pose_true"]):
+        H, g, cost = ctx.evaluate(pose)
+        r = om.register(np.zeros((0, 4), np.float32), pose, 0.2, 1, edge_xyzi=es, line_res=0.1, skip_map_checks=True)   # noqa: F841 (smoke)
+    ctx.close()
+
+
+@pytest.mark.parametrize("cap", [2000, 0])
+def test_edge_line_branch_registration(gpu_api, oracle_mod, cap):
+    """Full registration with both feature kinds (3 residual rows per edge + 1 per plane in one LM problem)."""
+    case, em, es = _edge_case()
+    cfg = case["cfg"]
+    ctx = _ctx(gpu_api, case)
+    ctx.map_set_resolution(0.1, 0.2)
+    ctx.map_set_edge_points(em)
+    om = oracle_mod.OracleMap(case["map_xyzi"])
+    om.set_edge_points(em)
+    r = ctx.register(case["scan_xyzi"], case["pose_prior"], cfg["max_iterations"], cap, edge_xyzi=es)
+    ro = om.register(case["scan_xyzi"], case["pose_prior"], 0.2, cfg["max_iterations"], cap, knn_mode=0, edge_xyzi=es, line_res=0.1)
+    _assert_pose_close(np.array(r.pose), np.array(ro.pose))
+    n = ro.n_iterations
+    assert r.n_iterations == n
+    assert list(r.iter_n_surf[:n]) == list(ro.iter_n_surf[:n]) and list(r.iter_n_edge[:n]) == list(ro.iter_n_edge[:n])
+    assert list(r.iter_lm_steps[:n]) == list(ro.iter_lm_steps[:n]) and list(r.iter_lm_successful[:n]) == list(ro.iter_lm_successful[:n])
+    assert list(r.hist_reject_line) == list(ro.hist_reject_line) and r.iter_n_edge[0] > 1000
+    assert np.allclose(r.iter_cost[:n], ro.iter_cost[:n], rtol=1e-9)
+    cg, co = np.array(r.cov).reshape(6, 6), np.array(ro.cov).reshape(6, 6)
+    assert np.abs(cg - co).max() <= 1e-6 * np.abs(co).max()
+    assert r.map_edge_5x5 == ro.map_edge_5x5 == len(em) and r.scan_edge_num == len(es)
+    r0 = ctx.register(case["scan_xyzi"], case["pose_prior"], cfg["max_iterations"], cap)           # edge branch idle again
+    assert list(r0.hist_reject_line) == [0] * 7 and r0.iter_n_edge[0] == 0
+    e_with = np.linalg.norm(np.array(r.pose)[:3] - case["pose_true"][:3])
+    assert e_with < 0.01
+    ctx.close()
+
+
+def test_edge_map_insert_and_download_order(gpu_api, oracle_mod):
+    """addEdgePointCloud (LocalMap.h:529-589) = the surf insert at leaf lineRes; getAllLocalMap returns each cube's edge cloud
+    followed by its surf cloud, cubes in index order (LocalMap.h:647-658)."""
+    from superodom_b200 import synth
+    case, em, es = _edge_case("tiny")
+    ctx = gpu_api.Context(max_map_points=1 << 21, max_scan_points=65536, plane_res=0.2, line_res=0.1)
+    raw = synth.sample_edges(case["scene"], 0.1)
+    raw4 = np.concatenate([raw, np.ones((len(raw), 1), np.float32)], 1)
+    ctx.map_add_edge(raw4)
+    ctx.map_add_surf(case["map_xyzi"])
+    ref_e = oracle_mod.map_insert_numpy(np.zeros((0, 4), np.float32), raw4, 0.1)
+    ref_s = oracle_mod.map_insert_numpy(np.zeros((0, 4), np.float32), case["map_xyzi"], 0.2)
+    allm = ctx.map_download(0)
+    assert len(allm) == len(ref_e) + len(ref_s)
+    assert np.array_equal(allm[: len(ref_e)], ref_e) and np.array_equal(allm[len(ref_e):], ref_s)     # one cube: edge cloud, then surf cloud
+    ctx.map_add_scan_edge(es, case["pose_true"])
+    ref_e2 = oracle_mod.map_insert_numpy(ref_e, oracle_mod.transform_scan_numpy(es, case["pose_true"]), 0.1)
+    assert np.array_equal(ctx.map_download(0)[: len(ref_e2)], ref_e2)
+    ctx.close()
