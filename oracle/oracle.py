@@ -369,3 +369,11 @@ def adjust_voxel_size_numpy(scan_xyzi, line_res, plane_res, auto_voxel_size=True
         acc[seg[m]] = acc[seg[m]] + s[m]
     cnt = np.bincount(seg, minlength=nseg).astype(np.float32)
     return (acc / cnt[:, None]).astype(np.float32), float(np.float32(line_res)), float(np.float32(plane_res)), avg
+
+
+def cube_order(xyzi, origin=(10, 10, 5)):
+    """Stable permutation that lists a cloud cube by cube in cube-index order -- the order LocalMap::getAllLocalMap emits
+    (LocalMap.h:647-658) given per-cube clouds in their internal order."""
+    from superodom_b200 import synth
+    lin = synth.block_linear(synth.block_of(np.ascontiguousarray(xyzi, dtype=np.float32)[:, :3], origin))
+    return np.argsort(lin, kind="stable")

@@ -58,7 +58,7 @@ def test_shim_sequence_matches_abi_and_oracle(tmp_path, gpu_api, oracle_mod):
     ctx.map_add_scan(scans[0], priors[0])
     om_points = oracle_mod.map_insert_numpy(np.zeros((0, 4), np.float32), oracle_mod.transform_scan_numpy(scans[0], priors[0]), 0.2,
                                             origin=tuple(ctx.map_origin()))
-    assert np.array_equal(ctx.map_download(0), om_points)
+    assert np.array_equal(ctx.map_download(0), om_points[oracle_mod.cube_order(om_points, tuple(ctx.map_origin()))])
     assert np.allclose(rows[0][1:8], priors[0])
     for i in range(1, len(scans)):
         r = ctx.register(scans[i], priors[i], 5, 0)
@@ -73,7 +73,7 @@ def test_shim_sequence_matches_abi_and_oracle(tmp_path, gpu_api, oracle_mod):
         ctx.map_add_scan(scans[i], np.array(r.pose))
         om_points = oracle_mod.map_insert_numpy(om_points, oracle_mod.transform_scan_numpy(scans[i], np.array(r.pose)), 0.2,
                                                 origin=tuple(ctx.map_origin()))
-        assert np.array_equal(ctx.map_download(0), om_points)                         # voxel-filter insert: bit-exact vs the restatement
+        assert np.array_equal(ctx.map_download(0), om_points[oracle_mod.cube_order(om_points, tuple(ctx.map_origin()))])   # voxel-filter insert: bit-exact
         assert int(rows[i][10]) == len(om_points)
         # the map here is whatever the previous sparse VLP-16 scans inserted (weak floor coverage): only x, y are well observed
         assert np.linalg.norm(np.array(r.pose)[:2] - get_case("tiny", i)["pose_true"][:2]) < 0.03

@@ -344,13 +344,14 @@ def test_map_insert_voxel_filter_bit_exact(gpu_api, oracle_mod):
     b = np.concatenate([rng.uniform(-20, 20, size=(50000, 2)), rng.uniform(-2, 6, size=(50000, 1)), rng.uniform(0, 255, size=(50000, 1))], 1).astype(np.float32)
     ctx.map_add_surf(b)
     ref2 = oracle_mod.map_insert_numpy(ref, b, 0.4)
-    got2 = ctx.map_download(0)
-    assert got2.shape == ref2.shape and np.array_equal(got2, ref2)
+    got2 = ctx.map_download(0)                                # emitted cube by cube (getAllLocalMap order)
+    ref2_cubes = ref2[oracle_mod.cube_order(ref2)]
+    assert got2.shape == ref2.shape and np.array_equal(got2, ref2_cubes)
     lin_before = synth.block_linear(synth.block_of(ref[:, :3]))
     lin_after = synth.block_linear(synth.block_of(got2[:, :3]))
     centre = 10 + 21 * 10 + 21 * 21 * 5
-    untouched = lin_before != centre                          # blocks the second cloud did not reach keep their clouds verbatim
-    assert np.array_equal(got2[: untouched.sum()], ref[untouched]) and (lin_after[untouched.sum():] == centre).all()
+    for cube in np.unique(lin_before[lin_before != centre]):   # cubes the second cloud did not reach keep their clouds verbatim
+        assert np.array_equal(got2[lin_after == cube], ref[lin_before == cube])
     # the index over the new map answers k-NN exactly
     om = oracle_mod.OracleMap(ref2)
     q = ref2[::50, :3] + rng.normal(0, 0.05, size=ref2[::50, :3].shape).astype(np.float32)
@@ -459,7 +460,11 @@ def test_edge_line_branch_correspondences(gpu_api, oracle_mod):
         omask |= np.where(np.arange(10)[None, :] < oc["n_sel"][:, None], (oc["sel"] == j), False).any(1).astype(np.uint32) << np.uint32(j)
     assert np.array_equal(gc["selected_mask"][searched], omask[searched])                          # same inlier selection
     ok = oc["status"] == 0
-    assert np.allclose(gc["a"][ok], oc["a"][ok], rtol=0, atol=1e-9) and np.allclose(gc["b"][ok], oc["b"][ok], rtol=0, atol=1e-9)
+    # the line direction is an eigenvector: its sign is arbitrary, so (a, b) may come out swapped (the residual's J^T J, J^T r,
+    # |r|^2 are invariant under the swap)
+    same = np.abs(gc["a"][ok] - oc["a"][ok]).max(1) + np.abs(gc["b"][ok] - oc["b"][ok]).max(1)
+    swap = np.abs(gc["a"][ok] - oc["b"][ok]).max(1) + np.abs(gc["b"][ok] - oc["a"][ok]).max(1)
+    assert (np.minimum(same, swap) < 1e-9).all()
     assert np.allclose(gc["w"][ok], oc["w"][ok], rtol=1e-9)
     # normal equations of the edge rows alone
     for pose in (case["pose_prior"], case["pose_true"]):
