@@ -7,6 +7,7 @@
 //                  warp/CTA-reduced in FP64 (21+6+1 accumulators).                                  [K3+K4+K5]
 //   k_evaluate   : per correspondence -- residual, 1x6 Jacobian, Tukey/Scaled robust weight at the LM candidate pose,
 //                  same reduction.                                                          [K5]
+//   k_edge_fit / k_edge_evaluate : the edge / line branch (10-NN in the edge map, best-line selection, line factor).   [a19]
 //   k_lm_step    : fixed-order cross-CTA reduction, then ONE thread per scan advances the device-resident state
 //                  machine: Ceres' trust-region LM (step solve by 6x6 Cholesky, accept/reject, tolerances), the outer
 //                  ICP convergence rule, and at the end the covariance pseudo-inverse + 3x3 eigen analysis. [K6+K7]
