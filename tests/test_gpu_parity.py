@@ -464,7 +464,7 @@ def test_edge_line_branch_correspondences(gpu_api, oracle_mod):
     # |r|^2 are invariant under the swap)
     same = np.abs(gc["a"][ok] - oc["a"][ok]).max(1) + np.abs(gc["b"][ok] - oc["b"][ok]).max(1)
     swap = np.abs(gc["a"][ok] - oc["b"][ok]).max(1) + np.abs(gc["b"][ok] - oc["a"][ok]).max(1)
-    assert (np.minimum(same, swap) < 1e-9).all()
+    assert (np.minimum(same, swap) < 1e-7).all()          # eigenvector of a 2-10 point scatter: conditioning-limited
     assert np.allclose(gc["w"][ok], oc["w"][ok], rtol=1e-9)
     # normal equations of the edge rows alone
     for pose in (case["pose_prior"], case["pose_true"]):
