@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsuperodom_b200.so")
+LIB_PATH = os.environ.get("SO_LIB_PATH") or os.path.join(_HERE, "libsuperodom_b200.so")      # SO_LIB_PATH: A/B builds (scripts/)
 MAX_ICP_ITERS = 32
 
 EXPORTS = [

@@ -249,7 +249,7 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
         for (int it = 0; it < iters; ++it) {
             if (any_in(PH_CORR)) {
                 timed_launch_begin(c); launch_knn_scan(mv, bv, c->nn, grid_x, n_scans, c->stream); timed_launch_end(c, 0);
-                timed_launch_begin(c); launch_fit(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, &me, &eb, grid_e); c->launches += 1 + (grid_e ? 1 : 0); timed_launch_end(c, 4);
+                timed_launch_begin(c); launch_fit(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, &me, &eb, grid_e); c->launches += 1 + kFitSplit + (grid_e ? 1 : 0); timed_launch_end(c, 4);
             }
             for (int k = 0; k < lm; ++k)
                 if (any_in(PH_EVAL)) { timed_launch_begin(c); launch_evaluate(bv, cb, grid_x, n_scans, c->stream, &eb, grid_e); c->launches += 1 + (grid_e ? 1 : 0); timed_launch_end(c, 1); }
@@ -309,7 +309,7 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
     slot->used = ++c->graph_clock;
     SO_CUDA_TRY(cudaGraphLaunch(slot->exec, c->stream));
     *was_loop = slot->is_loop;
-    if (!slot->is_loop) c->launches += uint64_t(iters) * (3 + 2 * lm + (grid_e ? 1 + lm : 0));      // loop form: counted from the iterations executed
+    if (!slot->is_loop) c->launches += uint64_t(iters) * (3 + kFitSplit + 2 * lm + (grid_e ? 1 + lm : 0));      // loop form: counted from the iterations executed
     return SO_OK;
 }
 
@@ -446,7 +446,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             if (!loop_flags[k]) continue;
             int max_it = 0;
             for (uint32_t s = chunks[k].first; s < chunks[k].first + chunks[k].count; ++s) max_it = std::max(max_it, int(c->h_state[s].n_iterations));
-            c->launches += uint64_t(max_it) * uint64_t(4 + 2 * o.lm_max_iterations + (chunks[k].grid_e ? 1 + o.lm_max_iterations : 0));
+            c->launches += uint64_t(max_it) * uint64_t(4 + kFitSplit + 2 * o.lm_max_iterations + (chunks[k].grid_e ? 1 + o.lm_max_iterations : 0));
         }
         for (size_t s = 0; s < n_scans; ++s) {
             if (results[s].status == SO_STATUS_NOT_ENOUGH_FEATURES || n_points[s] == 0) continue;
@@ -797,7 +797,7 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     if (rc) return rc;
     const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, c->d_scan_sorted);
-    timed_launch_begin(c); launch_correspond(mv, bv, c->corr, c->nn, grid_x, 1, c->stream); c->launches += 2; timed_launch_end(c, 0);
+    timed_launch_begin(c); launch_correspond(mv, bv, c->corr, c->nn, grid_x, 1, c->stream); c->launches += 2 + kFitSplit; timed_launch_end(c, 0);
     SO_CUDA_TRY(cudaGetLastError());
     std::vector<double4> nd(n); std::vector<double> w(n); std::vector<uchar4> fl(n); std::vector<uint32_t> nn(n * 5); std::vector<float> d2(n * 5);
     std::vector<float4> sorted(n);

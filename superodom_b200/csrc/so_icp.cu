@@ -269,21 +269,33 @@ __device__ __forceinline__ void knn_search(const MapView& m, const QueryCell& qc
 // (keeping that scalar FP64 code out of the per-point kernels saves ~70 registers per thread in them).
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void reduce_to_partials(double acc[kAcc], const BatchView& bv, int s, uint32_t slot_offset = 0) {
-    __shared__ double s_red[kThreads / 32][kAcc];
+    static_assert(kAcc <= 32, "one component per lane");
+    __shared__ double s_red[kThreads / 32][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // Warp stage: a halving butterfly.  At distance o each lane keeps the half of its (padded to 32) components that matches
+    // its lane bit, hands the other half to its partner and adds what it receives, so lane l ends up with the warp total of
+    // component l after 16+8+4+2+1 = 31 FP64 shuffles -- the SHFL pipe (one warp-wide shuffle per clock per SM) was the
+    // cost of the plain 28 x 5 butterfly.
+    double v[32];
 #pragma unroll
-    for (int k = 0; k < kAcc; ++k) {
-        double v = acc[k];
+    for (int k = 0; k < 32; ++k) v[k] = k < kAcc ? acc[k] : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[warp][k] = v;
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+            const double send = up ? v[k] : v[k + o];
+            const double keep = up ? v[k + o] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
     }
+    s_red[warp][lane] = v[0];
     __syncthreads();
     if (threadIdx.x < kAcc) {
-        double v = 0.0;
+        double t = 0.0;
 #pragma unroll
-        for (int wv = 0; wv < kThreads / 32; ++wv) v += s_red[wv][threadIdx.x];
-        bv.partials[(size_t(s) * bv.partial_stride + slot_offset + blockIdx.x) * kAcc + threadIdx.x] = v;
+        for (int wv = 0; wv < kThreads / 32; ++wv) t += s_red[wv][threadIdx.x];
+        bv.partials[(size_t(s) * bv.partial_stride + slot_offset + blockIdx.x) * kAcc + threadIdx.x] = t;
     }
 }
 
@@ -625,12 +637,20 @@ __global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, 
     }
 }
 
+// A 16-byte global load the compiler may neither merge with an earlier load of the same address nor hoist: k_fit re-reads
+// its neighbours (L1 hits) rather than keeping them live in registers.
+__device__ __forceinline__ float4 ld_f4_again(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // k_fit: the rest of LidarSLAM::ComputePlaneDistanceParameters (LidarSlam.cpp:536-572) for every point that has its
 // five neighbours -- PCA, plane fit, gates, observability -- plus the first residual/Jacobian evaluation of the
 // following ceres::Solve and the histogram / normal-equation reductions.  FP64 throughout.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, CorrBuf cb, NnBuf nb) {
+__global__ void __launch_bounds__(kFitThreads, SO_FIT_MINB) k_fit(MapView m, BatchView bv, CorrBuf cb, NnBuf nb) {
     const int s = blockIdx.y;
     IcpState* st = bv.st + s;
     if (st->phase != PH_CORR) return;
@@ -644,13 +664,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, Co
     __syncthreads();
     const uint32_t n = uint32_t(st->n_points);
 
+#if !SO_FIT_SPLIT
     double acc[kAcc];
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+#endif
 
 #pragma unroll 1
-    for (int rr = 0; rr < kFitPts; ++rr) {          // kFitPts points per thread before the one CTA reduction
-    const uint32_t i = (blockIdx.x * kFitPts + rr) * kThreads + threadIdx.x;
+    for (int rr = 0; rr < kFitPts; ++rr) {          // kFitPts points per thread
+    const uint32_t i = (blockIdx.x * kFitPts + rr) * kFitThreads + threadIdx.x;
     const size_t gi = size_t(bv.offset[s]) + i;
     if (i < n) {
         int status = nb.pre[gi];
@@ -664,14 +686,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, Co
             qrot(s_pose + 3, pin, pf);
             pf[0] += s_pose[0]; pf[1] += s_pose[1]; pf[2] += s_pose[2];
             const float qx = float(pf[0]), qy = float(pf[1]), qz = float(pf[2]);
-            // computePCAForFeature (:749-790) + utils::ComputePCA (superodom_utils.h:143-151)
-            double mm[5][3];
+            // computePCAForFeature (:749-790) + utils::ComputePCA (superodom_utils.h:143-151).  The five neighbours are read
+            // three times (here, for the QR, for the distances) from k_knn_scan's coalesced hand-over instead of being held
+            // in 30 FP64 registers across the eigen-solve: the re-reads hit L1 and the kernel fits 3 CTAs per SM.
+            const float4* npts = nb.pts + gi;
             double mean[3] = {0, 0, 0};
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-                const float4 c = nb.pts[size_t(j) * nb.cap + gi];
-                mm[j][0] = double(c.x); mm[j][1] = double(c.y); mm[j][2] = double(c.z);
-                mean[0] += mm[j][0]; mean[1] += mm[j][1]; mean[2] += mm[j][2];
+                const float4 c = ld_f4_again(npts + size_t(j) * nb.cap);
+                mean[0] += double(c.x); mean[1] += double(c.y); mean[2] += double(c.z);
                 if (cb.nn) {
                     const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
                     cb.nn[gi * 5 + j] = __float_as_uint(c.w);
@@ -682,20 +705,42 @@ __global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, Co
             double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-                const double c0 = mm[j][0] - mean[0], c1 = mm[j][1] - mean[1], c2 = mm[j][2] - mean[2];
+                const float4 c = ld_f4_again(npts + size_t(j) * nb.cap);
+                const double c0 = double(c.x) - mean[0], c1 = double(c.y) - mean[1], c2 = double(c.z) - mean[2];
                 S[0] += c0 * c0; S[1] += c0 * c1; S[2] += c0 * c2; S[4] += c1 * c1; S[5] += c1 * c2; S[8] += c2 * c2;
             }
             S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
-            double V[9], ev[3];
-            jacobi_eig<3, 12>(S, V, ev);
+            const double sxx = S[0], sxy = S[1], sxz = S[2], syy = S[4], syz = S[5], szz = S[8];
+            double ev[3];
+            jacobi_eig<3, 12, false>(S, nullptr, ev);
             if (ev[0] < 1e-6 || ev[1] / ev[2] < 0.1) status = SO_MATCH_BAD_PCA_STRUCTURE;      // (:772)
             else {
+                // What FeatureObservabilityAnalysis (:574-693) needs from the PCA -- the oriented normal (:553-561) and the
+                // planarity -- is reduced to four floats here, ahead of the register-hungry QR.
+                float nf[3], cr[3], planar_sq;
+                {
+                    double no[3];
+                    eigvec3_from_value(sxx, sxy, sxz, syy, syz, szz, ev[0], no);
+                    if (pf[0] * no[0] + pf[1] * no[1] + pf[2] * no[2] < 0) { no[0] = -no[0]; no[1] = -no[1]; no[2] = -no[2]; }
+                    const double l1 = sqrt(ev[2]), l2 = sqrt(ev[1]), l3 = sqrt(ev[0]);
+                    const double planar_2 = (l2 - l3) / l1;
+                    planar_sq = float(planar_2 * planar_2);
+                    nf[0] = float(no[0]); nf[1] = float(no[1]); nf[2] = float(no[2]);
+                    cr[0] = __fmul_rn(qy, nf[2]) - __fmul_rn(qz, nf[1]);
+                    cr[1] = __fmul_rn(qz, nf[0]) - __fmul_rn(qx, nf[2]);
+                    cr[2] = __fmul_rn(qx, nf[1]) - __fmul_rn(qy, nf[0]);
+                }
                 // computePlaneQualityMetrics (:792-844)
-                double A[5][3], b[5];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) { A[j][0] = mm[j][0]; A[j][1] = mm[j][1]; A[j][2] = mm[j][2]; b[j] = -1.0; }
                 double x[3];
-                colpiv_qr_solve_5x3(A, b, x);
+                {
+                    double A[5][3], b[5];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const float4 c = ld_f4_again(npts + size_t(j) * nb.cap);
+                        A[j][0] = double(c.x); A[j][1] = double(c.y); A[j][2] = double(c.z); b[j] = -1.0;
+                    }
+                    colpiv_qr_solve_5x3(A, b, x);
+                }
                 if (!(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]))) status = SO_MATCH_INVALID_NUMERICAL;
                 else {
                     const double nn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
@@ -706,24 +751,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, Co
                     bool ok = true;
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
-                        const double dist = fabs(x[0] * mm[j][0] + x[1] * mm[j][1] + x[2] * mm[j][2] + dd);
+                        const float4 c = ld_f4_again(npts + size_t(j) * nb.cap);
+                        const double dist = fabs(x[0] * double(c.x) + x[1] * double(c.y) + x[2] * double(c.z) + dd);
                         if (ok && dist > maxd) ok = false;
                         msum += dist;
                     }
                     if (!ok) status = SO_MATCH_MSE_TOO_LARGE;
                     else {
                         const double mean_dist = msum / 5.0;
-                        // normal orientation (:553-561) on the PCA normal, then FeatureObservabilityAnalysis (:574-693)
-                        double no[3] = {V[0], V[3], V[6]};
-                        if (pf[0] * no[0] + pf[1] * no[1] + pf[2] * no[2] < 0) { no[0] = -no[0]; no[1] = -no[1]; no[2] = -no[2]; }
-                        const double l1 = sqrt(ev[2]), l2 = sqrt(ev[1]), l3 = sqrt(ev[0]);
-                        const double planar_2 = (l2 - l3) / l1;
-                        const float nf[3] = {float(no[0]), float(no[1]), float(no[2])};
-                        const float cr[3] = {__fmul_rn(qy, nf[2]) - __fmul_rn(qz, nf[1]), __fmul_rn(qz, nf[0]) - __fmul_rn(qx, nf[2]),
-                                             __fmul_rn(qx, nf[1]) - __fmul_rn(qy, nf[0])};
                         const float fq[4] = {float(s_pose[3]), float(s_pose[4]), float(s_pose[5]), float(s_pose[6])};
                         float rotq[6], trq[3];
-                        const float planar_sq = float(planar_2 * planar_2);
 #pragma unroll
                         for (int a = 0; a < 3; ++a) {
                             // computeRotatedAxes (:624-638): float quaternion * e_a, no FMA contraction (host code is plain IEEE)
@@ -755,7 +792,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, Co
                         nrm[0] = x[0]; nrm[1] = x[1]; nrm[2] = x[2]; dpl = dd;
                         wq = 1.0 - sqrt(mean_dist / double(m.bound_d2));        // fitQualityCoeff (:568)
                         status = SO_MATCH_SUCCESS;
+#if !SO_FIT_SPLIT
                         accumulate(acc, nrm, dpl, wq, pin, pf, s_R, bv.tukey_a2);
+#endif
                     }
                 }
             }
@@ -778,21 +817,24 @@ __global__ void __launch_bounds__(kThreads, 2) k_fit(MapView m, BatchView bv, Co
     }
     __syncthreads();
     if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&bv.hist[s * kHistStride + threadIdx.x], s_hist[threadIdx.x]);
-
+#if !SO_FIT_SPLIT
     reduce_to_partials(acc, bv, s);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_evaluate: robustified normal equations at the candidate pose over the stored correspondences.
 // kEvalPts points per thread (strided by the CTA width, so loads stay coalesced) before the one warp/CTA reduction.
 // ------------------------------------------------------------------------------------------------------------------
+template <int PHASE>
 __global__ void __launch_bounds__(kThreads, 2) k_evaluate(BatchView bv, CorrBuf cb) {
     const int s = blockIdx.y;
     IcpState* st = bv.st + s;
-    if (st->phase != PH_EVAL) return;
+    if (st->phase != PHASE) return;
     __shared__ double s_pose[7];
     __shared__ double s_R[9];
-    if (threadIdx.x < 7) s_pose[threadIdx.x] = st->cand[threadIdx.x];
+    // PH_EVAL: the LM candidate; PH_CORR: the first evaluation of a new solve, at the pose k_fit just matched at
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = PHASE == PH_EVAL ? st->cand[threadIdx.x] : st->x[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) qtoR(s_pose + 3, s_R);
     __syncthreads();
@@ -801,22 +843,36 @@ __global__ void __launch_bounds__(kThreads, 2) k_evaluate(BatchView bv, CorrBuf 
     double acc[kAcc];
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+    // Software-pipelined: the three loads of point r+1 are issued (unconditionally, so they do not chain behind the weight)
+    // before the FP64 work of point r, which keeps two points' worth of the 56 B/pt stream in flight per thread.
+    const uint32_t i0 = blockIdx.x * kEvalPts * kThreads + threadIdx.x;
+    double w_n = 0.0;
+    double4 nd_n = make_double4(0.0, 0.0, 0.0, 0.0);
+    float4 sp_n = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 < n) {
+        w_n = cb.w[base + i0];
+        nd_n = cb.nd[base + i0];
+        sp_n = __ldg(&bv.scan[base + i0]);
+    }
 #pragma unroll 1
     for (int r = 0; r < kEvalPts; ++r) {
-        const uint32_t i = (blockIdx.x * kEvalPts + r) * kThreads + threadIdx.x;
-        if (i < n) {
-            const size_t gi = base + i;
-            const double w = cb.w[gi];
-            if (w != 0.0) {
-                const double4 nd = cb.nd[gi];
-                const float4 sp = __ldg(&bv.scan[gi]);
-                const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
-                double pw[3];
-                qrot(s_pose + 3, pin, pw);
-                pw[0] += s_pose[0]; pw[1] += s_pose[1]; pw[2] += s_pose[2];
-                const double nn[3] = {nd.x, nd.y, nd.z};
-                accumulate(acc, nn, nd.w, w, pin, pw, s_R, bv.tukey_a2);
-            }
+        const double w = w_n;
+        const double4 nd = nd_n;
+        const float4 sp = sp_n;
+        const uint32_t inext = i0 + (r + 1) * kThreads;
+        w_n = 0.0;
+        if (r + 1 < kEvalPts && inext < n) {
+            w_n = cb.w[base + inext];
+            nd_n = cb.nd[base + inext];
+            sp_n = __ldg(&bv.scan[base + inext]);
+        }
+        if (w != 0.0) {
+            const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+            double pw[3];
+            qrot(s_pose + 3, pin, pw);
+            pw[0] += s_pose[0]; pw[1] += s_pose[1]; pw[2] += s_pose[2];
+            const double nn[3] = {nd.x, nd.y, nd.z};
+            accumulate(acc, nn, nd.w, w, pin, pw, s_R, bv.tukey_a2);
         }
     }
     reduce_to_partials(acc, bv, s);
@@ -1032,7 +1088,7 @@ __global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partia
     double v = 0.0;
     if (comp < kAcc) {
         const double* base = bv.partials + size_t(s) * bv.partial_stride * kAcc;
-        const uint32_t np = (AFTER == PH_CORR) ? (uint32_t(st->n_points) + kThreads * kFitPts - 1) / (kThreads * kFitPts)
+        const uint32_t np = (AFTER == PH_CORR && !kFitSplit) ? (uint32_t(st->n_points) + kThreads * kFitPts - 1) / (kThreads * kFitPts)
                                                : (uint32_t(st->n_points) + kThreads * kEvalPts - 1) / (kThreads * kEvalPts);
         for (uint32_t b = sub; b < np && b < n_partials; b += 4) v += base[size_t(b) * kAcc + comp];
         const uint32_t ne = (uint32_t(st->n_edge) + kThreads - 1) / kThreads;          // edge branch partials (0 when no edge cloud)
@@ -1126,10 +1182,16 @@ void launch_knn_scan(const MapView& m, const BatchView& bv, const NnBuf& nb, uin
 // sums the partials of both.
 void launch_fit(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st,
                 const MapView* medge, const EdgeBuf* eb, uint32_t grid_e) {
-    const uint32_t gf = (grid_x + kFitPts - 1) / kFitPts;
-    if (gf) k_fit<<<dim3(gf, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
+    const uint32_t gf = (grid_x * kThreads + kFitPts * kFitThreads - 1) / (kFitPts * kFitThreads);
+    if (gf) k_fit<<<dim3(gf, n_scans), kFitThreads, 0, st>>>(m, bv, cb, nb);
+#if SO_FIT_SPLIT
+    const uint32_t gp = (grid_x + kEvalPts - 1) / kEvalPts;
+    if (gp) k_evaluate<PH_CORR><<<dim3(gp, n_scans), kThreads, 0, st>>>(bv, cb);
+#else
+    const uint32_t gp = gf;
+#endif
     if (grid_e) k_edge_fit<<<dim3(grid_e, n_scans), kThreads, 0, st>>>(*medge, bv, *eb, bv.edge_partial_offset);
-    k_lm_step<PH_CORR><<<n_scans, 128, 0, st>>>(bv, gf, bv.edge_partial_offset);
+    k_lm_step<PH_CORR><<<n_scans, 128, 0, st>>>(bv, gp, bv.edge_partial_offset);
 }
 void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st,
                        const MapView* medge, const EdgeBuf* eb, uint32_t grid_e) {
@@ -1138,7 +1200,7 @@ void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb,
 }
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const EdgeBuf* eb, uint32_t grid_e) {
     const uint32_t gx = (grid_x + kEvalPts - 1) / kEvalPts;
-    if (gx) k_evaluate<<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb);
+    if (gx) k_evaluate<PH_EVAL><<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb);
     if (grid_e) k_edge_evaluate<<<dim3(grid_e, n_scans), kThreads, 0, st>>>(bv, *eb, bv.edge_partial_offset);
     k_lm_step<PH_EVAL><<<n_scans, 128, 0, st>>>(bv, gx, bv.edge_partial_offset);
 }

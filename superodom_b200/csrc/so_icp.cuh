@@ -46,11 +46,27 @@ struct NnBuf {
     size_t cap;
 };
 
-constexpr int kEvalPts = 4;     // points per thread in k_evaluate
+#ifndef SO_EVAL_PTS
+#define SO_EVAL_PTS 8
+#endif
+constexpr int kEvalPts = SO_EVAL_PTS;     // points per thread in k_evaluate
 #ifndef SO_FIT_PTS
 #define SO_FIT_PTS 2
 #endif
 constexpr int kFitPts = SO_FIT_PTS;      // points per thread in k_fit
+// 1: k_fit only matches/fits and the first evaluation of the solve is a k_evaluate<PH_CORR> launch (k_fit then carries no
+// normal-equation accumulators: fewer registers, more resident warps); 0: k_fit accumulates in place.
+#ifndef SO_FIT_SPLIT
+#define SO_FIT_SPLIT 1
+#endif
+constexpr int kFitSplit = SO_FIT_SPLIT;
+#ifndef SO_FIT_THREADS
+#define SO_FIT_THREADS 256
+#endif
+#ifndef SO_FIT_MINB
+#define SO_FIT_MINB 4
+#endif
+constexpr int kFitThreads = SO_FIT_SPLIT ? SO_FIT_THREADS : 256;      // the in-place reduction needs the common CTA width
 
 void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st);

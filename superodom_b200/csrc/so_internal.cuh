@@ -115,12 +115,15 @@ __host__ __device__ inline void rel_motion(const double a[7], const double b[7],
 // Cyclic Jacobi for a symmetric NxN (row-major full storage).  On return a's diagonal holds the eigenvalues and
 // v (row-major) the eigenvectors in columns; then sorted ascending.  With N a compile-time constant and full
 // unrolling every index is static, so for N=3 the whole thing lives in registers.
-template <int N, int SWEEPS>
+// WITH_V = false: eigenvalues only (v is not touched and may be null).
+template <int N, int SWEEPS, bool WITH_V = true>
 __device__ inline void jacobi_eig(double* a, double* v, double* w) {
+    if (WITH_V) {
 #pragma unroll
-    for (int i = 0; i < N; ++i)
+        for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = 0; j < N; ++j) v[i * N + j] = (i == j) ? 1.0 : 0.0;
+            for (int j = 0; j < N; ++j) v[i * N + j] = (i == j) ? 1.0 : 0.0;
+    }
 #pragma unroll 1
     for (int sweep = 0; sweep < SWEEPS; ++sweep) {
         double off = 0.0, dia = 0.0;
@@ -155,9 +158,11 @@ __device__ inline void jacobi_eig(double* a, double* v, double* w) {
                             a[r * N + p] = a[p * N + r] = c * arp - s * arq;
                             a[r * N + q] = a[q * N + r] = s * arp + c * arq;
                         }
-                        const double vrp = v[r * N + p], vrq = v[r * N + q];
-                        v[r * N + p] = c * vrp - s * vrq;
-                        v[r * N + q] = s * vrp + c * vrq;
+                        if (WITH_V) {
+                            const double vrp = v[r * N + p], vrq = v[r * N + q];
+                            v[r * N + p] = c * vrp - s * vrq;
+                            v[r * N + q] = s * vrp + c * vrq;
+                        }
                     }
                 }
             }
@@ -172,11 +177,33 @@ __device__ inline void jacobi_eig(double* a, double* v, double* w) {
         for (int j = i + 1; j < N; ++j) {
             if (w[j] < w[i]) {
                 const double t = w[i]; w[i] = w[j]; w[j] = t;
+                if (WITH_V) {
 #pragma unroll
-                for (int r = 0; r < N; ++r) { const double u = v[r * N + i]; v[r * N + i] = v[r * N + j]; v[r * N + j] = u; }
+                    for (int r = 0; r < N; ++r) { const double u = v[r * N + i]; v[r * N + i] = v[r * N + j]; v[r * N + j] = u; }
+                }
             }
         }
     }
+}
+
+// Unit eigenvector of the symmetric 3x3 S = [xx xy xz; xy yy yz; xz yz zz] for its (simple) eigenvalue lam: S - lam I has rank
+// two, so the cross product of any two independent rows spans its null space; the pair with the longest product is the
+// best conditioned.  Direction error ~ eps * |S| / gap, the same as an iterative solver's; the sign is arbitrary (the caller
+// orients it).
+__device__ __forceinline__ void eigvec3_from_value(double xx, double xy, double xz, double yy, double yz, double zz, double lam, double n[3]) {
+    const double a = xx - lam, d = yy - lam, f = zz - lam, b = xy, c = xz, e = yz;
+    const double c01[3] = {b * e - c * d, c * b - a * e, a * d - b * b};
+    const double c02[3] = {b * f - c * e, c * c - a * f, a * e - b * c};
+    const double c12[3] = {d * f - e * e, e * c - b * f, b * e - d * c};
+    const double n01 = c01[0] * c01[0] + c01[1] * c01[1] + c01[2] * c01[2];
+    const double n02 = c02[0] * c02[0] + c02[1] * c02[1] + c02[2] * c02[2];
+    const double n12 = c12[0] * c12[0] + c12[1] * c12[1] + c12[2] * c12[2];
+    double m = n01;
+    n[0] = c01[0]; n[1] = c01[1]; n[2] = c01[2];
+    if (n02 > m) { m = n02; n[0] = c02[0]; n[1] = c02[1]; n[2] = c02[2]; }
+    if (n12 > m) { m = n12; n[0] = c12[0]; n[1] = c12[1]; n[2] = c12[2]; }
+    const double inv = 1.0 / sqrt(m);
+    n[0] *= inv; n[1] *= inv; n[2] *= inv;
 }
 
 // Least-squares solve of the 5x3 system A n = b by column-pivoted Householder QR -- the operation
