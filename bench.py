@@ -72,7 +72,16 @@ class ClockSampler(threading.Thread):
 
 
 def make_inputs(first_scan: int, n_scans: int):
+    """Seeded synthetic cfg2 inputs.  SO_BENCH_CACHE=<dir>: keep the generated arrays there so that several runs
+    inside one GPU session do not repeat the (CPU, ~1 min) ray casting; the cache holds inputs only."""
     from superodom_b200 import synth
+    cache = os.environ.get("SO_BENCH_CACHE")
+    path = os.path.join(cache, f"cfg2_{first_scan}_{n_scans}.npz") if cache else None
+    if path and os.path.exists(path):
+        z = np.load(path)
+        nn = z["n"]
+        offs = np.concatenate([[0], np.cumsum(nn)])
+        return z["map"], [z["flat"][offs[i]:offs[i + 1]] for i in range(len(nn))], z["priors"], z["truths"]
     scene, map_xyzi = synth.make_map_for("cfg2")
     scans, priors, truths = [], [], []
     for i in range(first_scan, first_scan + n_scans):
@@ -80,6 +89,9 @@ def make_inputs(first_scan: int, n_scans: int):
         scans.append(c["scan_xyzi"])
         priors.append(c["pose_prior"])
         truths.append(c["pose_true"])
+    if path:
+        os.makedirs(cache, exist_ok=True)
+        np.savez(path, map=map_xyzi, flat=np.concatenate(scans, 0), n=np.array([len(x) for x in scans]), priors=np.stack(priors), truths=np.stack(truths))
     return map_xyzi, scans, np.stack(priors), np.stack(truths)
 
 

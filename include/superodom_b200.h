@@ -184,6 +184,27 @@ size_t so_map_size(so_ctx* ctx);
 int so_scan_prefilter(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset, int auto_voxel_size,
                       float* line_res, float* plane_res, float* out_xyzi, size_t cap_points, size_t* n_out, double* average_distance);
 
+/* replaces: featureExtraction::removePointDistortion<BufferType> (src/FeatureExtraction/featureExtraction.cpp:222-314).
+ * points: n records of stride_bytes, float x,y,z first and the per-point float `time` (seconds after lidar_start_time,
+ * point_os::PointcloudXYZITR: stride 32, time at byte 20) at time_offset; x,y,z are rewritten in place into the sensor frame
+ * at lidar_start_time, non-finite points are left alone.  The pose buffer (MapRingBuffer::measMap_) is passed as n_samples
+ * strictly ascending stamps + poses {tx,ty,tz,qx,qy,qz,qw}; interpolation = std::map::upper_bound, slerp + lerp, with the
+ * `< 0.0001` rewind of :258-260.  imu_only != 0 is the Imu::Ptr instantiation: samples contribute rotation only and the motion
+ * is conjugated by the IMU-lidar extrinsic T_i_l (parameter.cpp:192-193).  start_pose_out (optional) receives
+ * {t_w_original_l, q_w_original_l} (:283-289).  *n_past_end (optional) counts points stamped after the last sample -- the
+ * reference dereferences end() there and relies on synchronize_measurements (:187-196) to prevent it; the last interval is
+ * extrapolated here. */
+int so_scan_deskew(so_ctx* ctx, void* points, size_t n, size_t stride_bytes, size_t time_offset, double lidar_start_time,
+                   const double* sample_times, const double* sample_poses, size_t n_samples, int imu_only, const double T_i_l[7],
+                   double start_pose_out[7], size_t* n_past_end);
+/* replaces: featureExtraction::uniformFeatureExtraction (featureExtraction.cpp:504-525): every skip_num-th point from index 1
+ * that differs from its predecessor -- |dx| > 1e-7 || |dy| > 1e-7 || (|dz| > 1e-7 && x*x+y*y+z*z > block_range^2), with that
+ * precedence -- is emitted as packed float4 {x, y, z, intensity = time}, input order.  int_abs != 0 evaluates the
+ * unqualified abs() of :515-517 as ::abs(int) (its meaning when only <cmath> declared abs); 0 = the float overload.
+ * *n_out = points produced (may exceed cap_points; only cap_points are written). */
+int so_scan_extract_uniform(so_ctx* ctx, const void* points, size_t n, size_t stride_bytes, size_t time_offset, int skip_num,
+                            float block_range, int int_abs, float* out_xyzi, size_t cap_points, size_t* n_out);
+
 /* ---- registration (LidarSLAM) --------------------------------------------------------------------- */
 /* replaces: LidarSLAM::Localization(true, predictodom, position, edge, planner, t) -> performLocalizationAndMapping
  * (LidarSlam.cpp:30-51,107-171), excluding the map insert at its end (call so_map_add_surf with the

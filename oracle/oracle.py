@@ -100,6 +100,10 @@ def lib():
     L.orc_correspond_edge.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_sizeof_edge_corr.restype = C.c_size_t
     L.orc_sym_eig.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_deskew.restype = C.c_int64
+    L.orc_deskew.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_extract_uniform.restype = C.c_int64
+    L.orc_extract_uniform.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_size_t]
     L.orc_colpiv_qr_solve.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_pose_plus.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_yaw_round_trip.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
@@ -280,6 +284,27 @@ def yaw_round_trip(last, T, yaw_ratio=0.0):
     T = np.array(T, dtype=np.float64)
     lib().orc_yaw_round_trip(_p(last), _p(T), C.c_double(yaw_ratio))
     return T
+
+
+def deskew(points, time_col, lidar_start_time, sample_times, sample_poses, imu_only=False, T_i_l=None):
+    """featureExtraction::removePointDistortion (featureExtraction.cpp:222-314) on a copy of float32 [n, C] points.
+    -> (deskewed copy, start_pose7, n_past_end)"""
+    a = np.array(points, dtype=np.float32, order="C", copy=True)
+    st = np.ascontiguousarray(sample_times, np.float64)
+    sp = np.ascontiguousarray(sample_poses, np.float64).reshape(-1, 7)
+    til = np.ascontiguousarray(T_i_l if T_i_l is not None else [0, 0, 0, 0, 0, 0, 1], np.float64)
+    out = np.zeros(7)
+    past = lib().orc_deskew(_p(a), a.shape[0], a.shape[1], time_col, float(lidar_start_time), _p(st), _p(sp), len(st), int(imu_only), _p(til), _p(out))
+    return a, out, int(past)
+
+
+def extract_uniform(points, time_col, skip_num, block_range, int_abs=False):
+    """featureExtraction::uniformFeatureExtraction (featureExtraction.cpp:504-525) -> float32 [m, 4] {x,y,z,time}"""
+    a = np.ascontiguousarray(points, dtype=np.float32)
+    out = np.zeros((max(len(a), 1), 4), np.float32)
+    m = lib().orc_extract_uniform(_p(a), a.shape[0], a.shape[1], time_col, int(skip_num), float(block_range), int(int_abs), _p(out), len(out))
+    assert m >= 0
+    return out[:m]
 
 
 def lidar_uncertainty(hist9):

@@ -1300,6 +1300,183 @@ int orc_register(void* m, const float* scan_xyzi, size_t n, size_t stride_floats
 }
 
 // EstimateLidarUncertainty (LidarSlam.cpp:915-964) from a 9-bin observability histogram
+// ------------------------------------------------------------------------------------------------------------------
+// Scan preparation in front of the path: featureExtraction::removePointDistortion and
+// featureExtraction::uniformFeatureExtraction, restated with the Eigen 3.4.0 operations they go through.
+// ------------------------------------------------------------------------------------------------------------------
+namespace orc_prep {
+struct Q { double w, x, y, z; };
+struct T { Q q; double p[3]; };
+
+static Q q_normalized(Q a) {
+    const double n = std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
+    return {a.w / n, a.x / n, a.y / n, a.z / n};
+}
+// Eigen::QuaternionBase::toRotationMatrix (Quaternion.h)
+static void q_to_R(const Q& q, double R[9]) {
+    const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y, tyz = tz * q.y,
+                 tzz = tz * q.z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+// Eigen::internal::quaternionbase_assign_impl<Other,3,3>::run (rotation matrix -> quaternion)
+static Q R_to_q(const double m[9]) {
+    Q q;
+    double t = m[0] + m[4] + m[8];
+    if (t > 0) {
+        t = std::sqrt(t + 1.0);
+        q.w = 0.5 * t;
+        t = 0.5 / t;
+        q.x = (m[7] - m[5]) * t; q.y = (m[2] - m[6]) * t; q.z = (m[3] - m[1]) * t;
+    } else {
+        int i = 0;
+        if (m[4] > m[0]) i = 1;
+        if (m[8] > m[i * 4]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(m[i * 4] - m[j * 4] - m[k * 4] + 1.0);
+        double v[3];
+        v[i] = 0.5 * t;
+        t = 0.5 / t;
+        q.w = (m[k * 3 + j] - m[j * 3 + k]) * t;
+        v[j] = (m[j * 3 + i] + m[i * 3 + j]) * t;
+        v[k] = (m[k * 3 + i] + m[i * 3 + k]) * t;
+        q.x = v[0]; q.y = v[1]; q.z = v[2];
+    }
+    return q;
+}
+// Eigen::QuaternionBase::_transformVector
+static void q_rot(const Q& q, const double v[3], double out[3]) {
+    double uv[3] = {q.y * v[2] - q.z * v[1], q.z * v[0] - q.x * v[2], q.x * v[1] - q.y * v[0]};
+    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+    out[0] = v[0] + q.w * uv[0] + (q.y * uv[2] - q.z * uv[1]);
+    out[1] = v[1] + q.w * uv[1] + (q.z * uv[0] - q.x * uv[2]);
+    out[2] = v[2] + q.w * uv[2] + (q.x * uv[1] - q.y * uv[0]);
+}
+// Eigen::QuaternionBase::slerp
+static Q q_slerp(const Q& a, double t, const Q& b) {
+    const double one = 1.0 - std::numeric_limits<double>::epsilon();
+    const double d = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    const double absD = std::fabs(d);
+    double s0, s1;
+    if (absD >= one) { s0 = 1.0 - t; s1 = t; }
+    else {
+        const double theta = std::acos(absD), sinTheta = std::sin(theta);
+        s0 = std::sin((1.0 - t) * theta) / sinTheta;
+        s1 = std::sin(t * theta) / sinTheta;
+    }
+    if (d < 0) s1 = -s1;
+    return {s0 * a.w + s1 * b.w, s0 * a.x + s1 * b.x, s0 * a.y + s1 * b.y, s0 * a.z + s1 * b.z};
+}
+// Twist::inverse (Twist.h:172-179)
+static T t_inverse(const T& a) {
+    T r;
+    r.q = {a.q.w, -a.q.x, -a.q.y, -a.q.z};
+    double R[9];
+    q_to_R(r.q, R);
+    for (int i = 0; i < 3; ++i) r.p[i] = -(R[i * 3] * a.p[0] + R[i * 3 + 1] * a.p[1] + R[i * 3 + 2] * a.p[2]);
+    return r;
+}
+// Twist::operator*(Twist) (Twist.h:181-185): through Eigen::Transform (normalised rotations), back to a normalised quaternion
+static T t_mul(const T& a, const T& b) {
+    double Ra[9], Rb[9], R[9];
+    q_to_R(q_normalized(a.q), Ra);
+    q_to_R(q_normalized(b.q), Rb);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[i * 3 + j] = Ra[i * 3] * Rb[j] + Ra[i * 3 + 1] * Rb[3 + j] + Ra[i * 3 + 2] * Rb[6 + j];
+    T r;
+    for (int i = 0; i < 3; ++i) r.p[i] = Ra[i * 3] * b.p[0] + Ra[i * 3 + 1] * b.p[1] + Ra[i * 3 + 2] * b.p[2] + a.p[i];
+    r.q = q_normalized(R_to_q(R));
+    return r;
+}
+static T from7(const double* p) { return T{{p[6], p[3], p[4], p[5]}, {p[0], p[1], p[2]}}; }
+static void to7(const T& t, double* p) { p[0] = t.p[0]; p[1] = t.p[1]; p[2] = t.p[2]; p[3] = t.q.x; p[4] = t.q.y; p[5] = t.q.z; p[6] = t.q.w; }
+
+// getInterpolatedPoseAtTime (featureExtraction.cpp:256-276): std::map::upper_bound over the sample times; the `< 0.0001`
+// rewind; first sample as is when nothing precedes; else slerp + lerp.  *past_end is set where the reference would
+// dereference end() (it relies on synchronize_measurements, :187-196, to make that impossible); the last interval is used.
+static T interpolate(const double* times, const double* poses, size_t ns, bool imu_only, double ts, bool* past_end) {
+    size_t after = size_t(std::upper_bound(times, times + ns, ts) - times);
+    if (after == ns) { if (past_end) *past_end = true; after = ns - 1; }
+    if (times[after] < 0.0001) after = 0;
+    auto extract = [&](size_t i) {
+        T t = from7(poses + 7 * i);
+        if (imu_only) t.p[0] = t.p[1] = t.p[2] = 0.0;      // Imu::Ptr: rotation only (:232-236)
+        return t;
+    };
+    if (after == 0) return extract(0);
+    const size_t before = after - 1;
+    const double ratio = (ts - times[before]) / (times[after] - times[before]);
+    const T a = extract(before), b = extract(after);
+    T r;
+    r.q = q_slerp(a.q, ratio, b.q);
+    for (int i = 0; i < 3; ++i) r.p[i] = (1 - ratio) * a.p[i] + ratio * b.p[i];
+    return r;
+}
+}  // namespace orc_prep
+
+// featureExtraction::removePointDistortion<BufferType> (featureExtraction.cpp:222-314).  pts: n points of `stride_floats`
+// floats, x,y,z first, per-point time (seconds since lidar_start_time) at float index time_idx; rewritten in place.
+// sample_poses: n_samples x {tx,ty,tz,qx,qy,qz,qw}.  start_pose_out = {t_w_original_l, q_w_original_l}.
+// Returns the number of points whose time lay past the last sample (undefined behaviour upstream).
+int64_t orc_deskew(float* pts, size_t n, size_t stride_floats, size_t time_idx, double lidar_start_time, const double* sample_times,
+                   const double* sample_poses, size_t n_samples, int imu_only, const double T_i_l7[7], double start_pose_out[7]) {
+    using namespace orc_prep;
+    if (n_samples == 0) return -1;
+    const bool imu = imu_only != 0;
+    const T Til = from7(T_i_l7), Tli = t_inverse(Til);                      // parameter.cpp:192-193
+    const T start = interpolate(sample_times, sample_poses, n_samples, imu, lidar_start_time, nullptr);
+    const T Two = start;                                                     // T_w_original(start.rot, start.pos)
+    const T Two_sensor = imu ? t_mul(Two, Til) : Two;
+    to7(Two_sensor, start_pose_out);
+    const T Two_inv = t_inverse(Two);
+    int64_t past = 0;
+    for (size_t i = 0; i < n; ++i) {
+        float* p = pts + i * stride_floats;
+        if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+        const double point_time = p[time_idx] + lidar_start_time;           // float + double
+        bool pe = false;
+        const T Twc = interpolate(sample_times, sample_poses, n_samples, imu, point_time, &pe);
+        past += pe;
+        const T Toc = t_mul(Two_inv, Twc);
+        const T Tf = imu ? t_mul(t_mul(Tli, Toc), Til) : Toc;
+        const double v[3] = {double(p[0]), double(p[1]), double(p[2])};
+        double r[3];
+        q_rot(Tf.q, v, r);
+        p[0] = float(r[0] + Tf.p[0]); p[1] = float(r[1] + Tf.p[1]); p[2] = float(r[2] + Tf.p[2]);
+    }
+    return past;
+}
+
+// featureExtraction::uniformFeatureExtraction (featureExtraction.cpp:504-525): every skip_num-th point from index 1 whose
+// predecessor differs -- `|dx| > 1e-7 || |dy| > 1e-7 || (|dz| > 1e-7 && r^2 > block_range^2)`, exactly that precedence --
+// becomes {x, y, z, intensity = time}.  int_abs != 0 evaluates the unqualified abs() as ::abs(int), which is what the
+// expression means in a translation unit where only <cmath>/<cstdlib> (not <math.h>/<stdlib.h>) declared abs.
+int64_t orc_extract_uniform(const float* pts, size_t n, size_t stride_floats, size_t time_idx, int skip_num, float block_range, int int_abs,
+                            float* out_xyzi, size_t cap) {
+    if (skip_num <= 0) return -1;
+    int64_t m = 0;
+    for (size_t i = 1; i < n; i += size_t(skip_num)) {
+        const float* p = pts + i * stride_floats;
+        const float* q = p - stride_floats;
+        const float dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+        double ax, ay, az;
+        if (int_abs) {
+            // int(NaN / inf / |d| >= 2^31) is undefined upstream; such a difference counts as "no difference" here and on the GPU
+            auto ia = [](float d) { return (std::isfinite(d) && std::fabs(d) < 2147483648.0f) ? double(std::abs(int(d))) : 0.0; };
+            ax = ia(dx); ay = ia(dy); az = ia(dz);
+        }
+        else { ax = std::fabs(dx); ay = std::fabs(dy); az = std::fabs(dz); }
+        const float r2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+        if (ax > 1e-7 || ay > 1e-7 || (az > 1e-7 && r2 > block_range * block_range)) {
+            if (size_t(m) < cap) { float* o = out_xyzi + 4 * m; o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = p[time_idx]; }
+            ++m;
+        }
+    }
+    return m;
+}
+
 void orc_lidar_uncertainty(const int32_t h[9], double u[6]) {
     const double tt = double(h[6]) + double(h[7]) + double(h[8]);
     const double tr = double(h[0]) + h[1] + h[2] + h[3] + h[4] + h[5];

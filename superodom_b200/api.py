@@ -20,7 +20,7 @@ EXPORTS = [
     "so_create", "so_destroy", "so_last_error", "so_device_available", "so_set_stream",
     "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
     "so_map_set_edge_points", "so_map_add_surf", "so_map_add_edge", "so_map_add_scan", "so_map_add_scan_edge", "so_map_counts_5x5", "so_map_download", "so_map_size",
-    "so_scan_prefilter", "so_register", "so_register_batch", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
+    "so_scan_prefilter", "so_scan_deskew", "so_scan_extract_uniform", "so_register", "so_register_batch", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
     "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_profile_enable", "so_profile_get",
 ]
 
@@ -92,6 +92,10 @@ def load_library():
     L.so_map_size.argtypes = [C.c_void_p]
     L.so_scan_prefilter.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.so_scan_deskew.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t,
+                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_scan_extract_uniform.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_float, C.c_int,
+                                          C.c_void_p, C.c_size_t, C.c_void_p]
     L.so_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                               C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_register_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
@@ -257,6 +261,28 @@ class Context:
         self._chk(self.L.so_scan_prefilter(self.h, _p(a), a.shape[0], stride, 12 if a.shape[1] >= 4 else stride, int(auto_voxel_size),
                                            C.byref(lr), C.byref(pr), _p(out), len(out), C.byref(n), C.byref(avg)), "so_scan_prefilter")
         return out[: n.value], lr.value, pr.value, avg.value
+
+    def scan_deskew(self, points: np.ndarray, time_col: int, lidar_start_time: float, sample_times, sample_poses, imu_only: bool = False, T_i_l=None):
+        """points: float32 [n, C] with x,y,z first and the per-point time in column time_col; rewritten IN PLACE.
+        -> (start_pose7, n_past_end)"""
+        assert points.dtype == np.float32 and points.flags.c_contiguous and points.ndim == 2
+        st = np.ascontiguousarray(sample_times, np.float64)
+        sp = np.ascontiguousarray(sample_poses, np.float64).reshape(-1, 7)
+        til = np.ascontiguousarray(T_i_l if T_i_l is not None else [0, 0, 0, 0, 0, 0, 1], np.float64)
+        out = np.zeros(7, np.float64)
+        past = C.c_size_t(0)
+        self._chk(self.L.so_scan_deskew(self.h, _p(points), points.shape[0], points.shape[1] * 4, time_col * 4, float(lidar_start_time), _p(st), _p(sp),
+                                        len(st), int(imu_only), _p(til), _p(out), C.byref(past)), "so_scan_deskew")
+        return out, past.value
+
+    def scan_extract_uniform(self, points: np.ndarray, time_col: int, skip_num: int, block_range: float, int_abs: bool = False):
+        """-> float32 [m, 4] {x, y, z, intensity = time} (featureExtraction::uniformFeatureExtraction)"""
+        a = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.zeros((max(len(a), 1), 4), np.float32)
+        n = C.c_size_t()
+        self._chk(self.L.so_scan_extract_uniform(self.h, _p(a), a.shape[0], a.shape[1] * 4, time_col * 4, int(skip_num), float(block_range), int(int_abs),
+                                                 _p(out), len(out), C.byref(n)), "so_scan_extract_uniform")
+        return out[: n.value]
 
     # ---- registration
     @staticmethod

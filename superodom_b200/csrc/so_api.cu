@@ -71,6 +71,9 @@ static int ctx_alloc(Ctx* c) {
     SO_CUDA_TRY(cudaEventCreate(&c->ev0)); SO_CUDA_TRY(cudaEventCreate(&c->ev1));
     SO_CUDA_TRY(cudaEventCreate(&c->evp0)); SO_CUDA_TRY(cudaEventCreate(&c->evp1));
     SO_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    SO_CUDA_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    SO_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    SO_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (auto& e : c->ev_copy) SO_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int rc = map_alloc(c);
     if (rc) return rc;
@@ -123,10 +126,13 @@ static void ctx_free(Ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (auto& e : c->ev_copy) if (e) cudaEventDestroy(e);
     map_free(c);
     cudaFree(c->d_scan_sorted); cudaFree(c->d_skeys); cudaFree(c->d_skeys_out); cudaFree(c->d_svals); cudaFree(c->d_svals_out);
-    cudaFree(c->d_sort_tmp); cudaFree(c->nn.pos); cudaFree(c->nn.pts); cudaFree(c->nn.d5); cudaFree(c->nn.pre);
+    cudaFree(c->d_sort_tmp); cudaFree(c->d_sort_tmp2); cudaFree(c->nn.pos); cudaFree(c->nn.pts); cudaFree(c->nn.d5); cudaFree(c->nn.pre);
     cudaFree(c->d_scan); cudaFree(c->d_offset); cudaFree(c->d_state); cudaFreeHost(c->h_state); cudaFreeHost(c->h_offset);
     cudaFree(c->d_partials); cudaFree(c->d_counters); cudaFree(c->d_hist);
     cudaFree(c->d_escan); cudaFree(c->d_eoffset); cudaFree(c->ebuf.a); cudaFree(c->ebuf.b); cudaFree(c->ebuf.flags); cudaFree(c->ebuf.nn); cudaFree(c->ebuf.selmask);
@@ -206,15 +212,15 @@ static void timed_launch_end(Ctx* c, int cls) {
 struct Chunk { uint32_t first, count, pt_first, pt_count, grid_x, grid_e = 0; };
 
 // Once per registration: order every scan by map cell at its prior pose (k_scan_keys -> radix sort -> k_scan_gather).
-static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch) {
+static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch, cudaStream_t st) {
     const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, d_scan_in, ch.first);
     timed_launch_begin(c);
-    launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, ch.grid_x, ch.count, c->stream);
-    int rc = scan_sort(c, ch.pt_first, ch.pt_count, int(ch.count));
+    launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, ch.grid_x, ch.count, st);
+    int rc = scan_sort(c, ch.pt_first, ch.pt_count, int(ch.count), st);
     if (rc) return rc;
     launch_scan_gather(d_scan_in, c->d_svals_out + ch.pt_first, c->d_skeys_out + ch.pt_first, c->d_offset + ch.first, ch.pt_count,
-                       c->d_scan_sorted + ch.pt_first, c->stream);
+                       c->d_scan_sorted + ch.pt_first, st);
     c->launches++;
     timed_launch_end(c, 3);
     SO_CUDA_TRY(cudaGetLastError());
@@ -225,7 +231,8 @@ static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch) {
 // scan is not in the matching phase, so a fixed schedule follows whatever path the device-side state machine takes.
 // Preferred form: a CUDA-graph WHILE node around ONE iteration (k_loop_cond ends the loop when every scan of the chunk
 // is done); fallback: the schedule unrolled max_icp_iters times.  Returns whether the loop form ran.
-static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn, bool* was_loop) {
+static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn, bool* was_loop, cudaStream_t run_stream = nullptr) {
+    if (!run_stream) run_stream = c->stream;
     const float4* d_scan = c->d_scan_sorted;
     const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, d_scan, ch.first);
@@ -307,7 +314,7 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
         slot->first = ch.first; slot->count = n_scans; slot->grid_x = grid_x; slot->grid_e = grid_e; slot->iters = iters; slot->lm = lm; slot->epoch = c->map_epoch;
     }
     slot->used = ++c->graph_clock;
-    SO_CUDA_TRY(cudaGraphLaunch(slot->exec, c->stream));
+    SO_CUDA_TRY(cudaGraphLaunch(slot->exec, run_stream));
     *was_loop = slot->is_loop;
     if (!slot->is_loop) c->launches += uint64_t(iters) * (3 + kFitSplit + 2 * lm + (grid_e ? 1 + lm : 0));      // loop form: counted from the iterations executed
     return SO_OK;
@@ -398,11 +405,23 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, n_scans * sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
         SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, n_scans * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
         count_h2d(c, n_scans * (sizeof(IcpState) + sizeof(uint32_t)));
-        // Chunk the batch: with host input the H2D of chunk k+1 (copy stream) overlaps the kernels of chunk k.
-        const size_t n_chunks = (!host_src || c->profiling) ? 1 : (n_scans >= 32 ? 4 : (n_scans >= 16 ? 2 : 1));     // keep chunks >= 8 scans
+        // Chunk the batch.  Even chunks run on `stream`, odd ones on aux_stream, so that one chunk's serial stretches (the
+        // one-CTA optimiser steps, kernel tails, the loop condition) sit under the other's wide kernels; with host input
+        // the H2D of chunk k+1 (copy stream) also overlaps the kernels of chunk k.
+        // Device-resident scans: two chunks (one per stream).  Host scans: four, the first one small so that the only upload
+        // nothing can hide (chunk 0's) is short.  Chunks stay >= 8 scans: below that the wide kernels stop filling the GPU.
+        const size_t n_chunks = c->profiling ? 1 : (c->chunk_override ? size_t(c->chunk_override)
+                                                   : (host_src ? (n_scans >= 32 ? 4 : (n_scans >= 16 ? 2 : 1)) : (n_scans >= 16 ? 2 : 1)));
+        std::vector<uint32_t> bounds(n_chunks + 1);
+        for (size_t k = 0; k <= n_chunks; ++k) bounds[k] = uint32_t(k * n_scans / n_chunks);
+        if (host_src && n_chunks == 4 && n_scans >= 64 && !c->chunk_override) {
+            bounds[1] = uint32_t(n_scans / 8);
+            bounds[2] = bounds[1] + uint32_t((n_scans - bounds[1]) / 3);
+            bounds[3] = bounds[2] + uint32_t((n_scans - bounds[2]) / 2);
+        }
         std::vector<Chunk> chunks;
         for (size_t k = 0; k < n_chunks; ++k) {
-            const uint32_t f = uint32_t(k * n_scans / n_chunks), e = uint32_t((k + 1) * n_scans / n_chunks);
+            const uint32_t f = bounds[k], e = bounds[k + 1];
             if (e == f) continue;
             Chunk ch{f, e - f, c->h_offset[f], (e < n_scans ? c->h_offset[e] : off) - c->h_offset[f], 0};
             uint32_t mx = 0;
@@ -412,9 +431,14 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             chunks.push_back(ch);
         }
         SO_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+        const bool two_streams = chunks.size() > 1 && !c->single_stream;
+        if (two_streams) {
+            SO_CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));                    // aux starts after the state upload and all earlier work
+            SO_CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        }
         if (host_src) {
-            SO_CUDA_TRY(cudaEventRecord(c->ev_copy[7], c->stream));                 // copies must not overtake earlier work on d_scan
-            SO_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[7], 0));
+            SO_CUDA_TRY(cudaEventRecord(c->ev_copy[16], c->stream));                // copies must not overtake earlier work on d_scan
+            SO_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[16], 0));
             for (size_t k = 0; k < chunks.size(); ++k) {
                 const Chunk& ch = chunks[k];
                 if (ch.pt_count)
@@ -427,14 +451,19 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         std::vector<char> loop_flags(chunks.size(), 0);
         for (size_t k = 0; k < chunks.size(); ++k) {
             const Chunk& ch = chunks[k];
-            if (host_src) SO_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copy[k], 0));
+            cudaStream_t st = (two_streams && (k & 1)) ? c->aux_stream : c->stream;
+            if (host_src) SO_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copy[k], 0));
             if (ch.grid_x == 0) continue;
-            int rc = prepare_scans(c, d_scan, ch);
+            int rc = prepare_scans(c, d_scan, ch, st);
             if (rc) return rc;
             bool was_loop = false;
-            rc = run_schedule(c, ch, o.max_icp_iters, o.lm_max_iterations, false, &was_loop);
+            rc = run_schedule(c, ch, o.max_icp_iters, o.lm_max_iterations, false, &was_loop, st);
             if (rc) return rc;
             loop_flags[k] = was_loop;
+        }
+        if (two_streams) {
+            SO_CUDA_TRY(cudaEventRecord(c->ev_join, c->aux_stream));
+            SO_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         }
         SO_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, n_scans * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
@@ -491,7 +520,9 @@ so_ctx* so_create(const so_config* cfg_in) {
     c->cfg = cfg;
     if (cfg.plane_res > 0) c->surf.res = cfg.plane_res;
     if (cfg.line_res > 0) c->edge.res = cfg.line_res;
-    if (std::getenv("SO_NO_COND_GRAPH")) c->no_cond_graph = true;      // profiling aid: ncu cannot see inside conditional-node bodies
+    if (std::getenv("SO_NO_COND_GRAPH")) c->no_cond_graph = true;
+    if (std::getenv("SO_SINGLE_STREAM")) c->single_stream = true;
+    if (const char* e = std::getenv("SO_CHUNKS")) c->chunk_override = std::max(0, std::min(16, std::atoi(e)));      // profiling aid: ncu cannot see inside conditional-node bodies
     if (ctx_alloc(c) != SO_OK) { ctx_free(c); return nullptr; }
     return reinterpret_cast<so_ctx*>(c);
 }
@@ -717,6 +748,153 @@ int so_scan_prefilter(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, si
     return SO_OK;
 }
 
+// ---- scan preparation: deskew + uniform extraction (featureExtraction.cpp:222-314,504-525) ----------------------
+namespace {
+struct HPose { double q[4]; double p[3]; };      // xyzw
+HPose hpose_from7(const double* v) { return HPose{{v[3], v[4], v[5], v[6]}, {v[0], v[1], v[2]}}; }
+void hnormalize(double q[4]) {
+    const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int k = 0; k < 4; ++k) q[k] /= n;
+}
+// Eigen::QuaternionBase::slerp
+void hslerp(const double a[4], double t, const double b[4], double o[4]) {
+    const double one = 1.0 - std::numeric_limits<double>::epsilon();
+    const double d = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+    const double ad = std::fabs(d);
+    double s0, s1;
+    if (ad >= one) { s0 = 1.0 - t; s1 = t; }
+    else {
+        const double th = std::acos(ad), st = std::sin(th);
+        s0 = std::sin((1.0 - t) * th) / st;
+        s1 = std::sin(t * th) / st;
+    }
+    if (d < 0) s1 = -s1;
+    for (int k = 0; k < 4; ++k) o[k] = s0 * a[k] + s1 * b[k];
+}
+// the sign Eigen's matrix -> quaternion conversion produces (w > 0 when the trace is positive, else the dominant axis > 0)
+void hcanonical_sign(double q[4]) {
+    const double tr = 4.0 * q[3] * q[3] - 1.0;        // trace of R(q) for a unit q
+    bool flip;
+    if (tr > 0) flip = q[3] < 0;
+    else {
+        int i = 0;
+        if (std::fabs(q[1]) > std::fabs(q[0])) i = 1;
+        if (std::fabs(q[2]) > std::fabs(q[i])) i = 2;
+        flip = q[i] < 0;
+    }
+    if (flip) for (int k = 0; k < 4; ++k) q[k] = -q[k];
+}
+}  // namespace
+
+int so_scan_deskew(so_ctx* ctx, void* points, size_t n, size_t stride, size_t time_offset, double lidar_start_time, const double* sample_times,
+                   const double* sample_poses, size_t n_samples, int imu_only, const double T_i_l[7], double start_pose_out[7], size_t* n_past_end) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || (!points && n) || stride < 12 || time_offset + 4 > stride || !sample_times || !sample_poses || n_samples == 0 || (imu_only && !T_i_l))
+        return fail(SO_ERR_ARG, "bad args");
+    if (n > c->scan_cap) return fail(SO_ERR_CAPACITY, "cloud larger than the scan buffers");
+    if (n_samples * 8 > c->scan_cap) return fail(SO_ERR_CAPACITY, "more pose samples than the scratch holds (max_scan_points / 8)");
+    for (size_t k = 1; k < n_samples; ++k)
+        if (!(sample_times[k] > sample_times[k - 1])) return fail(SO_ERR_ARG, "sample_times must be strictly ascending (std::map keys)");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    // getInterpolatedPoseAtTime(lidar_start_time) on the host (:279): same rule as the kernel
+    size_t after = size_t(std::upper_bound(sample_times, sample_times + n_samples, lidar_start_time) - sample_times);
+    if (after == n_samples) after = n_samples - 1;
+    if (sample_times[after] < 0.0001) after = 0;
+    HPose start;
+    if (after == 0) start = hpose_from7(sample_poses);
+    else {
+        const HPose a = hpose_from7(sample_poses + 7 * (after - 1)), b = hpose_from7(sample_poses + 7 * after);
+        const double ratio = (lidar_start_time - sample_times[after - 1]) / (sample_times[after] - sample_times[after - 1]);
+        hslerp(a.q, ratio, b.q, start.q);
+        for (int k = 0; k < 3; ++k) start.p[k] = (1 - ratio) * a.p[k] + ratio * b.p[k];
+    }
+    if (imu_only) start.p[0] = start.p[1] = start.p[2] = 0.0;          // Imu::Ptr samples carry no translation (:232-236)
+    hnormalize(start.q);
+    DeskewParams P{};
+    P.start_time = lidar_start_time;
+    P.n_samples = uint32_t(n_samples);
+    P.n_smem = uint32_t(std::min<size_t>(n_samples, 2048));
+    P.imu_only = imu_only ? 1 : 0;
+    P.q0_conj[0] = -start.q[0]; P.q0_conj[1] = -start.q[1]; P.q0_conj[2] = -start.q[2]; P.q0_conj[3] = start.q[3];
+    for (int k = 0; k < 3; ++k) P.p0[k] = start.p[k];
+    double out7[7] = {start.p[0], start.p[1], start.p[2], start.q[0], start.q[1], start.q[2], start.q[3]};
+    if (imu_only) {
+        HPose il = hpose_from7(T_i_l);
+        hnormalize(il.q);
+        for (int k = 0; k < 4; ++k) P.q_il[k] = il.q[k];
+        for (int k = 0; k < 3; ++k) P.t_il[k] = il.p[k];
+        P.q_li[0] = -il.q[0]; P.q_li[1] = -il.q[1]; P.q_li[2] = -il.q[2]; P.q_li[3] = il.q[3];
+        double r[3];
+        qrot(P.q_li, il.p, r);                                           // Twist::inverse (Twist.h:172-179)
+        P.t_li[0] = -r[0]; P.t_li[1] = -r[1]; P.t_li[2] = -r[2];
+        // T_w_original_sensor = T_w_original * T_i_l (:283-286)
+        double q[4];
+        qmul(start.q, il.q, q);
+        hnormalize(q);
+        hcanonical_sign(q);
+        qrot(start.q, il.p, r);
+        out7[0] = r[0] + start.p[0]; out7[1] = r[1] + start.p[1]; out7[2] = r[2] + start.p[2];
+        out7[3] = q[0]; out7[4] = q[1]; out7[5] = q[2]; out7[6] = q[3];
+    }
+    if (start_pose_out) std::memcpy(start_pose_out, out7, sizeof(out7));
+    if (n_past_end) *n_past_end = 0;
+    if (n == 0) return SO_OK;
+    int rc = upload_cloud(c, points, n, stride, time_offset, c->d_scan);          // float4 {x, y, z, time}
+    if (rc) return rc;
+    // pose samples into device scratch (the scan-sort key buffer): [times n][poses 7n]; IMU samples lose their translation here
+    std::vector<double> hs(n_samples * 8);
+    for (size_t k = 0; k < n_samples; ++k) {
+        hs[k] = sample_times[k];
+        for (int j = 0; j < 7; ++j) hs[n_samples + 7 * k + j] = (imu_only && j < 3) ? 0.0 : sample_poses[7 * k + j];
+    }
+    double* d_samples = reinterpret_cast<double*>(c->d_skeys);
+    SO_CUDA_TRY(cudaMemcpyAsync(d_samples, hs.data(), hs.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    count_h2d(c, hs.size() * sizeof(double));
+    SO_CUDA_TRY(cudaMemsetAsync(c->d_svals, 0, 4, c->stream));
+    P.times = d_samples; P.poses = d_samples + n_samples; P.past_end = c->d_svals;
+    timed_launch_begin(c);
+    launch_deskew(c->d_scan, uint32_t(n), P, c->stream);
+    c->launches++;
+    timed_launch_end(c, 3);
+    rc = ensure_stage(c, n * sizeof(float4));
+    if (rc) return rc;
+    uint32_t past = 0;
+    SO_CUDA_TRY(cudaMemcpyAsync(c->h_stage, c->d_scan, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA_TRY(cudaMemcpyAsync(&past, c->d_svals, 4, cudaMemcpyDeviceToHost, c->stream));
+    count_d2h(c, n * sizeof(float4) + 4);
+    SO_CUDA_TRY(cudaStreamSynchronize(c->stream));                                 // also covers hs going out of scope
+    const float4* h = static_cast<const float4*>(c->h_stage);
+    unsigned char* dst = static_cast<unsigned char*>(points);
+    for (size_t i = 0; i < n; ++i, dst += stride) std::memcpy(dst, &h[i], 12);     // x, y, z only; every other field untouched
+    if (n_past_end) *n_past_end = past;
+    return SO_OK;
+}
+
+int so_scan_extract_uniform(so_ctx* ctx, const void* points, size_t n, size_t stride, size_t time_offset, int skip_num, float block_range,
+                            int int_abs, float* out_xyzi, size_t cap, size_t* n_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || (!points && n) || stride < 12 || time_offset + 4 > stride || !n_out || (!out_xyzi && cap)) return fail(SO_ERR_ARG, "bad args");
+    if (skip_num <= 0) return fail(SO_ERR_ARG, "skip_num must be positive (the reference loop would not terminate)");
+    if (n > c->scan_cap) return fail(SO_ERR_CAPACITY, "cloud larger than the scan buffers");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    *n_out = 0;
+    int rc = upload_cloud(c, points, n, stride, time_offset, c->d_scan);
+    if (rc) return rc;
+    uint32_t m = 0;
+    timed_launch_begin(c);
+    rc = scan_extract_uniform(c, uint32_t(n), uint32_t(skip_num), block_range, int_abs, &m);
+    timed_launch_end(c, 3);
+    if (rc) return rc;
+    *n_out = m;
+    const size_t ncopy = std::min<size_t>(m, cap);
+    if (ncopy) {
+        SO_CUDA_TRY(cudaMemcpyAsync(out_xyzi, c->d_scan_sorted, ncopy * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+        count_d2h(c, ncopy * sizeof(float4));
+        SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return SO_OK;
+}
+
 // ---- registration ----------------------------------------------------------------------------------------------
 int so_register(so_ctx* ctx, const void* surf, size_t n_surf, const void* edge, size_t n_edge, size_t stride, size_t ioff,
                 const double pose_in[7], const so_icp_opts* opts, so_icp_result* out) {
@@ -793,7 +971,7 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     const uint32_t grid_x = (uint32_t(n) + kThreads - 1) / kThreads;
     const Chunk ch{0, 1, 0, uint32_t(n), grid_x};
-    rc = prepare_scans(c, c->d_scan, ch);
+    rc = prepare_scans(c, c->d_scan, ch, c->stream);
     if (rc) return rc;
     const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, c->d_scan_sorted);

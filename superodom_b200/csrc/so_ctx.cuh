@@ -62,6 +62,7 @@ struct Ctx {
     uint64_t* d_skeys = nullptr; uint64_t* d_skeys_out = nullptr;   // scan sort keys (scan id << 32 | cell)
     uint32_t* d_svals = nullptr; uint32_t* d_svals_out = nullptr;
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
+    void* d_sort_tmp2 = nullptr;                   // second radix-sort scratch: scan ordering of the chunks that run on aux_stream
     NnBuf nn{};
     uint32_t* d_offset = nullptr;
     IcpState* d_state = nullptr;
@@ -88,12 +89,17 @@ struct Ctx {
         cudaGraphExec_t exec = nullptr;
         uint32_t first = 0, count = 0, grid_x = 0, grid_e = 0; int iters = 0, lm = 0; uint64_t epoch = 0; bool is_loop = false; uint64_t used = 0;
     };
-    GraphSlot graphs[8];
+    GraphSlot graphs[20];
     uint64_t graph_clock = 0;
     uint64_t map_epoch = 1;
+    bool single_stream = false;                    // SO_SINGLE_STREAM: tuning aid, all chunks on `stream`
+    int chunk_override = 0;                        // SO_CHUNKS: tuning aid, upload/compute chunks per host batch (0 = built-in rule)
     bool no_cond_graph = false;                    // conditional nodes unavailable (or SO_NO_COND_GRAPH): unrolled schedule
+    cudaStream_t aux_stream = nullptr;             // odd chunks of a batch run here, concurrently with the even ones on `stream`:
+                                                   // one chunk's serial optimiser steps and kernel tails hide under the other's wide kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t copy_stream = nullptr;            // H2D of batch chunks overlaps the previous chunk's kernels
-    cudaEvent_t ev_copy[8] = {};
+    cudaEvent_t ev_copy[17] = {};           // [0..15]: per upload chunk; [16]: guard
 
     // ---- instrumentation ----------------------------------------------------------------------------------------
     uint64_t launches = 0;
@@ -108,13 +114,26 @@ int map_alloc(Ctx* c);
 void map_free(Ctx* c);
 int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new);   // ms.d_xyzi[n .. n+n_new) holds the new points: voxel-filter touched blocks, rebuild
 int map_transform_tail(Ctx* c, MapStore& ms, uint32_t n_new, const double pose[7]);   // sensor-frame tail points -> world frame
-int scan_voxel_filter(Ctx* c, uint32_t n, float leaf, uint32_t* n_out);   // d_scan -> d_scan_sorted (VoxelGrid on a scan)
+int scan_voxel_filter(Ctx* c, uint32_t n, float leaf, uint32_t* n_out);
+// so_scan.cu
+struct DeskewParams {
+    double start_time;                     // lidar_start_time
+    const double* times;                   // n_samples ascending sample stamps (device)
+    const double* poses;                   // n_samples x {tx,ty,tz,qx,qy,qz,qw} (device; translation zeroed for IMU samples)
+    uint32_t n_samples, n_smem;            // n_smem: stamps cached in shared memory
+    int imu_only;
+    double q0_conj[4], p0[3];              // T_w_original: conjugate of its (normalised) rotation, its position
+    double q_il[4], t_il[3], q_li[4], t_li[3];   // T_i_l and its inverse (parameter.cpp:192-193)
+    uint32_t* past_end;                    // points later than the last sample
+};
+void launch_deskew(float4* pts, uint32_t n, const DeskewParams& P, cudaStream_t st);
+int scan_extract_uniform(Ctx* c, uint32_t n, uint32_t skip, float block_range, int int_abs, uint32_t* n_out);   // d_scan -> d_scan_sorted   // d_scan -> d_scan_sorted (VoxelGrid on a scan)
 int map_rebuild(Ctx* c, MapStore& ms);    // (re)bin, drop off-grid points, sort, build cell table
 MapView map_view(const Ctx* c, const MapStore& ms);
 int map_cells_per_block(float plane_res);
 int scan_sort_alloc(Ctx* c);             // temp storage for the per-registration scan sort
 int query_sort(Ctx* c, size_t n);         // d_qkeys/d_qvals -> *_out (allocates on growth)
 int query_sort_reserve(Ctx* c, size_t n);
-int scan_sort(Ctx* c, size_t first, size_t n, int n_scans);   // d_skeys/d_svals[first..first+n) -> *_out
+int scan_sort(Ctx* c, size_t first, size_t n, int n_scans, cudaStream_t st);   // d_skeys/d_svals[first..first+n) -> *_out
 
 }  // namespace so

@@ -222,6 +222,7 @@ int scan_sort_alloc(Ctx* c) {
     cub::DeviceRadixSort::SortPairs(nullptr, need, c->d_skeys, c->d_skeys_out, c->d_svals, c->d_svals_out, int(c->scan_cap), 0, 64);
     c->sort_tmp_bytes = need + 256;
     SO_CUDA_TRY(cudaMalloc(&c->d_sort_tmp, c->sort_tmp_bytes));
+    SO_CUDA_TRY(cudaMalloc(&c->d_sort_tmp2, c->sort_tmp_bytes));
     return SO_OK;
 }
 
@@ -248,12 +249,12 @@ int query_sort(Ctx* c, size_t n) {
     return SO_OK;
 }
 
-int scan_sort(Ctx* c, size_t first, size_t n, int n_scans) {
+int scan_sort(Ctx* c, size_t first, size_t n, int n_scans, cudaStream_t st) {
     int bits = 32;
     while ((1 << (bits - 32)) < n_scans) ++bits;
     size_t tmp = c->sort_tmp_bytes;
-    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_skeys + first, c->d_skeys_out + first, c->d_svals + first,
-                                                c->d_svals_out + first, int(n), 0, bits, c->stream));
+    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(st == c->aux_stream ? c->d_sort_tmp2 : c->d_sort_tmp, tmp, c->d_skeys + first, c->d_skeys_out + first,
+                                                c->d_svals + first, c->d_svals_out + first, int(n), 0, bits, st));
     c->launches += 5;
     return SO_OK;
 }

@@ -503,3 +503,63 @@ def make_case_on(scene, map_xyzi, name: str, scan_index: int = 0, max_radius: fl
     scan = make_scan(scene, cfg["sensor"], pose_true, 1000 + scan_index)
     prior = perturb_pose(pose_true, 2000 + scan_index)
     return dict(scene=scene, map_xyzi=map_xyzi, scan_xyzi=scan, pose_true=pose_true, pose_prior=prior, cfg=cfg)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Raw driver clouds for the scan-preparation rows: point_os::PointcloudXYZITR records
+# {x, y, z, pad, intensity, time, ring(+pad), pad} = 8 floats, time at float index 5, plus a pose-sample buffer.
+# ---------------------------------------------------------------------------------------------------------------
+def _quat_axis_angle(axis, ang):
+    axis = np.asarray(axis, np.float64)
+    axis = axis / np.linalg.norm(axis)
+    return np.r_[axis * np.sin(ang / 2), np.cos(ang / 2)]
+
+
+def make_raw_sweep(n: int = 50_000, seed: int = 4000, sweep_s: float = 0.1, start_time: float = 1_700_000_000.25, rate_hz: float = 200.0,
+                   with_defects: bool = True):
+    """-> dict(points float32 [n,8], start_time, sample_times [m], sample_poses [m,7], T_i_l [7]).
+    Points: a spinning-lidar-like shell 0.5..60 m, per-point time ascending over the sweep; with_defects adds what real
+    drivers deliver and the reference's predicates react to: exact repeats of the previous point, (0,0,0) returns, a few
+    NaN / inf records, points inside the blind range.  Pose samples: smooth 6-DoF motion sampled at rate_hz from before the
+    sweep starts to after it ends (synchronize_measurements' precondition, featureExtraction.cpp:187-214)."""
+    rng = np.random.default_rng(seed)
+    az = np.linspace(0, 2 * np.pi * 1.0, n, endpoint=False)
+    el = np.deg2rad(rng.uniform(-22.5, 22.5, n))
+    r = rng.uniform(0.5, 60.0, n)
+    pts = np.zeros((n, 8), np.float32)
+    pts[:, 0] = r * np.cos(el) * np.cos(az)
+    pts[:, 1] = r * np.cos(el) * np.sin(az)
+    pts[:, 2] = r * np.sin(el)
+    pts[:, 4] = rng.uniform(0, 255, n)
+    pts[:, 5] = np.linspace(0.0, sweep_s, n)
+    pts[:, 6] = rng.integers(0, 128, n).astype(np.float32)           # stands in for the ring bytes: must come back untouched
+    if with_defects:
+        k = rng.choice(np.arange(1, n), size=n // 50, replace=False)
+        pts[k, :3] = pts[k - 1, :3]                                    # exact repeats
+        k = rng.choice(np.arange(1, n), size=n // 100, replace=False)
+        pts[k, :3] = 0.0                                               # zero returns
+        k = rng.choice(np.arange(1, n), size=n // 100, replace=False)
+        pts[k, :2] = pts[k - 1, :2]                                    # same x,y as the predecessor, different z
+        pts[k, 2] = pts[k - 1, 2] + 0.05
+        k2 = k[: len(k) // 2]
+        pts[k2, :3] *= np.float32(0.001)                               # ... half of them inside the blind range
+        pts[k2 - 1, :2] = pts[k2, :2]
+        k = rng.choice(np.arange(1, n), size=8, replace=False)
+        pts[k[:4], 0] = np.nan
+        pts[k[4:], 1] = np.inf
+    t0 = start_time - 2.5 / rate_hz
+    m = int(np.ceil((sweep_s + 5.0 / rate_hz) * rate_hz)) + 1
+    st = t0 + np.arange(m) / rate_hz
+    sp = np.zeros((m, 7))
+    for i, t in enumerate(st):
+        u = t - start_time
+        sp[i, :3] = [1.5 * u + 0.3 * u * u, -0.4 * u, 0.1 * np.sin(3 * u)]
+        q = _quat_axis_angle([0.1, -0.2, 1.0], 0.8 * u + 0.5 * u * u)
+        q2 = _quat_axis_angle([1.0, 0.3, 0.0], 0.2 * np.sin(5 * u))
+        # Hamilton product q * q2 (xyzw)
+        x1, y1, z1, w1 = q
+        x2, y2, z2, w2 = q2
+        sp[i, 3:] = [w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2, w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2,
+                     w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2]
+    T_i_l = np.r_[0.05, -0.02, 0.11, _quat_axis_angle([0.2, 1.0, -0.1], 0.35)]
+    return dict(points=pts, start_time=start_time, sample_times=st, sample_poses=sp, T_i_l=T_i_l)

@@ -246,3 +246,85 @@ def test_golden_fixtures(oracle_mod):
     if O.has_ref_octree():
         r2 = m.register(G["scan_xyzi"], G["pose_prior"], float(G["plane_res"]), int(G["max_iterations"]), 0, knn_mode=2)
         assert np.allclose(np.array(r2.pose), G["pose_ref_octree"], atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# scan preparation: deskew + uniform extraction
+# ---------------------------------------------------------------------------------------------------------------
+def _interp_pose_scipy(st, sp, t):
+    """Independent formulation: geodesic interpolation through the rotation vector (== quaternion slerp)."""
+    from scipy.spatial.transform import Rotation as R
+    k = int(np.searchsorted(st, t, side="right"))          # upper_bound
+    assert 0 < k < len(st)
+    ratio = (t - st[k - 1]) / (st[k] - st[k - 1])
+    Ra, Rb = R.from_quat(sp[k - 1, 3:]), R.from_quat(sp[k, 3:])
+    Rt = Ra * R.from_rotvec(ratio * (Ra.inv() * Rb).as_rotvec())
+    return Rt, (1 - ratio) * sp[k - 1, :3] + ratio * sp[k, :3]
+
+
+@pytest.mark.parametrize("imu_only", [False, True])
+def test_deskew_against_first_principles(oracle_mod, imu_only):
+    from scipy.spatial.transform import Rotation as R
+    from superodom_b200 import synth
+    d = synth.make_raw_sweep(4000, seed=4001)
+    pts, st, sp, t0 = d["points"], d["sample_times"], d["sample_poses"], d["start_time"]
+    out, start, past = oracle_mod.deskew(pts, 5, t0, st, sp, imu_only=imu_only, T_i_l=d["T_i_l"])
+    assert past == 0
+    assert np.array_equal(out[:, 3:], pts[:, 3:], equal_nan=True)              # only x, y, z move
+    bad = ~np.isfinite(pts[:, :3]).all(1)
+    assert bad.sum() == 8 and np.array_equal(out[bad, :3], pts[bad, :3], equal_nan=True)   # non-finite points are skipped (:292-294)
+    R0, p0 = _interp_pose_scipy(st, sp, t0)
+    Ril, til = R.from_quat(d["T_i_l"][3:]), d["T_i_l"][:3]
+    if imu_only:
+        p0 = np.zeros(3)
+        exp_start_q, exp_start_t = (R0 * Ril).as_quat(), R0.apply(til)
+    else:
+        exp_start_q, exp_start_t = R0.as_quat(), p0
+    assert np.abs(start[:3] - exp_start_t).max() < 1e-12
+    assert min(np.abs(start[3:] - exp_start_q).max(), np.abs(start[3:] + exp_start_q).max()) < 1e-12
+    for i in np.random.default_rng(0).choice(np.flatnonzero(~bad), 200, replace=False):
+        Rc, pc = _interp_pose_scipy(st, sp, float(pts[i, 5]) + t0)
+        if imu_only:
+            pc = np.zeros(3)
+        v = pts[i, :3].astype(np.float64)
+        if imu_only:
+            v = Ril.apply(v) + til                       # T_i_l
+        v = R0.inv().apply(Rc.apply(v) + pc - p0)        # T_w_original^-1 * T_w_current
+        if imu_only:
+            v = Ril.inv().apply(v - til)                 # T_l_i
+        assert np.abs(out[i, :3] - v).max() <= 8e-6, (i, out[i, :3], v)     # float32 store at <= 60 m
+
+
+def test_deskew_buffer_edges(oracle_mod):
+    from superodom_b200 import synth
+    d = synth.make_raw_sweep(500, seed=4002, with_defects=False)
+    pts, st, sp, t0 = d["points"], d["sample_times"], d["sample_poses"], d["start_time"]
+    # every point earlier than the first sample: upper_bound == begin -> first sample as is, for the start pose too => no motion
+    out, start, past = oracle_mod.deskew(pts, 5, t0, st + 10.0, sp)
+    assert past == 0 and np.abs(out[:, :3] - pts[:, :3]).max() < 1e-5 and np.allclose(start, sp[0], atol=1e-15)
+    # samples ending inside the sweep: the reference would dereference end(); counted, last interval extrapolated
+    out, _, past = oracle_mod.deskew(pts, 5, t0, st[:12], sp[:12])
+    assert past == int((pts[:, 5].astype(np.float64) + t0 >= st[11]).sum()) and past > 0 and np.isfinite(out[:, :3]).all()
+    # a following stamp below 1e-4 rewinds to the first sample (:258-260): start pose == sample 0, not an interpolation
+    out, start, past = oracle_mod.deskew(pts, 5, -0.032, st - st[0] - 0.05, sp)
+    assert np.allclose(start, sp[0], atol=1e-15)
+    _, start2, _ = oracle_mod.deskew(pts, 5, 0.032, st - st[0] - 0.05, sp)
+    assert not np.allclose(start2, sp[0], atol=1e-6)
+
+
+@pytest.mark.parametrize("skip,block_range", [(1, 0.2), (3, 0.2), (4, 1.5), (7, 0.0)])
+def test_extract_uniform_against_numpy(oracle_mod, skip, block_range):
+    from superodom_b200 import synth
+    pts = synth.make_raw_sweep(20_000, seed=4003)["points"]
+    for int_abs in (False, True):
+        got = oracle_mod.extract_uniform(pts, 5, skip, block_range, int_abs=int_abs)
+        i = np.arange(1, len(pts), skip)
+        with np.errstate(invalid="ignore", over="ignore"):
+            d = pts[i, :3] - pts[i - 1, :3]
+            a = np.where(np.isfinite(d), np.abs(np.trunc(d)), 0.0).astype(np.float64) if int_abs else np.abs(d).astype(np.float64)
+            r2 = (pts[i, 0] * pts[i, 0] + pts[i, 1] * pts[i, 1]) + pts[i, 2] * pts[i, 2]
+            keep = (a[:, 0] > 1e-7) | (a[:, 1] > 1e-7) | ((a[:, 2] > 1e-7) & (r2 > np.float32(block_range) * np.float32(block_range)))
+        exp = pts[i][keep]
+        assert len(got) == keep.sum()
+        assert np.array_equal(got[:, :3], exp[:, :3], equal_nan=True) and np.array_equal(got[:, 3], exp[:, 5])
+    assert 0 < len(got) < len(i)
