@@ -28,7 +28,7 @@ METRIC = "ICP scans/sec (128-beam, 1M-pt map)"
 UNIT = "scans/s"
 WORKLOAD = "cfg2: OS1-128 synthetic scans (131072 pts) vs 1M-pt local map, 20 ICP iters, planeRes 0.2, all points active"
 KNN_BYTES_PER_POINT = 16 + 21 + 80              # scan float4 read + 5 positions + flag + 5 neighbour float4 written by k_knn_scan
-NCU_KNN_DRAM_BYTES_PER_POINT = None             # filled from profiles/ once the final ncu capture of this round is in
+NCU_KNN_DRAM_BYTES_PER_POINT = 81.7            # profiles/ncu_prof_r1k_metrics.csv: (27.08 MB read + 58.60 MB written) / 1 048 576 points of one k_knn_scan launch
 
 
 def _peaks():
@@ -235,7 +235,7 @@ def run_ours(args):
                     "traffic_source": "profiles/ (ncu --set full, dram__bytes_read+write per point of one k_knn_scan launch, scaled to this launch size)",
                     "peak_source": peak_src, "launches_profiled": int(n_k), "avg_launch_ms": ms_k / max(n_k, 1),
                     "algorithmic_bytes_per_launch": alg_bytes / max(n_k, 1),
-                    "note": "instruction-issue bound (ncu: 70% issue-active), L1/L2-resident gathers; see DESIGN.md section 4",
+                    "note": "instruction-issue bound (ncu: 67% issue-active), L1/L2-resident gathers; see DESIGN.md section 4",
                     "k_fit": {"launches": int(n_f), "avg_launch_ms": ms_f / max(n_f, 1)},
                     "k_evaluate": {"launches": int(n_e), "avg_launch_ms": ms_e / max(n_e, 1)},
                     "share_of_step": {"k_knn_scan": ms_k / tot, "k_fit": ms_f / tot, "k_evaluate": ms_e / tot, "scan_ordering": ms_p / tot}}

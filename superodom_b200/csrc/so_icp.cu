@@ -534,6 +534,10 @@ __device__ __forceinline__ void accumulate(double acc[kAcc], const double n[3], 
     acc[27] += 0.5 * rho0;
 }
 
+#ifndef SO_SCAN_ORDER
+#define SO_SCAN_ORDER 0      // 0: cell-linear (x fastest), 1: Morton, 2: x-runs in 2x2 row bundles -- tuning variants of the scan order
+#endif
+
 // shouldProcessPoint (LidarSlam.cpp:353-359)
 __device__ __forceinline__ bool should_process(uint32_t i, double rate) {
     if (rate < 0.0) return true;
@@ -562,7 +566,20 @@ __global__ void __launch_bounds__(kThreads) k_scan_keys(MapView m, BatchView bv,
     QueryCell qc;
     locate(m, float(pf[0] + st->x[0]), float(pf[1] + st->x[1]), float(pf[2] + st->x[2]), qc);
     uint32_t cell = 0xFFFFFFFFu;
+#if SO_SCAN_ORDER == 1
+    // Morton order of the cell inside its block (nb <= 192: 8 bits per axis)
+    if (qc.slot >= 0) {
+        auto spread = [](uint32_t v) { v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; return (v | (v << 2)) & 0x09249249u; };
+        cell = (uint32_t(qc.slot) << 24) | spread(uint32_t(qc.c[0])) | (spread(uint32_t(qc.c[1])) << 1) | (spread(uint32_t(qc.c[2])) << 2);
+    }
+#elif SO_SCAN_ORDER == 2
+    // x-runs inside 2x2 bundles of (y, z) rows
+    if (qc.slot >= 0)
+        cell = uint32_t(qc.slot) * uint32_t(m.nb * m.nb * m.nb) +
+               uint32_t((((qc.c[2] >> 1) * ((m.nb + 1) >> 1) + (qc.c[1] >> 1)) * m.nb + qc.c[0]) * 4 + (qc.c[2] & 1) * 2 + (qc.c[1] & 1));
+#else
     if (qc.slot >= 0) cell = uint32_t(qc.slot) * uint32_t(m.nb * m.nb * m.nb) + uint32_t((qc.c[2] * m.nb + qc.c[1]) * m.nb + qc.c[0]);
+#endif
     keys[gi] = (uint64_t(s) << 32) | uint64_t(cell);
     vals[gi] = uint32_t(gi);
 }
@@ -582,7 +599,10 @@ __global__ void __launch_bounds__(kThreads) k_scan_gather(const float4* __restri
 // Light on registers (FP32 search, FP64 only for the pose transform and the exact d2 of real contenders) so that
 // many warps per SM hide the L1/L2 latency of the cell walks.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_knn_scan(MapView m, BatchView bv, NnBuf nb) {
+#ifndef SO_KNN_MINB
+#define SO_KNN_MINB 4
+#endif
+__global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_scan(MapView m, BatchView bv, NnBuf nb) {
     const int s = blockIdx.y;
     const IcpState* st = bv.st + s;
     if (st->phase != PH_CORR) return;

@@ -602,8 +602,8 @@ def test_scan_chain_deskew_extract_register(gpu_api, oracle_mod):
     exp_feat = oracle_mod.extract_uniform(raw, 5, 1, 0.2)
     assert np.array_equal(feat, exp_feat) and len(feat) >= n - 2
     cfg = case["cfg"]
-    rg = ctx.register(feat, case["pose_prior"], cfg["max_icp_iters"], cfg["max_surface_features"])
+    rg = ctx.register(feat, case["pose_prior"], cfg["max_iterations"], cfg["max_surface_features"])
     om = oracle_mod.OracleMap(case["map_xyzi"])
-    ro = om.register(exp_feat, case["pose_prior"], cfg["plane_res"], cfg["max_icp_iters"], cfg["max_surface_features"])
+    ro = om.register(exp_feat, case["pose_prior"], cfg["plane_res"], cfg["max_iterations"], cfg["max_surface_features"])
     assert rg.status == ro.status == 0 and rg.n_iterations == ro.n_iterations
     _assert_pose_close(np.array(rg.pose), np.array(ro.pose))
