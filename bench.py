@@ -27,8 +27,9 @@ sys.path.insert(0, ROOT)
 METRIC = "ICP scans/sec (128-beam, 1M-pt map)"
 UNIT = "scans/s"
 WORKLOAD = "cfg2: OS1-128 synthetic scans (131072 pts) vs 1M-pt local map, 20 ICP iters, planeRes 0.2, all points active"
-KNN_BYTES_PER_POINT = 16 + 21 + 80              # scan float4 read + 5 positions + flag + 5 neighbour float4 written by k_knn_scan
-NCU_KNN_DRAM_BYTES_PER_POINT = 81.7            # profiles/ncu_prof_r1k_metrics.csv: (27.08 MB read + 58.60 MB written) / 1 048 576 points of one k_knn_scan launch
+KNN_BYTES_PER_POINT = 16 + 21 + 80              # unfused build: scan float4 read + 5 positions + flag + 5 neighbour float4 written by k_knn_scan
+MATCH_BYTES_PER_POINT = 16 + 25 + 45            # fused k_knn_fit: scan float4 read; 5 positions + d5 + flag; correspondence {n,d} 32 + w 8 + flags 4 + status 1
+NCU_DRAM_BYTES_PER_POINT = {"k_knn_scan": 81.7, "k_knn_fit": None}   # per kernel; k_knn_scan:           # profiles/ncu_prof_r1k_metrics.csv: (27.08 MB read + 58.60 MB written) / 1 048 576 points of one k_knn_scan launch
 
 
 def _peaks():
@@ -40,42 +41,73 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with NVML while the timed region runs."""
+    """Samples SM clocks / throttle reasons with NVML while the timed region runs.  One sampler per job (rank 0) polls every
+    GPU of the job: NVML is initialised BEFORE the warm-up (nvmlInit enumerates all GPUs and holds driver locks for a long
+    time -- inside a 40 ms timed region, in N processes at once, it stalled kernel launches), then polls at a low rate."""
 
-    def __init__(self, index: int, period: float = 0.1):
+    def __init__(self, indices, period: float = 0.02):
         super().__init__(daemon=True)
-        self.index, self.period, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, period, [], set(), False, None
-
-    def run(self):
+        self.indices, self.period, self.samples, self.reasons, self.stop_flag, self.max_mhz = list(indices), period, [], set(), False, None
+        self.window = None
+        self.nv, self.handles = None, []
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
-            while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(self.period)
+            self.nv = nv
+            self.handles = [self._handle(nv, i) for i in self.indices]
+            self.max_mhz = min(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM) for h in self.handles)
         except Exception as e:      # NVML missing: report that rather than fail the bench
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    @staticmethod
+    def _handle(nv, cuda_index):
+        """NVML handle of CUDA device `cuda_index` (CUDA_VISIBLE_DEVICES may renumber): by UUID, else by index."""
+        try:
+            import torch
+            u = str(torch.cuda.get_device_properties(cuda_index).uuid)
+            return nv.nvmlDeviceGetHandleByUUID(u if u.startswith("GPU-") else "GPU-" + u)
+        except Exception:
+            return nv.nvmlDeviceGetHandleByIndex(cuda_index)
+
+    def run(self):
+        nv = self.nv
+        if nv is None:
+            return
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        try:
+            while not self.stop_flag:
+                if self.window is not None:                      # only while a timed region is open
+                    mhz = min(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM) for h in self.handles)
+                    self.samples.append(mhz)
+                    for h in self.handles:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for bit, name in names.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as e:
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
+
+    def open(self):
+        self.window = time.perf_counter()
+
+    def close(self):
+        self.window = None
 
     def result(self):
         self.stop_flag = True
         self.join(timeout=2)
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "gpus_sampled": len(self.handles)}
 
 
 def make_inputs(first_scan: int, n_scans: int):
-    """Seeded synthetic cfg2 inputs.  SO_BENCH_CACHE=<dir>: keep the generated arrays there so that several runs
-    inside one GPU session do not repeat the (CPU, ~1 min) ray casting; the cache holds inputs only."""
+    """Seeded synthetic cfg2 inputs.  The generated arrays are kept under SO_BENCH_CACHE (default a /tmp
+    directory) so that back-to-back runs on one box (N = 1, 2, 4, 8) do not repeat the CPU-side synthesis; the cache holds
+    inputs only, never results."""
     from superodom_b200 import synth
-    cache = os.environ.get("SO_BENCH_CACHE")
+    cache = os.environ.get("SO_BENCH_CACHE", "/tmp/superodom_b200_bench_inputs")       # "" disables
     path = os.path.join(cache, f"cfg2_{first_scan}_{n_scans}.npz") if cache else None
     if path and os.path.exists(path):
         z = np.load(path)
@@ -91,7 +123,9 @@ def make_inputs(first_scan: int, n_scans: int):
         truths.append(c["pose_true"])
     if path:
         os.makedirs(cache, exist_ok=True)
-        np.savez(path, map=map_xyzi, flat=np.concatenate(scans, 0), n=np.array([len(x) for x in scans]), priors=np.stack(priors), truths=np.stack(truths))
+        tmp = path + f".{os.getpid()}.tmp.npz"
+        np.savez(tmp, map=map_xyzi, flat=np.concatenate(scans, 0), n=np.array([len(x) for x in scans]), priors=np.stack(priors), truths=np.stack(truths))
+        os.replace(tmp, path)                              # atomic: ranks / back-to-back runs may race on the same file
     return map_xyzi, scans, np.stack(priors), np.stack(truths)
 
 
@@ -141,14 +175,25 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    t_phase = [time.perf_counter()]
+
+    def phase(label):                                  # wall-clock of the untimed set-up phases, to stderr
+        now = time.perf_counter()
+        print(f"[bench rank {rank}] {label}: {now - t_phase[0]:.1f} s", file=sys.stderr, flush=True)
+        t_phase[0] = now
+
+    # input synthesis (numba ray casting) must not oversubscribe the host when several ranks generate at once
+    os.environ.setdefault("NUMBA_NUM_THREADS", str(max(1, min(16, (os.cpu_count() or 8) // max(world, 1)))))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    phase("import torch + process group")
     B = args.batch
     n_total = B * world
     b0, b1 = replay.shard_range(n_total, rank, world)
     map_xyzi, scans, priors, truths = make_inputs(b0, b1 - b0)
+    phase(f"synthetic inputs ({b1 - b0} scans)")
     n_points = np.array([len(s) for s in scans], np.uint32)
     flat = np.ascontiguousarray(np.concatenate(scans, 0))
 
@@ -190,26 +235,36 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), res, allp
 
+    sampler = ClockSampler(range(world)) if rank == 0 else None      # torchrun on one node: local GPU indices 0..world-1
+    if sampler:
+        sampler.start()
+    phase("context, map upload, pinned staging, NVML init")
     for _ in range(max(args.warmup, 3)):
         res, allp = step_device()
+    phase("warm-up steps")
     # correctness guard: the timed thing really registers the scans (cm-level agreement with ground truth)
     err = np.linalg.norm(np.array([list(r.pose) for r in res])[:, :3] - truths[:, :3], axis=1)
     assert all(r.status == 0 for r in res) and err.max() < 0.05, (err.max(), [r.status for r in res])
 
-    sampler = ClockSampler(local)
-    sampler.start()
     ctx.kernel_launches(reset=True)
+    if sampler:
+        sampler.open()
     ms, res, allp = timed(step_device, args.steps)
+    if sampler:
+        sampler.close()
     launches = ctx.kernel_launches()
-    clocks = sampler.result()
     value = n_total * args.steps / (ms * 1e-3)
 
     for _ in range(2):
         step_host()
     ctx.bytes_copied(reset=True)
+    if sampler:
+        sampler.open()
     ms_e2e, _, _ = timed(step_host, args.steps)
+    clocks = sampler.result() if sampler else None
     h2d, d2h = ctx.bytes_copied()
     e2e = n_total * args.steps / (ms_e2e * 1e-3)
+    phase("timed regions (device-resident + e2e)")
 
     line = None
     if rank == 0:
@@ -227,18 +282,20 @@ def run_ours(args):
         scan_passes = sum(int(r.n_iterations) * int(n) for r, n in zip(pres, n_points))
         # algorithmic bytes of the k-NN kernel: 16 B scan read + 21 B neighbour ids/flag + 80 B neighbour
         # points handed to k_fit, per processed point and ICP iteration, + the map streamed once per launch
-        alg_bytes = scan_passes * KNN_BYTES_PER_POINT + n_k * len(map_xyzi) * 16
+        fused = bool(api.build_flags() & 1)
+        kname = "k_knn_fit" if fused else "k_knn_scan"
+        alg_bytes = scan_passes * (MATCH_BYTES_PER_POINT if fused else KNN_BYTES_PER_POINT) + n_k * len(map_xyzi) * 16
         achieved = alg_bytes / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
         tot = ms_k + ms_f + ms_e + ms_p + 1e-12
-        roofline = {"bound": "hbm", "kernel": "k_knn_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": NCU_KNN_DRAM_BYTES_PER_POINT * scan_passes / max(n_k, 1) if NCU_KNN_DRAM_BYTES_PER_POINT else None,
-                    "traffic_source": "profiles/ (ncu --set full, dram__bytes_read+write per point of one k_knn_scan launch, scaled to this launch size)",
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": NCU_DRAM_BYTES_PER_POINT[kname] * scan_passes / max(n_k, 1) if NCU_DRAM_BYTES_PER_POINT.get(kname) else None,
+                    "traffic_source": f"profiles/ (ncu --set full, dram__bytes_read+write per point of one {kname} launch, scaled to this launch size)",
                     "peak_source": peak_src, "launches_profiled": int(n_k), "avg_launch_ms": ms_k / max(n_k, 1),
                     "algorithmic_bytes_per_launch": alg_bytes / max(n_k, 1),
                     "note": "instruction-issue bound (ncu: 67% issue-active), L1/L2-resident gathers; see DESIGN.md section 4",
-                    "k_fit": {"launches": int(n_f), "avg_launch_ms": ms_f / max(n_f, 1)},
+                    "first_evaluation": {"launches": int(n_f), "avg_launch_ms": ms_f / max(n_f, 1)},
                     "k_evaluate": {"launches": int(n_e), "avg_launch_ms": ms_e / max(n_e, 1)},
-                    "share_of_step": {"k_knn_scan": ms_k / tot, "k_fit": ms_f / tot, "k_evaluate": ms_e / tot, "scan_ordering": ms_p / tot}}
+                    "share_of_step": {kname: ms_k / tot, "first_evaluation": ms_f / tot, "k_evaluate": ms_e / tot, "scan_ordering": ms_p / tot}}
         # CPU baseline on the host cores: the oracle (reference octree verbatim when oracle/_ref travelled), 1 thread, bounded sample
         cpu = None
         if not args.no_cpu_baseline:
@@ -255,6 +312,7 @@ def run_ours(args):
             cpu = {"value": ns / dt, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{ns} of the step's cfg2 scans, whole ICP, 1 thread (the reference's feature loop and Ceres solve are serial); "
                              f"k-NN = {'reference octree.h compiled verbatim' if mode == 2 else 'oracle exact grid'}; last |dpos| vs GPU {dpos:.2e} m"}
+        phase("profiling pass + cpu baseline")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",

@@ -21,7 +21,7 @@ EXPORTS = [
     "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
     "so_map_set_edge_points", "so_map_add_surf", "so_map_add_edge", "so_map_add_scan", "so_map_add_scan_edge", "so_map_counts_5x5", "so_map_download", "so_map_size",
     "so_scan_prefilter", "so_scan_deskew", "so_scan_extract_uniform", "so_register", "so_register_batch", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
-    "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_profile_enable", "so_profile_get",
+    "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_build_flags", "so_profile_enable", "so_profile_get",
 ]
 
 
@@ -113,6 +113,10 @@ def load_library():
     L.so_profile_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     _lib = L
     return L
+
+
+def build_flags() -> int:
+    return int(load_library().so_build_flags())
 
 
 def device_available() -> bool:

@@ -255,8 +255,8 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
         };
         for (int it = 0; it < iters; ++it) {
             if (any_in(PH_CORR)) {
-                timed_launch_begin(c); launch_knn_scan(mv, bv, c->nn, grid_x, n_scans, c->stream); timed_launch_end(c, 0);
-                timed_launch_begin(c); launch_fit(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, &me, &eb, grid_e); c->launches += 1 + kFitSplit + (grid_e ? 1 : 0); timed_launch_end(c, 4);
+                timed_launch_begin(c); launch_match(mv, bv, cb, c->nn, grid_x, n_scans, c->stream); c->launches += kCorrLaunches - 1; timed_launch_end(c, 0);
+                timed_launch_begin(c); launch_first_eval(bv, cb, grid_x, n_scans, c->stream, &me, &eb, grid_e); c->launches += 1 + (grid_e ? 1 : 0); timed_launch_end(c, 4);
             }
             for (int k = 0; k < lm; ++k)
                 if (any_in(PH_EVAL)) { timed_launch_begin(c); launch_evaluate(bv, cb, grid_x, n_scans, c->stream, &eb, grid_e); c->launches += 1 + (grid_e ? 1 : 0); timed_launch_end(c, 1); }
@@ -316,7 +316,7 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
     slot->used = ++c->graph_clock;
     SO_CUDA_TRY(cudaGraphLaunch(slot->exec, run_stream));
     *was_loop = slot->is_loop;
-    if (!slot->is_loop) c->launches += uint64_t(iters) * (3 + kFitSplit + 2 * lm + (grid_e ? 1 + lm : 0));      // loop form: counted from the iterations executed
+    if (!slot->is_loop) c->launches += uint64_t(iters) * (kCorrLaunches + 2 + 2 * lm + (grid_e ? 1 + lm : 0));      // loop form: counted from the iterations executed
     return SO_OK;
 }
 
@@ -475,7 +475,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             if (!loop_flags[k]) continue;
             int max_it = 0;
             for (uint32_t s = chunks[k].first; s < chunks[k].first + chunks[k].count; ++s) max_it = std::max(max_it, int(c->h_state[s].n_iterations));
-            c->launches += uint64_t(max_it) * uint64_t(4 + kFitSplit + 2 * o.lm_max_iterations + (chunks[k].grid_e ? 1 + o.lm_max_iterations : 0));
+            c->launches += uint64_t(max_it) * uint64_t(kCorrLaunches + 3 + 2 * o.lm_max_iterations + (chunks[k].grid_e ? 1 + o.lm_max_iterations : 0));
         }
         for (size_t s = 0; s < n_scans; ++s) {
             if (results[s].status == SO_STATUS_NOT_ENOUGH_FEATURES || n_points[s] == 0) continue;
@@ -975,7 +975,7 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     if (rc) return rc;
     const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, c->d_scan_sorted);
-    timed_launch_begin(c); launch_correspond(mv, bv, c->corr, c->nn, grid_x, 1, c->stream); c->launches += 2 + kFitSplit; timed_launch_end(c, 0);
+    timed_launch_begin(c); launch_correspond(mv, bv, c->corr, c->nn, grid_x, 1, c->stream); c->launches += kCorrLaunches + 2; timed_launch_end(c, 0);
     SO_CUDA_TRY(cudaGetLastError());
     std::vector<double4> nd(n); std::vector<double> w(n); std::vector<uchar4> fl(n); std::vector<uint32_t> nn(n * 5); std::vector<float> d2(n * 5);
     std::vector<float4> sorted(n);
@@ -1019,7 +1019,7 @@ int so_correspond_edge(so_ctx* ctx, const void* edge, size_t n, size_t stride, s
     const MapView mv = map_view(c, c->surf), me = map_view(c, c->edge);
     const BatchView bv = batch_view(c, c->d_scan_sorted);
     timed_launch_begin(c);
-    launch_fit(mv, bv, c->corr, c->nn, 0, 1, c->stream, &me, &c->ebuf, grid_e);     // 0 plane CTAs: only the edge kernel + k_lm_step have work
+    launch_first_eval(bv, c->corr, 0, 1, c->stream, &me, &c->ebuf, grid_e);     // 0 plane CTAs: only the edge kernel + k_lm_step have work
     c->launches += 2;
     timed_launch_end(c, 4);
     SO_CUDA_TRY(cudaGetLastError());
@@ -1131,6 +1131,8 @@ int so_bytes_copied(so_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset) {
     if (reset) { c->bytes_h2d = 0; c->bytes_d2h = 0; }
     return SO_OK;
 }
+
+int so_build_flags(void) { return SO_FUSE_KNN_FIT ? SO_BUILD_FUSED_MATCH : 0; }
 
 int so_profile_enable(so_ctx* ctx, int on) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);

@@ -670,176 +670,231 @@ __device__ __forceinline__ float4 ld_f4_again(const float4* p) {
 // five neighbours -- PCA, plane fit, gates, observability -- plus the first residual/Jacobian evaluation of the
 // following ceres::Solve and the histogram / normal-equation reductions.  FP64 throughout.
 // ------------------------------------------------------------------------------------------------------------------
+// The rest of LidarSLAM::ComputePlaneDistanceParameters (LidarSlam.cpp:536-572) for one scan point whose k-NN outcome is
+// `status`: PCA, plane fit, gates, observability labels, fit weight; writes the correspondence record and counts the
+// histograms.  nbr(j) re-reads neighbour j (a volatile, L1-hit load: the neighbours are read three times rather than held in
+// 30 FP64 registers across the eigen-solve).  FP64 throughout.
+template <class NbrLoad>
+__device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, const NnBuf& nb, size_t gi, const float4 sp, const double* s_pose,
+                                          int status, NbrLoad nbr, int* s_hist) {
+    int o0 = 0, o1 = 0, o2 = 0;
+    double nrm[3] = {0, 0, 0}, dpl = 0.0, wq = 0.0;
+    if (status == SO_MATCH_SUCCESS) {
+                    // ComputePointInitAndFinalPose (:382-400): pInit = double(p), pFinal = T_w_lidar * pInit
+        const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+        double pf[3];
+        qrot(s_pose + 3, pin, pf);
+        pf[0] += s_pose[0]; pf[1] += s_pose[1]; pf[2] += s_pose[2];
+        const float qx = float(pf[0]), qy = float(pf[1]), qz = float(pf[2]);
+        // computePCAForFeature (:749-790) + utils::ComputePCA (superodom_utils.h:143-151).  The five neighbours are read
+        // three times (here, for the QR, for the distances) from k_knn_scan's coalesced hand-over instead of being held
+        // in 30 FP64 registers across the eigen-solve: the re-reads hit L1 and the kernel fits 3 CTAs per SM.
+        double mean[3] = {0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float4 c = nbr(j);
+            mean[0] += double(c.x); mean[1] += double(c.y); mean[2] += double(c.z);
+            if (cb.nn) {
+                const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+                cb.nn[gi * 5 + j] = __float_as_uint(c.w);
+                cb.nn_d2[gi * 5 + j] = float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz));
+            }
+        }
+        mean[0] /= 5.0; mean[1] /= 5.0; mean[2] /= 5.0;
+        double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float4 c = nbr(j);
+            const double c0 = double(c.x) - mean[0], c1 = double(c.y) - mean[1], c2 = double(c.z) - mean[2];
+            S[0] += c0 * c0; S[1] += c0 * c1; S[2] += c0 * c2; S[4] += c1 * c1; S[5] += c1 * c2; S[8] += c2 * c2;
+        }
+        S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
+        const double sxx = S[0], sxy = S[1], sxz = S[2], syy = S[4], syz = S[5], szz = S[8];
+        double ev[3];
+        jacobi_eig<3, 12, false>(S, nullptr, ev);
+        if (ev[0] < 1e-6 || ev[1] / ev[2] < 0.1) status = SO_MATCH_BAD_PCA_STRUCTURE;      // (:772)
+        else {
+            // What FeatureObservabilityAnalysis (:574-693) needs from the PCA -- the oriented normal (:553-561) and the
+            // planarity -- is reduced to four floats here, ahead of the register-hungry QR.
+            float nf[3], cr[3], planar_sq;
+            {
+                double no[3];
+                eigvec3_from_value(sxx, sxy, sxz, syy, syz, szz, ev[0], no);
+                if (pf[0] * no[0] + pf[1] * no[1] + pf[2] * no[2] < 0) { no[0] = -no[0]; no[1] = -no[1]; no[2] = -no[2]; }
+                const double l1 = sqrt(ev[2]), l2 = sqrt(ev[1]), l3 = sqrt(ev[0]);
+                const double planar_2 = (l2 - l3) / l1;
+                planar_sq = float(planar_2 * planar_2);
+                nf[0] = float(no[0]); nf[1] = float(no[1]); nf[2] = float(no[2]);
+                cr[0] = __fmul_rn(qy, nf[2]) - __fmul_rn(qz, nf[1]);
+                cr[1] = __fmul_rn(qz, nf[0]) - __fmul_rn(qx, nf[2]);
+                cr[2] = __fmul_rn(qx, nf[1]) - __fmul_rn(qy, nf[0]);
+            }
+            // computePlaneQualityMetrics (:792-844)
+            double x[3];
+            {
+                double A[5][3], b[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float4 c = nbr(j);
+                    A[j][0] = double(c.x); A[j][1] = double(c.y); A[j][2] = double(c.z); b[j] = -1.0;
+                }
+                colpiv_qr_solve_5x3(A, b, x);
+            }
+            if (!(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]))) status = SO_MATCH_INVALID_NUMERICAL;
+            else {
+                const double nn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+                const double dd = 1.0 / nn;
+                x[0] /= nn; x[1] /= nn; x[2] /= nn;
+                const double maxd = double(m.plane_res) / 2.0;
+                double msum = 0.0;
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float4 c = nbr(j);
+                    const double dist = fabs(x[0] * double(c.x) + x[1] * double(c.y) + x[2] * double(c.z) + dd);
+                    if (ok && dist > maxd) ok = false;
+                    msum += dist;
+                }
+                if (!ok) status = SO_MATCH_MSE_TOO_LARGE;
+                else {
+                    const double mean_dist = msum / 5.0;
+                    const float fq[4] = {float(s_pose[3]), float(s_pose[4]), float(s_pose[5]), float(s_pose[6])};
+                    float rotq[6], trq[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        // computeRotatedAxes (:624-638): float quaternion * e_a, no FMA contraction (host code is plain IEEE)
+                        const float v0 = a == 0 ? 1.f : 0.f, v1 = a == 1 ? 1.f : 0.f, v2 = a == 2 ? 1.f : 0.f;
+                        float ux = __fsub_rn(__fmul_rn(fq[1], v2), __fmul_rn(fq[2], v1));
+                        float uy = __fsub_rn(__fmul_rn(fq[2], v0), __fmul_rn(fq[0], v2));
+                        float uz = __fsub_rn(__fmul_rn(fq[0], v1), __fmul_rn(fq[1], v0));
+                        ux = __fadd_rn(ux, ux); uy = __fadd_rn(uy, uy); uz = __fadd_rn(uz, uz);
+                        const float ax = __fadd_rn(__fadd_rn(v0, __fmul_rn(fq[3], ux)), __fsub_rn(__fmul_rn(fq[1], uz), __fmul_rn(fq[2], uy)));
+                        const float ay = __fadd_rn(__fadd_rn(v1, __fmul_rn(fq[3], uy)), __fsub_rn(__fmul_rn(fq[2], ux), __fmul_rn(fq[0], uz)));
+                        const float az = __fadd_rn(__fadd_rn(v2, __fmul_rn(fq[3], uz)), __fsub_rn(__fmul_rn(fq[0], uy), __fmul_rn(fq[1], ux)));
+                        // Eigen's unrolled 3-vector dot associates as a0*b0 + (a1*b1 + a2*b2)
+                        const float rc = __fadd_rn(__fmul_rn(cr[0], ax), __fadd_rn(__fmul_rn(cr[1], ay), __fmul_rn(cr[2], az)));
+                        rotq[2 * a] = rc; rotq[2 * a + 1] = -rc;
+                        const float dn = __fadd_rn(__fmul_rn(nf[0], ax), __fadd_rn(__fmul_rn(nf[1], ay), __fmul_rn(nf[2], az)));
+                        trq[a] = __fmul_rn(planar_sq, fabsf(dn));
+                    }
+                    // top-2 rotation labels and top-1 translation label of a stable descending sort (:654-679)
+                    int r0 = 0;
+#pragma unroll
+                    for (int q = 1; q < 6; ++q) if (rotq[q] > rotq[r0]) r0 = q;
+                    int r1 = (r0 == 0) ? 1 : 0;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) if (q != r0 && q != r1 && rotq[q] > rotq[r1]) r1 = q;
+                    int t0 = 0;
+#pragma unroll
+                    for (int q = 1; q < 3; ++q) if (trq[q] > trq[t0]) t0 = q;
+                    o0 = r0; o1 = r1; o2 = 6 + t0;
+                    nrm[0] = x[0]; nrm[1] = x[1]; nrm[2] = x[2]; dpl = dd;
+                    wq = 1.0 - sqrt(mean_dist / double(m.bound_d2));        // fitQualityCoeff (:568)
+                    status = SO_MATCH_SUCCESS;
+                }
+            }
+        }
+    } else if (cb.nn) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const uint32_t pos = nb.pos[size_t(j) * nb.cap + gi];
+            cb.nn[gi * 5 + j] = pos != 0xFFFFFFFFu ? __float_as_uint(__ldg(&m.pts[pos]).w) : 0xFFFFFFFFu;
+            cb.nn_d2[gi * 5 + j] = 0.f;
+        }
+    }
+    if (status != SO_MATCH_SKIPPED) {
+        if (status == SO_MATCH_SUCCESS) { atomicAdd(&s_hist[o0], 1); atomicAdd(&s_hist[o1], 1); atomicAdd(&s_hist[o2], 1); }
+        atomicAdd(&s_hist[9 + status], 1);
+    }
+    cb.nd[gi] = make_double4(nrm[0], nrm[1], nrm[2], dpl);
+    cb.w[gi] = wq;
+    cb.flags[gi] = make_uchar4((unsigned char)status, (unsigned char)o0, (unsigned char)o1, (unsigned char)o2);
+}
+
 __global__ void __launch_bounds__(kFitThreads, SO_FIT_MINB) k_fit(MapView m, BatchView bv, CorrBuf cb, NnBuf nb) {
     const int s = blockIdx.y;
     IcpState* st = bv.st + s;
     if (st->phase != PH_CORR) return;
     __shared__ double s_pose[7];
-    __shared__ double s_R[9];
     __shared__ int s_hist[16];
     if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
     if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) qtoR(s_pose + 3, s_R);
-    __syncthreads();
     const uint32_t n = uint32_t(st->n_points);
-
-#if !SO_FIT_SPLIT
-    double acc[kAcc];
-#pragma unroll
-    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
-#endif
-
 #pragma unroll 1
     for (int rr = 0; rr < kFitPts; ++rr) {          // kFitPts points per thread
-    const uint32_t i = (blockIdx.x * kFitPts + rr) * kFitThreads + threadIdx.x;
-    const size_t gi = size_t(bv.offset[s]) + i;
-    if (i < n) {
-        int status = nb.pre[gi];
-        int o0 = 0, o1 = 0, o2 = 0;
-        double nrm[3] = {0, 0, 0}, dpl = 0.0, wq = 0.0;
-        if (status == SO_MATCH_SUCCESS) {
-            const float4 sp = __ldg(&bv.scan[gi]);
-            // ComputePointInitAndFinalPose (:382-400): pInit = double(p), pFinal = T_w_lidar * pInit
-            const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
-            double pf[3];
-            qrot(s_pose + 3, pin, pf);
-            pf[0] += s_pose[0]; pf[1] += s_pose[1]; pf[2] += s_pose[2];
-            const float qx = float(pf[0]), qy = float(pf[1]), qz = float(pf[2]);
-            // computePCAForFeature (:749-790) + utils::ComputePCA (superodom_utils.h:143-151).  The five neighbours are read
-            // three times (here, for the QR, for the distances) from k_knn_scan's coalesced hand-over instead of being held
-            // in 30 FP64 registers across the eigen-solve: the re-reads hit L1 and the kernel fits 3 CTAs per SM.
+        const uint32_t i = (blockIdx.x * kFitPts + rr) * kFitThreads + threadIdx.x;
+        const size_t gi = size_t(bv.offset[s]) + i;
+        if (i < n) {
             const float4* npts = nb.pts + gi;
-            double mean[3] = {0, 0, 0};
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const float4 c = ld_f4_again(npts + size_t(j) * nb.cap);
-                mean[0] += double(c.x); mean[1] += double(c.y); mean[2] += double(c.z);
-                if (cb.nn) {
-                    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-                    cb.nn[gi * 5 + j] = __float_as_uint(c.w);
-                    cb.nn_d2[gi * 5 + j] = float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz));
-                }
-            }
-            mean[0] /= 5.0; mean[1] /= 5.0; mean[2] /= 5.0;
-            double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const float4 c = ld_f4_again(npts + size_t(j) * nb.cap);
-                const double c0 = double(c.x) - mean[0], c1 = double(c.y) - mean[1], c2 = double(c.z) - mean[2];
-                S[0] += c0 * c0; S[1] += c0 * c1; S[2] += c0 * c2; S[4] += c1 * c1; S[5] += c1 * c2; S[8] += c2 * c2;
-            }
-            S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
-            const double sxx = S[0], sxy = S[1], sxz = S[2], syy = S[4], syz = S[5], szz = S[8];
-            double ev[3];
-            jacobi_eig<3, 12, false>(S, nullptr, ev);
-            if (ev[0] < 1e-6 || ev[1] / ev[2] < 0.1) status = SO_MATCH_BAD_PCA_STRUCTURE;      // (:772)
-            else {
-                // What FeatureObservabilityAnalysis (:574-693) needs from the PCA -- the oriented normal (:553-561) and the
-                // planarity -- is reduced to four floats here, ahead of the register-hungry QR.
-                float nf[3], cr[3], planar_sq;
-                {
-                    double no[3];
-                    eigvec3_from_value(sxx, sxy, sxz, syy, syz, szz, ev[0], no);
-                    if (pf[0] * no[0] + pf[1] * no[1] + pf[2] * no[2] < 0) { no[0] = -no[0]; no[1] = -no[1]; no[2] = -no[2]; }
-                    const double l1 = sqrt(ev[2]), l2 = sqrt(ev[1]), l3 = sqrt(ev[0]);
-                    const double planar_2 = (l2 - l3) / l1;
-                    planar_sq = float(planar_2 * planar_2);
-                    nf[0] = float(no[0]); nf[1] = float(no[1]); nf[2] = float(no[2]);
-                    cr[0] = __fmul_rn(qy, nf[2]) - __fmul_rn(qz, nf[1]);
-                    cr[1] = __fmul_rn(qz, nf[0]) - __fmul_rn(qx, nf[2]);
-                    cr[2] = __fmul_rn(qx, nf[1]) - __fmul_rn(qy, nf[0]);
-                }
-                // computePlaneQualityMetrics (:792-844)
-                double x[3];
-                {
-                    double A[5][3], b[5];
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) {
-                        const float4 c = ld_f4_again(npts + size_t(j) * nb.cap);
-                        A[j][0] = double(c.x); A[j][1] = double(c.y); A[j][2] = double(c.z); b[j] = -1.0;
-                    }
-                    colpiv_qr_solve_5x3(A, b, x);
-                }
-                if (!(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]))) status = SO_MATCH_INVALID_NUMERICAL;
-                else {
-                    const double nn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-                    const double dd = 1.0 / nn;
-                    x[0] /= nn; x[1] /= nn; x[2] /= nn;
-                    const double maxd = double(m.plane_res) / 2.0;
-                    double msum = 0.0;
-                    bool ok = true;
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) {
-                        const float4 c = ld_f4_again(npts + size_t(j) * nb.cap);
-                        const double dist = fabs(x[0] * double(c.x) + x[1] * double(c.y) + x[2] * double(c.z) + dd);
-                        if (ok && dist > maxd) ok = false;
-                        msum += dist;
-                    }
-                    if (!ok) status = SO_MATCH_MSE_TOO_LARGE;
-                    else {
-                        const double mean_dist = msum / 5.0;
-                        const float fq[4] = {float(s_pose[3]), float(s_pose[4]), float(s_pose[5]), float(s_pose[6])};
-                        float rotq[6], trq[3];
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) {
-                            // computeRotatedAxes (:624-638): float quaternion * e_a, no FMA contraction (host code is plain IEEE)
-                            const float v0 = a == 0 ? 1.f : 0.f, v1 = a == 1 ? 1.f : 0.f, v2 = a == 2 ? 1.f : 0.f;
-                            float ux = __fsub_rn(__fmul_rn(fq[1], v2), __fmul_rn(fq[2], v1));
-                            float uy = __fsub_rn(__fmul_rn(fq[2], v0), __fmul_rn(fq[0], v2));
-                            float uz = __fsub_rn(__fmul_rn(fq[0], v1), __fmul_rn(fq[1], v0));
-                            ux = __fadd_rn(ux, ux); uy = __fadd_rn(uy, uy); uz = __fadd_rn(uz, uz);
-                            const float ax = __fadd_rn(__fadd_rn(v0, __fmul_rn(fq[3], ux)), __fsub_rn(__fmul_rn(fq[1], uz), __fmul_rn(fq[2], uy)));
-                            const float ay = __fadd_rn(__fadd_rn(v1, __fmul_rn(fq[3], uy)), __fsub_rn(__fmul_rn(fq[2], ux), __fmul_rn(fq[0], uz)));
-                            const float az = __fadd_rn(__fadd_rn(v2, __fmul_rn(fq[3], uz)), __fsub_rn(__fmul_rn(fq[0], uy), __fmul_rn(fq[1], ux)));
-                            // Eigen's unrolled 3-vector dot associates as a0*b0 + (a1*b1 + a2*b2)
-                            const float rc = __fadd_rn(__fmul_rn(cr[0], ax), __fadd_rn(__fmul_rn(cr[1], ay), __fmul_rn(cr[2], az)));
-                            rotq[2 * a] = rc; rotq[2 * a + 1] = -rc;
-                            const float dn = __fadd_rn(__fmul_rn(nf[0], ax), __fadd_rn(__fmul_rn(nf[1], ay), __fmul_rn(nf[2], az)));
-                            trq[a] = __fmul_rn(planar_sq, fabsf(dn));
-                        }
-                        // top-2 rotation labels and top-1 translation label of a stable descending sort (:654-679)
-                        int r0 = 0;
-#pragma unroll
-                        for (int q = 1; q < 6; ++q) if (rotq[q] > rotq[r0]) r0 = q;
-                        int r1 = (r0 == 0) ? 1 : 0;
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) if (q != r0 && q != r1 && rotq[q] > rotq[r1]) r1 = q;
-                        int t0 = 0;
-#pragma unroll
-                        for (int q = 1; q < 3; ++q) if (trq[q] > trq[t0]) t0 = q;
-                        o0 = r0; o1 = r1; o2 = 6 + t0;
-                        nrm[0] = x[0]; nrm[1] = x[1]; nrm[2] = x[2]; dpl = dd;
-                        wq = 1.0 - sqrt(mean_dist / double(m.bound_d2));        // fitQualityCoeff (:568)
-                        status = SO_MATCH_SUCCESS;
-#if !SO_FIT_SPLIT
-                        accumulate(acc, nrm, dpl, wq, pin, pf, s_R, bv.tukey_a2);
-#endif
-                    }
-                }
-            }
-        } else if (cb.nn) {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const uint32_t pos = nb.pos[size_t(j) * nb.cap + gi];
-                cb.nn[gi * 5 + j] = pos != 0xFFFFFFFFu ? __float_as_uint(__ldg(&m.pts[pos]).w) : 0xFFFFFFFFu;
-                cb.nn_d2[gi * 5 + j] = 0.f;
-            }
+            fit_point(m, cb, nb, gi, __ldg(&bv.scan[gi]), s_pose, int(nb.pre[gi]), [&](int j) { return ld_f4_again(npts + size_t(j) * nb.cap); }, s_hist);
         }
-        if (status != SO_MATCH_SKIPPED) {
-            if (status == SO_MATCH_SUCCESS) { atomicAdd(&s_hist[o0], 1); atomicAdd(&s_hist[o1], 1); atomicAdd(&s_hist[o2], 1); }
-            atomicAdd(&s_hist[9 + status], 1);
-        }
-        cb.nd[gi] = make_double4(nrm[0], nrm[1], nrm[2], dpl);
-        cb.w[gi] = wq;
-        cb.flags[gi] = make_uchar4((unsigned char)status, (unsigned char)o0, (unsigned char)o1, (unsigned char)o2);
-    }
     }
     __syncthreads();
     if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&bv.hist[s * kHistStride + threadIdx.x], s_hist[threadIdx.x]);
-#if !SO_FIT_SPLIT
-    reduce_to_partials(acc, bv, s);
-#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_knn_fit: k_knn_scan and k_fit for the same point in one thread.  Both halves fit 64 registers, so fusing costs no
+// occupancy, and it (a) drops the 80 B/point neighbour hand-over through HBM (write + read back) and the second read of the
+// scan, (b) removes a kernel boundary per ICP iteration, and (c) lets warps that are in the integer-heavy search and warps
+// that are in the FP64-heavy fit share an SM, so both pipes stay busy.  The fit reads its neighbours straight from the
+// search-ordered map at the positions the search just visited (L1/L2 hits).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_fit(MapView m, BatchView bv, CorrBuf cb, NnBuf nb) {
+    const int s = blockIdx.y;
+    const IcpState* st = bv.st + s;
+    if (st->phase != PH_CORR) return;
+    __shared__ double s_pose[7];
+    __shared__ int s_hist[16];
+    __shared__ uint32_t s_buf[kBufCap * kThreads];
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
+    if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n = uint32_t(st->n_points);
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) {
+        const size_t gi = size_t(bv.offset[s]) + i;
+        const float4 sp = __ldg(&bv.scan[gi]);
+        int pre = SO_MATCH_SKIPPED;
+        TopK<5> tk;
+        tk.init(m.bound_d2);
+        if (should_process(__float_as_uint(sp.w), st->sampling_rate)) {
+            const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+            double pf[3];
+            qrot(s_pose + 3, pin, pf);
+            const float qx = float(pf[0] + s_pose[0]), qy = float(pf[1] + s_pose[1]), qz = float(pf[2] + s_pose[2]);
+            QueryCell qc;
+            locate(m, qx, qy, qz, qc);
+            if (qc.slot < 0 || qc.nblock < 5) pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
+            else {
+                float u_seed = -1.f;
+                if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) {        // see k_knn_scan
+                    float u = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const float4 c = __ldg(&m.pts[nb.pos[size_t(j) * nb.cap + gi]]);
+                        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+                        u = fmaxf(u, float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)));
+                    }
+                    if (u <= 1.3f * nb.d5[gi]) u_seed = u;
+                }
+                knn_select<5>(m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
+                pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
+            }
+        }
+        nb.pre[gi] = (unsigned char)pre;
+        nb.d5[gi] = tk.d2[4];
+        uint32_t pos[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            pos[j] = tk.id[j] != 0xFFFFFFFFu ? tk.pos[j] : 0xFFFFFFFFu;
+            nb.pos[size_t(j) * nb.cap + gi] = pos[j];
+        }
+        fit_point(m, cb, nb, gi, sp, s_pose, pre, [&](int j) { return ld_f4_again(m.pts + pos[j]); }, s_hist);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(&bv.hist[s * kHistStride + threadIdx.x], s_hist[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1108,8 +1163,7 @@ __global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partia
     double v = 0.0;
     if (comp < kAcc) {
         const double* base = bv.partials + size_t(s) * bv.partial_stride * kAcc;
-        const uint32_t np = (AFTER == PH_CORR && !kFitSplit) ? (uint32_t(st->n_points) + kThreads * kFitPts - 1) / (kThreads * kFitPts)
-                                               : (uint32_t(st->n_points) + kThreads * kEvalPts - 1) / (kThreads * kEvalPts);
+        const uint32_t np = (uint32_t(st->n_points) + kThreads * kEvalPts - 1) / (kThreads * kEvalPts);
         for (uint32_t b = sub; b < np && b < n_partials; b += 4) v += base[size_t(b) * kAcc + comp];
         const uint32_t ne = (uint32_t(st->n_edge) + kThreads - 1) / kThreads;          // edge branch partials (0 when no edge cloud)
         for (uint32_t b = sub; b < ne; b += 4) v += base[size_t(edge_partial_offset + b) * kAcc + comp];
@@ -1195,28 +1249,30 @@ void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uin
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st) {
     k_scan_gather<<<uint32_t((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(in, vals, keys, offset, total, out);
 }
-void launch_knn_scan(const MapView& m, const BatchView& bv, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+// Correspondence stage of one ICP iteration = launch_match (search + fit of every scan point) + launch_first_eval (first
+// evaluation of the new solve, the edge kernel when an edge cloud is present, and the optimiser's iteration zero).
+// medge / eb / grid_e: edge branch (grid_e == 0: idle); k_lm_step sums the partials of both branches.
+void launch_match(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+    if (!grid_x) return;
+#if SO_FUSE_KNN_FIT
+    k_knn_fit<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
+#else
     k_knn_scan<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, nb);
-}
-// medge / eb / grid_e: edge branch (grid_e == 0: idle).  The edge kernel runs between the plane kernel and k_lm_step, which
-// sums the partials of both.
-void launch_fit(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st,
-                const MapView* medge, const EdgeBuf* eb, uint32_t grid_e) {
     const uint32_t gf = (grid_x * kThreads + kFitPts * kFitThreads - 1) / (kFitPts * kFitThreads);
-    if (gf) k_fit<<<dim3(gf, n_scans), kFitThreads, 0, st>>>(m, bv, cb, nb);
-#if SO_FIT_SPLIT
+    k_fit<<<dim3(gf, n_scans), kFitThreads, 0, st>>>(m, bv, cb, nb);
+#endif
+}
+void launch_first_eval(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const MapView* medge, const EdgeBuf* eb,
+                       uint32_t grid_e) {
     const uint32_t gp = (grid_x + kEvalPts - 1) / kEvalPts;
     if (gp) k_evaluate<PH_CORR><<<dim3(gp, n_scans), kThreads, 0, st>>>(bv, cb);
-#else
-    const uint32_t gp = gf;
-#endif
     if (grid_e) k_edge_fit<<<dim3(grid_e, n_scans), kThreads, 0, st>>>(*medge, bv, *eb, bv.edge_partial_offset);
     k_lm_step<PH_CORR><<<n_scans, 128, 0, st>>>(bv, gp, bv.edge_partial_offset);
 }
 void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st,
                        const MapView* medge, const EdgeBuf* eb, uint32_t grid_e) {
-    launch_knn_scan(m, bv, nb, grid_x, n_scans, st);
-    launch_fit(m, bv, cb, nb, grid_x, n_scans, st, medge, eb, grid_e);
+    launch_match(m, bv, cb, nb, grid_x, n_scans, st);
+    launch_first_eval(bv, cb, grid_x, n_scans, st, medge, eb, grid_e);
 }
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const EdgeBuf* eb, uint32_t grid_e) {
     const uint32_t gx = (grid_x + kEvalPts - 1) / kEvalPts;

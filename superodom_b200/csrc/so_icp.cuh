@@ -54,25 +54,30 @@ constexpr int kEvalPts = SO_EVAL_PTS;     // points per thread in k_evaluate
 #define SO_FIT_PTS 2
 #endif
 constexpr int kFitPts = SO_FIT_PTS;      // points per thread in k_fit
-// 1: k_fit only matches/fits and the first evaluation of the solve is a k_evaluate<PH_CORR> launch (k_fit then carries no
-// normal-equation accumulators: fewer registers, more resident warps); 0: k_fit accumulates in place.
-#ifndef SO_FIT_SPLIT
-#define SO_FIT_SPLIT 1
-#endif
-constexpr int kFitSplit = SO_FIT_SPLIT;
+// k_fit only matches / fits; the first evaluation of the solve is a k_evaluate<PH_CORR> launch, so k_fit carries no
+// normal-equation accumulators (64 registers, 4 CTAs per SM).
 #ifndef SO_FIT_THREADS
 #define SO_FIT_THREADS 256
 #endif
 #ifndef SO_FIT_MINB
 #define SO_FIT_MINB 4
 #endif
-constexpr int kFitThreads = SO_FIT_SPLIT ? SO_FIT_THREADS : 256;      // the in-place reduction needs the common CTA width
+constexpr int kFitThreads = SO_FIT_THREADS;
+// 1: search and fit of a point run in one kernel (k_knn_fit); 0: k_knn_scan hands the neighbours to k_fit through HBM.
+// Measured on B200 (cfg2, 64 scans): fused 1.907 ms per matching stage vs 1.833 ms split (8 224 vs 8 508 scans/s) -- the stage
+// is issue-bound on the SUM of both halves' instructions (ncu: 223 M = 149 M + 82 M warp-instructions, 64 % issue-active either
+// way), so sharing an SM between search and fit warps buys nothing and the fused kernel spills a little more.  Split stays the
+// default; the fused form saves 105 B/point of HBM traffic and the 80 B/point neighbour buffer.
+#ifndef SO_FUSE_KNN_FIT
+#define SO_FUSE_KNN_FIT 0
+#endif
+constexpr int kCorrLaunches = SO_FUSE_KNN_FIT ? 1 : 2;      // launches of the correspondence stage before the first evaluation
 
 void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st);
-void launch_knn_scan(const MapView& m, const BatchView& bv, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
-void launch_fit(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st,
-                const MapView* medge = nullptr, const EdgeBuf* eb = nullptr, uint32_t grid_e = 0);
+void launch_match(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
+void launch_first_eval(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const MapView* medge = nullptr,
+                       const EdgeBuf* eb = nullptr, uint32_t grid_e = 0);
 void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st,
                        const MapView* medge = nullptr, const EdgeBuf* eb = nullptr, uint32_t grid_e = 0);
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const EdgeBuf* eb = nullptr, uint32_t grid_e = 0);
