@@ -270,12 +270,13 @@ def run_ours(args):
     if rank == 0:
         # roofline of the dominant kernel (k_correspond): one profiled step, CUDA events around every launch that has work
         ctx.profile_enable(True)
-        for k in range(5):
+        for k in range(6):
             ctx.profile_get(k, reset=True)
         pres = ctx.register_batch_device(d_scans.data_ptr(), n_points, priors, 20, 0, skip_map_checks=True)
         ctx.profile_enable(False)
         ms_k, n_k = ctx.profile_get(0)          # k_knn_scan
-        ms_f, n_f = ctx.profile_get(4)          # k_fit (+ k_lm_step)
+        ms_f, n_f = ctx.profile_get(4)          # first evaluation of each solve (k_evaluate<PH_CORR> + k_lm_step)
+        ms_q, n_q = ctx.profile_get(5)          # k_fit (split build)
         ms_e, n_e = ctx.profile_get(1)          # k_evaluate (+ k_lm_step)
         ms_p, n_p = ctx.profile_get(3)          # scan ordering (keys + radix sort + gather)
         peak, peak_src = _peaks()
@@ -286,7 +287,7 @@ def run_ours(args):
         kname = "k_knn_fit" if fused else "k_knn_scan"
         alg_bytes = scan_passes * (MATCH_BYTES_PER_POINT if fused else KNN_BYTES_PER_POINT) + n_k * len(map_xyzi) * 16
         achieved = alg_bytes / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
-        tot = ms_k + ms_f + ms_e + ms_p + 1e-12
+        tot = ms_k + ms_q + ms_f + ms_e + ms_p + 1e-12
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": NCU_DRAM_BYTES_PER_POINT[kname] * scan_passes / max(n_k, 1) if NCU_DRAM_BYTES_PER_POINT.get(kname) else None,
                     "traffic_source": f"profiles/ (ncu --set full, dram__bytes_read+write per point of one {kname} launch, scaled to this launch size)",
@@ -295,7 +296,8 @@ def run_ours(args):
                     "note": "instruction-issue bound (ncu: 67% issue-active), L1/L2-resident gathers; see DESIGN.md section 4",
                     "first_evaluation": {"launches": int(n_f), "avg_launch_ms": ms_f / max(n_f, 1)},
                     "k_evaluate": {"launches": int(n_e), "avg_launch_ms": ms_e / max(n_e, 1)},
-                    "share_of_step": {kname: ms_k / tot, "first_evaluation": ms_f / tot, "k_evaluate": ms_e / tot, "scan_ordering": ms_p / tot}}
+                    "k_fit": {"launches": int(n_q), "avg_launch_ms": ms_q / max(n_q, 1)},
+                    "share_of_step": {kname: ms_k / tot, "k_fit": ms_q / tot, "first_evaluation": ms_f / tot, "k_evaluate": ms_e / tot, "scan_ordering": ms_p / tot}}
         # CPU baseline on the host cores: the oracle (reference octree verbatim when oracle/_ref travelled), 1 thread, bounded sample
         cpu = None
         if not args.no_cpu_baseline:

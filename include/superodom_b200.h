@@ -255,9 +255,9 @@ uint64_t so_kernel_launches(so_ctx* ctx, int reset);
  * last reset (bench.py e2e accounting). */
 int so_bytes_copied(so_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);
 /* Accumulated device time (ms, CUDA events on the context stream) and launch count of a kernel class since the last
- * reset; classes: 0 the matching stage (k_knn_fit: k-NN + plane fit of every scan point; k_knn_scan + k_fit in a build
- * without SO_BUILD_FUSED_MATCH), 1 k_evaluate + k_lm_step (LM step), 2 k_knn (so_knn*), 3 scan ordering / map build / map
- * insert / scan preparation, 4 first evaluation of a solve (k_evaluate + k_lm_step iteration zero).
+ * reset; classes: 0 k_knn_scan (scan k-NN; k_knn_fit = k-NN + plane fit in a SO_BUILD_FUSED_MATCH build), 1 k_evaluate +
+ * k_lm_step (LM step), 2 k_knn (so_knn*), 3 scan ordering / map build / map insert / scan preparation, 4 first evaluation of
+ * a solve (k_evaluate + k_lm_step iteration zero), 5 k_fit (plane fit; empty in a fused build).
  * Profiling mode serialises kernels; enable only for roofline runs. */
 /* Build-time switches of the loaded library: bit 0 (SO_BUILD_FUSED_MATCH) = search and fit run as one kernel. */
 #define SO_BUILD_FUSED_MATCH 1

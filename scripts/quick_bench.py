@@ -17,9 +17,9 @@ for _ in range(5):
     res = ctx.register_batch(flat, n_points, priors, 20, 0, skip_map_checks=True)
 dt = (time.perf_counter() - t) / 5
 ctx.profile_enable(True)
-for k in range(5): ctx.profile_get(k, reset=True)
+for k in range(6): ctx.profile_get(k, reset=True)
 res = ctx.register_batch(flat, n_points, priors, 20, 0, skip_map_checks=True)
 ctx.profile_enable(False)
 err = np.abs(np.array([list(r.pose) for r in res])[:, :3] - truths[:, :3]).max()
 print(f"{os.environ.get('TAG','')} B={B} host-timed step {dt*1e3:.2f} ms -> {B/dt:.0f} scans/s e2e | err {err:.4f} | " +
-      " | ".join(f"class{k}: {ctx.profile_get(k)[0]:.3f} ms / {ctx.profile_get(k)[1]} launches" for k in range(5)))
+      " | ".join(f"class{k}: {ctx.profile_get(k)[0]:.3f} ms / {ctx.profile_get(k)[1]} launches" for k in range(6)))

@@ -255,7 +255,11 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
         };
         for (int it = 0; it < iters; ++it) {
             if (any_in(PH_CORR)) {
-                timed_launch_begin(c); launch_match(mv, bv, cb, c->nn, grid_x, n_scans, c->stream); c->launches += kCorrLaunches - 1; timed_launch_end(c, 0);
+                if (kCorrLaunches == 1) { timed_launch_begin(c); launch_match(mv, bv, cb, c->nn, grid_x, n_scans, c->stream); timed_launch_end(c, 0); }
+                else {
+                    timed_launch_begin(c); launch_match(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, 1); timed_launch_end(c, 0);      // k_knn_scan
+                    timed_launch_begin(c); launch_match(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, 2); timed_launch_end(c, 5);      // k_fit
+                }
                 timed_launch_begin(c); launch_first_eval(bv, cb, grid_x, n_scans, c->stream, &me, &eb, grid_e); c->launches += 1 + (grid_e ? 1 : 0); timed_launch_end(c, 4);
             }
             for (int k = 0; k < lm; ++k)
@@ -1143,7 +1147,7 @@ int so_profile_enable(so_ctx* ctx, int on) {
 
 int so_profile_get(so_ctx* ctx, int cls, double* ms, uint64_t* launches, int reset) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (!c || cls < 0 || cls > 4) return fail(SO_ERR_ARG, "bad args");
+    if (!c || cls < 0 || cls > 5) return fail(SO_ERR_ARG, "bad args");
     if (ms) *ms = c->prof[cls].ms;
     if (launches) *launches = c->prof[cls].launches;
     if (reset) c->prof[cls] = ProfileSlot{};

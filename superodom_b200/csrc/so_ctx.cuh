@@ -105,7 +105,7 @@ struct Ctx {
     uint64_t launches = 0;
     uint64_t bytes_h2d = 0, bytes_d2h = 0;         // host<->device bytes moved by registration / k-NN calls
     bool profiling = false;
-    ProfileSlot prof[5];
+    ProfileSlot prof[6];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
 };
 

@@ -1252,14 +1252,15 @@ void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* 
 // Correspondence stage of one ICP iteration = launch_match (search + fit of every scan point) + launch_first_eval (first
 // evaluation of the new solve, the edge kernel when an edge cloud is present, and the optimiser's iteration zero).
 // medge / eb / grid_e: edge branch (grid_e == 0: idle); k_lm_step sums the partials of both branches.
-void launch_match(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+void launch_match(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, int part) {
     if (!grid_x) return;
 #if SO_FUSE_KNN_FIT
+    (void)part;
     k_knn_fit<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
 #else
-    k_knn_scan<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, nb);
+    if (part != 2) k_knn_scan<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, nb);
     const uint32_t gf = (grid_x * kThreads + kFitPts * kFitThreads - 1) / (kFitPts * kFitThreads);
-    k_fit<<<dim3(gf, n_scans), kFitThreads, 0, st>>>(m, bv, cb, nb);
+    if (part != 1) k_fit<<<dim3(gf, n_scans), kFitThreads, 0, st>>>(m, bv, cb, nb);
 #endif
 }
 void launch_first_eval(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const MapView* medge, const EdgeBuf* eb,

@@ -13,17 +13,18 @@ from conftest import get_case, quat_angle
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp_path):
+def _build(tmp_path, name="shim_test"):
     from superodom_b200 import build
     lib = build.build()
-    exe = str(tmp_path / "shim_test")
+    exe = str(tmp_path / name)
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "shim_test.cpp"), "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)])
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)])
     return exe
 
 
 def test_shim_compiles_and_links(tmp_path):
     assert os.path.exists(_build(tmp_path))
+    assert os.path.exists(_build(tmp_path, "feature_test"))
 
 
 def _sequence(n_scans=4):
@@ -79,4 +80,40 @@ def test_shim_sequence_matches_abi_and_oracle(tmp_path, gpu_api, oracle_mod):
         assert np.linalg.norm(np.array(r.pose)[:2] - get_case("tiny", i)["pose_true"][:2]) < 0.03
     n_all, n_near = map(int, lines[-1].split()[1:])
     assert n_all == len(om_points) and 0 < n_near <= n_all
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("imu_only", [0, 1])
+def test_feature_extraction_shim_matches_abi(tmp_path, gpu_api, imu_only):
+    """FeatureExtraction.hpp (removePointDistortion + uniformFeatureExtraction on PointcloudXYZITR records and a std::map pose
+    buffer) == the same calls through the C ABI from Python, bit for bit."""
+    from superodom_b200 import synth
+    exe = _build(tmp_path, "feature_test")
+    d = synth.make_raw_sweep(30_000, seed=4200)
+    pts = d["points"].copy()
+    pts[~np.isfinite(pts)] = 0.0                 # the record reader of the test program casts the ring column to uint16
+    skip, block_range = 3, 0.2
+    path, outp = tmp_path / "raw.bin", tmp_path / "out.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iiiifd", len(pts), len(d["sample_times"]), imu_only, skip, block_range, d["start_time"]))
+        f.write(np.asarray(d["T_i_l"], np.float64).tobytes())
+        f.write(pts.tobytes())
+        for t, p in zip(d["sample_times"], d["sample_poses"]):
+            f.write(struct.pack("<d", t) + np.asarray(p, np.float64).tobytes())
+    out = subprocess.run([exe, str(path), str(outp)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    raw = open(outp, "rb").read()
+    start = np.frombuffer(raw[:56], np.float64)
+    xyz = np.frombuffer(raw[56:56 + 12 * len(pts)], np.float32).reshape(-1, 3)
+    k = struct.unpack("<i", raw[56 + 12 * len(pts):60 + 12 * len(pts)])[0]
+    feat = np.frombuffer(raw[60 + 12 * len(pts):], np.float32).reshape(-1, 4)
+    assert len(feat) == k
+    ctx = gpu_api.Context(max_map_points=1024, max_scan_points=1 << 18, plane_res=0.2)
+    got = pts.copy()
+    st, past = ctx.scan_deskew(got, 5, d["start_time"], d["sample_times"], d["sample_poses"], imu_only=bool(imu_only), T_i_l=d["T_i_l"])
+    assert past == 0 and np.array_equal(start, st)
+    assert np.array_equal(xyz, got[:, :3]) and np.abs(xyz - pts[:, :3]).max() > 0.05
+    exp_feat = ctx.scan_extract_uniform(got, 5, skip, block_range)
+    assert np.array_equal(feat, exp_feat) and 0 < k < len(pts)
     ctx.close()
