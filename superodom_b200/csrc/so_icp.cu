@@ -514,7 +514,7 @@ __device__ __forceinline__ void accumulate(double acc[kAcc], const double n[3], 
     const double r = n[0] * pw[0] + n[1] * pw[1] + n[2] * pw[2] + d;
     const double s = r * r;
     double rho0, rho1;
-    if (s <= a2) { const double v = 1.0 - s / a2, v2 = v * v; rho0 = a2 / 6.0 * (1.0 - v2 * v); rho1 = 0.5 * v2; }
+    if (s <= a2) { const double v = 1.0 - s * (1.0 / a2), v2 = v * v; rho0 = a2 / 6.0 * (1.0 - v2 * v); rho1 = 0.5 * v2; }
     else { rho0 = a2 / 6.0; rho1 = 0.0; }
     rho0 *= w; rho1 *= w;
     // J = [ n^T , -n^T R [p]x ] ;  -a^T [p]x = p x a  with a = R^T n
@@ -700,7 +700,7 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
                 cb.nn_d2[gi * 5 + j] = float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz));
             }
         }
-        mean[0] /= 5.0; mean[1] /= 5.0; mean[2] /= 5.0;
+        mean[0] *= 0.2; mean[1] *= 0.2; mean[2] *= 0.2;        // (the reference divides by 5: same to an ulp, a multiply is 1 instruction)
         double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
@@ -712,7 +712,7 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
         const double sxx = S[0], sxy = S[1], sxz = S[2], syy = S[4], syz = S[5], szz = S[8];
         double ev[3];
         jacobi_eig<3, 12, false>(S, nullptr, ev);
-        if (ev[0] < 1e-6 || ev[1] / ev[2] < 0.1) status = SO_MATCH_BAD_PCA_STRUCTURE;      // (:772)
+        if (ev[0] < 1e-6 || ev[1] < 0.1 * ev[2]) status = SO_MATCH_BAD_PCA_STRUCTURE;      // lambda1/lambda2 < 0.1 (:772)
         else {
             // What FeatureObservabilityAnalysis (:574-693) needs from the PCA -- the oriented normal (:553-561) and the
             // planarity -- is reduced to four floats here, ahead of the register-hungry QR.
@@ -742,9 +742,8 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
             }
             if (!(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]))) status = SO_MATCH_INVALID_NUMERICAL;
             else {
-                const double nn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-                const double dd = 1.0 / nn;
-                x[0] /= nn; x[1] /= nn; x[2] /= nn;
+                const double dd = rsqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);      // 1 / |n|
+                x[0] *= dd; x[1] *= dd; x[2] *= dd;
                 const double maxd = double(m.plane_res) / 2.0;
                 double msum = 0.0;
                 bool ok = true;
@@ -789,7 +788,7 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
                     for (int q = 1; q < 3; ++q) if (trq[q] > trq[t0]) t0 = q;
                     o0 = r0; o1 = r1; o2 = 6 + t0;
                     nrm[0] = x[0]; nrm[1] = x[1]; nrm[2] = x[2]; dpl = dd;
-                    wq = 1.0 - sqrt(mean_dist / double(m.bound_d2));        // fitQualityCoeff (:568)
+                    wq = 1.0 - sqrt(mean_dist * m.inv_bound_d2);        // fitQualityCoeff (:568)
                     status = SO_MATCH_SUCCESS;
                 }
             }

@@ -30,6 +30,7 @@ struct MapView {
     double inv_cs;              // nb / 50  (cells per metre)
     float cs;                   // cell edge (m)
     float bound_d2;             // float(3 * planeRes_)  -- the NEIGHBORS_TOO_FAR gate doubles as search radius^2
+    double inv_bound_d2;        // 1 / double(bound_d2)
     float plane_res;
     int32_t R;                  // search rings: R * cs >= sqrt(bound_d2)
 };
@@ -212,7 +213,7 @@ __device__ __forceinline__ void eigvec3_from_value(double xx, double xy, double 
 __host__ __device__ inline void colpiv_qr_solve_5x3(double A[5][3], double b[5], double x[3]) {
     const double eps = 2.220446049250313e-16;
     int perm0 = 0, perm1 = 1, perm2 = 2;
-    double rdiag[3];
+    double rdiag[3], rinv[3] = {0.0, 0.0, 0.0};      // rinv[k] = 1 / R_kk
     double maxpivot = 0.0;
     int nonzero = 3;
     double n0 = 0, n1 = 0, n2 = 0;
@@ -250,15 +251,26 @@ __host__ __device__ inline void colpiv_qr_solve_5x3(double A[5][3], double b[5],
         double ess[5];
         if (tail2 <= DBL_MIN) {
             tau = 0.0; beta = c0;
+            rinv[k] = 1.0 / c0;
 #pragma unroll
             for (int i = 0; i < 5; ++i) ess[i] = 0.0;
         } else {
-            beta = sqrt(c0 * c0 + tail2);
-            if (c0 >= 0.0) beta = -beta;
+            // beta = -sign(c0) |col|, 1/beta from one reciprocal square root: the divisions Eigen writes ((beta - c0) / beta,
+            // s / R_kk in the back-substitution) become multiplications by it -- same values to an ulp, a third of the
+            // instructions (FP64 divide and square root are ~25-instruction software sequences on the GPU)
+            const double nrm2 = c0 * c0 + tail2;
+#ifdef __CUDA_ARCH__
+            double rb = rsqrt(nrm2);
+#else
+            double rb = 1.0 / sqrt(nrm2);
+#endif
+            beta = nrm2 * rb;
+            if (c0 >= 0.0) { beta = -beta; rb = -rb; }
+            rinv[k] = rb;
             const double inv = 1.0 / (c0 - beta);
 #pragma unroll
             for (int i = 0; i < 5; ++i) ess[i] = (i > k) ? A[i][k] * inv : 0.0;
-            tau = (beta - c0) / beta;
+            tau = (beta - c0) * rb;
         }
 #pragma unroll
         for (int j = k + 1; j < 3; ++j) {
@@ -294,7 +306,7 @@ __host__ __device__ inline void colpiv_qr_solve_5x3(double A[5][3], double b[5],
             double s = b[i];
 #pragma unroll
             for (int j = i + 1; j < 3; ++j) if (j < rank) s -= A[i][j] * y[j];
-            y[i] = s / A[i][i];
+            y[i] = s * rinv[i];
         }
     }
     x[0] = x[1] = x[2] = 0.0;

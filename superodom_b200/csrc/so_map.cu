@@ -142,6 +142,7 @@ MapView map_view(const Ctx* c, const MapStore& ms) {
     m.origin[0] = c->origin[0]; m.origin[1] = c->origin[1]; m.origin[2] = c->origin[2];
     m.nb = ms.nb; m.inv_cs = double(ms.nb) / kBlock; m.cs = float(kBlock / double(ms.nb));
     m.bound_d2 = 3 * ms.res;        // float product (LidarSlam.cpp:526)
+    m.inv_bound_d2 = 1.0 / double(m.bound_d2);
     m.plane_res = ms.res;
     m.R = map_rings(ms.res, ms.nb);
     return m;
