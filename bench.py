@@ -187,6 +187,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only (NCCL logs there by default)
         dist.init_process_group("nccl", device_id=dev)
     phase("import torch + process group")
     B = args.batch

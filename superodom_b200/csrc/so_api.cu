@@ -216,11 +216,18 @@ static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch, cudaS
     const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, d_scan_in, ch.first);
     timed_launch_begin(c);
-    launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, ch.grid_x, ch.count, st);
-    int rc = scan_sort(c, ch.pt_first, ch.pt_count, int(ch.count), st);
+    // key layout: [scan inside the chunk | cell]; 32-bit keys whenever both fit
+    const uint64_t n_cells = uint64_t(c->surf.n_slots) * uint64_t(mv.nb) * uint64_t(mv.nb) * uint64_t(mv.nb);
+    int cell_bits = 1, scan_bits = 0;
+    while (cell_bits < 32 && (uint64_t(1) << cell_bits) <= n_cells) ++cell_bits;       // cells 0..n_cells-1 < mask = 2^cell_bits - 1
+    while ((1u << scan_bits) < ch.count) ++scan_bits;
+    const bool key32 = cell_bits < 32 && cell_bits + scan_bits <= 32;
+    if (!key32) cell_bits = 32;
+    launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, ch.grid_x, ch.count, cell_bits, key32, st);
+    int rc = scan_sort(c, ch.pt_first, ch.pt_count, int(ch.count), cell_bits, key32, st);
     if (rc) return rc;
-    launch_scan_gather(d_scan_in, c->d_svals_out + ch.pt_first, c->d_skeys_out + ch.pt_first, c->d_offset + ch.first, ch.pt_count,
-                       c->d_scan_sorted + ch.pt_first, st);
+    launch_scan_gather(d_scan_in, c->d_svals_out, c->d_skeys_out, ch.pt_first, c->d_offset + ch.first, ch.pt_count,
+                       c->d_scan_sorted + ch.pt_first, cell_bits, key32, st);
     c->launches++;
     timed_launch_end(c, 3);
     SO_CUDA_TRY(cudaGetLastError());

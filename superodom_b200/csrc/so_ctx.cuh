@@ -134,6 +134,6 @@ int map_cells_per_block(float plane_res);
 int scan_sort_alloc(Ctx* c);             // temp storage for the per-registration scan sort
 int query_sort(Ctx* c, size_t n);         // d_qkeys/d_qvals -> *_out (allocates on growth)
 int query_sort_reserve(Ctx* c, size_t n);
-int scan_sort(Ctx* c, size_t first, size_t n, int n_scans, cudaStream_t st);   // d_skeys/d_svals[first..first+n) -> *_out
+int scan_sort(Ctx* c, size_t first, size_t n, int n_scans, int cell_bits, bool key32, cudaStream_t st);   // d_skeys/d_svals[first..first+n) -> *_out
 
 }  // namespace so

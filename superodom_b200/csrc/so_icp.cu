@@ -552,7 +552,10 @@ __device__ __forceinline__ bool should_process(uint32_t i, double rate) {
 // coherent for all ICP iterations.  The sorted copy carries the point's original index in .w (the reference's
 // shouldProcessPoint() decimation is defined on the original index, LidarSlam.cpp:353-359).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_scan_keys(MapView m, BatchView bv, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// Key = (scan index inside the chunk) << cell_bits | cell; cells beyond the mask and off-map points sort last inside their scan.
+// KeyT = uint32_t when cell_bits + scan bits fit (the usual case: 4 radix passes over 8-byte pairs instead of 5 over 12-byte ones).
+template <class KeyT>
+__global__ void __launch_bounds__(kThreads) k_scan_keys(MapView m, BatchView bv, KeyT* __restrict__ keys, uint32_t* __restrict__ vals, int cell_bits) {
     const int s = blockIdx.y;
     const IcpState* st = bv.st + s;
     const uint32_t n = uint32_t(st->n_points);
@@ -580,16 +583,18 @@ __global__ void __launch_bounds__(kThreads) k_scan_keys(MapView m, BatchView bv,
 #else
     if (qc.slot >= 0) cell = uint32_t(qc.slot) * uint32_t(m.nb * m.nb * m.nb) + uint32_t((qc.c[2] * m.nb + qc.c[1]) * m.nb + qc.c[0]);
 #endif
-    keys[gi] = (uint64_t(s) << 32) | uint64_t(cell);
+    const uint32_t mask = cell_bits >= 32 ? 0xFFFFFFFFu : ((1u << cell_bits) - 1u);
+    keys[gi] = KeyT((KeyT(s) << cell_bits) | KeyT(cell < mask ? cell : mask));
     vals[gi] = uint32_t(gi);
 }
 
-__global__ void __launch_bounds__(kThreads) k_scan_gather(const float4* __restrict__ in, const uint32_t* __restrict__ vals, const uint64_t* __restrict__ keys,
-                                                          const uint32_t* __restrict__ offset, size_t total, float4* __restrict__ out) {
+template <class KeyT>
+__global__ void __launch_bounds__(kThreads) k_scan_gather(const float4* __restrict__ in, const uint32_t* __restrict__ vals, const KeyT* __restrict__ keys,
+                                                          const uint32_t* __restrict__ offset, size_t total, float4* __restrict__ out, int cell_bits) {
     const size_t j = size_t(blockIdx.x) * kThreads + threadIdx.x;
     if (j >= total) return;
     const uint32_t g = vals[j];
-    const uint32_t s = uint32_t(keys[j] >> 32);
+    const uint32_t s = uint32_t(keys[j] >> cell_bits);
     const float4 p = __ldg(&in[g]);
     out[j] = make_float4(p.x, p.y, p.z, __uint_as_float(g - offset[s]));
 }
@@ -1242,11 +1247,17 @@ __global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __res
 // ------------------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------------------
-void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
-    k_scan_keys<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, keys, vals);
+// keys: the 64-bit key buffer; with key32 it is used as an array of uint32_t (same point indexing)
+void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, int cell_bits, bool key32,
+                      cudaStream_t st) {
+    if (key32) k_scan_keys<uint32_t><<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, reinterpret_cast<uint32_t*>(keys), vals, cell_bits);
+    else k_scan_keys<uint64_t><<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, keys, vals, cell_bits);
 }
-void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st) {
-    k_scan_gather<<<uint32_t((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(in, vals, keys, offset, total, out);
+void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, size_t first, const uint32_t* offset, size_t total, float4* out,
+                        int cell_bits, bool key32, cudaStream_t st) {
+    const uint32_t grid = uint32_t((total + kThreads - 1) / kThreads);
+    if (key32) k_scan_gather<uint32_t><<<grid, kThreads, 0, st>>>(in, vals + first, reinterpret_cast<const uint32_t*>(keys) + first, offset, total, out, cell_bits);
+    else k_scan_gather<uint64_t><<<grid, kThreads, 0, st>>>(in, vals + first, keys + first, offset, total, out, cell_bits);
 }
 // Correspondence stage of one ICP iteration = launch_match (search + fit of every scan point) + launch_first_eval (first
 // evaluation of the new solve, the edge kernel when an edge cloud is present, and the optimiser's iteration zero).

@@ -73,8 +73,10 @@ constexpr int kFitThreads = SO_FIT_THREADS;
 #endif
 constexpr int kCorrLaunches = SO_FUSE_KNN_FIT ? 1 : 2;      // launches of the correspondence stage before the first evaluation
 
-void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, cudaStream_t st);
-void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, const uint32_t* offset, size_t total, float4* out, cudaStream_t st);
+void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, int cell_bits, bool key32,
+                      cudaStream_t st);
+void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, size_t first, const uint32_t* offset, size_t total, float4* out,
+                        int cell_bits, bool key32, cudaStream_t st);
 // part: 0 = the whole stage; split build only: 1 = k_knn_scan alone, 2 = k_fit alone (profiling)
 void launch_match(const MapView& m, const BatchView& bv, const CorrBuf& cb, const NnBuf& nb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, int part = 0);
 void launch_first_eval(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const MapView* medge = nullptr,

@@ -250,12 +250,17 @@ int query_sort(Ctx* c, size_t n) {
     return SO_OK;
 }
 
-int scan_sort(Ctx* c, size_t first, size_t n, int n_scans, cudaStream_t st) {
-    int bits = 32;
-    while ((1 << (bits - 32)) < n_scans) ++bits;
+int scan_sort(Ctx* c, size_t first, size_t n, int n_scans, int cell_bits, bool key32, cudaStream_t st) {
+    int bits = cell_bits;
+    while ((1 << (bits - cell_bits)) < n_scans) ++bits;
     size_t tmp = c->sort_tmp_bytes;
-    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(st == c->aux_stream ? c->d_sort_tmp2 : c->d_sort_tmp, tmp, c->d_skeys + first, c->d_skeys_out + first,
-                                                c->d_svals + first, c->d_svals_out + first, int(n), 0, bits, st));
+    void* scratch = st == c->aux_stream ? c->d_sort_tmp2 : c->d_sort_tmp;
+    if (key32)
+        SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(scratch, tmp, reinterpret_cast<uint32_t*>(c->d_skeys) + first, reinterpret_cast<uint32_t*>(c->d_skeys_out) + first,
+                                                    c->d_svals + first, c->d_svals_out + first, int(n), 0, bits, st));
+    else
+        SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(scratch, tmp, c->d_skeys + first, c->d_skeys_out + first,
+                                                    c->d_svals + first, c->d_svals_out + first, int(n), 0, bits, st));
     c->launches += 5;
     return SO_OK;
 }
