@@ -221,7 +221,7 @@ static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch, cudaS
     int cell_bits = 1, scan_bits = 0;
     while (cell_bits < 32 && (uint64_t(1) << cell_bits) <= n_cells) ++cell_bits;       // cells 0..n_cells-1 < mask = 2^cell_bits - 1
     while ((1u << scan_bits) < ch.count) ++scan_bits;
-    const bool key32 = cell_bits < 32 && cell_bits + scan_bits <= 32;
+    const bool key32 = !c->force_key64 && cell_bits < 32 && cell_bits + scan_bits <= 32;
     if (!key32) cell_bits = 32;
     launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, ch.grid_x, ch.count, cell_bits, key32, st);
     int rc = scan_sort(c, ch.pt_first, ch.pt_count, int(ch.count), cell_bits, key32, st);
@@ -533,6 +533,7 @@ so_ctx* so_create(const so_config* cfg_in) {
     if (cfg.line_res > 0) c->edge.res = cfg.line_res;
     if (std::getenv("SO_NO_COND_GRAPH")) c->no_cond_graph = true;
     if (std::getenv("SO_SINGLE_STREAM")) c->single_stream = true;
+    if (std::getenv("SO_FORCE_KEY64")) c->force_key64 = true;
     if (const char* e = std::getenv("SO_CHUNKS")) c->chunk_override = std::max(0, std::min(16, std::atoi(e)));      // profiling aid: ncu cannot see inside conditional-node bodies
     if (ctx_alloc(c) != SO_OK) { ctx_free(c); return nullptr; }
     return reinterpret_cast<so_ctx*>(c);

@@ -92,6 +92,7 @@ struct Ctx {
     GraphSlot graphs[20];
     uint64_t graph_clock = 0;
     uint64_t map_epoch = 1;
+    bool force_key64 = false;                      // SO_FORCE_KEY64: test aid, take the 64-bit scan-order key path even when 32 bits suffice
     bool single_stream = false;                    // SO_SINGLE_STREAM: tuning aid, all chunks on `stream`
     int chunk_override = 0;                        // SO_CHUNKS: tuning aid, upload/compute chunks per host batch (0 = built-in rule)
     bool no_cond_graph = false;                    // conditional nodes unavailable (or SO_NO_COND_GRAPH): unrolled schedule

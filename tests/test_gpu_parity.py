@@ -607,3 +607,26 @@ def test_scan_chain_deskew_extract_register(gpu_api, oracle_mod):
     ro = om.register(exp_feat, case["pose_prior"], cfg["plane_res"], cfg["max_iterations"], cfg["max_surface_features"])
     assert rg.status == ro.status == 0 and rg.n_iterations == ro.n_iterations
     _assert_pose_close(np.array(rg.pose), np.array(ro.pose))
+
+
+def test_scan_order_key_paths_and_stream_modes_agree(gpu_api, monkeypatch):
+    """The scan-order keys (32-bit when cell + scan bits fit, else 64-bit) and the chunk scheduling (two streams, one stream,
+    conditional graph or unrolled) are execution details: a batch must come out bit-identical under all of them."""
+    case = get_case("cfg1")
+    scans = [get_case("cfg1", i)["scan_xyzi"] for i in range(16)]
+    priors = np.stack([get_case("cfg1", i)["pose_prior"] for i in range(16)])
+    n_points = np.array([len(s) for s in scans], np.uint32)
+    flat = np.ascontiguousarray(np.concatenate(scans, 0))
+
+    def run():
+        ctx = gpu_api.Context(max_map_points=1 << 20, max_scan_points=int(n_points.max()), max_batch=16, plane_res=0.2)
+        ctx.map_set_points(case["map_xyzi"])
+        res = ctx.register_batch(flat, n_points, priors, 5, 2000)
+        out = np.array([list(r.pose) + [r.n_iterations] + list(r.hist_obs) for r in res])
+        ctx.close()
+        return out
+    base = run()
+    for env in ("SO_FORCE_KEY64", "SO_SINGLE_STREAM", "SO_NO_COND_GRAPH"):
+        monkeypatch.setenv(env, "1")
+        assert np.array_equal(run(), base), env
+        monkeypatch.delenv(env)
