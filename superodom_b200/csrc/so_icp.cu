@@ -129,38 +129,50 @@ __device__ __forceinline__ void scan_range(const MapView& m, uint32_t beg, uint3
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kBufCap = 24;
 
+// Offsets are visited nearest slab / row first: 0, -1, +1, -2, +2.
+__device__ __forceinline__ int walk_offset(int t) { return (t & 1) ? -((t + 1) >> 1) : (t >> 1); }
+// Distance from a point at offset f inside its cell (edge cs) to the cell `o` cells away along one axis (0 for its own cell).
+__device__ __forceinline__ float axis_gap(int o, float f, float cs_minus_f, float cs) {
+    const int ao = o < 0 ? -o : o;
+    const float side = o < 0 ? f : cs_minus_f;
+    return ao == 0 ? 0.f : side + float(ao - 1) * cs;
+}
+
 template <class F>
 __device__ __forceinline__ void walk_cube(const MapView& m, const QueryCell& qc, float U, int R, F&& f) {
     const int nb = m.nb;
     const uint32_t base = uint32_t(qc.slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
     const float cs = m.cs;
     const float fx = qc.f[0], fy = qc.f[1], fz = qc.f[2];
+    const float gx = cs - fx, gy = cs - fy, gz = cs - fz;
+    const int cx = qc.c[0], cy = qc.c[1], cz = qc.c[2];
+    const float Um = U * 1.0001f;                            // a row / cell is skipped when its lower bound exceeds U by this margin
 #pragma unroll 1
-    for (int zi = 0; zi <= 2 * R; ++zi) {                    // offsets 0,-1,+1,-2,+2: nearest slabs first
-        const int oz = (zi & 1) ? -((zi + 1) >> 1) : (zi >> 1);
-        const int zz = qc.c[2] + oz;
+    for (int zi = 0; zi <= 2 * R; ++zi) {
+        const int oz = walk_offset(zi);
+        const int zz = cz + oz;
         if (zz < 0 || zz >= nb) continue;                    // stay inside the query's block (LocalMap.h:488-507)
-        const float lz = oz < 0 ? fz + float(-oz - 1) * cs : (oz > 0 ? (cs - fz) + float(oz - 1) * cs : 0.f);
+        const float lz = axis_gap(oz, fz, gz, cs);
         const float lz2 = lz * lz;
-        if (lz2 * 0.9999f > U) continue;
+        if (lz2 > Um) continue;
 #pragma unroll 1
         for (int yi = 0; yi <= 2 * R; ++yi) {
-            const int oy = (yi & 1) ? -((yi + 1) >> 1) : (yi >> 1);
-            const int yy = qc.c[1] + oy;
+            const int oy = walk_offset(yi);
+            const int yy = cy + oy;
             if (yy < 0 || yy >= nb) continue;
-            const float ly = oy < 0 ? fy + float(-oy - 1) * cs : (oy > 0 ? (cs - fy) + float(oy - 1) * cs : 0.f);
-            const float lb = ly * ly + lz2;
-            if (lb * 0.9999f > U) continue;
-            int xlo = qc.c[0], xhi = qc.c[0];
-            for (int k = 1; k <= R; ++k) {
-                const float lx = fx + float(k - 1) * cs;
-                if (qc.c[0] - k < 0 || (lb + lx * lx) * 0.9999f > U) break;
-                xlo = qc.c[0] - k;
-            }
-            for (int k = 1; k <= R; ++k) {
-                const float lx = (cs - fx) + float(k - 1) * cs;
-                if (qc.c[0] + k > nb - 1 || (lb + lx * lx) * 0.9999f > U) break;
-                xhi = qc.c[0] + k;
+            const float ly = axis_gap(oy, fy, gy, cs);
+            const float lb = fmaf(ly, ly, lz2);
+            if (lb > Um) continue;
+            // x extent of the row, branch-free for the rings that exist by construction (R <= 2: cells are >= half the search
+            // radius); each step outwards needs the step before it
+            const bool l1 = cx >= 1 && fmaf(fx, fx, lb) <= Um;
+            const bool l2 = l1 && R >= 2 && cx >= 2 && fmaf(fx + cs, fx + cs, lb) <= Um;
+            const bool r1 = cx + 1 < nb && fmaf(gx, gx, lb) <= Um;
+            const bool r2 = r1 && R >= 2 && cx + 2 < nb && fmaf(gx + cs, gx + cs, lb) <= Um;
+            int xlo = cx - int(l1) - int(l2), xhi = cx + int(r1) + int(r2);
+            if (R > 2) {                                     // generic tail (not reached with the grids map_cells_per_block builds)
+                if (l2) for (int k = 3; k <= R; ++k) { const float lx = fx + float(k - 1) * cs; if (cx - k < 0 || fmaf(lx, lx, lb) > Um) break; xlo = cx - k; }
+                if (r2) for (int k = 3; k <= R; ++k) { const float lx = gx + float(k - 1) * cs; if (cx + k > nb - 1 || fmaf(lx, lx, lb) > Um) break; xhi = cx + k; }
             }
             const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
             uint32_t t = __ldg(&m.cell_start[row + xlo]);
