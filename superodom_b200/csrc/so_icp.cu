@@ -127,8 +127,14 @@ __device__ __forceinline__ void scan_range(const MapView& m, uint32_t beg, uint3
 // The result is identical to an exhaustive in-block search with the same ordering: every true neighbour has
 // approx d2 <= U (U carries a 4e-6 relative margin over the FP32 evaluation error of 4e-7).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kBufCap = 24;
+#ifndef SO_BUF_CAP
+#define SO_BUF_CAP 24
+#endif
+constexpr int kBufCap = SO_BUF_CAP;
 
+#ifndef SO_WALK_PRED
+#define SO_WALK_PRED 1
+#endif
 // Offsets are visited nearest slab / row first: 0, -1, +1, -2, +2.
 __device__ __forceinline__ int walk_offset(int t) { return (t & 1) ? -((t + 1) >> 1) : (t >> 1); }
 // Distance from a point at offset f inside its cell (edge cs) to the cell `o` cells away along one axis (0 for its own cell).
@@ -177,11 +183,24 @@ __device__ __forceinline__ void walk_cube(const MapView& m, const QueryCell& qc,
             const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
             uint32_t t = __ldg(&m.cell_start[row + xlo]);
             const uint32_t end = __ldg(&m.cell_start[row + xhi + 1]);
+#if SO_WALK_PRED
+            // groups of four with the tail predicated: the loads of a short row (most rows hold 1-3 points) are issued together
+            // instead of one per trip of a remainder loop; a lane past the end evaluates a far-away dummy that fails every test
+            const float4 far = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.f);
+            for (; t < end; t += 4) {
+                const float4 c0 = __ldg(&m.pts[t]);
+                const float4 c1 = t + 1 < end ? __ldg(&m.pts[t + 1]) : far;
+                const float4 c2 = t + 2 < end ? __ldg(&m.pts[t + 2]) : far;
+                const float4 c3 = t + 3 < end ? __ldg(&m.pts[t + 3]) : far;
+                f(c0, t); f(c1, t + 1); f(c2, t + 2); f(c3, t + 3);
+            }
+#else
             for (; t + 4 <= end; t += 4) {                   // four independent 16-byte loads in flight per lane
                 const float4 c0 = __ldg(&m.pts[t]), c1 = __ldg(&m.pts[t + 1]), c2 = __ldg(&m.pts[t + 2]), c3 = __ldg(&m.pts[t + 3]);
                 f(c0, t); f(c1, t + 1); f(c2, t + 2); f(c3, t + 3);
             }
             for (; t < end; ++t) f(__ldg(&m.pts[t]), t);
+#endif
         }
     }
 }

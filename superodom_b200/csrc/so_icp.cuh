@@ -47,7 +47,7 @@ struct NnBuf {
 };
 
 #ifndef SO_EVAL_PTS
-#define SO_EVAL_PTS 8
+#define SO_EVAL_PTS 16
 #endif
 constexpr int kEvalPts = SO_EVAL_PTS;     // points per thread in k_evaluate
 #ifndef SO_FIT_PTS
