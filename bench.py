@@ -29,7 +29,7 @@ UNIT = "scans/s"
 WORKLOAD = "cfg2: OS1-128 synthetic scans (131072 pts) vs 1M-pt local map, 20 ICP iters, planeRes 0.2, all points active"
 KNN_BYTES_PER_POINT = 16 + 21 + 80              # unfused build: scan float4 read + 5 positions + flag + 5 neighbour float4 written by k_knn_scan
 MATCH_BYTES_PER_POINT = 16 + 25 + 45            # fused k_knn_fit: scan float4 read; 5 positions + d5 + flag; correspondence {n,d} 32 + w 8 + flags 4 + status 1
-NCU_DRAM_BYTES_PER_POINT = {"k_knn_scan": 75.6, "k_knn_fit": 63.4}    # profiles/ncu_prof_r1o_metrics.csv: (26.86 MB read + 52.41 MB written) / 1 048 576 points of one
+NCU_DRAM_BYTES_PER_POINT = {"k_knn_scan": 75.1, "k_knn_fit": 63.4}    # profiles/ncu_prof_r1p_metrics.csv: (26.88 MB read + 51.89 MB written) / 1 048 576 points of one
                                                                        # k_knn_scan launch; fused build (gpurun capture r1m): (28.07 + 38.46) MB
 
 
@@ -295,7 +295,7 @@ def run_ours(args):
                     "traffic_source": f"profiles/ (ncu --set full, dram__bytes_read+write per point of one {kname} launch, scaled to this launch size)",
                     "peak_source": peak_src, "launches_profiled": int(n_k), "avg_launch_ms": ms_k / max(n_k, 1),
                     "algorithmic_bytes_per_launch": alg_bytes / max(n_k, 1),
-                    "note": "instruction-issue bound (ncu: 69% issue-active), L1/L2-resident gathers; see DESIGN.md section 4",
+                    "note": "instruction-issue bound (ncu: 74% issue-active), L1/L2-resident gathers; see DESIGN.md section 4",
                     "first_evaluation": {"launches": int(n_f), "avg_launch_ms": ms_f / max(n_f, 1)},
                     "k_evaluate": {"launches": int(n_e), "avg_launch_ms": ms_e / max(n_e, 1)},
                     "k_fit": {"launches": int(n_q), "avg_launch_ms": ms_q / max(n_q, 1)},
