@@ -234,7 +234,7 @@ static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch, cudaS
     return SO_OK;
 }
 
-// [k_knn_scan, k_fit, k_lm_step, (k_evaluate, k_lm_step) x lm] per ICP iteration; every kernel exits at once when its
+// [k_knn_scan, k_fit, k_evaluate<PH_CORR>, k_lm_step, (k_evaluate<PH_EVAL>, k_lm_step) x lm] per ICP iteration; every kernel exits at once when its
 // scan is not in the matching phase, so a fixed schedule follows whatever path the device-side state machine takes.
 // Preferred form: a CUDA-graph WHILE node around ONE iteration (k_loop_cond ends the loop when every scan of the chunk
 // is done); fallback: the schedule unrolled max_icp_iters times.  Returns whether the loop form ran.

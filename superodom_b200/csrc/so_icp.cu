@@ -1,16 +1,19 @@
 // so_icp.cu -- sm_100a kernels of the per-scan ICP registration path.
 //
 //   k_scan_keys / k_scan_gather : order the scan by map cell once per registration (warp-coherent cell walks).
-//   k_knn_scan   : per scan point -- pose transform, block lookup, radius-bounded 5-NN in the sorted hash grid.   [K2]
+//   k_knn_scan   : per scan point -- pose transform, block lookup, radius-bounded 5-NN in the sorted hash grid
+//                  (three-round select: bound, gather, refine); hands the five neighbours to k_fit.         [a5-a7]
 //   k_fit        : 3x3 PCA + 5x3 column-pivoted QR plane fit with the reference's accept/reject gates, observability
-//                  labels + histograms, AND the first residual/Jacobian evaluation of the following ceres::Solve,
-//                  warp/CTA-reduced in FP64 (21+6+1 accumulators).                                  [K3+K4+K5]
-//   k_evaluate   : per correspondence -- residual, 1x6 Jacobian, Tukey/Scaled robust weight at the LM candidate pose,
-//                  same reduction.                                                          [K5]
+//                  labels + histograms, fit weight; writes the correspondence record.                     [a8-a11]
+//   k_knn_fit    : optional fusion of the two (SO_FUSE_KNN_FIT; measured slower, see so_icp.cuh).
+//   k_evaluate   : per correspondence -- residual, 1x6 Jacobian, Tukey/Scaled robust weight at the matched pose (first
+//                  evaluation of a solve) or at the LM candidate, warp/CTA-reduced in FP64 (21+6+1 accumulators). [a12-a13]
 //   k_edge_fit / k_edge_evaluate : the edge / line branch (10-NN in the edge map, best-line selection, line factor).   [a19]
 //   k_lm_step    : fixed-order cross-CTA reduction, then ONE thread per scan advances the device-resident state
-//                  machine: Ceres' trust-region LM (step solve by 6x6 Cholesky, accept/reject, tolerances), the outer
-//                  ICP convergence rule, and at the end the covariance pseudo-inverse + 3x3 eigen analysis. [K6+K7]
+//                  machine: Ceres' trust-region LM (step solve by 6x6 Cholesky, accept/reject, tolerances), the SE3 prior
+//                  rows, the outer ICP convergence rule, and at the end the covariance pseudo-inverse + 3x3 eigen
+//                  analysis.                                                                        [a3, a14-a16, a20]
+//   k_loop_cond  : CUDA-graph WHILE condition of a chunk (any scan still iterating).
 //   k_knn        : stand-alone k-NN (so_knn*), radius-bounded or exact with ring expansion.
 //
 // Reference citations are relative to /root/reference/super_odometry/.
@@ -702,9 +705,9 @@ __device__ __forceinline__ float4 ld_f4_again(const float4* p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_fit: the rest of LidarSLAM::ComputePlaneDistanceParameters (LidarSlam.cpp:536-572) for every point that has its
-// five neighbours -- PCA, plane fit, gates, observability -- plus the first residual/Jacobian evaluation of the
-// following ceres::Solve and the histogram / normal-equation reductions.  FP64 throughout.
+// k_fit: the rest of LidarSLAM::ComputePlaneDistanceParameters (LidarSlam.cpp:536-572) for every scan point, from the
+// neighbours k_knn_scan handed over: fit_point() below + the per-scan histograms.  The first residual/Jacobian evaluation of
+// the following ceres::Solve is a separate k_evaluate<PH_CORR> launch, which keeps this kernel at 64 registers.
 // ------------------------------------------------------------------------------------------------------------------
 // The rest of LidarSLAM::ComputePlaneDistanceParameters (LidarSlam.cpp:536-572) for one scan point whose k-NN outcome is
 // `status`: PCA, plane fit, gates, observability labels, fit weight; writes the correspondence record and counts the
@@ -723,8 +726,8 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
         pf[0] += s_pose[0]; pf[1] += s_pose[1]; pf[2] += s_pose[2];
         const float qx = float(pf[0]), qy = float(pf[1]), qz = float(pf[2]);
         // computePCAForFeature (:749-790) + utils::ComputePCA (superodom_utils.h:143-151).  The five neighbours are read
-        // three times (here, for the QR, for the distances) from k_knn_scan's coalesced hand-over instead of being held
-        // in 30 FP64 registers across the eigen-solve: the re-reads hit L1 and the kernel fits 3 CTAs per SM.
+        // three times (here, for the QR, for the distances) through nbr() instead of being held in 30 FP64 registers across
+        // the eigen-solve: the re-reads hit L1 and the kernel fits 4 CTAs per SM.
         double mean[3] = {0, 0, 0};
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
