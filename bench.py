@@ -111,10 +111,14 @@ def make_inputs(first_scan: int, n_scans: int):
     cache = os.environ.get("SO_BENCH_CACHE", "/tmp/superodom_b200_bench_inputs")       # "" disables
     path = os.path.join(cache, f"cfg2_{first_scan}_{n_scans}.npz") if cache else None
     if path and os.path.exists(path):
-        z = np.load(path)
-        nn = z["n"]
-        offs = np.concatenate([[0], np.cumsum(nn)])
-        return z["map"], [z["flat"][offs[i]:offs[i + 1]] for i in range(len(nn))], z["priors"], z["truths"]
+        try:
+            z = np.load(path)
+            nn = z["n"]
+            offs = np.concatenate([[0], np.cumsum(nn)])
+            flat = z["flat"]
+            return z["map"], [flat[offs[i]:offs[i + 1]] for i in range(len(nn))], z["priors"], z["truths"]
+        except Exception as e:                                 # unreadable / half-written cache: regenerate
+            print(f"[bench] input cache {path} unusable ({type(e).__name__}), regenerating", file=sys.stderr)
     scene, map_xyzi = synth.make_map_for("cfg2")
     scans, priors, truths = [], [], []
     for i in range(first_scan, first_scan + n_scans):
@@ -123,10 +127,13 @@ def make_inputs(first_scan: int, n_scans: int):
         priors.append(c["pose_prior"])
         truths.append(c["pose_true"])
     if path:
-        os.makedirs(cache, exist_ok=True)
-        tmp = path + f".{os.getpid()}.tmp.npz"
-        np.savez(tmp, map=map_xyzi, flat=np.concatenate(scans, 0), n=np.array([len(x) for x in scans]), priors=np.stack(priors), truths=np.stack(truths))
-        os.replace(tmp, path)                              # atomic: ranks / back-to-back runs may race on the same file
+        try:
+            os.makedirs(cache, exist_ok=True)
+            tmp = path + f".{os.getpid()}.tmp.npz"
+            np.savez(tmp, map=map_xyzi, flat=np.concatenate(scans, 0), n=np.array([len(x) for x in scans]), priors=np.stack(priors), truths=np.stack(truths))
+            os.replace(tmp, path)                              # atomic: ranks / back-to-back runs may race on the same file
+        except Exception as e:                                 # read-only or full /tmp: the cache is only a convenience
+            print(f"[bench] input cache not written ({type(e).__name__}: {e})", file=sys.stderr)
     return map_xyzi, scans, np.stack(priors), np.stack(truths)
 
 

@@ -466,10 +466,13 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             if (host_src) SO_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copy[k], 0));
             if (ch.grid_x == 0) continue;
             int rc = prepare_scans(c, d_scan, ch, st);
-            if (rc) return rc;
             bool was_loop = false;
-            rc = run_schedule(c, ch, o.max_icp_iters, o.lm_max_iterations, false, &was_loop, st);
-            if (rc) return rc;
+            if (!rc) rc = run_schedule(c, ch, o.max_icp_iters, o.lm_max_iterations, false, &was_loop, st);
+            if (rc) {                                       // leave no work behind on the side streams before reporting the error
+                cudaStreamSynchronize(c->aux_stream);
+                cudaStreamSynchronize(c->copy_stream);
+                return rc;
+            }
             loop_flags[k] = was_loop;
         }
         if (two_streams) {
