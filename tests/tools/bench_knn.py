@@ -6,8 +6,8 @@ queries/results (CUDA events around so_knn_device, L2 flushed between iterations
 comparators on a bounded sample: the reference's own octree (oracle/_ref, verbatim) and scipy cKDTree (the exact
 kd-tree stand-in for pcl::KdTreeFLANN, SURVEY 8d).
 
-    python scripts/bench_knn.py [--cpu]                 # 1 GPU
-    torchrun --nproc-per-node N scripts/bench_knn.py    # queries split over N GPUs, map replicated
+    python tests/tools/bench_knn.py [--cpu]                 # 1 GPU
+    torchrun --nproc-per-node N tests/tools/bench_knn.py    # queries split over N GPUs, map replicated
 """
 import json
 import os
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch  # noqa: E402
 
 from superodom_b200 import api, synth  # noqa: E402
@@ -51,7 +51,7 @@ didx = torch.empty((nq, 5), dtype=torch.int32, device="cuda")
 dd2 = torch.empty((nq, 5), dtype=torch.float32, device="cuda")
 peak = 6485.5
 try:
-    peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
 out = {"config": "cfg5", "map_points": M, "queries": NQ, "k": 5, "n_gpus": world, "peak_gbs_per_gpu": peak}

@@ -1,7 +1,7 @@
 """Verbose GPU-vs-oracle check used during development (run under gpurun)."""
 import sys, time, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from superodom_b200 import synth, api
 from oracle import oracle as O
 

@@ -1,6 +1,6 @@
 """Single-scan registration latency through so_register (host scan in, pose out), beside the CPU oracle on one thread.
 
-    python scripts/latency.py            # cfg1 (VLP-16, 28 800 pts, cap 2000, 5 its) and cfg2 (OS1-128, 131 072 pts, 20 its)
+    python tests/tools/latency.py            # cfg1 (VLP-16, 28 800 pts, cap 2000, 5 its) and cfg2 (OS1-128, 131 072 pts, 20 its)
 """
 import json
 import os
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from superodom_b200 import api, synth  # noqa: E402
 
 out = {}
