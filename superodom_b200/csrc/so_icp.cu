@@ -215,6 +215,29 @@ __device__ __forceinline__ float approx_d2(const float4 c, float qx, float qy, f
 
 // s_buf: [kBufCap][kThreads] positions, column = this thread.  u_seed < 0: no seed.  `bound`: neighbours farther than this
 // (squared) are not wanted; tk must have been initialised with it.  Complete for d2 <= min(bound, (R*cs)^2).
+// Round 2 for one lane: record (or, past kBufCap, insert) every candidate with approx d2 <= U.
+template <int K>
+__device__ __forceinline__ void knn_record(const float4 c, uint32_t t, float qx, float qy, float qz, float U, uint32_t* s_buf, int& cnt, TopK<K>& tk) {
+    const float d = approx_d2(c, qx, qy, qz);
+    if (d <= U) {
+        if (cnt < kBufCap) { s_buf[cnt * kThreads + threadIdx.x] = t; ++cnt; }
+        else {                                                                 // overflow (dense cluster inside U): insert directly
+            const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+            tk.offer(float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)), __float_as_uint(c.w), t);
+        }
+    }
+}
+// Round 3 for one lane: exact d2 + ordered insertion of the recorded candidates.
+template <int K>
+__device__ __forceinline__ void knn_refine(const MapView& m, float qx, float qy, float qz, const uint32_t* s_buf, int cnt, TopK<K>& tk) {
+    for (int e = 0; e < cnt; ++e) {
+        const uint32_t t = s_buf[e * kThreads + threadIdx.x];
+        const float4 c = __ldg(&m.pts[t]);
+        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+        tk.offer(float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)), __float_as_uint(c.w), t);
+    }
+}
+
 template <int K>
 __device__ __forceinline__ void knn_select(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, float u_seed, float bound,
                                            uint32_t* s_buf, TopK<K>& tk) {
@@ -234,22 +257,102 @@ __device__ __forceinline__ void knn_select(const MapView& m, const QueryCell& qc
     }
     U = fminf(U, bound * 1.000004f);
     int cnt = 0;
-    walk_cube(m, qc, U, m.R, [&](const float4 c, uint32_t t) {
-        const float d = approx_d2(c, qx, qy, qz);
-        if (d <= U) {
-            if (cnt < kBufCap) { s_buf[cnt * kThreads + threadIdx.x] = t; ++cnt; }
-            else {                                                             // overflow (dense cluster inside U): insert directly
-                const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-                tk.offer(float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)), __float_as_uint(c.w), t);
+    walk_cube(m, qc, U, m.R, [&](const float4 c, uint32_t t) { knn_record<K>(c, t, qx, qy, qz, U, s_buf, cnt, tk); });
+    knn_refine<K>(m, qx, qy, qz, s_buf, cnt, tk);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-cooperative form of the select k-NN (SO_KNN_COOP).  The 32 queries of a warp are consecutive in cell order, so most
+// warps sit in one to three cells of one x-row.  When the valid lanes share a block and their cell box is small, the warp
+// walks ONE candidate set -- the box grown by the needed rings -- with warp-uniform loops: every candidate is fetched once
+// with a uniform (broadcast) load and tested by all lanes against their own query, and the row bookkeeping that dominates
+// the per-lane walk is paid once per warp.  Each lane still gathers exactly the candidates within its own U (any point
+// within sqrt(U) of a query lies inside that query's ring cube, which the grown box contains), so results are identical
+// to knn_select.  Returns false (nothing done) when the warp does not qualify; the caller then runs knn_select per lane.
+// Must be called by all 32 lanes.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef SO_COOP_MAX_CELLS
+#define SO_COOP_MAX_CELLS 160        // (ex+2)(ey+2)(ez+2) above which the shared candidate set stops paying
+#endif
+#ifndef SO_COOP_MIN_LANES
+#define SO_COOP_MIN_LANES 8
+#endif
+
+// Rows of the cell box [lo-R, hi+R] clipped to the block; a row whose cell gap to the box of queries already exceeds Umax is
+// skipped (only possible for R = 2).  f(point, position) runs for every point of every visited row, warp-uniformly.
+template <class F>
+__device__ __forceinline__ void coop_walk(const MapView& m, int slot, int lox, int loy, int loz, int hix, int hiy, int hiz, int R, float Umax, F&& f) {
+    const int nb = m.nb;
+    const uint32_t base = uint32_t(slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
+    const float cs2 = m.cs * m.cs, Um = Umax * 1.0001f;
+    const int x0 = max(lox - R, 0), x1 = min(hix + R, nb - 1);
+    const int y0 = max(loy - R, 0), y1 = min(hiy + R, nb - 1);
+    const int z0 = max(loz - R, 0), z1 = min(hiz + R, nb - 1);
+    const float4 far = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.f);
+#pragma unroll 1
+    for (int zz = z0; zz <= z1; ++zz) {
+        const int gz = max(max(loz - zz - 1, zz - hiz - 1), 0);
+#pragma unroll 1
+        for (int yy = y0; yy <= y1; ++yy) {
+            const int gy = max(max(loy - yy - 1, yy - hiy - 1), 0);
+            if (float(gy * gy + gz * gz) * cs2 > Um) continue;
+            const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
+            uint32_t t = __ldg(&m.cell_start[row + x0]);
+            const uint32_t end = __ldg(&m.cell_start[row + x1 + 1]);
+            for (; t < end; t += 4) {
+                const float4 c0 = __ldg(&m.pts[t]);
+                const float4 c1 = t + 1 < end ? __ldg(&m.pts[t + 1]) : far;
+                const float4 c2 = t + 2 < end ? __ldg(&m.pts[t + 2]) : far;
+                const float4 c3 = t + 3 < end ? __ldg(&m.pts[t + 3]) : far;
+                f(c0, t); f(c1, t + 1); f(c2, t + 2); f(c3, t + 3);
             }
         }
-    });
-    for (int e = 0; e < cnt; ++e) {
-        const uint32_t t = s_buf[e * kThreads + threadIdx.x];
-        const float4 c = __ldg(&m.pts[t]);
-        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-        tk.offer(float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)), __float_as_uint(c.w), t);
     }
+}
+
+template <int K>
+__device__ __forceinline__ bool knn_select_coop(const MapView& m, const QueryCell& qc, bool valid, float qx, float qy, float qz, float u_seed,
+                                                float bound, uint32_t* s_buf, TopK<K>& tk) {
+    const unsigned full = 0xffffffffu;
+    const unsigned vmask = __ballot_sync(full, valid);
+    if (__popc(vmask) < SO_COOP_MIN_LANES) return false;
+    const int slot0 = __shfl_sync(full, qc.slot, __ffs(vmask) - 1);
+    if (!__all_sync(full, !valid || qc.slot == slot0)) return false;
+    const int lox = __reduce_min_sync(full, valid ? qc.c[0] : 0x7fffffff), hix = __reduce_max_sync(full, valid ? qc.c[0] : -1);
+    const int loy = __reduce_min_sync(full, valid ? qc.c[1] : 0x7fffffff), hiy = __reduce_max_sync(full, valid ? qc.c[1] : -1);
+    const int loz = __reduce_min_sync(full, valid ? qc.c[2] : 0x7fffffff), hiz = __reduce_max_sync(full, valid ? qc.c[2] : -1);
+    const int ex = hix - lox + 1, ey = hiy - loy + 1, ez = hiz - loz + 1;
+    if ((ex + 2) * (ey + 2) * (ez + 2) > SO_COOP_MAX_CELLS) return false;
+    // round 1: bound on the K-th neighbour distance from the box grown by one ring (a superset of every lane's 27 cells)
+    float U;
+    if (__any_sync(full, valid && u_seed < 0.f)) {
+        float a[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) a[j] = bound;
+        coop_walk(m, slot0, lox, loy, loz, hix, hiy, hiz, 1, bound, [&](const float4 c, uint32_t) {
+            const float d = approx_d2(c, qx, qy, qz);
+#pragma unroll
+            for (int j = K - 1; j > 0; --j) a[j] = fminf(a[j], fmaxf(a[j - 1], d));
+            a[0] = fminf(a[0], d);
+        });
+        U = (u_seed >= 0.f ? u_seed : a[K - 1]) * 1.000004f;
+    } else U = u_seed * 1.000004f;
+    U = fminf(U, bound * 1.000004f);
+    if (!valid) U = 0.f;
+    // round 2: rings the widest lane needs; box grown by that; every lane records what lies within its own U
+    const float cs = m.cs;
+    const int need = (U * 1.0001f <= cs * cs) ? 1 : 2;                           // (need * cs)^2 >= U, rings <= 2 by construction of the grid
+    const int Rw = min(__reduce_max_sync(full, valid ? need : 1), m.R);
+    const float Umax = __uint_as_float(__reduce_max_sync(full, __float_as_uint(U)));       // U >= 0: the bit patterns order like the values
+    int cnt = 0;
+    if (Rw == 1 || (ex + 4) * (ey + 4) * (ez + 4) <= 3 * SO_COOP_MAX_CELLS)
+        coop_walk(m, slot0, lox, loy, loz, hix, hiy, hiz, Rw, Umax, [&](const float4 c, uint32_t t) {
+            if (valid) knn_record<K>(c, t, qx, qy, qz, U, s_buf, cnt, tk);
+        });
+    else if (valid)
+        walk_cube(m, qc, U, m.R, [&](const float4 c, uint32_t t) { knn_record<K>(c, t, qx, qy, qz, U, s_buf, cnt, tk); });
+    if (valid) knn_refine<K>(m, qx, qy, qz, s_buf, cnt, tk);
+    return true;
 }
 
 // Unpruned cube [c-R, c+R]^3 clipped to the block (fallback rings of the exact, unbounded search).
@@ -641,6 +744,9 @@ __global__ void __launch_bounds__(kThreads) k_scan_gather(const float4* __restri
 #ifndef SO_KNN_MINB
 #define SO_KNN_MINB 4
 #endif
+#ifndef SO_KNN_COOP
+#define SO_KNN_COOP 0
+#endif
 __global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_scan(MapView m, BatchView bv, NnBuf nb) {
     const int s = blockIdx.y;
     const IcpState* st = bv.st + s;
@@ -651,22 +757,31 @@ __global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_scan(MapView m, B
     __syncthreads();
     const uint32_t n = uint32_t(st->n_points);
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+#if SO_KNN_COOP
+    if ((i & ~31u) >= n) return;                          // whole warp past the end; partial warps stay together for the collectives
+    const bool in_range = i < n;
+#else
     if (i >= n) return;
-    const size_t gi = size_t(bv.offset[s]) + i;
+    const bool in_range = true;
+#endif
+    const size_t gi = size_t(bv.offset[s]) + (in_range ? i : 0);
     const float4 sp = __ldg(&bv.scan[gi]);
     int pre = SO_MATCH_SKIPPED;
     TopK<5> tk;
     tk.init(m.bound_d2);
-    if (should_process(__float_as_uint(sp.w), st->sampling_rate)) {
+    bool searchable = false;
+    float qx = 0.f, qy = 0.f, qz = 0.f, u_seed = -1.f;
+    QueryCell qc;
+    qc.slot = -1; qc.nblock = 0; qc.c[0] = qc.c[1] = qc.c[2] = 0; qc.f[0] = qc.f[1] = qc.f[2] = 0.f;
+    if (in_range && should_process(__float_as_uint(sp.w), st->sampling_rate)) {
         const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
         double pf[3];
         qrot(s_pose + 3, pin, pf);
-        const float qx = float(pf[0] + s_pose[0]), qy = float(pf[1] + s_pose[1]), qz = float(pf[2] + s_pose[2]);
-        QueryCell qc;
+        qx = float(pf[0] + s_pose[0]); qy = float(pf[1] + s_pose[1]); qz = float(pf[2] + s_pose[2]);
         locate(m, qx, qy, qz, qc);
         if (qc.slot < 0 || qc.nblock < 5) pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
         else {
-            float u_seed = -1.f;
+            searchable = true;
             if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) {
                 // ICP iterations after the first: the previous iteration's five neighbours still exist, so the largest
                 // of their (exact) distances to the moved query bounds the new 5th-neighbour distance.
@@ -681,10 +796,16 @@ __global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_scan(MapView m, B
                 // after a large update the 27-cell estimate of round 1 prunes better than a loose seed
                 if (u <= 1.3f * nb.d5[gi]) u_seed = u;
             }
-            knn_select<5>(m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
-            pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
         }
     }
+#if SO_KNN_COOP
+    if (!knn_select_coop<5>(m, qc, searchable, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk) && searchable)
+        knn_select<5>(m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
+#else
+    if (searchable) knn_select<5>(m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
+#endif
+    if (searchable) pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
+    if (!in_range) return;
     nb.pre[gi] = (unsigned char)pre;
     nb.d5[gi] = tk.d2[4];
 #pragma unroll
