@@ -270,6 +270,9 @@ __device__ __forceinline__ void knn_select(const MapView& m, const QueryCell& qc
 // within sqrt(U) of a query lies inside that query's ring cube, which the grown box contains), so results are identical
 // to knn_select.  Returns false (nothing done) when the warp does not qualify; the caller then runs knn_select per lane.
 // Must be called by all 32 lanes.
+// Status (B200, cfg2, 64 scans): parity tests identical to the per-lane path, but k_knn_scan 1.19 ms vs 1.07 ms -- every lane
+// tests every candidate of the shared box in both rounds (43-59 per round against ~35 + ~33 pruned per lane), which outweighs
+// the row bookkeeping saved.  Off by default (SO_KNN_COOP=0).
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef SO_COOP_MAX_CELLS
 #define SO_COOP_MAX_CELLS 160        // (ex+2)(ey+2)(ez+2) above which the shared candidate set stops paying
