@@ -272,8 +272,13 @@ __device__ __forceinline__ void knn_select(const MapView& m, const QueryCell& qc
 // Must be called by all 32 lanes.
 // Status (B200, cfg2, 64 scans): parity tests identical to the per-lane path, but k_knn_scan 1.19 ms vs 1.07 ms -- every lane
 // tests every candidate of the shared box in both rounds (43-59 per round against ~35 + ~33 pruned per lane), which outweighs
-// the row bookkeeping saved.  Off by default (SO_KNN_COOP=0).
+// the row bookkeeping saved.  The hybrid (SO_KNN_COOP=2: cooperative bound, per-lane gather) measures 1.125 ms.  Off by
+// default (SO_KNN_COOP=0); not yet tried: a tighter cell limit (the box+1 candidate count has a heavy tail: median 43-59,
+// p90 200-700 at the 160-cell limit) and a shared-memory candidate tile.
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef SO_KNN_COOP
+#define SO_KNN_COOP 0            // 0: per-lane walk; 1: cooperative rounds 1 + 2; 2: cooperative round 1, per-lane round 2
+#endif
 #ifndef SO_COOP_MAX_CELLS
 #define SO_COOP_MAX_CELLS 160        // (ex+2)(ey+2)(ez+2) above which the shared candidate set stops paying
 #endif
@@ -348,7 +353,9 @@ __device__ __forceinline__ bool knn_select_coop(const MapView& m, const QueryCel
     const int Rw = min(__reduce_max_sync(full, valid ? need : 1), m.R);
     const float Umax = __uint_as_float(__reduce_max_sync(full, __float_as_uint(U)));       // U >= 0: the bit patterns order like the values
     int cnt = 0;
-    if (Rw == 1 || (ex + 4) * (ey + 4) * (ez + 4) <= 3 * SO_COOP_MAX_CELLS)
+    if (SO_KNN_COOP == 2) {                                  // hybrid: cooperative bound, per-lane pruned gather with the tight U
+        if (valid) walk_cube(m, qc, U, m.R, [&](const float4 c, uint32_t t) { knn_record<K>(c, t, qx, qy, qz, U, s_buf, cnt, tk); });
+    } else if (Rw == 1 || (ex + 4) * (ey + 4) * (ez + 4) <= 3 * SO_COOP_MAX_CELLS)
         coop_walk(m, slot0, lox, loy, loz, hix, hiy, hiz, Rw, Umax, [&](const float4 c, uint32_t t) {
             if (valid) knn_record<K>(c, t, qx, qy, qz, U, s_buf, cnt, tk);
         });
@@ -746,9 +753,6 @@ __global__ void __launch_bounds__(kThreads) k_scan_gather(const float4* __restri
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef SO_KNN_MINB
 #define SO_KNN_MINB 4
-#endif
-#ifndef SO_KNN_COOP
-#define SO_KNN_COOP 0
 #endif
 __global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_scan(MapView m, BatchView bv, NnBuf nb) {
     const int s = blockIdx.y;
