@@ -138,6 +138,9 @@ constexpr int kBufCap = SO_BUF_CAP;
 #ifndef SO_WALK_PRED
 #define SO_WALK_PRED 1
 #endif
+#ifndef SO_WALK_V2
+#define SO_WALK_V2 0              // 1: tabulated slab / row gaps + single-address candidate groups (prepared from the per-line profile; not yet measured)
+#endif
 // Offsets are visited nearest slab / row first: 0, -1, +1, -2, +2.
 __device__ __forceinline__ int walk_offset(int t) { return (t & 1) ? -((t + 1) >> 1) : (t >> 1); }
 // Distance from a point at offset f inside its cell (edge cs) to the cell `o` cells away along one axis (0 for its own cell).
@@ -155,23 +158,48 @@ __device__ __forceinline__ void walk_cube(const MapView& m, const QueryCell& qc,
     const float fx = qc.f[0], fy = qc.f[1], fz = qc.f[2];
     const float gx = cs - fx, gy = cs - fy, gz = cs - fz;
     const int cx = qc.c[0], cy = qc.c[1], cz = qc.c[2];
+#if SO_WALK_V2
+    // Squared gaps to the five slabs / rows (3.0e38 = outside the block, never within any U) tabulated once per walk and read
+    // back by loop index (a small per-thread local array), instead of being recomputed for each of the 25 (slab, row) pairs:
+    // the per-line profile (profiles/knn_scan_r1p_per_source_line.txt) puts walk_offset + axis_gap at 11 % of the kernel.
+    const float Um = fminf(U * 1.0001f, 1.0e30f);
+    float g2y[5], g2z[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int o = (k & 1) ? -((k + 1) >> 1) : (k >> 1);
+        const float ly = axis_gap(o, fy, gy, cs), lz = axis_gap(o, fz, gz, cs);
+        g2y[k] = (cy + o < 0 || cy + o >= nb) ? 3.0e38f : ly * ly;
+        g2z[k] = (cz + o < 0 || cz + o >= nb) ? 3.0e38f : lz * lz;
+    }
+#else
     const float Um = U * 1.0001f;                            // a row / cell is skipped when its lower bound exceeds U by this margin
+#endif
 #pragma unroll 1
     for (int zi = 0; zi <= 2 * R; ++zi) {
         const int oz = walk_offset(zi);
         const int zz = cz + oz;
+#if SO_WALK_V2
+        const float lz2 = g2z[zi];
+        if (lz2 > Um) continue;                              // also: slab outside the query's block (LocalMap.h:488-507)
+#else
         if (zz < 0 || zz >= nb) continue;                    // stay inside the query's block (LocalMap.h:488-507)
         const float lz = axis_gap(oz, fz, gz, cs);
         const float lz2 = lz * lz;
         if (lz2 > Um) continue;
+#endif
 #pragma unroll 1
         for (int yi = 0; yi <= 2 * R; ++yi) {
             const int oy = walk_offset(yi);
             const int yy = cy + oy;
+#if SO_WALK_V2
+            const float lb = g2y[yi] + lz2;
+            if (lb > Um) continue;
+#else
             if (yy < 0 || yy >= nb) continue;
             const float ly = axis_gap(oy, fy, gy, cs);
             const float lb = fmaf(ly, ly, lz2);
             if (lb > Um) continue;
+#endif
             // x extent of the row, branch-free for the rings that exist by construction (R <= 2: cells are >= half the search
             // radius); each step outwards needs the step before it
             const bool l1 = cx >= 1 && fmaf(fx, fx, lb) <= Um;
@@ -191,10 +219,18 @@ __device__ __forceinline__ void walk_cube(const MapView& m, const QueryCell& qc,
             // instead of one per trip of a remainder loop; a lane past the end evaluates a far-away dummy that fails every test
             const float4 far = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.f);
             for (; t < end; t += 4) {
+#if SO_WALK_V2
+                const float4* p = m.pts + t;                 // one address, three immediate offsets
+                const float4 c0 = __ldg(p);
+                const float4 c1 = t + 1 < end ? __ldg(p + 1) : far;
+                const float4 c2 = t + 2 < end ? __ldg(p + 2) : far;
+                const float4 c3 = t + 3 < end ? __ldg(p + 3) : far;
+#else
                 const float4 c0 = __ldg(&m.pts[t]);
                 const float4 c1 = t + 1 < end ? __ldg(&m.pts[t + 1]) : far;
                 const float4 c2 = t + 2 < end ? __ldg(&m.pts[t + 2]) : far;
                 const float4 c3 = t + 3 < end ? __ldg(&m.pts[t + 3]) : far;
+#endif
                 f(c0, t); f(c1, t + 1); f(c2, t + 2); f(c3, t + 3);
             }
 #else
