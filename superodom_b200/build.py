@@ -40,7 +40,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"])
+    # the arch flag also goes to the link step: without it nvcc adds an (empty) device-link stub for its default architecture
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"])
     return LIB
 
 

@@ -70,3 +70,18 @@ def test_product_never_imports_the_oracle():
                 if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                     txt = open(os.path.join(dp, fn), errors="ignore").read()
                     assert "so_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, fn
+
+
+def test_library_holds_only_sm_100a_images():
+    """Write for B200 only: every device ELF inside the shared library is an sm_100a image (no other architecture, no PTX)."""
+    import shutil
+    import subprocess
+    from superodom_b200 import build
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    lib = build.build()
+    elfs = [ln for ln in subprocess.run([tool, "-lelf", lib], capture_output=True, text=True).stdout.splitlines() if "ELF file" in ln]
+    assert elfs and all("sm_100a" in ln for ln in elfs), elfs
+    ptx = [ln for ln in subprocess.run([tool, "-lptx", lib], capture_output=True, text=True).stdout.splitlines() if "PTX file" in ln]
+    assert not ptx, ptx
