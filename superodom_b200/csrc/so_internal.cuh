@@ -117,6 +117,12 @@ __host__ __device__ inline void rel_motion(const double a[7], const double b[7],
 // v (row-major) the eigenvectors in columns; then sorted ascending.  With N a compile-time constant and full
 // unrolling every index is static, so for N=3 the whole thing lives in registers.
 // WITH_V = false: eigenvalues only (v is not touched and may be null).
+// Convergence test of the sweeps: sum of squared off-diagonals <= SO_JACOBI_OFF_TOL * sum of squared diagonals.  1e-33 drives the
+// off-diagonals to full double precision (4 sweeps for the 3x3 scatter matrices of k_fit); 1e-30 would usually stop a sweep
+// earlier at an eigenvalue error far below an ulp -- left for a measured change.
+#ifndef SO_JACOBI_OFF_TOL
+#define SO_JACOBI_OFF_TOL 1e-33
+#endif
 template <int N, int SWEEPS, bool WITH_V = true>
 __device__ inline void jacobi_eig(double* a, double* v, double* w) {
     if (WITH_V) {
@@ -134,7 +140,7 @@ __device__ inline void jacobi_eig(double* a, double* v, double* w) {
 #pragma unroll
             for (int q = p + 1; q < N; ++q) off += a[p * N + q] * a[p * N + q];
         }
-        if (off <= 1e-33 * dia || off == 0.0) break;
+        if (off <= SO_JACOBI_OFF_TOL * dia || off == 0.0) break;
 #pragma unroll
         for (int p = 0; p < N - 1; ++p) {
 #pragma unroll
