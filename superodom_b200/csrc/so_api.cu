@@ -1031,7 +1031,7 @@ int so_correspond_edge(so_ctx* ctx, const void* edge, size_t n, size_t stride, s
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     const uint32_t grid_e = (uint32_t(n) + kThreads - 1) / kThreads;
-    const MapView mv = map_view(c, c->surf), me = map_view(c, c->edge);
+    const MapView me = map_view(c, c->edge);
     const BatchView bv = batch_view(c, c->d_scan_sorted);
     timed_launch_begin(c);
     launch_first_eval(bv, c->corr, 0, 1, c->stream, &me, &c->ebuf, grid_e);     // 0 plane CTAs: only the edge kernel + k_lm_step have work
