@@ -228,6 +228,16 @@ int so_register_batch(so_ctx* ctx, const void* surf_xyzi, const uint32_t* n_poin
 int so_register_batch_device(so_ctx* ctx, const void* d_scans_xyzi, const uint32_t* n_points, size_t n_scans,
                              const double* poses_in, const so_icp_opts* opts, so_icp_result* results);
 
+/* Test hook: so_register (surf cloud only) with the neighbour SEARCH replaced by caller-supplied neighbour sets --
+ * nn_ids[it][i][0..4] = the five map point ids (so_map_set_points order, ascending distance; 0xFFFFFFFF = no result) that
+ * findNearestNeighbors (LidarSlam.cpp:720-747) returned for scan point i in ICP iteration it, n_trace_iters iterations of them.
+ * Everything after the search (the 3*planeRes gate on the 5th distance, PCA, plane fit, solve, covariance) runs as in
+ * so_register.  Feeding the neighbour sets of the reference's own octree (flann/octree.h:1004-1055, compiled verbatim in
+ * oracle/_ref) proves that exactness of the k-NN is the only deviation of this library from the reference path. */
+int so_register_injected(so_ctx* ctx, const void* surf_xyzi, size_t n_surf, size_t stride_bytes, size_t intensity_offset,
+                         const double pose_in[7], const so_icp_opts* opts, const uint32_t* nn_ids, int32_t n_trace_iters,
+                         so_icp_result* out);
+
 /* Stage-level entry points used by the parity tests (same kernels as so_register). */
 /* processPlannerFeatures at a fixed pose (LidarSlam.cpp:323-344): fills corr[n], hist_obs[9], hist_rej[7]. */
 int so_correspond(so_ctx* ctx, const void* surf_xyzi, size_t n, size_t stride_bytes, size_t intensity_offset,

@@ -101,7 +101,23 @@ inline bool readPointCloud(const std::string& file_path, CloudPtr cloud_out) {
     if (!have_points) points = width * height;
     if (points > (size_t(1) << 31)) { std::cerr << "Error reading PCD file: " << file_path << " (implausible point count)" << std::endl; return false; }
     size_t rec = 0;
-    for (auto& fl : fields) { if (fl.size <= 0 || fl.count < 0) { std::cerr << "Error reading PCD file: " << file_path << std::endl; return false; } fl.offset = rec; rec += size_t(fl.size) * size_t(fl.count); }
+    for (auto& fl : fields) {
+        // untrusted header: element sizes PCL knows (1/2/4/8), at least one element per field (a COUNT 0 field would add no bytes to
+        // the record while read_scalar still reads `size` bytes from it), bounded counts so that the record size cannot wrap
+        if (!(fl.size == 1 || fl.size == 2 || fl.size == 4 || fl.size == 8) || fl.count < 1 || fl.count > 4096) {
+            std::cerr << "Error reading PCD file: " << file_path << " (bad SIZE / COUNT)" << std::endl; return false;
+        }
+        fl.offset = rec; rec += size_t(fl.size) * size_t(fl.count);
+    }
+    if (rec == 0 || rec > (size_t(1) << 20) || points > (size_t(1) << 40) / rec) { std::cerr << "Error reading PCD file: " << file_path << " (implausible record / cloud size)" << std::endl; return false; }
+    // the body cannot be larger than what is left of the file: checked before any allocation sized from the header
+    const std::streampos body_pos = f.tellg();
+    f.seekg(0, std::ios::end);
+    const std::streampos end_pos = f.tellg();
+    f.seekg(body_pos);
+    const size_t remaining = (body_pos >= 0 && end_pos >= body_pos) ? size_t(end_pos - body_pos) : 0;
+    if (data_mode == "binary" && points * rec > remaining) { std::cerr << "Error reading PCD file: " << file_path << " (truncated)" << std::endl; return false; }
+    if (data_mode == "ascii" && points > remaining) { std::cerr << "Error reading PCD file: " << file_path << " (truncated)" << std::endl; return false; }
     int ix = -1, iy = -1, iz = -1, ii = -1;
     for (size_t k = 0; k < fields.size(); ++k) {
         if (fields[k].name == "x") ix = int(k); else if (fields[k].name == "y") iy = int(k); else if (fields[k].name == "z") iz = int(k);
@@ -109,7 +125,8 @@ inline bool readPointCloud(const std::string& file_path, CloudPtr cloud_out) {
     }
     if (ix < 0 || iy < 0 || iz < 0) { std::cerr << "Error reading PCD file: " << file_path << " (no x/y/z fields)" << std::endl; return false; }
     cloud_out->points.clear();
-    cloud_out->points.resize(points);
+    try { cloud_out->points.resize(points); }
+    catch (const std::exception&) { std::cerr << "Error reading PCD file: " << file_path << " (out of memory)" << std::endl; cloud_out->points.clear(); return false; }
     auto set = [&](size_t i, double x, double y, double z, double it) {
         PointT p{};
         p.x = float(x); p.y = float(y); p.z = float(z); p.intensity = float(it);
@@ -144,7 +161,9 @@ inline bool readPointCloud(const std::string& file_path, CloudPtr cloud_out) {
         uint32_t csize = 0, usize = 0;
         f.read(reinterpret_cast<char*>(&csize), 4);
         f.read(reinterpret_cast<char*>(&usize), 4);
-        if (!f.good() || size_t(usize) != points * rec) { std::cerr << "Error reading PCD file: " << file_path << " (bad compressed header)" << std::endl; return false; }
+        if (!f.good() || size_t(usize) != points * rec || remaining < 8 || size_t(csize) > remaining - 8) {
+            std::cerr << "Error reading PCD file: " << file_path << " (bad compressed header)" << std::endl; return false;
+        }
         std::vector<unsigned char> comp(csize);
         f.read(reinterpret_cast<char*>(comp.data()), std::streamsize(csize));
         if (size_t(f.gcount()) != size_t(csize)) { std::cerr << "Error reading PCD file: " << file_path << " (truncated)" << std::endl; return false; }

@@ -94,6 +94,7 @@ def lib():
     L.orc_solve.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_covariance.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_float, C.c_void_p]
     L.orc_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_set_nn_trace.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
     L.orc_register_full.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_map_set_edge_points.restype = C.c_int64
     L.orc_map_set_edge_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
@@ -205,8 +206,10 @@ class OracleMap:
         return corr, ho, hr
 
     def register(self, scan_xyzi, pose7, plane_res, max_icp_iters, max_surface_features=0, knn_mode=0, n_threads=1,
-                 lm_max_iterations=4, yaw_ratio=0.0, skip_map_checks=False, pose_prior=None, edge_xyzi=None, line_res=0.1) -> Result:
-        """pose_prior = (visual_confidence_factor, (ux, uy, uz)) enables the SE3AbsolutatePoseFactor rows."""
+                 lm_max_iterations=4, yaw_ratio=0.0, skip_map_checks=False, pose_prior=None, edge_xyzi=None, line_res=0.1,
+                 nn_trace: np.ndarray | None = None) -> Result:
+        """pose_prior = (visual_confidence_factor, (ux, uy, uz)) enables the SE3AbsolutatePoseFactor rows.
+        nn_trace: optional int64 [iters, n, 5] array that receives the neighbour ids of every ICP iteration (-1 = none)."""
         s = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
         pose = np.ascontiguousarray(pose7, dtype=np.float64)
         o = Opts(plane_res, max_icp_iters, max_surface_features, lm_max_iterations, knn_mode, n_threads, yaw_ratio, int(skip_map_checks),
@@ -216,12 +219,20 @@ class OracleMap:
             o.visual_confidence_factor = float(pose_prior[0])
             o.prior_uncertainty = (C.c_float * 3)(*[float(v) for v in pose_prior[1]])
         r = Result()
-        if edge_xyzi is not None and len(edge_xyzi):
-            e = np.ascontiguousarray(edge_xyzi, dtype=np.float32)
-            assert e.shape[1] == s.shape[1]
-            self.L.orc_register_full(self.h, _p(s), s.shape[0], _p(e), e.shape[0], s.shape[1], _p(pose), C.byref(o), C.byref(r))
-        else:
-            self.L.orc_register(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.byref(o), C.byref(r))
+        if nn_trace is not None:
+            assert nn_trace.dtype == np.int64 and nn_trace.flags.c_contiguous and nn_trace.shape[1:] == (s.shape[0], 5)
+            nn_trace[:] = -1
+            self.L.orc_set_nn_trace(_p(nn_trace), s.shape[0], nn_trace.shape[0])
+        try:
+            if edge_xyzi is not None and len(edge_xyzi):
+                e = np.ascontiguousarray(edge_xyzi, dtype=np.float32)
+                assert e.shape[1] == s.shape[1]
+                self.L.orc_register_full(self.h, _p(s), s.shape[0], _p(e), e.shape[0], s.shape[1], _p(pose), C.byref(o), C.byref(r))
+            else:
+                self.L.orc_register(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.byref(o), C.byref(r))
+        finally:
+            if nn_trace is not None:
+                self.L.orc_set_nn_trace(None, 0, 0)
         return r
 
 

@@ -1207,6 +1207,15 @@ void orc_colpiv_qr_solve(int m, const double* A, const double* b, double* x) { o
 void orc_pose_plus(const double x[7], const double d[6], double out[7]) { orc::pose_plus(x, d, out); }
 void orc_yaw_round_trip(const double last[7], double T[7], double yaw_ratio) { orc::manual_yaw_correction(last, T, yaw_ratio); }
 
+// Optional per-ICP-iteration neighbour trace of the next orc_register* call on this thread: ids[it][i][0..4] = the five neighbour
+// ids (caller's map index) findNearestNeighbors returned for scan point i in ICP iteration it, -1 where no search result exists
+// (skipped by sampling, off-grid, block with < 5 points).  Lets a test feed the reference octree's own neighbour sets into the
+// GPU fit / solve stages (tests/test_gpu_parity.py::test_injected_reference_octree_neighbours_*).
+static thread_local int64_t* g_nn_trace = nullptr;
+static thread_local size_t g_nn_trace_n = 0;
+static thread_local int g_nn_trace_iters = 0;
+void orc_set_nn_trace(int64_t* buf, size_t n_points, int max_iters) { g_nn_trace = buf; g_nn_trace_n = n_points; g_nn_trace_iters = max_iters; }
+
 // LidarSLAM::Localization, initialization==true branch -> performLocalizationAndMapping (LidarSlam.cpp:30-51,107-171),
 // without the map insert at the end (transformAndAddToMap is a "next" row; use orc_voxel_filter + orc_map_set_points).
 int orc_register_full(void* m, const float* scan_xyzi, size_t n, const float* edge_xyzi, size_t n_edge, size_t stride_floats,
@@ -1245,6 +1254,8 @@ int orc_register_full(void* m, const float* scan_xyzi, size_t n, const float* ed
         }
         correspond_all(*M, scan_xyzi, n, stride_floats, T, opt->plane_res, opt->max_surface_features, opt->knn_mode, opt->n_threads, corr.data(), out->hist_obs, out->hist_reject_plane);
         knn_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk).count();
+        if (g_nn_trace && it < g_nn_trace_iters && g_nn_trace_n == n)
+            for (size_t i = 0; i < n; ++i) for (int j = 0; j < 5; ++j) g_nn_trace[(size_t(it) * n + i) * 5 + j] = corr[i].status < 0 ? -1 : corr[i].nn[j];
         E.blocks.clear();
         for (size_t i = 0; i < n; ++i) if (corr[i].status == SUCCESS) E.blocks.push_back(&corr[i]);
         E.prior.on = false;

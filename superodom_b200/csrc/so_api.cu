@@ -82,7 +82,7 @@ static int ctx_alloc(Ctx* c) {
     c->grid_x_cap = (c->cfg.max_scan_points + kThreads - 1) / kThreads;
     SO_CUDA_TRY(cudaMalloc(&c->d_scan, c->scan_cap * sizeof(float4)));
     SO_CUDA_TRY(cudaMalloc(&c->d_scan_sorted, c->scan_cap * sizeof(float4)));
-    SO_CUDA_TRY(cudaMalloc(&c->d_skeys, c->scan_cap * sizeof(uint64_t)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_skeys, c->scan_cap * sizeof(uint64_t) + 64));      // + slack: scan_voxel_filter lays [count 16 B][heads][ranks] over it
     SO_CUDA_TRY(cudaMalloc(&c->d_skeys_out, c->scan_cap * sizeof(uint64_t)));
     SO_CUDA_TRY(cudaMalloc(&c->d_svals, c->scan_cap * sizeof(uint32_t)));
     SO_CUDA_TRY(cudaMalloc(&c->d_svals_out, c->scan_cap * sizeof(uint32_t)));
@@ -137,7 +137,7 @@ static void ctx_free(Ctx* c) {
     cudaFree(c->d_partials); cudaFree(c->d_counters); cudaFree(c->d_hist);
     cudaFree(c->d_escan); cudaFree(c->d_eoffset); cudaFree(c->ebuf.a); cudaFree(c->ebuf.b); cudaFree(c->ebuf.flags); cudaFree(c->ebuf.nn); cudaFree(c->ebuf.selmask);
     cudaFree(c->corr.nd); cudaFree(c->corr.w); cudaFree(c->corr.flags); cudaFree(c->corr.nn); cudaFree(c->corr.nn_d2);
-    cudaFree(c->d_q); cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2);
+    cudaFree(c->d_q); cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2); cudaFree(c->d_inject);
     cudaFree(c->d_qkeys); cudaFree(c->d_qkeys_out); cudaFree(c->d_qvals); cudaFree(c->d_qvals_out); cudaFree(c->d_qsort_tmp);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -238,7 +238,8 @@ static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch, cudaS
 // scan is not in the matching phase, so a fixed schedule follows whatever path the device-side state machine takes.
 // Preferred form: a CUDA-graph WHILE node around ONE iteration (k_loop_cond ends the loop when every scan of the chunk
 // is done); fallback: the schedule unrolled max_icp_iters times.  Returns whether the loop form ran.
-static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn, bool* was_loop, cudaStream_t run_stream = nullptr) {
+static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn, bool* was_loop, cudaStream_t run_stream = nullptr,
+                        const uint32_t* d_inject = nullptr, int inject_iters = 0) {
     if (!run_stream) run_stream = c->stream;
     const float4* d_scan = c->d_scan_sorted;
     const MapView mv = map_view(c, c->surf);
@@ -250,7 +251,8 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
     EdgeBuf eb = c->ebuf;
     if (!with_nn) { eb.nn = nullptr; eb.selmask = nullptr; }
     *was_loop = false;
-    if (c->profiling || with_nn) {
+    if (d_inject && kCorrLaunches != 2) return fail(SO_ERR_ARG, "so_register_injected needs the split k_knn_scan / k_fit build");
+    if (c->profiling || with_nn || d_inject) {
         // profiling mode: one launch at a time, timed with events, and only launches that have work (the host peeks
         // at the phases) so that the per-class average is the duration of a kernel that actually ran
         std::vector<IcpState> peek(n_scans);
@@ -264,7 +266,10 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
             if (any_in(PH_CORR)) {
                 if (kCorrLaunches == 1) { timed_launch_begin(c); launch_match(mv, bv, cb, c->nn, grid_x, n_scans, c->stream); timed_launch_end(c, 0); }
                 else {
-                    timed_launch_begin(c); launch_match(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, 1); timed_launch_end(c, 0);      // k_knn_scan
+                    timed_launch_begin(c);
+                    if (d_inject) launch_inject(mv, c->surf.d_xyzi, c->surf.n, bv, c->nn, d_inject, inject_iters, grid_x, n_scans, c->stream);
+                    else launch_match(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, 1);                                               // k_knn_scan
+                    timed_launch_end(c, 0);
                     timed_launch_begin(c); launch_match(mv, bv, cb, c->nn, grid_x, n_scans, c->stream, 2); timed_launch_end(c, 5);      // k_fit
                 }
                 timed_launch_begin(c); launch_first_eval(bv, cb, grid_x, n_scans, c->stream, &me, &eb, grid_e); c->launches += 1 + (grid_e ? 1 : 0); timed_launch_end(c, 4);
@@ -275,9 +280,16 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
         SO_CUDA_TRY(cudaGetLastError());
         return SO_OK;
     }
+    Ctx::GraphKey key;
+    std::memset(&key, 0, sizeof(key));                      // padding bytes take part in the memcmp below
+    key.first = ch.first; key.count = n_scans; key.grid_x = grid_x; key.grid_e = grid_e; key.iters = iters; key.lm = lm;
+    key.ptrs[0] = mv.pts; key.ptrs[1] = mv.cell_start; key.ptrs[2] = mv.block_slot; key.ptrs[3] = mv.block_count;
+    key.ptrs[4] = me.pts; key.ptrs[5] = me.cell_start; key.ptrs[6] = me.block_slot; key.ptrs[7] = me.block_count;
+    for (int a = 0; a < 3; ++a) key.origin[a] = mv.origin[a];
+    key.nb[0] = mv.nb; key.nb[1] = me.nb; key.res[0] = mv.plane_res; key.res[1] = me.plane_res;
     Ctx::GraphSlot* slot = nullptr;
     for (auto& g : c->graphs)
-        if (g.exec && g.first == ch.first && g.count == n_scans && g.grid_x == grid_x && g.grid_e == grid_e && g.iters == iters && g.lm == lm && g.epoch == c->map_epoch) slot = &g;
+        if (g.exec && std::memcmp(&g.key, &key, sizeof(key)) == 0) slot = &g;
     if (!slot) {
         slot = &c->graphs[0];
         for (auto& g : c->graphs) { if (!g.exec) { slot = &g; break; } if (g.used < slot->used) slot = &g; }
@@ -322,7 +334,7 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
             cudaGraphDestroy(g);
             if (e != cudaSuccess) { slot->exec = nullptr; return fail(SO_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
         }
-        slot->first = ch.first; slot->count = n_scans; slot->grid_x = grid_x; slot->grid_e = grid_e; slot->iters = iters; slot->lm = lm; slot->epoch = c->map_epoch;
+        slot->key = key;
     }
     slot->used = ++c->graph_clock;
     SO_CUDA_TRY(cudaGraphLaunch(slot->exec, run_stream));
@@ -379,7 +391,7 @@ static void fill_result(const Ctx* c, const IcpState& s, const double pose_in[7]
 // function uploads them into d_scan chunk by chunk on the copy stream.
 static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points, size_t n_scans, const double* poses,
                          const so_icp_opts* opts_in, so_icp_result* results, bool allow_shift, const void* host_src = nullptr,
-                         uint32_t n_edge0 = 0) {
+                         uint32_t n_edge0 = 0, const uint32_t* d_inject = nullptr, int inject_iters = 0) {
     so_icp_opts o = *opts_in;
     if (o.lm_max_iterations <= 0) o.lm_max_iterations = 4;
     if (o.max_icp_iters <= 0 || o.max_icp_iters > SO_MAX_ICP_ITERS) return fail(SO_ERR_ARG, "max_icp_iters must be in [1,32]");
@@ -438,6 +450,9 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             uint32_t mx = 0;
             for (uint32_t s = f; s < e; ++s) if (c->h_state[s].phase == PH_CORR) mx = std::max(mx, n_points[s]);
             ch.grid_x = (mx + kThreads - 1) / kThreads;
+            // rounded up to a bucket of 16 CTAs so that scans of slightly different sizes (live SLAM: every scan differs) share one
+            // captured graph; the kernels guard i < n_points and k_lm_step sums only the partial rows n_points implies
+            if (ch.grid_x) ch.grid_x = std::min<uint32_t>(c->grid_x_cap, (ch.grid_x + 15u) & ~15u);
             if (f == 0 && n_edge0 && c->h_state[0].phase == PH_CORR) ch.grid_e = (n_edge0 + kThreads - 1) / kThreads;
             chunks.push_back(ch);
         }
@@ -467,7 +482,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             if (ch.grid_x == 0) continue;
             int rc = prepare_scans(c, d_scan, ch, st);
             bool was_loop = false;
-            if (!rc) rc = run_schedule(c, ch, o.max_icp_iters, o.lm_max_iterations, false, &was_loop, st);
+            if (!rc) rc = run_schedule(c, ch, o.max_icp_iters, o.lm_max_iterations, false, &was_loop, st, d_inject, inject_iters);
             if (rc) {                                       // leave no work behind on the side streams before reporting the error
                 cudaStreamSynchronize(c->aux_stream);
                 cudaStreamSynchronize(c->copy_stream);
@@ -928,6 +943,27 @@ int so_register(so_ctx* ctx, const void* surf, size_t n_surf, const void* edge, 
     if (rc) return rc;
     out->scan_edge_num = int32_t(n_edge);
     out->time_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return out->status;
+}
+
+int so_register_injected(so_ctx* ctx, const void* surf, size_t n_surf, size_t stride, size_t ioff, const double pose_in[7], const so_icp_opts* opts,
+                         const uint32_t* nn_ids, int32_t n_trace_iters, so_icp_result* out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !pose_in || !opts || !out || !surf || !nn_ids || n_surf == 0 || n_trace_iters <= 0 || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (n_surf > c->cfg.max_scan_points) return fail(SO_ERR_CAPACITY, "scan larger than so_config.max_scan_points");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    const size_t words = size_t(n_trace_iters) * n_surf * 5;
+    if (words > c->inject_cap) {
+        cudaFree(c->d_inject); c->d_inject = nullptr; c->inject_cap = 0;
+        SO_CUDA_TRY(cudaMalloc(&c->d_inject, words * sizeof(uint32_t)));
+        c->inject_cap = words;
+    }
+    SO_CUDA_TRY(cudaMemcpyAsync(c->d_inject, nn_ids, words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    int rc = upload_cloud(c, surf, n_surf, stride, ioff, c->d_scan);
+    if (rc) return rc;
+    const uint32_t n = uint32_t(n_surf);
+    rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true, nullptr, 0, c->d_inject, int(n_trace_iters));
+    if (rc) return rc;
     return out->status;
 }
 

@@ -76,6 +76,7 @@ struct Ctx {
     size_t edge_cap = 0; uint32_t edge_grid_cap = 0;
     float4* d_escan = nullptr; uint32_t* d_eoffset = nullptr; EdgeBuf ebuf{};
     uint32_t grid_x_cap = 0;
+    uint32_t* d_inject = nullptr; size_t inject_cap = 0;   // so_register_injected: caller-supplied neighbour ids [iters][n][5]
     void* h_stage = nullptr;                       // pinned staging for strided host clouds
     size_t h_stage_bytes = 0;
 
@@ -85,9 +86,16 @@ struct Ctx {
     void* d_qsort_tmp = nullptr; size_t qsort_tmp_bytes = 0; size_t qsort_cap = 0;      // cell ordering of so_knn* queries
 
     // ---- CUDA graph cache for the ICP schedule (one entry per batch chunk shape) ------------------------------------
+    // Everything a captured schedule bakes into its kernel arguments: the chunk shape and both MapViews (pointers, origin, grid,
+    // resolutions).  Keyed on these VALUES, not on a "map changed" counter, so that a map insert that leaves the index arrays
+    // where they are (the usual live-SLAM case) keeps hitting the cache.
+    struct GraphKey {
+        uint32_t first, count, grid_x, grid_e; int32_t iters, lm;
+        const void* ptrs[8]; int32_t origin[3]; int32_t nb[2]; float res[2];
+    };
     struct GraphSlot {
         cudaGraphExec_t exec = nullptr;
-        uint32_t first = 0, count = 0, grid_x = 0, grid_e = 0; int iters = 0, lm = 0; uint64_t epoch = 0; bool is_loop = false; uint64_t used = 0;
+        GraphKey key{}; bool is_loop = false; uint64_t used = 0;
     };
     GraphSlot graphs[20];
     uint64_t graph_clock = 0;

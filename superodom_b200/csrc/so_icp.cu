@@ -697,7 +697,7 @@ __device__ __forceinline__ void accumulate(double acc[kAcc], const double n[3], 
     const double r = n[0] * pw[0] + n[1] * pw[1] + n[2] * pw[2] + d;
     const double s = r * r;
     double rho0, rho1;
-    if (s <= a2) { const double v = 1.0 - s * (1.0 / a2), v2 = v * v; rho0 = a2 / 6.0 * (1.0 - v2 * v); rho1 = 0.5 * v2; }
+    if (s <= a2) { const double v = 1.0 - s / a2, v2 = v * v; rho0 = a2 / 6.0 * (1.0 - v2 * v); rho1 = 0.5 * v2; }      // TukeyLoss::Evaluate divides (loss_function.cc)
     else { rho0 = a2 / 6.0; rho1 = 0.0; }
     rho0 *= w; rho1 *= w;
     // J = [ n^T , -n^T R [p]x ] ;  -a^T [p]x = p x a  with a = R^T n
@@ -715,6 +715,28 @@ __device__ __forceinline__ void accumulate(double acc[kAcc], const double n[3], 
 #pragma unroll
     for (int i = 0; i < 6; ++i) acc[21 + i] += rho1 * J[i] * r;
     acc[27] += 0.5 * rho0;
+}
+
+// ICP iterations after the first: the previous iteration's five neighbours still exist, so the largest of their (exact)
+// distances to the moved query bounds the new 5th-neighbour distance -- provided they lie in the block the query is in NOW
+// (the search is block-local, LocalMap.h:488-507: after a pose update that carries the point across a 50 m block face the old
+// neighbours belong to another block and bound nothing).  Returns the bound or -1 (no usable seed).
+__device__ __forceinline__ float seed_bound(const MapView& m, const QueryCell& qc, const NnBuf& nb, size_t gi, float qx, float qy, float qz) {
+    const uint32_t cells = uint32_t(m.nb) * uint32_t(m.nb) * uint32_t(m.nb);
+    const uint32_t lo = __ldg(&m.cell_start[uint32_t(qc.slot) * cells]), hi = __ldg(&m.cell_start[uint32_t(qc.slot) * cells + cells]);
+    float u = 0.f;
+    bool same_block = true;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const uint32_t pos = nb.pos[size_t(j) * nb.cap + gi];
+        same_block = same_block && pos >= lo && pos < hi;
+        const float4 c = __ldg(&m.pts[same_block ? pos : lo]);
+        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+        u = fmaxf(u, float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)));
+    }
+    // use it only while it is about as tight as a freshly estimated bound would be (small pose update); after a large update
+    // the cell-neighbourhood estimate of round 1 prunes better than a loose seed
+    return (same_block && u <= 1.3f * nb.d5[gi]) ? u : -1.f;
 }
 
 #ifndef SO_SCAN_ORDER
@@ -825,20 +847,7 @@ __global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_scan(MapView m, B
         if (qc.slot < 0 || qc.nblock < 5) pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
         else {
             searchable = true;
-            if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) {
-                // ICP iterations after the first: the previous iteration's five neighbours still exist, so the largest
-                // of their (exact) distances to the moved query bounds the new 5th-neighbour distance.
-                float u = 0.f;
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const float4 c = __ldg(&m.pts[nb.pos[size_t(j) * nb.cap + gi]]);
-                    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-                    u = fmaxf(u, float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)));
-                }
-                // use it only while it is about as tight as a freshly estimated bound would be (small pose update);
-                // after a large update the 27-cell estimate of round 1 prunes better than a loose seed
-                if (u <= 1.3f * nb.d5[gi]) u_seed = u;
-            }
+            if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) u_seed = seed_bound(m, qc, nb, gi, qx, qy, qz);
         }
     }
 #if SO_KNN_COOP
@@ -858,6 +867,59 @@ __global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_scan(MapView m, B
         // the five points are L1-hot here; handing them on as coalesced 16-byte stores saves k_fit five scattered gathers
         if (pre == SO_MATCH_SUCCESS) nb.pts[size_t(j) * nb.cap + gi] = __ldg(&m.pts[tk.pos[j]]);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_knn_inject: test hook behind so_register_injected -- the neighbour SEARCH of k_knn_scan replaced by caller-supplied
+// neighbour ids (ids[it][original point index][5], map point ids in so_map_set_points order, 0xFFFFFFFF = no result), everything
+// after it (the NEIGHBORS_TOO_FAR gate on the 5th distance, LidarSlam.cpp:741-744, the hand-off to k_fit) unchanged.  Feeding it
+// the neighbour sets of the reference's own octree (oracle knn_mode 2) isolates the one known deviation of this library from the
+// reference path: exact in-block k-NN instead of the octree's data-dependent misses (flann/octree.h:383-385,984-1001).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_knn_inject(MapView m, const float4* __restrict__ by_id, uint32_t n_map, BatchView bv, NnBuf nb,
+                                                         const uint32_t* __restrict__ ids, int n_trace_iters) {
+    const int s = blockIdx.y;
+    const IcpState* st = bv.st + s;
+    if (st->phase != PH_CORR) return;
+    __shared__ double s_pose[7];
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
+    __syncthreads();
+    const uint32_t n = uint32_t(st->n_points);
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const size_t gi = size_t(bv.offset[s]) + i;
+    const float4 sp = __ldg(&bv.scan[gi]);
+    const uint32_t orig = __float_as_uint(sp.w);
+    int pre = SO_MATCH_SKIPPED;
+    float d5 = m.bound_d2;
+    if (should_process(orig, st->sampling_rate)) {
+        pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
+        const int it = st->icp_iter;
+        if (it < n_trace_iters) {
+            const uint32_t* p = ids + (size_t(it) * n + orig) * 5;
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) ok = ok && p[j] < n_map;
+            if (ok) {
+                const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+                double pf[3];
+                qrot(s_pose + 3, pin, pf);
+                const float qx = float(pf[0] + s_pose[0]), qy = float(pf[1] + s_pose[1]), qz = float(pf[2] + s_pose[2]);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float4 c = __ldg(&by_id[p[j]]);
+                    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+                    d5 = float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz));
+                    nb.pts[size_t(j) * nb.cap + gi] = make_float4(c.x, c.y, c.z, __uint_as_float(p[j]));
+                }
+                pre = double(d5) > double(m.bound_d2) ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;      // pointSearchSqDis[4] > 3*planeRes_ (:741-744)
+            }
+        }
+    }
+    nb.pre[gi] = (unsigned char)pre;
+    nb.d5[gi] = d5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) nb.pos[size_t(j) * nb.cap + gi] = 0xFFFFFFFFu;
 }
 
 // A 16-byte global load the compiler may neither merge with an earlier load of the same address nor hoist: k_fit re-reads
@@ -903,7 +965,7 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
                 cb.nn_d2[gi * 5 + j] = float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz));
             }
         }
-        mean[0] *= 0.2; mean[1] *= 0.2; mean[2] *= 0.2;        // (the reference divides by 5: same to an ulp, a multiply is 1 instruction)
+        mean[0] /= 5.0; mean[1] /= 5.0; mean[2] /= 5.0;        // utils::ComputePCA divides (superodom_utils.h:146): the eigenvalue gates below read this
         double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
@@ -915,7 +977,7 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
         const double sxx = S[0], sxy = S[1], sxz = S[2], syy = S[4], syz = S[5], szz = S[8];
         double ev[3];
         jacobi_eig<3, 12, false>(S, nullptr, ev);
-        if (ev[0] < 1e-6 || ev[1] < 0.1 * ev[2]) status = SO_MATCH_BAD_PCA_STRUCTURE;      // lambda1/lambda2 < 0.1 (:772)
+        if (ev[0] < 1e-6 || ev[1] / ev[2] < 0.1) status = SO_MATCH_BAD_PCA_STRUCTURE;      // the reference's quotient, literally (:772)
         else {
             // What FeatureObservabilityAnalysis (:574-693) needs from the PCA -- the oriented normal (:553-561) and the
             // planarity -- is reduced to four floats here, ahead of the register-hungry QR.
@@ -945,8 +1007,11 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
             }
             if (!(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]))) status = SO_MATCH_INVALID_NUMERICAL;
             else {
-                const double dd = rsqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);      // 1 / |n|
-                x[0] *= dd; x[1] *= dd; x[2] *= dd;
+                // negative_OA_dot_norm = 1 / norm.norm(); norm.normalize()  (:812-816): square root and divisions as written there,
+                // because the planeRes/2 gate below reads both
+                const double nn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+                const double dd = 1.0 / nn;
+                x[0] /= nn; x[1] /= nn; x[2] /= nn;
                 const double maxd = double(m.plane_res) / 2.0;
                 double msum = 0.0;
                 bool ok = true;
@@ -991,7 +1056,7 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
                     for (int q = 1; q < 3; ++q) if (trq[q] > trq[t0]) t0 = q;
                     o0 = r0; o1 = r1; o2 = 6 + t0;
                     nrm[0] = x[0]; nrm[1] = x[1]; nrm[2] = x[2]; dpl = dd;
-                    wq = 1.0 - sqrt(mean_dist * m.inv_bound_d2);        // fitQualityCoeff (:568)
+                    wq = 1.0 - sqrt(mean_dist / double(m.bound_d2));     // fitQualityCoeff = 1 - sqrt(meanDist / (3*planeRes_)) (:568)
                     status = SO_MATCH_SUCCESS;
                 }
             }
@@ -1071,16 +1136,7 @@ __global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_fit(MapView m, Ba
             if (qc.slot < 0 || qc.nblock < 5) pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
             else {
                 float u_seed = -1.f;
-                if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) {        // see k_knn_scan
-                    float u = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) {
-                        const float4 c = __ldg(&m.pts[nb.pos[size_t(j) * nb.cap + gi]]);
-                        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-                        u = fmaxf(u, float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)));
-                    }
-                    if (u <= 1.3f * nb.d5[gi]) u_seed = u;
-                }
+                if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) u_seed = seed_bound(m, qc, nb, gi, qx, qy, qz);        // see k_knn_scan
                 knn_select<5>(m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
                 pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
             }
@@ -1470,6 +1526,10 @@ void launch_match(const MapView& m, const BatchView& bv, const CorrBuf& cb, cons
     const uint32_t gf = (grid_x * kThreads + kFitPts * kFitThreads - 1) / (kFitPts * kFitThreads);
     if (part != 1) k_fit<<<dim3(gf, n_scans), kFitThreads, 0, st>>>(m, bv, cb, nb);
 #endif
+}
+void launch_inject(const MapView& m, const float4* by_id, uint32_t n_map, const BatchView& bv, const NnBuf& nb, const uint32_t* ids, int n_trace_iters,
+                   uint32_t grid_x, uint32_t n_scans, cudaStream_t st) {
+    if (grid_x) k_knn_inject<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, by_id, n_map, bv, nb, ids, n_trace_iters);
 }
 void launch_first_eval(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const MapView* medge, const EdgeBuf* eb,
                        uint32_t grid_e) {

@@ -188,6 +188,11 @@ int map_rebuild(Ctx* c, MapStore& ms) {
     if (kept == 0) { SO_CUDA_TRY(cudaStreamSynchronize(st)); return SO_OK; }
     const uint32_t m = ms.n;
     const size_t cells = size_t(ms.n_slots) * ms.nb * ms.nb * ms.nb;
+    if (cells + 1 >= (size_t(1) << 31)) {          // cell indices are 32-bit in the kernels and the scan length is an int
+        SO_CUDA_TRY(cudaStreamSynchronize(st));
+        set_error("map spans too many 50 m blocks for the dense cell table (n_slots * nb^3 >= 2^31)");
+        return SO_ERR_CAPACITY;
+    }
     if (cells + 1 > ms.cell_cap) {
         SO_CUDA_TRY(cudaStreamSynchronize(st));
         cudaFree(ms.d_cell_start);
@@ -278,8 +283,12 @@ __global__ void k_mark_touched(const int32_t* __restrict__ block_of_point, uint3
     if (i < n && block_of_point[i] >= 0) touched[block_of_point[i]] = 1;
 }
 
+// Sort key of the insert: [63] touched flag | [48..60] grid block (13 bits: 0..4850) | 3 x 16 bits of BLOCK-LOCAL voxel index (k, j, i).
+// PCL orders a block's output by the voxel index relative to the block cloud's bounding box; subtracting any per-block constant
+// keeps that order, so the index is taken relative to the block's minimum corner (minus a 2-voxel guard for the float rounding of
+// x * inv_leaf at the faces): 50 m / leaf + 4 values per axis -- 16 bits hold leaf >= 1 mm, wherever the block is in the world.
 __global__ void k_voxel_keys(const float4* __restrict__ raw, const int32_t* __restrict__ block_of_point, const uint8_t* __restrict__ touched,
-                             uint32_t n, float inv_leaf, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                             uint32_t n, float inv_leaf, int3 origin, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int32_t b = block_of_point[i];
@@ -288,10 +297,16 @@ __global__ void k_voxel_keys(const float4* __restrict__ raw, const int32_t* __re
     else if (!touched[b]) key = 0;                                  // untouched block: keep, in place (stable sort)
     else {
         const float4 p = raw[i];
-        const int64_t vi = int64_t(floorf(__fmul_rn(p.x, inv_leaf))) + 65536;
-        const int64_t vj = int64_t(floorf(__fmul_rn(p.y, inv_leaf))) + 65536;
-        const int64_t vk = int64_t(floorf(__fmul_rn(p.z, inv_leaf))) + 65536;
-        key = (uint64_t(1) << 63) | (uint64_t(b) << 51) | (uint64_t(vk & 0x1FFFF) << 34) | (uint64_t(vj & 0x1FFFF) << 17) | uint64_t(vi & 0x1FFFF);
+        const int gx = b % kW, gy = (b / kW) % kH, gz = b / (kW * kH);
+        const double il = double(inv_leaf);
+        const int64_t bx = int64_t(floor((double(gx - origin.x) * kBlock - kHalfBlock) * il)) - 2;
+        const int64_t by = int64_t(floor((double(gy - origin.y) * kBlock - kHalfBlock) * il)) - 2;
+        const int64_t bz = int64_t(floor((double(gz - origin.z) * kBlock - kHalfBlock) * il)) - 2;
+        auto local = [](int64_t v) { return uint64_t(v < 0 ? 0 : (v > 65535 ? 65535 : v)); };
+        const uint64_t vi = local(int64_t(floorf(__fmul_rn(p.x, inv_leaf))) - bx);      // pcl::VoxelGrid: floor(coord * inverse_leaf_size) in float
+        const uint64_t vj = local(int64_t(floorf(__fmul_rn(p.y, inv_leaf))) - by);
+        const uint64_t vk = local(int64_t(floorf(__fmul_rn(p.z, inv_leaf))) - bz);
+        key = (uint64_t(1) << 63) | (uint64_t(b) << 48) | (vk << 32) | (vj << 16) | vi;
     }
     keys[i] = key;
     vals[i] = i;
@@ -361,7 +376,7 @@ int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new) {
     uint8_t* d_touched2 = reinterpret_cast<uint8_t*>(c->d_cub_tmp);
     SO_CUDA_TRY(cudaMemcpyAsync(d_touched2, h_touched.data(), kNumBlocks, cudaMemcpyHostToDevice, st));
     const float inv_leaf = 1.0f / ms.res;                               // Eigen::Array4f::Ones() / leaf_size_
-    k_voxel_keys<<<grid, 256, 0, st>>>(ms.d_xyzi, c->d_block_of_point, d_touched2, total, inv_leaf, c->d_keys, c->d_vals);
+    k_voxel_keys<<<grid, 256, 0, st>>>(ms.d_xyzi, c->d_block_of_point, d_touched2, total, inv_leaf, origin, c->d_keys, c->d_vals);
     SO_CUDA_TRY(cudaStreamSynchronize(st));                                   // d_cub_tmp is reused by the sort next
     size_t tmp = c->cub_tmp_bytes;
     SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, tmp, c->d_keys, c->d_keys_out, c->d_vals, c->d_vals_out, int(total), 0, 64, st));

@@ -61,6 +61,9 @@ int main(int argc, char** argv) {
             printf(" %d %d %zu %.17g %.17g %d %d %d", slam.stats.n_iterations, slam.stats.laser_cloud_surf_from_map_num, slam.localMap.size(),
                    slam.LocalizationUncertainty.PositionError, slam.stats.uncertainty_x, slam.localMap.origin_.x(), slam.pos_in_localmap.x(),
                    slam.PlaneFeatureHistogramObs[6]);
+            // EstimateLidarUncertainty (LidarSlam.cpp:915-986): the six values the node publishes, computed from the PREVIOUS scan's histogram
+            printf(" %.17g %.17g %.17g %.17g %.17g %.17g", slam.stats.uncertainty_x, slam.stats.uncertainty_y, slam.stats.uncertainty_z,
+                   slam.stats.uncertainty_roll, slam.stats.uncertainty_pitch, slam.stats.uncertainty_yaw);
             printf("\n");
         }
         Cloud all = slam.localMap.getAllLocalMap<Cloud>();

@@ -61,9 +61,16 @@ def test_shim_sequence_matches_abi_and_oracle(tmp_path, gpu_api, oracle_mod):
                                             origin=tuple(ctx.map_origin()))
     assert np.array_equal(ctx.map_download(0), om_points[oracle_mod.cube_order(om_points, tuple(ctx.map_origin()))])
     assert np.allclose(rows[0][1:8], priors[0])
+    prev_hist = np.zeros(9, np.int32)                   # PlaneFeatureHistogramObs before the first registration
     for i in range(1, len(scans)):
         r = ctx.register(scans[i], priors[i], 5, 0)
         assert np.array_equal(np.array(r.pose), np.array(rows[i][1:8]))              # shim == ABI, bit for bit
+        # a17 EstimateLidarUncertainty (LidarSlam.cpp:915-986): stats.uncertainty_* of scan i come from scan i-1's observability histogram
+        assert np.array_equal(np.array(rows[i][16:22]), oracle_mod.lidar_uncertainty(prev_hist)), (rows[i][16:22], prev_hist)
+        assert rows[i][12] == rows[i][16]
+        if i > 1:
+            assert 0 < min(rows[i][16:22]) and max(rows[i][16:22]) <= 1.0
+        prev_hist = np.array(list(r.hist_obs), np.int32)
         assert int(rows[i][8]) == r.n_iterations and int(rows[i][9]) == r.map_surf_5x5
         # oracle on the same (device-built) map
         om = oracle_mod.OracleMap()

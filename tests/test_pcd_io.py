@@ -124,3 +124,23 @@ def test_missing_intensity_other_types_and_errors(exe, tmp_path):
     assert _read(exe, p, tmp_path)[0] == 1
     p.write_bytes(b"VERSION .7\nFIELDS a b\nSIZE 4 4\nTYPE F F\nCOUNT 1 1\nWIDTH 1\nHEIGHT 1\nDATA ascii\n1 2\n")
     assert _read(exe, p, tmp_path)[0] == 1
+
+
+def test_hostile_headers_are_rejected_without_reading_out_of_bounds(exe, tmp_path):
+    """Untrusted files: COUNT 0 fields, odd SIZEs, record / point counts that would wrap or exhaust memory, and a compressed
+    size larger than the file all return false (exit code 1) instead of reading past a buffer or throwing."""
+    p = tmp_path / "h.pcd"
+    body = np.zeros(8, np.float32).tobytes()
+    cases = [
+        "VERSION .7\nFIELDS x y z i\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 0\nWIDTH 2\nHEIGHT 1\nDATA binary\n",          # last field COUNT 0
+        "VERSION .7\nFIELDS x y z\nSIZE 4 4 3\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2\nHEIGHT 1\nDATA binary\n",                  # SIZE 3
+        "VERSION .7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1000000\nWIDTH 2\nHEIGHT 1\nDATA binary\n",            # huge COUNT
+        "VERSION .7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2000000000\nHEIGHT 1\nDATA binary\n",          # points * rec >> file
+        "VERSION .7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2000000000\nHEIGHT 1\nDATA ascii\n",           # ascii rows >> file
+    ]
+    for hdr in cases:
+        p.write_bytes(hdr.encode() + body)
+        assert _read(exe, p, tmp_path)[0] == 1, hdr
+    hdr = "VERSION .7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2\nHEIGHT 1\nDATA binary_compressed\n"
+    p.write_bytes(hdr.encode() + struct.pack("<II", 0xFFFFFFF0, 24) + body)                                                 # csize >> file
+    assert _read(exe, p, tmp_path)[0] == 1
