@@ -228,6 +228,14 @@ int so_register_batch(so_ctx* ctx, const void* surf_xyzi, const uint32_t* n_poin
 int so_register_batch_device(so_ctx* ctx, const void* d_scans_xyzi, const uint32_t* n_points, size_t n_scans,
                              const double* poses_in, const so_icp_opts* opts, so_icp_result* results);
 
+/* Sharded-replay plumbing (BASELINE cfg4; SURVEY 8e "K8"): a caller-owned DEVICE buffer of cap_rows x 8 doubles.  Every following
+ * so_register / so_register_batch* call appends one row per scan, starting at first_row and advancing: {pose_opt[7] (the
+ * optimiser output, so_icp_result.pose_opt), status + 256 * n_iterations}; scans that were not registered (soft statuses) carry
+ * their prior.  The rows are written by a kernel on the context stream right after the last optimiser step, so a collective
+ * enqueued on that stream (ncclAllGather / torch.distributed.all_gather_into_tensor) gathers the poses of a whole replay without
+ * a host round trip.  d_rows == NULL detaches the sink.  The reference has no counterpart (single process, one scan at a time). */
+int so_set_pose_sink(so_ctx* ctx, void* d_rows, size_t cap_rows, size_t first_row);
+
 /* Test hook: so_register (surf cloud only) with the neighbour SEARCH replaced by caller-supplied neighbour sets --
  * nn_ids[it][i][0..4] = the five map point ids (so_map_set_points order, ascending distance; 0xFFFFFFFF = no result) that
  * findNearestNeighbors (LidarSlam.cpp:720-747) returned for scan point i in ICP iteration it, n_trace_iters iterations of them.

@@ -20,7 +20,7 @@ EXPORTS = [
     "so_create", "so_destroy", "so_last_error", "so_device_available", "so_set_stream",
     "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
     "so_map_set_edge_points", "so_map_add_surf", "so_map_add_edge", "so_map_add_scan", "so_map_add_scan_edge", "so_map_counts_5x5", "so_map_download", "so_map_size",
-    "so_scan_prefilter", "so_scan_deskew", "so_scan_extract_uniform", "so_register", "so_register_injected", "so_register_batch", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
+    "so_scan_prefilter", "so_scan_deskew", "so_scan_extract_uniform", "so_register", "so_register_injected", "so_set_pose_sink", "so_register_batch", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
     "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_build_flags", "so_profile_enable", "so_profile_get",
 ]
 
@@ -99,6 +99,7 @@ def load_library():
     L.so_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                               C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_register_injected.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.so_set_pose_sink.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
     L.so_register_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_register_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -314,6 +315,10 @@ class Context:
         self._chk(self.L.so_register(self.h, _p(s), s.shape[0], e, ne, stride, 12 if s.shape[1] >= 4 else stride,
                                      _p(pose), C.byref(o), C.byref(r)), "so_register")
         return r
+
+    def set_pose_sink(self, d_rows_ptr: int | None, cap_rows: int = 0, first_row: int = 0):
+        """Device buffer [cap_rows, 8] float64 that every following registration call appends {pose_opt[7], status + 256 n_iter} rows to."""
+        self._chk(self.L.so_set_pose_sink(self.h, C.c_void_p(d_rows_ptr or 0), cap_rows, first_row), "so_set_pose_sink")
 
     def register_injected(self, scan_xyzi: np.ndarray, pose7, max_icp_iters: int, nn_ids: np.ndarray, max_surface_features: int = 0, **kw) -> IcpResult:
         """so_register with caller-supplied neighbour sets: nn_ids [iters, n, 5] (int64 with -1 = none, or uint32 with 0xFFFFFFFF)."""

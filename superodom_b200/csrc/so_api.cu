@@ -418,11 +418,17 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         off += n_points[s];
         if (!o.skip_map_checks && !(r->map_surf_5x5 > 50)) {       // hasEnoughFeatures (:379-381): pose stays the prior
             r->status = SO_STATUS_NOT_ENOUGH_FEATURES;
-            c->h_state[s].phase = PH_DONE;
+            c->h_state[s].phase = PH_DONE; c->h_state[s].status = r->status;
         } else if (n_points[s] == 0) {
             r->status = SO_STATUS_NO_CORRESPONDENCES;
-            c->h_state[s].phase = PH_DONE;
+            c->h_state[s].phase = PH_DONE; c->h_state[s].status = r->status;
         } else { any = true; max_n = std::max(max_n, n_points[s]); }
+    }
+    if (c->d_pose_sink && c->sink_cursor + n_scans > c->sink_cap) return fail(SO_ERR_CAPACITY, "pose sink full (so_set_pose_sink)");
+    if (!any && c->d_pose_sink) {                               // nothing to register: the rows are the priors
+        SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, n_scans * sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
+        launch_pack_poses(c->d_state, uint32_t(n_scans), c->d_pose_sink + c->sink_cursor * 8, c->stream);
+        SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
     if (any) {
         SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, n_scans * sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
@@ -495,6 +501,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             SO_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         }
         SO_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+        if (c->d_pose_sink) { launch_pack_poses(c->d_state, uint32_t(n_scans), c->d_pose_sink + c->sink_cursor * 8, c->stream); c->launches++; }
         SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, n_scans * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
         count_d2h(c, n_scans * sizeof(IcpState));
         SO_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -512,6 +519,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             results[s].time_ms = double(ms);
         }
     }
+    if (c->d_pose_sink) c->sink_cursor += n_scans;
     return SO_OK;
 }
 
@@ -1002,6 +1010,14 @@ int so_register_batch_device(so_ctx* ctx, const void* d_scans, const uint32_t* n
     if (rc) return rc;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     for (size_t s = 0; s < n_scans; ++s) results[s].time_total_ms = ms;
+    return SO_OK;
+}
+
+int so_set_pose_sink(so_ctx* ctx, void* d_rows, size_t cap_rows, size_t first_row) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || (d_rows && first_row > cap_rows)) return fail(SO_ERR_ARG, "bad args");
+    // no synchronisation: rows are written by kernels on the context stream, so work already enqueued there keeps its order
+    c->d_pose_sink = static_cast<double*>(d_rows); c->sink_cap = d_rows ? cap_rows : 0; c->sink_cursor = d_rows ? first_row : 0;
     return SO_OK;
 }
 

@@ -76,6 +76,7 @@ struct Ctx {
     size_t edge_cap = 0; uint32_t edge_grid_cap = 0;
     float4* d_escan = nullptr; uint32_t* d_eoffset = nullptr; EdgeBuf ebuf{};
     uint32_t grid_x_cap = 0;
+    double* d_pose_sink = nullptr; size_t sink_cap = 0, sink_cursor = 0;   // so_set_pose_sink: device rows the batch calls append to
     uint32_t* d_inject = nullptr; size_t inject_cap = 0;   // so_register_injected: caller-supplied neighbour ids [iters][n][5]
     void* h_stage = nullptr;                       // pinned staging for strided host clouds
     size_t h_stage_bytes = 0;

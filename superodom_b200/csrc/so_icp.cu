@@ -1498,6 +1498,17 @@ __global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __res
     }
 }
 
+// Replay plumbing: one row of 8 doubles per scan -- the optimiser's pose {tx,ty,tz,qx,qy,qz,qw} (so_icp_result.pose_opt)
+// and status + 256 * n_iterations -- into a caller-owned device buffer, so that the NCCL gather of a sharded replay reads device
+// memory on the compute stream instead of waiting for a host round trip.
+__global__ void k_pack_poses(const IcpState* __restrict__ st, uint32_t n_scans, double* __restrict__ rows) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) rows[size_t(s) * 8 + k] = st[s].x[k];
+    rows[size_t(s) * 8 + 7] = double(st[s].status + 256 * st[s].n_iterations);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------------------
@@ -1551,6 +1562,9 @@ void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, ui
 }
 void launch_loop_cond(const BatchView& bv, uint32_t n_scans, cudaGraphConditionalHandle handle, cudaStream_t st) {
     k_loop_cond<<<1, 32, 0, st>>>(bv.st, n_scans, handle);
+}
+void launch_pack_poses(const IcpState* st, uint32_t n_scans, double* rows, cudaStream_t stream) {
+    k_pack_poses<<<(n_scans + 63) / 64, 64, 0, stream>>>(st, n_scans, rows);
 }
 void launch_query_keys(const MapView& m, const float4* q, size_t nq, uint32_t* keys, uint32_t* vals, cudaStream_t st) {
     k_query_keys<<<uint32_t((nq + kThreads - 1) / kThreads), kThreads, 0, st>>>(m, q, nq, keys, vals);

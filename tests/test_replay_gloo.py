@@ -29,6 +29,15 @@ def _worker(rank, world, port, n_total, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         out = replay.replay(lambda b, e: np.stack([_fake_pose(i) for i in range(b, e)]), n_total, rank, world, batch=3)
+        # the pose-sink form: every rank holds [cap, 8] rows {pose7, status + 256 n_iter}; one all-gather; unpack in scan order
+        import torch
+        b, e = replay.shard_range(n_total, rank, world)
+        rows = torch.zeros((replay.shard_cap(n_total, world), replay.ROW), dtype=torch.float64)
+        for k, i in enumerate(range(b, e)):
+            rows[k, :7] = torch.from_numpy(_fake_pose(i))
+            rows[k, 7] = float((i % 3) + 256 * (i + 1))
+        poses, status, iters = replay.unpack_rows(replay.gather_rows(rows).numpy(), n_total, world)
+        assert np.array_equal(poses, out) and np.array_equal(status, np.arange(n_total) % 3) and np.array_equal(iters, np.arange(n_total) + 1)
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
