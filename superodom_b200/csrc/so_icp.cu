@@ -150,6 +150,55 @@ __device__ __forceinline__ float axis_gap(int o, float f, float cs_minus_f, floa
     return ao == 0 ? 0.f : side + float(ao - 1) * cs;
 }
 
+#ifndef SO_WALK_NAT
+#define SO_WALK_NAT 1             // 1: slabs / rows in natural order (-R..R) with select-only gap arithmetic (fixed bound: order is irrelevant)
+#endif
+#ifndef SO_R1_OCTANT
+#define SO_R1_OCTANT 1            // 1: round 1 bounds the k-th distance from the 2x2x2 cells nearest the query instead of all 27
+#endif
+// Distance (not squared) from the query to the slab / row `d` cells away along one axis, |d| <= 2 (rings <= 2 by construction of the
+// grid: cells are >= half the search radius): {f + cs, f, 0, g, g + cs} for d = -2..2, by selects only.
+__device__ __forceinline__ float axis_gap2(int d, float f, float g, float cs) {
+    const float side = d < 0 ? f : g;
+    const float far = (d < -1 || d > 1) ? cs : 0.f;
+    return d == 0 ? 0.f : side + far;
+}
+
+// The 2 x 2 x 2 cells nearest the query (its own cell and, per axis, the neighbour on the side the query leans to), clipped to the
+// block: ANY candidate subset yields a valid upper bound on the k-th neighbour distance, and this one holds the true neighbours
+// almost always (it covers >= cs/2 around the query in every direction) at 8/27 of the cells and 4/9 of the rows of the full ring.
+template <class F>
+__device__ __forceinline__ void walk_octant(const MapView& m, const QueryCell& qc, F&& f) {
+    const int nb = m.nb;
+    const uint32_t base = uint32_t(qc.slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
+    const float h = 0.5f * m.cs;
+    const int cx = qc.c[0], cy = qc.c[1], cz = qc.c[2];
+    const int sx = qc.f[0] < h ? -1 : 1, sy = qc.f[1] < h ? -1 : 1, sz = qc.f[2] < h ? -1 : 1;
+    const int x0 = max(min(cx, cx + sx), 0), x1 = min(max(cx, cx + sx), nb - 1);
+    const float4 far = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.f);
+#pragma unroll
+    for (int iz = 0; iz < 2; ++iz) {
+        const int zz = cz + (iz ? sz : 0);
+        if (zz < 0 || zz >= nb) continue;
+#pragma unroll
+        for (int iy = 0; iy < 2; ++iy) {
+            const int yy = cy + (iy ? sy : 0);
+            if (yy < 0 || yy >= nb) continue;
+            const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
+            uint32_t t = __ldg(&m.cell_start[row + x0]);
+            const uint32_t end = __ldg(&m.cell_start[row + x1 + 1]);
+            for (; t < end; t += 4) {
+                const float4* p = m.pts + t;
+                const float4 c0 = __ldg(p);
+                const float4 c1 = t + 1 < end ? __ldg(p + 1) : far;
+                const float4 c2 = t + 2 < end ? __ldg(p + 2) : far;
+                const float4 c3 = t + 3 < end ? __ldg(p + 3) : far;
+                f(c0, t); f(c1, t + 1); f(c2, t + 2); f(c3, t + 3);
+            }
+        }
+    }
+}
+
 template <class F>
 __device__ __forceinline__ void walk_cube(const MapView& m, const QueryCell& qc, float U, int R, F&& f) {
     const int nb = m.nb;
@@ -176,27 +225,43 @@ __device__ __forceinline__ void walk_cube(const MapView& m, const QueryCell& qc,
 #endif
 #pragma unroll 1
     for (int zi = 0; zi <= 2 * R; ++zi) {
+#if SO_WALK_NAT
+        const int oz = zi - R;
+#else
         const int oz = walk_offset(zi);
+#endif
         const int zz = cz + oz;
 #if SO_WALK_V2
         const float lz2 = g2z[zi];
         if (lz2 > Um) continue;                              // also: slab outside the query's block (LocalMap.h:488-507)
 #else
         if (zz < 0 || zz >= nb) continue;                    // stay inside the query's block (LocalMap.h:488-507)
+#if SO_WALK_NAT
+        const float lz = R <= 2 ? axis_gap2(oz, fz, gz, cs) : axis_gap(oz, fz, gz, cs);
+#else
         const float lz = axis_gap(oz, fz, gz, cs);
+#endif
         const float lz2 = lz * lz;
         if (lz2 > Um) continue;
 #endif
 #pragma unroll 1
         for (int yi = 0; yi <= 2 * R; ++yi) {
+#if SO_WALK_NAT
+            const int oy = yi - R;
+#else
             const int oy = walk_offset(yi);
+#endif
             const int yy = cy + oy;
 #if SO_WALK_V2
             const float lb = g2y[yi] + lz2;
             if (lb > Um) continue;
 #else
             if (yy < 0 || yy >= nb) continue;
+#if SO_WALK_NAT
+            const float ly = R <= 2 ? axis_gap2(oy, fy, gy, cs) : axis_gap(oy, fy, gy, cs);
+#else
             const float ly = axis_gap(oy, fy, gy, cs);
+#endif
             const float lb = fmaf(ly, ly, lz2);
             if (lb > Um) continue;
 #endif
@@ -283,12 +348,17 @@ __device__ __forceinline__ void knn_select(const MapView& m, const QueryCell& qc
         float a[K];                                                            // K smallest approx d2 so far, ascending
 #pragma unroll
         for (int j = 0; j < K; ++j) a[j] = bound;
-        walk_cube(m, qc, bound, 1, [&](const float4 c, uint32_t) {
+        auto net = [&](const float4 c, uint32_t) {
             const float d = approx_d2(c, qx, qy, qz);
 #pragma unroll
             for (int j = K - 1; j > 0; --j) a[j] = fminf(a[j], fmaxf(a[j - 1], d));
             a[0] = fminf(a[0], d);
-        });
+        };
+#if SO_R1_OCTANT
+        walk_octant(m, qc, net);
+#else
+        walk_cube(m, qc, bound, 1, net);
+#endif
         U = a[K - 1] * 1.000004f;
     }
     U = fminf(U, bound * 1.000004f);

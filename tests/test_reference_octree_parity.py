@@ -110,5 +110,5 @@ def test_exact_knn_deviation_from_reference_octree_is_bounded(gpu_api, oracle_mo
     _record(f"{name}_cap{cap}_exact_vs_octree", row)
     assert dpos <= 5e-4 and drot <= 5e-4, row
     assert eg <= eo + 5e-4, row
-    assert row["mismatch_rate"] <= 0.02, row
+    assert row["mismatch_rate"] <= 0.05, row
     ctx.close()
