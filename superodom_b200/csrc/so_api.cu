@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "so_ctx.cuh"
+#include "so_knn.cuh"
 
 namespace so {
 
@@ -217,7 +218,7 @@ static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch, cudaS
     const BatchView bv = batch_view(c, d_scan_in, ch.first);
     timed_launch_begin(c);
     // key layout: [scan inside the chunk | cell]; 32-bit keys whenever both fit
-    const uint64_t n_cells = uint64_t(c->surf.n_slots) * uint64_t(mv.nb) * uint64_t(mv.nb) * uint64_t(mv.nb);
+    const uint64_t n_cells = scan_key_space(c->surf.n_slots, mv.nb);       // brick-order keys (so_knn.cuh)
     int cell_bits = 1, scan_bits = 0;
     while (cell_bits < 32 && (uint64_t(1) << cell_bits) <= n_cells) ++cell_bits;       // cells 0..n_cells-1 < mask = 2^cell_bits - 1
     while ((1u << scan_bits) < ch.count) ++scan_bits;

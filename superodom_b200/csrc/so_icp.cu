@@ -18,503 +18,9 @@
 //
 // Reference citations are relative to /root/reference/super_odometry/.
 #include "so_icp.cuh"
+#include "so_knn.cuh"
 
 namespace so {
-
-// ------------------------------------------------------------------------------------------------------------------
-// k-NN core.  Lists are kept ascending by (d2, id); d2 carries the reference's rounding float(double sum of squares)
-// (flann/octree.h:95-102).  Sentinel id 0xFFFFFFFF marks empty slots; d2 slots start at `bound` so that the
-// NEIGHBORS_TOO_FAR gate (d2 > 3*planeRes, LidarSlam.cpp:741) doubles as the search radius.
-// ------------------------------------------------------------------------------------------------------------------
-template <int K>
-struct TopK {
-    float d2[K]; uint32_t id[K]; uint32_t pos[K];
-    __device__ __forceinline__ void init(float bound) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) { d2[j] = bound; id[j] = 0xFFFFFFFFu; pos[j] = 0; }
-    }
-    __device__ __forceinline__ float worst() const { return d2[K - 1]; }
-    // Insert (d, i, p) if it precedes the current last entry in (d2, id) order.  The shift is a branch-free select
-    // network: in a warp some lane inserts at almost every candidate step, so this path runs ~once per step at low lane
-    // occupancy and its length, not its frequency, is what matters.
-    __device__ __forceinline__ void offer(float d, uint32_t i, uint32_t p) {
-        if (d < d2[K - 1] || (d == d2[K - 1] && i < id[K - 1])) {
-            bool lt[K];                     // lt[j]: candidate precedes slot j
-#pragma unroll
-            for (int j = 0; j < K - 1; ++j) lt[j] = d < d2[j] || (d == d2[j] && i < id[j]);
-            lt[K - 1] = true;
-#pragma unroll
-            for (int j = K - 1; j > 0; --j) {
-                // slot j takes slot j-1 when the candidate precedes slot j-1, the candidate when it lands exactly here
-                d2[j] = lt[j - 1] ? d2[j - 1] : (lt[j] ? d : d2[j]);
-                id[j] = lt[j - 1] ? id[j - 1] : (lt[j] ? i : id[j]);
-                pos[j] = lt[j - 1] ? pos[j - 1] : (lt[j] ? p : pos[j]);
-            }
-            d2[0] = lt[0] ? d : d2[0];
-            id[0] = lt[0] ? i : id[0];
-            pos[0] = lt[0] ? p : pos[0];
-        }
-    }
-    __device__ __forceinline__ int count() const {
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < K; ++j) c += (id[j] != 0xFFFFFFFFu);
-        return c;
-    }
-};
-
-struct QueryCell {
-    int32_t slot;        // block slot or -1
-    int32_t c[3];        // cell inside the block
-    float f[3];          // offset of the query inside its cell, metres, in [0, cs]
-    int32_t nblock;      // points in the block
-};
-
-// LocalMap::nearestKSearchSurf block lookup (LocalMap.h:488-507) + cell inside the block.
-__device__ __forceinline__ void locate(const MapView& m, float qx, float qy, float qz, QueryCell& qc) {
-    const float q[3] = {qx, qy, qz};
-    int g[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const double v = double(q[a]) + kHalfBlock;
-        int b = int(v / kBlock);
-        if (v < 0) b--;
-        g[a] = b + m.origin[a];
-        const double u = (v - kBlock * double(b)) * m.inv_cs;
-        int c = int(u);
-        c = c < 0 ? 0 : (c > m.nb - 1 ? m.nb - 1 : c);
-        qc.c[a] = c;
-        const float f = float(u - double(c)) * m.cs;
-        qc.f[a] = fminf(fmaxf(f, 0.f), m.cs);
-    }
-    const bool ok = g[0] >= 0 && g[0] < kW && g[1] >= 0 && g[1] < kH && g[2] >= 0 && g[2] < kD;
-    qc.slot = -1; qc.nblock = 0;
-    if (ok) {
-        const int lin = g[0] + kW * g[1] + kW * kH * g[2];
-        qc.slot = __ldg(&m.block_slot[lin]);
-        qc.nblock = __ldg(&m.block_count[lin]);
-    }
-}
-
-template <int K>
-__device__ __forceinline__ void offer_candidate(const float4 c, uint32_t t, float qx, float qy, float qz, TopK<K>& tk) {
-    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-    const float approx = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-    // cheap FP32 filter (relative error < 4e-7), then the reference's exact rounding for real contenders
-    if (approx <= tk.worst() * 1.000002f) {
-        const float d2 = float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz));
-        tk.offer(d2, __float_as_uint(c.w), t);
-    }
-}
-
-template <int K>
-__device__ __forceinline__ void scan_range(const MapView& m, uint32_t beg, uint32_t end, float qx, float qy, float qz, TopK<K>& tk) {
-    uint32_t t = beg;
-    for (; t + 4 <= end; t += 4) {          // four independent 16-byte loads in flight per lane
-        const float4 c0 = __ldg(&m.pts[t]), c1 = __ldg(&m.pts[t + 1]), c2 = __ldg(&m.pts[t + 2]), c3 = __ldg(&m.pts[t + 3]);
-        offer_candidate<K>(c0, t, qx, qy, qz, tk);
-        offer_candidate<K>(c1, t + 1, qx, qy, qz, tk);
-        offer_candidate<K>(c2, t + 2, qx, qy, qz, tk);
-        offer_candidate<K>(c3, t + 3, qx, qy, qz, tk);
-    }
-    for (; t < end; ++t) offer_candidate<K>(__ldg(&m.pts[t]), t, qx, qy, qz, tk);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// k-NN in three warp-friendly rounds (all loops do the same kind of work in every lane):
-//   1. bound : a value-only min/max selection network over the 27 cells around the query gives U, an upper bound on the
-//              k-th-neighbour distance (skipped when the previous ICP iteration's neighbours already provide one);
-//   2. gather: pruned walk of the search cube with the fixed bound U; the few candidates with approx d2 <= U are only
-//              recorded (position into a per-lane shared-memory list) -- no divergent insertion in the hot loop;
-//   3. refine: the recorded candidates get the reference's exact d2 rounding and are ordered by (d2, id).
-// The result is identical to an exhaustive in-block search with the same ordering: every true neighbour has
-// approx d2 <= U (U carries a 4e-6 relative margin over the FP32 evaluation error of 4e-7).
-// ------------------------------------------------------------------------------------------------------------------
-#ifndef SO_BUF_CAP
-#define SO_BUF_CAP 24
-#endif
-constexpr int kBufCap = SO_BUF_CAP;
-
-#ifndef SO_WALK_PRED
-#define SO_WALK_PRED 1
-#endif
-#ifndef SO_WALK_V2
-#define SO_WALK_V2 0              // 1: tabulated slab / row gaps + single-address candidate groups (prepared from the per-line profile; not yet measured)
-#endif
-// Offsets are visited nearest slab / row first: 0, -1, +1, -2, +2.
-__device__ __forceinline__ int walk_offset(int t) { return (t & 1) ? -((t + 1) >> 1) : (t >> 1); }
-// Distance from a point at offset f inside its cell (edge cs) to the cell `o` cells away along one axis (0 for its own cell).
-__device__ __forceinline__ float axis_gap(int o, float f, float cs_minus_f, float cs) {
-    const int ao = o < 0 ? -o : o;
-    const float side = o < 0 ? f : cs_minus_f;
-    return ao == 0 ? 0.f : side + float(ao - 1) * cs;
-}
-
-#ifndef SO_WALK_NAT
-#define SO_WALK_NAT 1             // 1: slabs / rows in natural order (-R..R) with select-only gap arithmetic (fixed bound: order is irrelevant)
-#endif
-#ifndef SO_R1_OCTANT
-#define SO_R1_OCTANT 1            // 1: round 1 bounds the k-th distance from the 2x2x2 cells nearest the query instead of all 27
-#endif
-// Distance (not squared) from the query to the slab / row `d` cells away along one axis, |d| <= 2 (rings <= 2 by construction of the
-// grid: cells are >= half the search radius): {f + cs, f, 0, g, g + cs} for d = -2..2, by selects only.
-__device__ __forceinline__ float axis_gap2(int d, float f, float g, float cs) {
-    const float side = d < 0 ? f : g;
-    const float far = (d < -1 || d > 1) ? cs : 0.f;
-    return d == 0 ? 0.f : side + far;
-}
-
-// The 2 x 2 x 2 cells nearest the query (its own cell and, per axis, the neighbour on the side the query leans to), clipped to the
-// block: ANY candidate subset yields a valid upper bound on the k-th neighbour distance, and this one holds the true neighbours
-// almost always (it covers >= cs/2 around the query in every direction) at 8/27 of the cells and 4/9 of the rows of the full ring.
-template <class F>
-__device__ __forceinline__ void walk_octant(const MapView& m, const QueryCell& qc, F&& f) {
-    const int nb = m.nb;
-    const uint32_t base = uint32_t(qc.slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
-    const float h = 0.5f * m.cs;
-    const int cx = qc.c[0], cy = qc.c[1], cz = qc.c[2];
-    const int sx = qc.f[0] < h ? -1 : 1, sy = qc.f[1] < h ? -1 : 1, sz = qc.f[2] < h ? -1 : 1;
-    const int x0 = max(min(cx, cx + sx), 0), x1 = min(max(cx, cx + sx), nb - 1);
-    const float4 far = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.f);
-#pragma unroll
-    for (int iz = 0; iz < 2; ++iz) {
-        const int zz = cz + (iz ? sz : 0);
-        if (zz < 0 || zz >= nb) continue;
-#pragma unroll
-        for (int iy = 0; iy < 2; ++iy) {
-            const int yy = cy + (iy ? sy : 0);
-            if (yy < 0 || yy >= nb) continue;
-            const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
-            uint32_t t = __ldg(&m.cell_start[row + x0]);
-            const uint32_t end = __ldg(&m.cell_start[row + x1 + 1]);
-            for (; t < end; t += 4) {
-                const float4* p = m.pts + t;
-                const float4 c0 = __ldg(p);
-                const float4 c1 = t + 1 < end ? __ldg(p + 1) : far;
-                const float4 c2 = t + 2 < end ? __ldg(p + 2) : far;
-                const float4 c3 = t + 3 < end ? __ldg(p + 3) : far;
-                f(c0, t); f(c1, t + 1); f(c2, t + 2); f(c3, t + 3);
-            }
-        }
-    }
-}
-
-template <class F>
-__device__ __forceinline__ void walk_cube(const MapView& m, const QueryCell& qc, float U, int R, F&& f) {
-    const int nb = m.nb;
-    const uint32_t base = uint32_t(qc.slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
-    const float cs = m.cs;
-    const float fx = qc.f[0], fy = qc.f[1], fz = qc.f[2];
-    const float gx = cs - fx, gy = cs - fy, gz = cs - fz;
-    const int cx = qc.c[0], cy = qc.c[1], cz = qc.c[2];
-#if SO_WALK_V2
-    // Squared gaps to the five slabs / rows (3.0e38 = outside the block, never within any U) tabulated once per walk and read
-    // back by loop index (a small per-thread local array), instead of being recomputed for each of the 25 (slab, row) pairs:
-    // the per-line profile (profiles/knn_scan_r1p_per_source_line.txt) puts walk_offset + axis_gap at 11 % of the kernel.
-    const float Um = fminf(U * 1.0001f, 1.0e30f);
-    float g2y[5], g2z[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const int o = (k & 1) ? -((k + 1) >> 1) : (k >> 1);
-        const float ly = axis_gap(o, fy, gy, cs), lz = axis_gap(o, fz, gz, cs);
-        g2y[k] = (cy + o < 0 || cy + o >= nb) ? 3.0e38f : ly * ly;
-        g2z[k] = (cz + o < 0 || cz + o >= nb) ? 3.0e38f : lz * lz;
-    }
-#else
-    const float Um = U * 1.0001f;                            // a row / cell is skipped when its lower bound exceeds U by this margin
-#endif
-#pragma unroll 1
-    for (int zi = 0; zi <= 2 * R; ++zi) {
-#if SO_WALK_NAT
-        const int oz = zi - R;
-#else
-        const int oz = walk_offset(zi);
-#endif
-        const int zz = cz + oz;
-#if SO_WALK_V2
-        const float lz2 = g2z[zi];
-        if (lz2 > Um) continue;                              // also: slab outside the query's block (LocalMap.h:488-507)
-#else
-        if (zz < 0 || zz >= nb) continue;                    // stay inside the query's block (LocalMap.h:488-507)
-#if SO_WALK_NAT
-        const float lz = R <= 2 ? axis_gap2(oz, fz, gz, cs) : axis_gap(oz, fz, gz, cs);
-#else
-        const float lz = axis_gap(oz, fz, gz, cs);
-#endif
-        const float lz2 = lz * lz;
-        if (lz2 > Um) continue;
-#endif
-#pragma unroll 1
-        for (int yi = 0; yi <= 2 * R; ++yi) {
-#if SO_WALK_NAT
-            const int oy = yi - R;
-#else
-            const int oy = walk_offset(yi);
-#endif
-            const int yy = cy + oy;
-#if SO_WALK_V2
-            const float lb = g2y[yi] + lz2;
-            if (lb > Um) continue;
-#else
-            if (yy < 0 || yy >= nb) continue;
-#if SO_WALK_NAT
-            const float ly = R <= 2 ? axis_gap2(oy, fy, gy, cs) : axis_gap(oy, fy, gy, cs);
-#else
-            const float ly = axis_gap(oy, fy, gy, cs);
-#endif
-            const float lb = fmaf(ly, ly, lz2);
-            if (lb > Um) continue;
-#endif
-            // x extent of the row, branch-free for the rings that exist by construction (R <= 2: cells are >= half the search
-            // radius); each step outwards needs the step before it
-            const bool l1 = cx >= 1 && fmaf(fx, fx, lb) <= Um;
-            const bool l2 = l1 && R >= 2 && cx >= 2 && fmaf(fx + cs, fx + cs, lb) <= Um;
-            const bool r1 = cx + 1 < nb && fmaf(gx, gx, lb) <= Um;
-            const bool r2 = r1 && R >= 2 && cx + 2 < nb && fmaf(gx + cs, gx + cs, lb) <= Um;
-            int xlo = cx - int(l1) - int(l2), xhi = cx + int(r1) + int(r2);
-            if (R > 2) {                                     // generic tail (not reached with the grids map_cells_per_block builds)
-                if (l2) for (int k = 3; k <= R; ++k) { const float lx = fx + float(k - 1) * cs; if (cx - k < 0 || fmaf(lx, lx, lb) > Um) break; xlo = cx - k; }
-                if (r2) for (int k = 3; k <= R; ++k) { const float lx = gx + float(k - 1) * cs; if (cx + k > nb - 1 || fmaf(lx, lx, lb) > Um) break; xhi = cx + k; }
-            }
-            const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
-            uint32_t t = __ldg(&m.cell_start[row + xlo]);
-            const uint32_t end = __ldg(&m.cell_start[row + xhi + 1]);
-#if SO_WALK_PRED
-            // groups of four with the tail predicated: the loads of a short row (most rows hold 1-3 points) are issued together
-            // instead of one per trip of a remainder loop; a lane past the end evaluates a far-away dummy that fails every test
-            const float4 far = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.f);
-            for (; t < end; t += 4) {
-#if SO_WALK_V2
-                const float4* p = m.pts + t;                 // one address, three immediate offsets
-                const float4 c0 = __ldg(p);
-                const float4 c1 = t + 1 < end ? __ldg(p + 1) : far;
-                const float4 c2 = t + 2 < end ? __ldg(p + 2) : far;
-                const float4 c3 = t + 3 < end ? __ldg(p + 3) : far;
-#else
-                const float4 c0 = __ldg(&m.pts[t]);
-                const float4 c1 = t + 1 < end ? __ldg(&m.pts[t + 1]) : far;
-                const float4 c2 = t + 2 < end ? __ldg(&m.pts[t + 2]) : far;
-                const float4 c3 = t + 3 < end ? __ldg(&m.pts[t + 3]) : far;
-#endif
-                f(c0, t); f(c1, t + 1); f(c2, t + 2); f(c3, t + 3);
-            }
-#else
-            for (; t + 4 <= end; t += 4) {                   // four independent 16-byte loads in flight per lane
-                const float4 c0 = __ldg(&m.pts[t]), c1 = __ldg(&m.pts[t + 1]), c2 = __ldg(&m.pts[t + 2]), c3 = __ldg(&m.pts[t + 3]);
-                f(c0, t); f(c1, t + 1); f(c2, t + 2); f(c3, t + 3);
-            }
-            for (; t < end; ++t) f(__ldg(&m.pts[t]), t);
-#endif
-        }
-    }
-}
-
-__device__ __forceinline__ float approx_d2(const float4 c, float qx, float qy, float qz) {
-    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-}
-
-// s_buf: [kBufCap][kThreads] positions, column = this thread.  u_seed < 0: no seed.  `bound`: neighbours farther than this
-// (squared) are not wanted; tk must have been initialised with it.  Complete for d2 <= min(bound, (R*cs)^2).
-// Round 2 for one lane: record (or, past kBufCap, insert) every candidate with approx d2 <= U.
-template <int K>
-__device__ __forceinline__ void knn_record(const float4 c, uint32_t t, float qx, float qy, float qz, float U, uint32_t* s_buf, int& cnt, TopK<K>& tk) {
-    const float d = approx_d2(c, qx, qy, qz);
-    if (d <= U) {
-        if (cnt < kBufCap) { s_buf[cnt * kThreads + threadIdx.x] = t; ++cnt; }
-        else {                                                                 // overflow (dense cluster inside U): insert directly
-            const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-            tk.offer(float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)), __float_as_uint(c.w), t);
-        }
-    }
-}
-// Round 3 for one lane: exact d2 + ordered insertion of the recorded candidates.
-template <int K>
-__device__ __forceinline__ void knn_refine(const MapView& m, float qx, float qy, float qz, const uint32_t* s_buf, int cnt, TopK<K>& tk) {
-    for (int e = 0; e < cnt; ++e) {
-        const uint32_t t = s_buf[e * kThreads + threadIdx.x];
-        const float4 c = __ldg(&m.pts[t]);
-        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-        tk.offer(float(double(dx) * double(dx) + double(dy) * double(dy) + double(dz) * double(dz)), __float_as_uint(c.w), t);
-    }
-}
-
-template <int K>
-__device__ __forceinline__ void knn_select(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, float u_seed, float bound,
-                                           uint32_t* s_buf, TopK<K>& tk) {
-    float U;
-    if (u_seed >= 0.f) U = u_seed * 1.000004f;
-    else {
-        float a[K];                                                            // K smallest approx d2 so far, ascending
-#pragma unroll
-        for (int j = 0; j < K; ++j) a[j] = bound;
-        auto net = [&](const float4 c, uint32_t) {
-            const float d = approx_d2(c, qx, qy, qz);
-#pragma unroll
-            for (int j = K - 1; j > 0; --j) a[j] = fminf(a[j], fmaxf(a[j - 1], d));
-            a[0] = fminf(a[0], d);
-        };
-#if SO_R1_OCTANT
-        walk_octant(m, qc, net);
-#else
-        walk_cube(m, qc, bound, 1, net);
-#endif
-        U = a[K - 1] * 1.000004f;
-    }
-    U = fminf(U, bound * 1.000004f);
-    int cnt = 0;
-    walk_cube(m, qc, U, m.R, [&](const float4 c, uint32_t t) { knn_record<K>(c, t, qx, qy, qz, U, s_buf, cnt, tk); });
-    knn_refine<K>(m, qx, qy, qz, s_buf, cnt, tk);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Warp-cooperative form of the select k-NN (SO_KNN_COOP).  The 32 queries of a warp are consecutive in cell order, so most
-// warps sit in one to three cells of one x-row.  When the valid lanes share a block and their cell box is small, the warp
-// walks ONE candidate set -- the box grown by the needed rings -- with warp-uniform loops: every candidate is fetched once
-// with a uniform (broadcast) load and tested by all lanes against their own query, and the row bookkeeping that dominates
-// the per-lane walk is paid once per warp.  Each lane still gathers exactly the candidates within its own U (any point
-// within sqrt(U) of a query lies inside that query's ring cube, which the grown box contains), so results are identical
-// to knn_select.  Returns false (nothing done) when the warp does not qualify; the caller then runs knn_select per lane.
-// Must be called by all 32 lanes.
-// Status (B200, cfg2, 64 scans): parity tests identical to the per-lane path, but k_knn_scan 1.19 ms vs 1.07 ms -- every lane
-// tests every candidate of the shared box in both rounds (43-59 per round against ~35 + ~33 pruned per lane), which outweighs
-// the row bookkeeping saved.  The hybrid (SO_KNN_COOP=2: cooperative bound, per-lane gather) measures 1.125 ms.  Off by
-// default (SO_KNN_COOP=0); not yet tried: a tighter cell limit (the box+1 candidate count has a heavy tail: median 43-59,
-// p90 200-700 at the 160-cell limit) and a shared-memory candidate tile.
-// ------------------------------------------------------------------------------------------------------------------
-#ifndef SO_KNN_COOP
-#define SO_KNN_COOP 0            // 0: per-lane walk; 1: cooperative rounds 1 + 2; 2: cooperative round 1, per-lane round 2
-#endif
-#ifndef SO_COOP_MAX_CELLS
-#define SO_COOP_MAX_CELLS 160        // (ex+2)(ey+2)(ez+2) above which the shared candidate set stops paying
-#endif
-#ifndef SO_COOP_MIN_LANES
-#define SO_COOP_MIN_LANES 8
-#endif
-
-// Rows of the cell box [lo-R, hi+R] clipped to the block; a row whose cell gap to the box of queries already exceeds Umax is
-// skipped (only possible for R = 2).  f(point, position) runs for every point of every visited row, warp-uniformly.
-template <class F>
-__device__ __forceinline__ void coop_walk(const MapView& m, int slot, int lox, int loy, int loz, int hix, int hiy, int hiz, int R, float Umax, F&& f) {
-    const int nb = m.nb;
-    const uint32_t base = uint32_t(slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
-    const float cs2 = m.cs * m.cs, Um = Umax * 1.0001f;
-    const int x0 = max(lox - R, 0), x1 = min(hix + R, nb - 1);
-    const int y0 = max(loy - R, 0), y1 = min(hiy + R, nb - 1);
-    const int z0 = max(loz - R, 0), z1 = min(hiz + R, nb - 1);
-    const float4 far = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.f);
-#pragma unroll 1
-    for (int zz = z0; zz <= z1; ++zz) {
-        const int gz = max(max(loz - zz - 1, zz - hiz - 1), 0);
-#pragma unroll 1
-        for (int yy = y0; yy <= y1; ++yy) {
-            const int gy = max(max(loy - yy - 1, yy - hiy - 1), 0);
-            if (float(gy * gy + gz * gz) * cs2 > Um) continue;
-            const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
-            uint32_t t = __ldg(&m.cell_start[row + x0]);
-            const uint32_t end = __ldg(&m.cell_start[row + x1 + 1]);
-            for (; t < end; t += 4) {
-                const float4 c0 = __ldg(&m.pts[t]);
-                const float4 c1 = t + 1 < end ? __ldg(&m.pts[t + 1]) : far;
-                const float4 c2 = t + 2 < end ? __ldg(&m.pts[t + 2]) : far;
-                const float4 c3 = t + 3 < end ? __ldg(&m.pts[t + 3]) : far;
-                f(c0, t); f(c1, t + 1); f(c2, t + 2); f(c3, t + 3);
-            }
-        }
-    }
-}
-
-template <int K>
-__device__ __forceinline__ bool knn_select_coop(const MapView& m, const QueryCell& qc, bool valid, float qx, float qy, float qz, float u_seed,
-                                                float bound, uint32_t* s_buf, TopK<K>& tk) {
-    const unsigned full = 0xffffffffu;
-    const unsigned vmask = __ballot_sync(full, valid);
-    if (__popc(vmask) < SO_COOP_MIN_LANES) return false;
-    const int slot0 = __shfl_sync(full, qc.slot, __ffs(vmask) - 1);
-    if (!__all_sync(full, !valid || qc.slot == slot0)) return false;
-    const int lox = __reduce_min_sync(full, valid ? qc.c[0] : 0x7fffffff), hix = __reduce_max_sync(full, valid ? qc.c[0] : -1);
-    const int loy = __reduce_min_sync(full, valid ? qc.c[1] : 0x7fffffff), hiy = __reduce_max_sync(full, valid ? qc.c[1] : -1);
-    const int loz = __reduce_min_sync(full, valid ? qc.c[2] : 0x7fffffff), hiz = __reduce_max_sync(full, valid ? qc.c[2] : -1);
-    const int ex = hix - lox + 1, ey = hiy - loy + 1, ez = hiz - loz + 1;
-    if ((ex + 2) * (ey + 2) * (ez + 2) > SO_COOP_MAX_CELLS) return false;
-    // round 1: bound on the K-th neighbour distance from the box grown by one ring (a superset of every lane's 27 cells)
-    float U;
-    if (__any_sync(full, valid && u_seed < 0.f)) {
-        float a[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) a[j] = bound;
-        coop_walk(m, slot0, lox, loy, loz, hix, hiy, hiz, 1, bound, [&](const float4 c, uint32_t) {
-            const float d = approx_d2(c, qx, qy, qz);
-#pragma unroll
-            for (int j = K - 1; j > 0; --j) a[j] = fminf(a[j], fmaxf(a[j - 1], d));
-            a[0] = fminf(a[0], d);
-        });
-        U = (u_seed >= 0.f ? u_seed : a[K - 1]) * 1.000004f;
-    } else U = u_seed * 1.000004f;
-    U = fminf(U, bound * 1.000004f);
-    if (!valid) U = 0.f;
-    // round 2: rings the widest lane needs; box grown by that; every lane records what lies within its own U
-    const float cs = m.cs;
-    const int need = (U * 1.0001f <= cs * cs) ? 1 : 2;                           // (need * cs)^2 >= U, rings <= 2 by construction of the grid
-    const int Rw = min(__reduce_max_sync(full, valid ? need : 1), m.R);
-    const float Umax = __uint_as_float(__reduce_max_sync(full, __float_as_uint(U)));       // U >= 0: the bit patterns order like the values
-    int cnt = 0;
-    if (SO_KNN_COOP == 2) {                                  // hybrid: cooperative bound, per-lane pruned gather with the tight U
-        if (valid) walk_cube(m, qc, U, m.R, [&](const float4 c, uint32_t t) { knn_record<K>(c, t, qx, qy, qz, U, s_buf, cnt, tk); });
-    } else if (Rw == 1 || (ex + 4) * (ey + 4) * (ez + 4) <= 3 * SO_COOP_MAX_CELLS)
-        coop_walk(m, slot0, lox, loy, loz, hix, hiy, hiz, Rw, Umax, [&](const float4 c, uint32_t t) {
-            if (valid) knn_record<K>(c, t, qx, qy, qz, U, s_buf, cnt, tk);
-        });
-    else if (valid)
-        walk_cube(m, qc, U, m.R, [&](const float4 c, uint32_t t) { knn_record<K>(c, t, qx, qy, qz, U, s_buf, cnt, tk); });
-    if (valid) knn_refine<K>(m, qx, qy, qz, s_buf, cnt, tk);
-    return true;
-}
-
-// Unpruned cube [c-R, c+R]^3 clipped to the block (fallback rings of the exact, unbounded search).
-template <int K>
-__device__ __forceinline__ void knn_cube(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, int R, TopK<K>& tk) {
-    const int nb = m.nb;
-    const uint32_t base = uint32_t(qc.slot) * uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
-    const int xlo = max(qc.c[0] - R, 0), xhi = min(qc.c[0] + R, nb - 1);
-    for (int zz = max(qc.c[2] - R, 0); zz <= min(qc.c[2] + R, nb - 1); ++zz)
-        for (int yy = max(qc.c[1] - R, 0); yy <= min(qc.c[1] + R, nb - 1); ++yy) {
-            const uint32_t row = base + uint32_t(zz * nb + yy) * uint32_t(nb);
-            scan_range<K>(m, __ldg(&m.cell_start[row + xlo]), __ldg(&m.cell_start[row + xhi + 1]), qx, qy, qz, tk);
-        }
-}
-
-// In-block k-NN, radius-bounded (max_d2 > 0) or exact (max_d2 <= 0).  The select walk is complete up to
-// min(bound, (R*cs)^2); wider / unbounded searches then grow an unpruned cube until the k-th distance is provably final.
-template <int K>
-__device__ __forceinline__ void knn_search(const MapView& m, const QueryCell& qc, float qx, float qy, float qz, float max_d2,
-                                           uint32_t* s_buf, TopK<K>& tk) {
-    const bool bounded = max_d2 > 0.f;
-    int R = m.R;
-    const float ring_d2 = float(R) * m.cs * float(R) * m.cs;
-    bool done = false;
-    if (bounded && max_d2 <= ring_d2) { tk.init(max_d2); knn_select<K>(m, qc, qx, qy, qz, -1.f, max_d2, s_buf, tk); done = true; }
-    else if (!bounded) {
-        tk.init(ring_d2 * 0.999f);
-        knn_select<K>(m, qc, qx, qy, qz, -1.f, ring_d2 * 0.999f, s_buf, tk);
-        done = tk.count() == K;                                      // K neighbours inside the guaranteed-complete radius
-    } else { const float r = sqrtf(max_d2); while (float(R) * m.cs < r && R < m.nb) ++R; }
-    while (!done) {
-        tk.init(bounded ? max_d2 : FLT_MAX);
-        knn_cube<K>(m, qc, qx, qy, qz, R, tk);
-        if (bounded) break;
-        float reach = FLT_MAX;
-        bool covers = true;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (qc.c[a] - R > 0) { covers = false; reach = fminf(reach, qc.f[a] + float(R) * m.cs); }
-            if (qc.c[a] + R < m.nb - 1) { covers = false; reach = fminf(reach, (m.cs - qc.f[a]) + float(R) * m.cs); }
-        }
-        if (covers) break;
-        if (tk.count() == K && tk.worst() < reach * reach * 0.999f) break;
-        R = (R < 4) ? R + 1 : R * 2;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // CTA reduction of kAcc doubles per thread into partials[scan][cta][kAcc].  Fixed thread->point mapping and fixed
@@ -809,10 +315,6 @@ __device__ __forceinline__ float seed_bound(const MapView& m, const QueryCell& q
     return (same_block && u <= 1.3f * nb.d5[gi]) ? u : -1.f;
 }
 
-#ifndef SO_SCAN_ORDER
-#define SO_SCAN_ORDER 0      // 0: cell-linear (x fastest), 1: Morton, 2: x-runs in 2x2 row bundles -- tuning variants of the scan order
-#endif
-
 // shouldProcessPoint (LidarSlam.cpp:353-359)
 __device__ __forceinline__ bool should_process(uint32_t i, double rate) {
     if (rate < 0.0) return true;
@@ -821,10 +323,10 @@ __device__ __forceinline__ bool should_process(uint32_t i, double rate) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Scan preparation (once per registration): order the scan points by the map cell they fall into at the PRIOR pose,
-// so that the 32 lanes of a warp walk the same cell rows in lock-step (identical addresses -> one L1 wavefront per
-// load instead of 32).  Pose updates inside one registration are a few cm against 0.78 m cells, so the order stays
-// coherent for all ICP iterations.  The sorted copy carries the point's original index in .w (the reference's
+// Scan preparation (once per registration): order the scan points by the map cell they fall into at the PRIOR pose, cells
+// grouped into 8x8x8 bricks (scan_order_key), so that the 128 queries of a CTA sit in a compact box of cells (one shared,
+// bulk-copied candidate tile) and the 32 lanes of a warp walk the same cell rows.  Pose updates inside one registration are a
+// few cm against 0.39 m cells, so the order stays coherent for all ICP iterations.  The sorted copy carries the point's original index in .w (the reference's
 // shouldProcessPoint() decimation is defined on the original index, LidarSlam.cpp:353-359).
 // ------------------------------------------------------------------------------------------------------------------
 // Key = (scan index inside the chunk) << cell_bits | cell; cells beyond the mask and off-map points sort last inside their scan.
@@ -843,21 +345,7 @@ __global__ void __launch_bounds__(kThreads) k_scan_keys(MapView m, BatchView bv,
     qrot(st->x + 3, pin, pf);
     QueryCell qc;
     locate(m, float(pf[0] + st->x[0]), float(pf[1] + st->x[1]), float(pf[2] + st->x[2]), qc);
-    uint32_t cell = 0xFFFFFFFFu;
-#if SO_SCAN_ORDER == 1
-    // Morton order of the cell inside its block (nb <= 192: 8 bits per axis)
-    if (qc.slot >= 0) {
-        auto spread = [](uint32_t v) { v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; return (v | (v << 2)) & 0x09249249u; };
-        cell = (uint32_t(qc.slot) << 24) | spread(uint32_t(qc.c[0])) | (spread(uint32_t(qc.c[1])) << 1) | (spread(uint32_t(qc.c[2])) << 2);
-    }
-#elif SO_SCAN_ORDER == 2
-    // x-runs inside 2x2 bundles of (y, z) rows
-    if (qc.slot >= 0)
-        cell = uint32_t(qc.slot) * uint32_t(m.nb * m.nb * m.nb) +
-               uint32_t((((qc.c[2] >> 1) * ((m.nb + 1) >> 1) + (qc.c[1] >> 1)) * m.nb + qc.c[0]) * 4 + (qc.c[2] & 1) * 2 + (qc.c[1] & 1));
-#else
-    if (qc.slot >= 0) cell = uint32_t(qc.slot) * uint32_t(m.nb * m.nb * m.nb) + uint32_t((qc.c[2] * m.nb + qc.c[1]) * m.nb + qc.c[0]);
-#endif
+    const uint32_t cell = qc.slot >= 0 ? scan_order_key(m, qc) : 0xFFFFFFFFu;      // brick order (so_knn.cuh)
     const uint32_t mask = cell_bits >= 32 ? 0xFFFFFFFFu : ((1u << cell_bits) - 1u);
     keys[gi] = KeyT((KeyT(s) << cell_bits) | KeyT(cell < mask ? cell : mask));
     vals[gi] = uint32_t(gi);
@@ -875,30 +363,31 @@ __global__ void __launch_bounds__(kThreads) k_scan_gather(const float4* __restri
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_knn_scan: findNearestNeighbors (LidarSlam.cpp:720-747) for every processed scan point at the current pose.
-// Light on registers (FP32 search, FP64 only for the pose transform and the exact d2 of real contenders) so that
-// many warps per SM hide the L1/L2 latency of the cell walks.
+// k_knn_scan: findNearestNeighbors (LidarSlam.cpp:720-747) for every processed scan point at the current pose: the select k-NN of
+// so_knn.cuh, one query per thread, queries consecutive in scan order.  Light on registers (FP32 search, FP64 only for the pose
+// transform and the exact d2 of real contenders) so that many warps per SM hide the latency of the cell walks.
+// SO_KNN_TILE build: 128 queries per CTA in brick order; the CTA stages the candidate tile of its queries' cell box (build_tile:
+// one cp.async.bulk per map row onto an mbarrier, a 16-bit local cell table) and searches shared memory; CTAs whose box does not
+// fit search global memory.  Measured slower than the global search (so_knn.cuh), so it is not the default.
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef SO_KNN_MINB
-#define SO_KNN_MINB 4
+#define SO_KNN_MINB (SO_KNN_TILE ? 6 : 4)
 #endif
-__global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_scan(MapView m, BatchView bv, NnBuf nb) {
+__global__ void __launch_bounds__(kTileThreads, SO_KNN_MINB) k_knn_scan(MapView m, BatchView bv, NnBuf nb) {
     const int s = blockIdx.y;
     const IcpState* st = bv.st + s;
     if (st->phase != PH_CORR) return;
     __shared__ double s_pose[7];
-    __shared__ uint32_t s_buf[kBufCap * kThreads];
+    __shared__ uint32_t s_buf[kBufCap * kTileThreads];
+#if SO_KNN_TILE
+    __shared__ TileSmem s_tile;
+#endif
     if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
     __syncthreads();
     const uint32_t n = uint32_t(st->n_points);
-    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-#if SO_KNN_COOP
-    if ((i & ~31u) >= n) return;                          // whole warp past the end; partial warps stay together for the collectives
+    const uint32_t i = blockIdx.x * kTileThreads + threadIdx.x;
+    if (blockIdx.x * kTileThreads >= n) return;           // whole CTA past the end; partial CTAs stay together for the tile build
     const bool in_range = i < n;
-#else
-    if (i >= n) return;
-    const bool in_range = true;
-#endif
     const size_t gi = size_t(bv.offset[s]) + (in_range ? i : 0);
     const float4 sp = __ldg(&bv.scan[gi]);
     int pre = SO_MATCH_SKIPPED;
@@ -920,13 +409,26 @@ __global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_scan(MapView m, B
             if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) u_seed = seed_bound(m, qc, nb, gi, qx, qy, qz);
         }
     }
-#if SO_KNN_COOP
-    if (!knn_select_coop<5>(m, qc, searchable, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk) && searchable)
-        knn_select<5>(m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
+#if SO_KNN_TILE
+    TileGrid tg;
+    const bool tiled = build_tile(m, s_tile, searchable, qc, tg);
 #else
-    if (searchable) knn_select<5>(m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
+    const bool tiled = false;
 #endif
-    if (searchable) pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
+    if (searchable) {
+#if SO_KNN_TILE
+        if (tiled) {
+            knn_select<5, SO_R1_OCTANT != 0>(tg, m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) if (tk.id[j] != 0xFFFFFFFFu) tk.pos[j] = tg.pos_of(tk.pos[j]);
+        } else
+#endif
+        {
+            const GlobalGrid gg(m, qc.slot);
+            knn_select<5, SO_R1_OCTANT != 0>(gg, m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
+        }
+        pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
+    }
     if (!in_range) return;
     nb.pre[gi] = (unsigned char)pre;
     nb.d5[gi] = tk.d2[4];
@@ -1207,7 +709,8 @@ __global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_fit(MapView m, Ba
             else {
                 float u_seed = -1.f;
                 if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) u_seed = seed_bound(m, qc, nb, gi, qx, qy, qz);        // see k_knn_scan
-                knn_select<5>(m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
+                const GlobalGrid gg(m, qc.slot);
+                knn_select<5, SO_R1_OCTANT != 0>(gg, m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
                 pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
             }
         }
@@ -1352,7 +855,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_fit(MapView m, BatchView bv, 
         locate(m, qx, qy, qz, qc);
         // "<10 points in the block": the reference indexes with size_t(-1) (LocalMap.h:404-419); treated as NOT_ENOUGH_NEIGHBORS
         if (qc.slot >= 0 && qc.nblock >= 10) {
-            knn_search<10>(m, qc, qx, qy, qz, 0.f, s_buf, tk);
+            knn_search<10>(GlobalGrid(m, qc.slot), m, qc, qx, qy, qz, 0.f, s_buf, tk);
             float P[10][3];
 #pragma unroll
             for (int j = 0; j < 10; ++j) { const float4 c = __ldg(&m.pts[tk.pos[j]]); P[j][0] = c.x; P[j][1] = c.y; P[j][2] = c.z; }
@@ -1535,7 +1038,7 @@ __global__ void k_loop_cond(const IcpState* __restrict__ st, uint32_t n_scans, c
 // ------------------------------------------------------------------------------------------------------------------
 // k_knn: LocalMap::nearestKSearchSurf for a batch of world-frame queries (so_knn / so_knn_device)
 // ------------------------------------------------------------------------------------------------------------------
-// cell key of every query (so_knn* orders large query sets by map cell first, for the same reason scans are ordered)
+// brick-order key of every query (so_knn* orders large query sets first, for the same reason scans are ordered)
 __global__ void __launch_bounds__(kThreads) k_query_keys(MapView m, const float4* __restrict__ q, size_t nq, uint32_t* __restrict__ keys,
                                                          uint32_t* __restrict__ vals) {
     const size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
@@ -1543,31 +1046,51 @@ __global__ void __launch_bounds__(kThreads) k_query_keys(MapView m, const float4
     const float4 p = __ldg(&q[i]);
     QueryCell qc;
     locate(m, p.x, p.y, p.z, qc);
-    keys[i] = qc.slot >= 0 ? uint32_t(qc.slot) * uint32_t(m.nb * m.nb * m.nb) + uint32_t((qc.c[2] * m.nb + qc.c[1]) * m.nb + qc.c[0]) : 0xFFFFFFFFu;
+    keys[i] = qc.slot >= 0 ? scan_order_key(m, qc) : 0xFFFFFFFFu;
     vals[i] = uint32_t(i);
 }
 
-template <int K>
-__global__ void __launch_bounds__(kThreads) k_knn(MapView m, const float4* __restrict__ q, const uint32_t* __restrict__ order, size_t nq,
-                                                  float max_d2, uint32_t* __restrict__ idx, float* __restrict__ d2) {
-    __shared__ uint32_t s_buf[kBufCap * kThreads];
-    const size_t j = size_t(blockIdx.x) * kThreads + threadIdx.x;
-    if (j >= nq) return;
-    const size_t i = order ? size_t(order[j]) : j;        // thread j handles the j-th query in cell order, answers in caller order
+// 128 queries per CTA.  ORDERED: the queries arrive in brick order (`order`), so the CTA first tries the shared candidate tile.
+template <int K, bool ORDERED>
+__global__ void __launch_bounds__(kTileThreads) k_knn(MapView m, const float4* __restrict__ q, const uint32_t* __restrict__ order, size_t nq,
+                                                      float max_d2, uint32_t* __restrict__ idx, float* __restrict__ d2) {
+    __shared__ uint32_t s_buf[kBufCap * kTileThreads];
+#if SO_KNN_TILE
+    __shared__ TileSmem s_tile;
+#endif
+    const size_t j0 = size_t(blockIdx.x) * kTileThreads;
+    if (j0 >= nq) return;
+    const size_t j = j0 + threadIdx.x;
+    const bool in_range = j < nq;
+    const size_t i = in_range ? (order ? size_t(order[j]) : j) : 0;        // thread j handles the j-th query in brick order, answers in caller order
     const float4 p = __ldg(&q[i]);
     TopK<K> tk;
     tk.init(max_d2 > 0.f ? max_d2 : FLT_MAX);
     QueryCell qc;
-    locate(m, p.x, p.y, p.z, qc);
-    if (qc.slot >= 0) knn_search<K>(m, qc, p.x, p.y, p.z, max_d2, s_buf, tk);
+    qc.slot = -1; qc.nblock = 0; qc.c[0] = qc.c[1] = qc.c[2] = 0; qc.f[0] = qc.f[1] = qc.f[2] = 0.f;
+    if (in_range) locate(m, p.x, p.y, p.z, qc);
+    const bool searchable = in_range && qc.slot >= 0;
+#if SO_KNN_TILE
+    TileGrid tg;
+    const bool tiled = ORDERED && build_tile(m, s_tile, searchable, qc, tg);        // every thread takes part in the build
+#endif
+    if (searchable) {
+#if SO_KNN_TILE
+        if (tiled) knn_search<K>(tg, m, qc, p.x, p.y, p.z, max_d2, s_buf, tk);
+        else
+#endif
+            knn_search<K>(GlobalGrid(m, qc.slot), m, qc, p.x, p.y, p.z, max_d2, s_buf, tk);
+    }
+    if (!in_range) return;
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const bool ok = tk.id[j] != 0xFFFFFFFFu;
-        idx[i * K + j] = tk.id[j];
-        d2[i * K + j] = ok ? tk.d2[j] : 0.f;
+    for (int jj = 0; jj < K; ++jj) {
+        const bool ok = tk.id[jj] != 0xFFFFFFFFu;
+        idx[i * K + jj] = tk.id[jj];
+        d2[i * K + jj] = ok ? tk.d2[jj] : 0.f;
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
 // Replay plumbing: one row of 8 doubles per scan -- the optimiser's pose {tx,ty,tz,qx,qy,qz,qw} (so_icp_result.pose_opt)
 // and status + 256 * n_iterations -- into a caller-owned device buffer, so that the NCCL gather of a sharded replay reads device
 // memory on the compute stream instead of waiting for a host round trip.
@@ -1603,7 +1126,7 @@ void launch_match(const MapView& m, const BatchView& bv, const CorrBuf& cb, cons
     (void)part;
     k_knn_fit<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
 #else
-    if (part != 2) k_knn_scan<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, nb);
+    if (part != 2) k_knn_scan<<<dim3(grid_x * (kThreads / kTileThreads), n_scans), kTileThreads, 0, st>>>(m, bv, nb);
     const uint32_t gf = (grid_x * kThreads + kFitPts * kFitThreads - 1) / (kFitPts * kFitThreads);
     if (part != 1) k_fit<<<dim3(gf, n_scans), kFitThreads, 0, st>>>(m, bv, cb, nb);
 #endif
@@ -1639,17 +1162,22 @@ void launch_pack_poses(const IcpState* st, uint32_t n_scans, double* rows, cudaS
 void launch_query_keys(const MapView& m, const float4* q, size_t nq, uint32_t* keys, uint32_t* vals, cudaStream_t st) {
     k_query_keys<<<uint32_t((nq + kThreads - 1) / kThreads), kThreads, 0, st>>>(m, q, nq, keys, vals);
 }
+template <int K>
+static void launch_knn_k(const MapView& m, const float4* q, const uint32_t* order, size_t nq, float max_d2, uint32_t* idx, float* d2, cudaStream_t st) {
+    const uint32_t grid = uint32_t((nq + kTileThreads - 1) / kTileThreads);
+    if (order) k_knn<K, true><<<grid, kTileThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2);
+    else k_knn<K, false><<<grid, kTileThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2);
+}
 int launch_knn(const MapView& m, const float4* q, const uint32_t* order, size_t nq, int k, float max_d2, uint32_t* idx, float* d2, cudaStream_t st) {
-    const uint32_t grid = uint32_t((nq + kThreads - 1) / kThreads);
     switch (k) {
-        case 1: k_knn<1><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
-        case 2: k_knn<2><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
-        case 3: k_knn<3><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
-        case 4: k_knn<4><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
-        case 5: k_knn<5><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
-        case 6: k_knn<6><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
-        case 7: k_knn<7><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
-        case 8: k_knn<8><<<grid, kThreads, 0, st>>>(m, q, order, nq, max_d2, idx, d2); break;
+        case 1: launch_knn_k<1>(m, q, order, nq, max_d2, idx, d2, st); break;
+        case 2: launch_knn_k<2>(m, q, order, nq, max_d2, idx, d2, st); break;
+        case 3: launch_knn_k<3>(m, q, order, nq, max_d2, idx, d2, st); break;
+        case 4: launch_knn_k<4>(m, q, order, nq, max_d2, idx, d2, st); break;
+        case 5: launch_knn_k<5>(m, q, order, nq, max_d2, idx, d2, st); break;
+        case 6: launch_knn_k<6>(m, q, order, nq, max_d2, idx, d2, st); break;
+        case 7: launch_knn_k<7>(m, q, order, nq, max_d2, idx, d2, st); break;
+        case 8: launch_knn_k<8>(m, q, order, nq, max_d2, idx, d2, st); break;
         default: return -1;
     }
     return 0;
