@@ -547,16 +547,26 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
         }
         S[3] = S[1]; S[6] = S[2]; S[7] = S[5];
         const double sxx = S[0], sxy = S[1], sxz = S[2], syy = S[4], syz = S[5], szz = S[8];
-        double ev[3];
+        // SelfAdjointEigenSolver<Matrix3d> (utils::ComputePCA, superodom_utils.h:150): eigenvalues by the closed form, the smallest
+        // eigenvector from its eigenvalue, then the smallest eigenvalue once more as the Rayleigh quotient of that vector (full
+        // double precision where the lambda0 < 1e-6 gate reads it)
+        double ev[3], no[3];
+#if SO_FIT_JACOBI
         jacobi_eig<3, 12, false>(S, nullptr, ev);
+        eigvec3_from_value(sxx, sxy, sxz, syy, syz, szz, ev[0], no);
+#else
+        sym3_eigenvalues(sxx, sxy, sxz, syy, syz, szz, ev);
+        eigvec3_from_value(sxx, sxy, sxz, syy, syz, szz, ev[0], no);
+        ev[0] = no[0] * (sxx * no[0] + sxy * no[1] + sxz * no[2]) + no[1] * (sxy * no[0] + syy * no[1] + syz * no[2]) +
+                no[2] * (sxz * no[0] + syz * no[1] + szz * no[2]);
+        ev[1] = (sxx + syy + szz) - ev[0] - ev[2];
+#endif
         if (ev[0] < 1e-6 || ev[1] / ev[2] < 0.1) status = SO_MATCH_BAD_PCA_STRUCTURE;      // the reference's quotient, literally (:772)
         else {
             // What FeatureObservabilityAnalysis (:574-693) needs from the PCA -- the oriented normal (:553-561) and the
             // planarity -- is reduced to four floats here, ahead of the register-hungry QR.
             float nf[3], cr[3], planar_sq;
             {
-                double no[3];
-                eigvec3_from_value(sxx, sxy, sxz, syy, syz, szz, ev[0], no);
                 if (pf[0] * no[0] + pf[1] * no[1] + pf[2] * no[2] < 0) { no[0] = -no[0]; no[1] = -no[1]; no[2] = -no[2]; }
                 const double l1 = sqrt(ev[2]), l2 = sqrt(ev[1]), l3 = sqrt(ev[0]);
                 const double planar_2 = (l2 - l3) / l1;
@@ -616,13 +626,19 @@ __device__ __forceinline__ void fit_point(const MapView& m, const CorrBuf& cb, c
                         const float dn = __fadd_rn(__fmul_rn(nf[0], ax), __fadd_rn(__fmul_rn(nf[1], ay), __fmul_rn(nf[2], az)));
                         trq[a] = __fmul_rn(planar_sq, fabsf(dn));
                     }
-                    // top-2 rotation labels and top-1 translation label of a stable descending sort (:654-679)
-                    int r0 = 0;
-#pragma unroll
-                    for (int q = 1; q < 6; ++q) if (rotq[q] > rotq[r0]) r0 = q;
-                    int r1 = (r0 == 0) ? 1 : 0;
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) if (q != r0 && q != r1 && rotq[q] > rotq[r1]) r1 = q;
+                    // top-2 rotation labels and top-1 translation label of a stable descending sort (:654-679).  The six rotation
+                    // scores are {+rc_a, -rc_a}, a = 0..2, so the largest is +|rc_a| of the axis with the largest magnitude (first axis
+                    // on ties, as the stable sort keeps index order; index 2a for rc_a >= 0, 2a+1 below) and the runner-up the same
+                    // among the other two axes -- unless every score is zero (or the winner's is NaN), when index order decides: 0, 1.
+                    const float m0 = fabsf(rotq[0]), m1 = fabsf(rotq[2]), m2 = fabsf(rotq[4]);
+                    int a0 = 0; float mb = m0;
+                    if (m1 > mb) { a0 = 1; mb = m1; }
+                    if (m2 > mb) { a0 = 2; mb = m2; }
+                    const int b0 = a0 == 0 ? 1 : 0, b1 = a0 == 2 ? 1 : 2;             // the other two axes, ascending
+                    const float mb0 = a0 == 0 ? m1 : m0, mb1 = a0 == 2 ? m1 : m2;
+                    const int a1 = mb1 > mb0 ? b1 : b0;
+                    const int r0 = 2 * a0 + (rotq[2 * a0] < 0.f ? 1 : 0);
+                    const int r1 = (mb > 0.f) ? 2 * a1 + (rotq[2 * a1] < 0.f ? 1 : 0) : 1;
                     int t0 = 0;
 #pragma unroll
                     for (int q = 1; q < 3; ++q) if (trq[q] > trq[t0]) t0 = q;

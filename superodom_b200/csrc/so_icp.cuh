@@ -56,6 +56,9 @@ constexpr int kEvalPts = SO_EVAL_PTS;     // points per thread in k_evaluate
 constexpr int kFitPts = SO_FIT_PTS;      // points per thread in k_fit
 // k_fit only matches / fits; the first evaluation of the solve is a k_evaluate<PH_CORR> launch, so k_fit carries no
 // normal-equation accumulators (64 registers, 4 CTAs per SM).
+#ifndef SO_FIT_JACOBI
+#define SO_FIT_JACOBI 0          // 1: eigenvalues of the 3x3 scatter by cyclic Jacobi (round-1 kernel; A/B aid)
+#endif
 #ifndef SO_FIT_THREADS
 #define SO_FIT_THREADS 256
 #endif

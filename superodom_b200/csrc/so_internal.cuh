@@ -193,6 +193,28 @@ __device__ inline void jacobi_eig(double* a, double* v, double* w) {
     }
 }
 
+// Eigenvalues (ascending) of the symmetric 3x3 [a00 a01 a02; . a11 a12; . . a22] by the trigonometric solution of its
+// characteristic cubic: with q = tr/3, p^2 = |A - qI|_F^2 / 6 and r = det((A - qI)/p)/2 in [-1, 1], the roots are
+// q + 2p cos(phi + 2k pi/3), phi = acos(r)/3 in [0, pi/3] -- one FP64 acos and one sincos instead of the ~12 Jacobi rotations an
+// iterative solver needs.  Absolute accuracy ~1e-13 |A| (measured against LAPACK on 800 k five-point scatter matrices); the
+// smallest eigenvalue, which a hard gate reads (lambda0 < 1e-6, LidarSlam.cpp:772), is therefore polished by the caller with the
+// Rayleigh quotient of its eigenvector (error ~1e-16 |A|, the class of an iterative solver).
+__device__ __forceinline__ void sym3_eigenvalues(double a00, double a01, double a02, double a11, double a12, double a22, double ev[3]) {
+    const double tr = a00 + a11 + a22, q = tr * (1.0 / 3.0);
+    const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+    const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * (a01 * a01 + a02 * a02 + a12 * a12);
+    if (!(p2 > 0.0)) { ev[0] = ev[1] = ev[2] = q; return; }          // a multiple of the identity (or NaN, which then propagates)
+    const double ip = rsqrt(p2 * (1.0 / 6.0)), p = p2 * (1.0 / 6.0) * ip;
+    const double detb = b00 * (b11 * b22 - a12 * a12) - a01 * (a01 * b22 - a12 * a02) + a02 * (a01 * a12 - b11 * a02);
+    double r = 0.5 * detb * ip * ip * ip;
+    r = fmin(fmax(r, -1.0), 1.0);
+    double sn, cs;
+    sincos(acos(r) * (1.0 / 3.0), &sn, &cs);
+    ev[2] = q + 2.0 * p * cs;
+    ev[0] = q - p * (cs + 1.7320508075688772 * sn);                   // q + 2p cos(phi + 2pi/3)
+    ev[1] = tr - ev[0] - ev[2];
+}
+
 // Unit eigenvector of the symmetric 3x3 S = [xx xy xz; xy yy yz; xz yz zz] for its (simple) eigenvalue lam: S - lam I has rank
 // two, so the cross product of any two independent rows spans its null space; the pair with the longest product is the
 // best conditioned.  Direction error ~ eps * |S| / gap, the same as an iterative solver's; the sign is arbitrary (the caller
