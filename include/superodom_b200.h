@@ -166,6 +166,9 @@ int so_map_add_edge(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes
 /* replaces: LidarSLAM::transformAndAddToMap(cloud, world_cloud, false) (LidarSlam.cpp:60-80): transform the
  * sensor-frame scan by pose (utils::TransformPoint: double math, float store) on the device, then so_map_add_surf. */
 int so_map_add_scan(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset, const double pose[7]);
+/* Same insert for the surf cloud most recently passed to so_register, which is still in device memory: the live loop
+ * Localization() -> transformAndAddToMap() (LidarSlam.cpp:155-171) without uploading the scan a second time. */
+int so_map_add_registered_scan(so_ctx* ctx, const double pose[7]);
 /* ... and transformAndAddToMap(cloud, world_cloud, true) for the edge cloud. */
 int so_map_add_scan_edge(so_ctx* ctx, const void* xyzi, size_t n, size_t stride_bytes, size_t intensity_offset, const double pose[7]);
 /* replaces: LocalMap::get5x5LocalMapFeatureSize (LocalMap.h:291-318) */

@@ -312,7 +312,7 @@ public:
         last_T_w_lidar = T_w_lidar;
         // checkMotionThresholds always accepts (:193) -> transformAndAddToMap (:163-167)
         if (edge_point && edge_point->size()) check(so_map_add_scan_edge(context.h, edge_point->points.data(), edge_point->size(), stride, ioff, r.pose), "so_map_add_scan_edge");
-        if (planner_point->size()) check(so_map_add_scan(context.h, surf, planner_point->size(), stride, ioff, r.pose), "so_map_add_scan");
+        if (planner_point->size()) check(so_map_add_registered_scan(context.h, r.pose), "so_map_add_registered_scan");   // the scan is still on the device
         lasttimeLaserOdometry = timeLaserOdometry;
     }
 

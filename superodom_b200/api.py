@@ -19,7 +19,7 @@ MAX_ICP_ITERS = 32
 EXPORTS = [
     "so_create", "so_destroy", "so_last_error", "so_device_available", "so_set_stream",
     "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
-    "so_map_set_edge_points", "so_map_add_surf", "so_map_add_edge", "so_map_add_scan", "so_map_add_scan_edge", "so_map_counts_5x5", "so_map_download", "so_map_size",
+    "so_map_set_edge_points", "so_map_add_surf", "so_map_add_edge", "so_map_add_scan", "so_map_add_registered_scan", "so_map_add_scan_edge", "so_map_counts_5x5", "so_map_download", "so_map_size",
     "so_scan_prefilter", "so_scan_deskew", "so_scan_extract_uniform", "so_register", "so_register_injected", "so_set_pose_sink", "so_register_batch", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
     "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_build_flags", "so_profile_enable", "so_profile_get",
 ]
@@ -82,6 +82,7 @@ def load_library():
     L.so_map_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
     L.so_map_add_surf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
     L.so_map_add_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    L.so_map_add_registered_scan.argtypes = [C.c_void_p, C.c_void_p]
     L.so_map_add_scan_edge.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
     L.so_map_set_edge_points.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
     L.so_map_add_edge.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
@@ -220,6 +221,11 @@ class Context:
         pose = np.ascontiguousarray(pose7, dtype=np.float64)
         stride = a.shape[1] * 4
         self._chk(self.L.so_map_add_scan(self.h, _p(a), a.shape[0], stride, 12 if a.shape[1] >= 4 else stride, _p(pose)), "so_map_add_scan")
+
+    def map_add_registered_scan(self, pose7):
+        """Insert the surf scan last passed to register() (still on the device) at pose7."""
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        self._chk(self.L.so_map_add_registered_scan(self.h, _p(pose)), "so_map_add_registered_scan")
 
     def map_set_origin(self, t):
         t = np.ascontiguousarray(t, dtype=np.float64)

@@ -192,6 +192,7 @@ static BatchView batch_view(const Ctx* c, const float4* scan, uint32_t first = 0
     bv.tukey_a2 = a * a;
     const double al = double(std::sqrt(3 * c->edge.res));     // TukeyLoss(std::sqrt(3*lineRes_)) (LidarSlam.cpp:263)
     bv.tukey_a2_line = al * al;
+    bv.counters = nullptr;
     return bv;
 }
 
@@ -244,10 +245,12 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
     if (!run_stream) run_stream = c->stream;
     const float4* d_scan = c->d_scan_sorted;
     const MapView mv = map_view(c, c->surf);
-    const BatchView bv = batch_view(c, d_scan, ch.first);
+    BatchView bv = batch_view(c, d_scan, ch.first);
     CorrBuf cb = c->corr;
     if (!with_nn) { cb.nn = nullptr; cb.nn_d2 = nullptr; }
     const uint32_t grid_x = ch.grid_x, n_scans = ch.count, grid_e = ch.grid_e;
+    // one or two scans in flight: launch-latency bound -> optimiser step folded into the evaluation kernels (k_evaluate_lm)
+    if (n_scans <= 2 && !c->profiling && !c->no_fused_lm) bv.counters = c->d_counters + ch.first;
     const MapView me = map_view(c, c->edge);
     EdgeBuf eb = c->ebuf;
     if (!with_nn) { eb.nn = nullptr; eb.selmask = nullptr; }
@@ -340,7 +343,7 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
     slot->used = ++c->graph_clock;
     SO_CUDA_TRY(cudaGraphLaunch(slot->exec, run_stream));
     *was_loop = slot->is_loop;
-    if (!slot->is_loop) c->launches += uint64_t(iters) * (kCorrLaunches + 2 + 2 * lm + (grid_e ? 1 + lm : 0));      // loop form: counted from the iterations executed
+    if (!slot->is_loop) c->launches += uint64_t(iters) * (bv.counters && !grid_e ? kCorrLaunches + 1 + lm : kCorrLaunches + 2 + 2 * lm + (grid_e ? 1 + lm : 0));      // loop form: counted from the iterations executed
     return SO_OK;
 }
 
@@ -512,7 +515,9 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             if (!loop_flags[k]) continue;
             int max_it = 0;
             for (uint32_t s = chunks[k].first; s < chunks[k].first + chunks[k].count; ++s) max_it = std::max(max_it, int(c->h_state[s].n_iterations));
-            c->launches += uint64_t(max_it) * uint64_t(kCorrLaunches + 3 + 2 * o.lm_max_iterations + (chunks[k].grid_e ? 1 + o.lm_max_iterations : 0));
+            const bool fused = chunks[k].count <= 2 && !chunks[k].grid_e && !c->no_fused_lm;
+            c->launches += uint64_t(max_it) * uint64_t(fused ? kCorrLaunches + 2 + o.lm_max_iterations
+                                                             : kCorrLaunches + 3 + 2 * o.lm_max_iterations + (chunks[k].grid_e ? 1 + o.lm_max_iterations : 0));
         }
         for (size_t s = 0; s < n_scans; ++s) {
             if (results[s].status == SO_STATUS_NOT_ENOUGH_FEATURES || n_points[s] == 0) continue;
@@ -560,6 +565,7 @@ so_ctx* so_create(const so_config* cfg_in) {
     if (cfg.line_res > 0) c->edge.res = cfg.line_res;
     if (std::getenv("SO_NO_COND_GRAPH")) c->no_cond_graph = true;
     if (std::getenv("SO_SINGLE_STREAM")) c->single_stream = true;
+    if (std::getenv("SO_NO_FUSED_LM")) c->no_fused_lm = true;
     if (std::getenv("SO_FORCE_KEY64")) c->force_key64 = true;
     if (const char* e = std::getenv("SO_CHUNKS")) c->chunk_override = std::max(0, std::min(16, std::atoi(e)));      // profiling aid: ncu cannot see inside conditional-node bodies
     if (ctx_alloc(c) != SO_OK) { ctx_free(c); return nullptr; }
@@ -651,12 +657,16 @@ static int store_set_points(Ctx* c, MapStore& ms, const void* xyzi, size_t n, si
     ms.n = uint32_t(n);
     return map_rebuild(c, ms);
 }
+// xyzi == nullptr with n != 0: the n points of the scan last uploaded by so_register (c->d_scan)
 static int store_add(Ctx* c, MapStore& ms, const void* xyzi, size_t n, size_t stride, size_t ioff, const double* pose) {
-    if (!c || (!xyzi && n) || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (!c || stride < 12) return fail(SO_ERR_ARG, "bad args");
     if (size_t(ms.n) + n > c->cfg.max_map_points) return fail(SO_ERR_CAPACITY, "map + new points exceed so_config.max_map_points");
     SO_CUDA_TRY(cudaSetDevice(c->device));
     if (n == 0) return SO_OK;
-    int rc = upload_cloud(c, xyzi, n, stride, ioff, ms.d_xyzi + ms.n);
+    int rc = SO_OK;
+    if (ms.dirty) { rc = map_rebuild(c, ms); if (rc) return rc; }           // pending origin / resolution change first: it may compact the cloud
+    if (xyzi) rc = upload_cloud(c, xyzi, n, stride, ioff, ms.d_xyzi + ms.n);
+    else SO_CUDA_TRY(cudaMemcpyAsync(ms.d_xyzi + ms.n, c->d_scan, n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));   // the registered scan, still on the device
     if (rc) return rc;
     if (pose) { rc = map_transform_tail(c, ms, uint32_t(n), pose); if (rc) return rc; }
     timed_launch_begin(c);
@@ -675,20 +685,28 @@ int so_map_set_edge_points(so_ctx* ctx, const void* xyzi, size_t n, size_t strid
 }
 int so_map_add_surf(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!xyzi && n) return fail(SO_ERR_ARG, "bad args");
     return c ? store_add(c, c->surf, xyzi, n, stride, ioff, nullptr) : fail(SO_ERR_ARG, "null ctx");
 }
 int so_map_add_edge(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!xyzi && n) return fail(SO_ERR_ARG, "bad args");
     return c ? store_add(c, c->edge, xyzi, n, stride, ioff, nullptr) : fail(SO_ERR_ARG, "null ctx");
 }
 int so_map_add_scan(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff, const double pose[7]) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (!pose) return fail(SO_ERR_ARG, "bad args");
+    if (!pose || (!xyzi && n)) return fail(SO_ERR_ARG, "bad args");
     return c ? store_add(c, c->surf, xyzi, n, stride, ioff, pose) : fail(SO_ERR_ARG, "null ctx");
+}
+int so_map_add_registered_scan(so_ctx* ctx, const double pose[7]) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !pose) return fail(SO_ERR_ARG, "bad args");
+    if (c->last_scan_n == 0) return SO_OK;
+    return store_add(c, c->surf, nullptr, c->last_scan_n, 16, 12, pose);
 }
 int so_map_add_scan_edge(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, size_t ioff, const double pose[7]) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (!pose) return fail(SO_ERR_ARG, "bad args");
+    if (!pose || (!xyzi && n)) return fail(SO_ERR_ARG, "bad args");
     return c ? store_add(c, c->edge, xyzi, n, stride, ioff, pose) : fail(SO_ERR_ARG, "null ctx");
 }
 
@@ -946,6 +964,7 @@ int so_register(so_ctx* ctx, const void* surf, size_t n_surf, const void* edge, 
     int rc = upload_cloud(c, surf, n_surf, stride, ioff, c->d_scan);
     if (rc) return rc;
     const uint32_t n = uint32_t(n_surf);
+    c->last_scan_n = n;                                                 // so_map_add_registered_scan inserts it without a second upload
     rc = upload_cloud(c, edge, n_edge, stride, ioff, c->d_escan);       // edge branch input (empty upstream: featureExtraction.cpp:429-436)
     if (rc) return rc;
     rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true, nullptr, uint32_t(n_edge));

@@ -53,10 +53,13 @@ struct Ctx {
     int32_t* d_block_of_point = nullptr;           // [max_map] grid block of each raw point or -1
     void* d_cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
+    void* d_insert_info = nullptr;                 // device-side bookkeeping of a map insert (InsertInfo + touched-block flags)
+    void* h_insert_info = nullptr;                 // pinned read-back target
 
     // ---- scans / correspondences / optimiser state -------------------------------------------------------------
     uint32_t max_batch = 1;
     size_t scan_cap = 0;                           // points over the whole batch
+    uint32_t last_scan_n = 0;                      // points of the scan so_register uploaded last (d_scan[0..n), original order)
     float4* d_scan = nullptr;                      // upload target for host scans (original order)
     float4* d_scan_sorted = nullptr;               // cell-ordered copy the kernels read; w = original index
     uint64_t* d_skeys = nullptr; uint64_t* d_skeys_out = nullptr;   // scan sort keys (scan id << 32 | cell)
@@ -102,6 +105,7 @@ struct Ctx {
     uint64_t graph_clock = 0;
     uint64_t map_epoch = 1;
     bool force_key64 = false;                      // SO_FORCE_KEY64: test aid, take the 64-bit scan-order key path even when 32 bits suffice
+    bool no_fused_lm = false;                      // SO_NO_FUSED_LM: A/B aid, always the two-kernel evaluation + optimiser step
     bool single_stream = false;                    // SO_SINGLE_STREAM: tuning aid, all chunks on `stream`
     int chunk_override = 0;                        // SO_CHUNKS: tuning aid, upload/compute chunks per host batch (0 = built-in rule)
     bool no_cond_graph = false;                    // conditional nodes unavailable (or SO_NO_COND_GRAPH): unrolled schedule

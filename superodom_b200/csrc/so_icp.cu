@@ -749,10 +749,8 @@ __global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_fit(MapView m, Ba
 // kEvalPts points per thread (strided by the CTA width, so loads stay coalesced) before the one warp/CTA reduction.
 // ------------------------------------------------------------------------------------------------------------------
 template <int PHASE>
-__global__ void __launch_bounds__(kThreads, 2) k_evaluate(BatchView bv, CorrBuf cb) {
-    const int s = blockIdx.y;
+__device__ __forceinline__ void evaluate_body(const BatchView& bv, const CorrBuf& cb, int s) {
     IcpState* st = bv.st + s;
-    if (st->phase != PHASE) return;
     __shared__ double s_pose[7];
     __shared__ double s_R[9];
     // PH_EVAL: the LM candidate; PH_CORR: the first evaluation of a new solve, at the pose k_fit just matched at
@@ -798,6 +796,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_evaluate(BatchView bv, CorrBuf 
         }
     }
     reduce_to_partials(acc, bv, s);
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(kThreads, 2) k_evaluate(BatchView bv, CorrBuf cb) {
+    const int s = blockIdx.y;
+    if (bv.st[s].phase != PHASE) return;
+    evaluate_body<PHASE>(bv, cb, s);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -999,47 +1004,95 @@ __global__ void __launch_bounds__(kThreads) k_edge_evaluate(BatchView bv, EdgeBu
 // k_lm_step: one CTA per scan.  Sums the per-CTA partials of the preceding k_fit (AFTER == PH_CORR) or k_evaluate
 // (AFTER == PH_EVAL) in a fixed order, then one thread advances the optimiser / ICP state machine.
 // ------------------------------------------------------------------------------------------------------------------
+// Called by >= 128 threads of one CTA (all of them: it synchronises the CTA); the first 128 do the work.
 template <int AFTER>
-__global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partials, uint32_t edge_partial_offset) {
-    const int s = blockIdx.x;
+__device__ __forceinline__ void lm_step_body(const BatchView& bv, int s, uint32_t n_partials, uint32_t edge_partial_offset) {
     IcpState* st = bv.st + s;
-    if (st->phase != AFTER) return;
     __shared__ double s_red[4][kAcc];
     __shared__ double s_sum[kAcc];
     const int comp = threadIdx.x & 31, sub = threadIdx.x >> 5;
     double v = 0.0;
-    if (comp < kAcc) {
+    if (comp < kAcc && sub < 4) {
         const double* base = bv.partials + size_t(s) * bv.partial_stride * kAcc;
         const uint32_t np = (uint32_t(st->n_points) + kThreads * kEvalPts - 1) / (kThreads * kEvalPts);
-        for (uint32_t b = sub; b < np && b < n_partials; b += 4) v += base[size_t(b) * kAcc + comp];
+        // __ldcg: straight from L2 -- in k_evaluate_lm the rows were written by other CTAs of the same launch
+        for (uint32_t b = sub; b < np && b < n_partials; b += 4) v += __ldcg(&base[size_t(b) * kAcc + comp]);
         const uint32_t ne = (uint32_t(st->n_edge) + kThreads - 1) / kThreads;          // edge branch partials (0 when no edge cloud)
-        for (uint32_t b = sub; b < ne; b += 4) v += base[size_t(edge_partial_offset + b) * kAcc + comp];
+        for (uint32_t b = sub; b < ne; b += 4) v += __ldcg(&base[size_t(edge_partial_offset + b) * kAcc + comp]);
         s_red[sub][comp] = v;
+    }
+    // The serial step works on a SHARED-MEMORY copy of the scan's state: through the global pointer every field access of the
+    // one working thread was a dependent L2 round trip (the step took 5-12 us, the covariance 40 us); the copy in and out is two
+    // coalesced passes of the CTA.
+    __shared__ IcpState s_st;
+    static_assert(sizeof(IcpState) % 8 == 0, "copied as 8-byte words");
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_st);
+        for (uint32_t k = threadIdx.x; k < sizeof(IcpState) / 8; k += blockDim.x) dst[k] = src[k];
     }
     __syncthreads();
     if (threadIdx.x < kAcc) s_sum[threadIdx.x] = (s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + (s_red[2][threadIdx.x] + s_red[3][threadIdx.x]);
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    if (AFTER == PH_CORR) {
-        // histograms of this ICP iteration (ResetDistanceParameters + processPlannerFeatures, :847-852,:336-341)
-        for (int k = 0; k < 9; ++k) st->hist_obs[k] = bv.hist[s * kHistStride + k];
-        for (int k = 0; k < 7; ++k) st->hist_rej[k] = bv.hist[s * kHistStride + 9 + k];
-        for (int k = 0; k < 7; ++k) st->hist_rej_line[k] = bv.hist[s * kHistStride + 16 + k];
-        st->n_ok_edge = st->hist_rej_line[0];
-        const int n_ok = st->hist_rej[0] + st->n_ok_edge;       // features_corres.size(): edges + planes
-        for (int k = 0; k < kHistStride; ++k) bv.hist[s * kHistStride + k] = 0;
-        if (st->max_icp_iters < 0) {          // stage mode (so_correspond): stop here
-            for (int k = 0; k < 21; ++k) st->H[k] = s_sum[k];
-            for (int k = 0; k < 6; ++k) st->g[k] = s_sum[21 + k];
-            st->cost = s_sum[27]; st->n_ok = n_ok; st->phase = PH_DONE;
-        } else lm_begin_solve(*st, s_sum, n_ok);
-    } else {
-        if (st->max_icp_iters < 0) {          // stage mode (so_evaluate): report and stop
-            for (int k = 0; k < 21; ++k) st->H[k] = s_sum[k];
-            for (int k = 0; k < 6; ++k) st->g[k] = s_sum[21 + k];
-            st->cost = s_sum[27]; st->phase = PH_DONE;
-        } else lm_after_eval(*st, s_sum);
+    if (threadIdx.x == 0) {
+        IcpState& S = s_st;
+        if (AFTER == PH_CORR) {
+            // histograms of this ICP iteration (ResetDistanceParameters + processPlannerFeatures, :847-852,:336-341)
+            for (int k = 0; k < 9; ++k) S.hist_obs[k] = bv.hist[s * kHistStride + k];
+            for (int k = 0; k < 7; ++k) S.hist_rej[k] = bv.hist[s * kHistStride + 9 + k];
+            for (int k = 0; k < 7; ++k) S.hist_rej_line[k] = bv.hist[s * kHistStride + 16 + k];
+            S.n_ok_edge = S.hist_rej_line[0];
+            const int n_ok = S.hist_rej[0] + S.n_ok_edge;       // features_corres.size(): edges + planes
+            for (int k = 0; k < kHistStride; ++k) bv.hist[s * kHistStride + k] = 0;
+            if (S.max_icp_iters < 0) {          // stage mode (so_correspond): stop here
+                for (int k = 0; k < 21; ++k) S.H[k] = s_sum[k];
+                for (int k = 0; k < 6; ++k) S.g[k] = s_sum[21 + k];
+                S.cost = s_sum[27]; S.n_ok = n_ok; S.phase = PH_DONE;
+            } else lm_begin_solve(S, s_sum, n_ok);
+        } else {
+            if (S.max_icp_iters < 0) {          // stage mode (so_evaluate): report and stop
+                for (int k = 0; k < 21; ++k) S.H[k] = s_sum[k];
+                for (int k = 0; k < 6; ++k) S.g[k] = s_sum[21 + k];
+                S.cost = s_sum[27]; S.phase = PH_DONE;
+            } else lm_after_eval(S, s_sum);
+        }
     }
+    __syncthreads();
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_st);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(st);
+        for (uint32_t k = threadIdx.x; k < sizeof(IcpState) / 8; k += blockDim.x) dst[k] = src[k];
+    }
+}
+
+template <int AFTER>
+__global__ void __launch_bounds__(128) k_lm_step(BatchView bv, uint32_t n_partials, uint32_t edge_partial_offset) {
+    const int s = blockIdx.x;
+    if (bv.st[s].phase != AFTER) return;
+    lm_step_body<AFTER>(bv, s, n_partials, edge_partial_offset);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_evaluate_lm: k_evaluate with the optimiser step of k_lm_step folded in -- the CTA that finishes LAST (ticket counter, after a
+// device-scope fence) sums the partial rows in their fixed order and advances the state machine.  Same arithmetic in the same
+// order as the two-kernel form, one launch less per cost evaluation: used when a registration is launch-latency bound (one or
+// two scans in flight, no edge cloud), where the ~190 registers of the serial step cost no occupancy that matters.
+// ------------------------------------------------------------------------------------------------------------------
+template <int PHASE>
+__global__ void __launch_bounds__(kThreads, 1) k_evaluate_lm(BatchView bv, CorrBuf cb, uint32_t* __restrict__ counters) {
+    const int s = blockIdx.y;
+    if (bv.st[s].phase != PHASE) return;
+    evaluate_body<PHASE>(bv, cb, s);
+    __shared__ uint32_t s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&counters[s], 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    if (threadIdx.x == 0) counters[s] = 0;               // ready for the next launch
+    __threadfence();
+    lm_step_body<PHASE>(bv, s, gridDim.x, bv.edge_partial_offset);
 }
 
 // Loop condition of the CUDA-graph WHILE node that wraps one ICP iteration: keep iterating while any scan of the
@@ -1154,6 +1207,7 @@ void launch_inject(const MapView& m, const float4* by_id, uint32_t n_map, const 
 void launch_first_eval(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const MapView* medge, const EdgeBuf* eb,
                        uint32_t grid_e) {
     const uint32_t gp = (grid_x + kEvalPts - 1) / kEvalPts;
+    if (bv.counters && gp && !grid_e) { k_evaluate_lm<PH_CORR><<<dim3(gp, n_scans), kThreads, 0, st>>>(bv, cb, bv.counters); return; }
     if (gp) k_evaluate<PH_CORR><<<dim3(gp, n_scans), kThreads, 0, st>>>(bv, cb);
     if (grid_e) k_edge_fit<<<dim3(grid_e, n_scans), kThreads, 0, st>>>(*medge, bv, *eb, bv.edge_partial_offset);
     k_lm_step<PH_CORR><<<n_scans, 128, 0, st>>>(bv, gp, bv.edge_partial_offset);
@@ -1165,6 +1219,7 @@ void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb,
 }
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const EdgeBuf* eb, uint32_t grid_e) {
     const uint32_t gx = (grid_x + kEvalPts - 1) / kEvalPts;
+    if (bv.counters && gx && !grid_e) { k_evaluate_lm<PH_EVAL><<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb, bv.counters); return; }
     if (gx) k_evaluate<PH_EVAL><<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb);
     if (grid_e) k_edge_evaluate<<<dim3(grid_e, n_scans), kThreads, 0, st>>>(bv, *eb, bv.edge_partial_offset);
     k_lm_step<PH_EVAL><<<n_scans, 128, 0, st>>>(bv, gx, bv.edge_partial_offset);

@@ -35,6 +35,7 @@ struct BatchView {
     uint32_t edge_partial_offset;   // first partial slot of the edge kernels
     double tukey_a2_line;     // a^2 for edges, a = double(sqrtf(3*lineRes_))  (LidarSlam.cpp:263)
     double tukey_a2;          // a^2, a = double(sqrtf(3*planeRes_))  (LidarSlam.cpp:271)
+    uint32_t* counters;       // [n_scans] CTA tickets of k_evaluate_lm; nullptr = two-kernel form (k_evaluate + k_lm_step)
 };
 
 // neighbour hand-off between k_knn_scan and k_fit

@@ -126,6 +126,8 @@ int map_alloc(Ctx* c) {
     cub::DeviceScan::ExclusiveSum(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, int(std::min<size_t>(max_cells, size_t(1) << 30)));
     c->cub_tmp_bytes = std::max(a, std::max(b, d)) + 256;
     SO_CUDA_TRY(cudaMalloc(&c->d_cub_tmp, c->cub_tmp_bytes));
+    SO_CUDA_TRY(cudaMalloc(&c->d_insert_info, 8192));
+    SO_CUDA_TRY(cudaMallocHost(&c->h_insert_info, 256));
     return SO_OK;
 }
 
@@ -134,6 +136,8 @@ void map_free(Ctx* c) {
         cudaFree(ms->d_xyzi); cudaFree(ms->d_sorted); cudaFree(ms->d_block_slot); cudaFree(ms->d_block_count); cudaFree(ms->d_cell_start);
     }
     cudaFree(c->d_keys); cudaFree(c->d_keys_out); cudaFree(c->d_vals); cudaFree(c->d_vals_out); cudaFree(c->d_block_of_point); cudaFree(c->d_cub_tmp);
+    cudaFree(c->d_insert_info);
+    if (c->h_insert_info) cudaFreeHost(c->h_insert_info);
 }
 
 MapView map_view(const Ctx* c, const MapStore& ms) {
@@ -335,27 +339,27 @@ __global__ void k_voxel_centroid(const float4* __restrict__ raw, const uint64_t*
     out[begin + rank[i - begin]] = make_float4(__fdiv_rn(ax, nf), __fdiv_rn(ay, nf), __fdiv_rn(az, nf), __fdiv_rn(aw, nf));
 }
 
-__global__ void k_transform_points(float4* __restrict__ pts, uint32_t n, const double* __restrict__ pose) {
+struct Pose7 { double v[7]; };
+__global__ void k_transform_points(float4* __restrict__ pts, uint32_t n, Pose7 pose) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pts[i];
     const double v[3] = {double(p.x), double(p.y), double(p.z)};
     double o[3];
-    qrot(pose + 3, v, o);                              // utils::TransformPoint (superodom_utils.h:116-127): double math, float store
-    p.x = float(o[0] + pose[0]); p.y = float(o[1] + pose[1]); p.z = float(o[2] + pose[2]);
+    qrot(pose.v + 3, v, o);                            // utils::TransformPoint (superodom_utils.h:116-127): double math, float store
+    p.x = float(o[0] + pose.v[0]); p.y = float(o[1] + pose.v[1]); p.z = float(o[2] + pose.v[2]);
     pts[i] = p;
 }
 
 int map_transform_tail(Ctx* c, MapStore& ms, uint32_t n_new, const double pose[7]) {
-    double* d_pose = reinterpret_cast<double*>(c->d_keys_out);               // scratch
-    SO_CUDA_TRY(cudaMemcpyAsync(d_pose, pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_transform_points<<<(n_new + 255) / 256, 256, 0, c->stream>>>(ms.d_xyzi + ms.n, n_new, d_pose);
+    Pose7 P;
+    for (int k = 0; k < 7; ++k) P.v[k] = pose[k];                            // by value in the launch: no staging copy, no wait
+    k_transform_points<<<(n_new + 255) / 256, 256, 0, c->stream>>>(ms.d_xyzi + ms.n, n_new, P);
     c->launches++;
-    SO_CUDA_TRY(cudaStreamSynchronize(c->stream));                           // `pose` is caller memory
     return SO_OK;
 }
 
-int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new) {
+static int map_add_points_sync(Ctx* c, MapStore& ms, uint32_t n_new) {
     cudaStream_t st = c->stream;
     const uint32_t total = ms.n + n_new;
     if (n_new == 0) return SO_OK;
@@ -402,6 +406,253 @@ int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new) {
     c->launches += 12;
     SO_CUDA_TRY(cudaGetLastError());
     return map_rebuild(c, ms);
+}
+
+// Device-side bookkeeping of an insert: everything the host used to read back between launches.
+struct InsertInfo {
+    uint32_t begin, end;        // sorted insert keys: [0, begin) untouched blocks, [begin, end) touched blocks, [end, total) dropped
+    uint32_t n_out;             // points of the new cloud
+    uint32_t n_slots;           // non-empty blocks of the new cloud
+    uint32_t error;             // 1: cell table capacity exceeded
+    uint32_t pad[3];
+};
+
+__global__ void k_mark_touched_new(const float4* __restrict__ pts, uint32_t n_new, int3 origin, uint8_t* __restrict__ touched) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_new) return;
+    const float4 p = pts[i];
+    const int gx = block_coord(double(p.x) + kHalfBlock, origin.x), gy = block_coord(double(p.y) + kHalfBlock, origin.y),
+              gz = block_coord(double(p.z) + kHalfBlock, origin.z);
+    if (gx >= 0 && gx < kW && gy >= 0 && gy < kH && gz >= 0 && gz < kD && isfinite(p.x) && isfinite(p.y) && isfinite(p.z))
+        touched[gx + kW * gy + kW * kH * gz] = 1;
+}
+
+// insert key of every point (old cloud followed by the new points), the block recomputed from the coordinates
+__global__ void k_insert_keys(const float4* __restrict__ raw, uint32_t n, float inv_leaf, int3 origin, const uint8_t* __restrict__ touched,
+                              uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = raw[i];
+    const int gx = block_coord(double(p.x) + kHalfBlock, origin.x), gy = block_coord(double(p.y) + kHalfBlock, origin.y),
+              gz = block_coord(double(p.z) + kHalfBlock, origin.z);
+    uint64_t key = ~uint64_t(0);                                          // off-grid / non-finite: dropped
+    if (gx >= 0 && gx < kW && gy >= 0 && gy < kH && gz >= 0 && gz < kD && isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const int b = gx + kW * gy + kW * kH * gz;
+        if (!touched[b]) key = 0;                                         // untouched block: kept in place (stable sort)
+        else {
+            const double il = double(inv_leaf);
+            const int64_t bx = int64_t(floor((double(gx - origin.x) * kBlock - kHalfBlock) * il)) - 2;
+            const int64_t by = int64_t(floor((double(gy - origin.y) * kBlock - kHalfBlock) * il)) - 2;
+            const int64_t bz = int64_t(floor((double(gz - origin.z) * kBlock - kHalfBlock) * il)) - 2;
+            auto local = [](int64_t v) { return uint64_t(v < 0 ? 0 : (v > 65535 ? 65535 : v)); };
+            const uint64_t vi = local(int64_t(floorf(__fmul_rn(p.x, inv_leaf))) - bx);      // pcl::VoxelGrid: floor(coord * inverse_leaf_size) in float
+            const uint64_t vj = local(int64_t(floorf(__fmul_rn(p.y, inv_leaf))) - by);
+            const uint64_t vk = local(int64_t(floorf(__fmul_rn(p.z, inv_leaf))) - bz);
+            key = (uint64_t(1) << 63) | (uint64_t(b) << 48) | (vk << 32) | (vj << 16) | vi;
+        }
+    }
+    keys[i] = key;
+    vals[i] = i;
+}
+
+// boundaries of the three key classes in the sorted keys, by binary search (one thread)
+__global__ void k_insert_bounds(const uint64_t* __restrict__ keys, uint32_t total, InsertInfo* __restrict__ info) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t lo = 0, hi = total;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[mid] >> 63) hi = mid; else lo = mid + 1; }      // first key with the touched flag
+    info->begin = lo;
+    hi = total;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[mid] == ~uint64_t(0)) hi = mid; else lo = mid + 1; }
+    info->end = lo;
+    info->error = 0;
+}
+
+__global__ void k_voxel_heads_dev(const uint64_t* __restrict__ keys, uint32_t total, const InsertInfo* __restrict__ info, uint32_t* __restrict__ head) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    head[i] = (i >= info->begin && i < info->end && (i == info->begin || keys[i] != keys[i - 1])) ? 1u : 0u;
+}
+
+// rank[] = exclusive scan of head[] over [0, total): rank[i] counts the voxels before sorted position i
+__global__ void k_voxel_centroid_dev(const float4* __restrict__ raw, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                     const uint32_t* __restrict__ head, const uint32_t* __restrict__ rank, uint32_t total, InsertInfo* __restrict__ info,
+                                     float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t begin = info->begin, end = info->end;
+    if (i == total - 1) info->n_out = begin + rank[i] + head[i];      // voxels in total
+    if (i < begin) { out[i] = raw[vals[i]]; return; }                   // untouched blocks: copied through in order
+    if (i >= end || !head[i]) return;
+    const uint64_t key = keys[i];
+    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+    uint32_t cnt = 0;
+    for (uint32_t j = i; j < end && keys[j] == key; ++j) {             // pcl::CentroidPoint: float accumulators, cloud order
+        const float4 p = raw[vals[j]];
+        ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z); aw = __fadd_rn(aw, p.w);
+        ++cnt;
+    }
+    const float nf = float(cnt);
+    out[begin + rank[i]] = make_float4(__fdiv_rn(ax, nf), __fdiv_rn(ay, nf), __fdiv_rn(az, nf), __fdiv_rn(aw, nf));
+}
+
+// ---- index of a cloud whose size lives on the device (every point on-grid): block counts, slots, cell keys, cell table ------------
+__global__ void k_block_count_dev(const float4* __restrict__ raw, const InsertInfo* __restrict__ info, int3 origin, int32_t* __restrict__ block_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= info->n_out) return;
+    const float4 p = raw[i];
+    const int gx = block_coord(double(p.x) + kHalfBlock, origin.x), gy = block_coord(double(p.y) + kHalfBlock, origin.y),
+              gz = block_coord(double(p.z) + kHalfBlock, origin.z);
+    if (gx >= 0 && gx < kW && gy >= 0 && gy < kH && gz >= 0 && gz < kD) atomicAdd(&block_count[gx + kW * gy + kW * kH * gz], 1);
+}
+
+// slots of the non-empty blocks in block order (what the host loop of map_rebuild does), one CTA
+__global__ void __launch_bounds__(1024) k_assign_slots(const int32_t* __restrict__ block_count, int32_t* __restrict__ block_slot, InsertInfo* __restrict__ info,
+                                                       uint32_t slot_cap) {
+    __shared__ uint32_t s_part[1024];
+    const int per = (kNumBlocks + 1023) / 1024;
+    const int b0 = threadIdx.x * per;
+    uint32_t mine = 0;
+    for (int k = 0; k < per; ++k) { const int b = b0 + k; if (b < kNumBlocks && block_count[b] > 0) ++mine; }
+    s_part[threadIdx.x] = mine;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                                // Hillis-Steele inclusive scan
+        const uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t slot = s_part[threadIdx.x] - mine;
+    for (int k = 0; k < per; ++k) {
+        const int b = b0 + k;
+        if (b < kNumBlocks) block_slot[b] = block_count[b] > 0 ? int32_t(slot++) : -1;
+    }
+    if (threadIdx.x == 1023) { info->n_slots = s_part[1023]; if (s_part[1023] > slot_cap) info->error = 1; }
+}
+
+__global__ void k_cell_clear_dev(uint32_t* __restrict__ cell_start, const InsertInfo* __restrict__ info, uint32_t cells_per_slot, size_t cap) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t cells = size_t(info->n_slots) * cells_per_slot + 1;
+    if (i < cap && (i < cells || info->error)) cell_start[i] = 0;
+}
+
+// cell key + histogram; positions >= n_out get the largest key so that they sort behind every real point
+__global__ void k_keys_dev(const float4* __restrict__ raw, uint32_t total, const InsertInfo* __restrict__ info, int3 origin, const int32_t* __restrict__ block_slot,
+                           int nb, double inv_cs, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ cell_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    vals[i] = i;
+    if (i >= info->n_out || info->error) { keys[i] = 0xFFFFFFFFu; return; }
+    const float4 p = raw[i];
+    const float q[3] = {p.x, p.y, p.z};
+    const int o[3] = {origin.x, origin.y, origin.z};
+    int g[3], c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double v = double(q[a]) + kHalfBlock;
+        int b = int(v / kBlock);
+        if (v < 0) b--;
+        g[a] = b + o[a];
+        int cc = int((v - kBlock * double(b)) * inv_cs);
+        c[a] = cc < 0 ? 0 : (cc > nb - 1 ? nb - 1 : cc);
+    }
+    const uint32_t slot = uint32_t(block_slot[g[0] + kW * g[1] + kW * kH * g[2]]);
+    const uint32_t key = slot * uint32_t(nb) * uint32_t(nb) * uint32_t(nb) + uint32_t((c[2] * nb + c[1]) * nb + c[0]);
+    keys[i] = key;
+    atomicAdd(&cell_count[key], 1u);
+}
+
+__global__ void k_gather_dev(const float4* __restrict__ raw, const uint32_t* __restrict__ vals, uint32_t total, const InsertInfo* __restrict__ info,
+                             float4* __restrict__ sorted) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total || i >= info->n_out) return;
+    const uint32_t id = vals[i];
+    const float4 p = raw[id];
+    sorted[i] = make_float4(p.x, p.y, p.z, __uint_as_float(id));
+}
+
+// LocalMap::addSurfPointCloud without a host round trip between its steps: mark touched blocks, one stable sort by
+// (touched, block, voxel), voxel heads + scan + centroids into the other cloud buffer, then the search index of the new cloud
+// (block counts and slots on the device, cell keys + histogram, sort, gather, scan).  The host reads the sizes, block tables and
+// the error flag back ONCE, at the end.  The two cloud buffers swap roles (no device-to-device copy of the map).
+int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new) {
+    cudaStream_t st = c->stream;
+    if (n_new == 0) return SO_OK;
+    const uint32_t total = ms.n + n_new;                                // the caller rebuilt a dirty store BEFORE appending the new points
+    const int3 origin = make_int3(c->origin[0], c->origin[1], c->origin[2]);
+    const uint32_t grid = (total + 255) / 256;
+    const int nb = map_cells_per_block(ms.res);
+    const uint32_t cells_per_slot = uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
+    // cell table capacity for the slots this insert can need: the current ones plus every block a new point may open
+    {
+        const size_t want_slots = size_t(ms.n_slots) + 8;
+        const size_t want = want_slots * cells_per_slot + 1;
+        if (want > ms.cell_cap || ms.nb != nb) {
+            size_t slots = std::max<size_t>(want_slots, size_t(ms.n_slots) * 2);
+            while (slots > want_slots && slots * cells_per_slot + 1 >= (size_t(1) << 31)) --slots;
+            if (slots * cells_per_slot + 1 >= (size_t(1) << 31)) return map_add_points_sync(c, ms, n_new);
+            SO_CUDA_TRY(cudaStreamSynchronize(st));
+            cudaFree(ms.d_cell_start);
+            ms.d_cell_start = nullptr;
+            ms.cell_cap = slots * cells_per_slot + 1;
+            SO_CUDA_TRY(cudaMalloc(&ms.d_cell_start, ms.cell_cap * sizeof(uint32_t)));
+            size_t need = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, need, ms.d_cell_start, ms.d_cell_start, int(ms.cell_cap));
+            if (need > c->cub_tmp_bytes) {
+                cudaFree(c->d_cub_tmp);
+                c->cub_tmp_bytes = need + 256;
+                SO_CUDA_TRY(cudaMalloc(&c->d_cub_tmp, c->cub_tmp_bytes));
+            }
+        }
+    }
+    const uint32_t slot_cap = uint32_t((ms.cell_cap - 1) / cells_per_slot);
+    ms.nb = nb;
+    InsertInfo* d_info = reinterpret_cast<InsertInfo*>(c->d_insert_info);
+    uint8_t* d_touched = reinterpret_cast<uint8_t*>(c->d_insert_info) + 64;         // 4851 bytes behind the info struct
+    SO_CUDA_TRY(cudaMemsetAsync(d_touched, 0, kNumBlocks, st));
+    k_mark_touched_new<<<(n_new + 255) / 256, 256, 0, st>>>(ms.d_xyzi + ms.n, n_new, origin, d_touched);
+    const float inv_leaf = 1.0f / ms.res;                               // Eigen::Array4f::Ones() / leaf_size_
+    k_insert_keys<<<grid, 256, 0, st>>>(ms.d_xyzi, total, inv_leaf, origin, d_touched, c->d_keys, c->d_vals);
+    size_t tmp = c->cub_tmp_bytes;
+    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, tmp, c->d_keys, c->d_keys_out, c->d_vals, c->d_vals_out, int(total), 0, 64, st));
+    k_insert_bounds<<<1, 32, 0, st>>>(c->d_keys_out, total, d_info);
+    uint32_t* d_head = reinterpret_cast<uint32_t*>(c->d_keys);          // keys_in is free after the sort: [heads total][ranks total]
+    uint32_t* d_rank = d_head + total;
+    k_voxel_heads_dev<<<grid, 256, 0, st>>>(c->d_keys_out, total, d_info, d_head);
+    tmp = c->cub_tmp_bytes;
+    SO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, tmp, d_head, d_rank, int(total), st));
+    k_voxel_centroid_dev<<<grid, 256, 0, st>>>(ms.d_xyzi, c->d_keys_out, c->d_vals_out, d_head, d_rank, total, d_info, ms.d_sorted);
+    std::swap(ms.d_xyzi, ms.d_sorted);                                  // d_xyzi: the new cloud in id order; d_sorted: free for the new index
+    // ---- search index of the new cloud
+    SO_CUDA_TRY(cudaMemsetAsync(ms.d_block_count, 0, kNumBlocks * sizeof(int32_t), st));
+    k_block_count_dev<<<grid, 256, 0, st>>>(ms.d_xyzi, d_info, origin, ms.d_block_count);
+    k_assign_slots<<<1, 1024, 0, st>>>(ms.d_block_count, ms.d_block_slot, d_info, slot_cap);
+    k_cell_clear_dev<<<uint32_t((ms.cell_cap + 255) / 256), 256, 0, st>>>(ms.d_cell_start, d_info, cells_per_slot, ms.cell_cap);
+    uint32_t* keys32 = reinterpret_cast<uint32_t*>(c->d_keys);          // heads / ranks are dead now
+    uint32_t* keys32_out = reinterpret_cast<uint32_t*>(c->d_keys_out);
+    k_keys_dev<<<grid, 256, 0, st>>>(ms.d_xyzi, total, d_info, origin, ms.d_block_slot, nb, double(nb) / kBlock, keys32, c->d_vals, ms.d_cell_start);
+    int bits = 1;
+    while (bits < 32 && (uint64_t(1) << bits) < uint64_t(ms.cell_cap)) ++bits;
+    tmp = c->cub_tmp_bytes;
+    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, tmp, keys32, keys32_out, c->d_vals, c->d_vals_out, int(total), 0, 32, st));
+    (void)bits;
+    k_gather_dev<<<grid, 256, 0, st>>>(ms.d_xyzi, c->d_vals_out, total, d_info, ms.d_sorted);
+    tmp = c->cub_tmp_bytes;
+    SO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, tmp, ms.d_cell_start, ms.d_cell_start, int(ms.cell_cap), st));
+    // ---- the one read-back
+    InsertInfo* h_info = reinterpret_cast<InsertInfo*>(c->h_insert_info);
+    SO_CUDA_TRY(cudaMemcpyAsync(h_info, d_info, sizeof(InsertInfo), cudaMemcpyDeviceToHost, st));
+    SO_CUDA_TRY(cudaMemcpyAsync(ms.h_block_count.data(), ms.d_block_count, kNumBlocks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SO_CUDA_TRY(cudaMemcpyAsync(ms.h_block_slot.data(), ms.d_block_slot, kNumBlocks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    c->launches += 26;
+    SO_CUDA_TRY(cudaGetLastError());
+    SO_CUDA_TRY(cudaStreamSynchronize(st));
+    ms.n = h_info->n_out;
+    ms.n_slots = int(h_info->n_slots);
+    if (h_info->error) {                                                // more new blocks than the table was sized for: index again, synchronously
+        ms.dirty = true;
+        return map_rebuild(c, ms);
+    }
+    return SO_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -60,7 +60,7 @@ def run(api, synth, device: int = 0, n_scans: int = 60, cpu: bool = False, senso
         t1 = time.perf_counter()
         r = ctx.register(s, priors[i], iters, cap)
         t2 = time.perf_counter()
-        ctx.map_add_scan(s, np.array(r.pose))
+        ctx.map_add_registered_scan(np.array(r.pose))
         t3 = time.perf_counter()
         if i >= 5:                                      # first scans warm caches / graphs
             t_pre.append((t1 - t0) * 1e3); t_reg.append((t2 - t1) * 1e3); t_ins.append((t3 - t2) * 1e3)
