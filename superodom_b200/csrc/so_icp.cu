@@ -68,10 +68,10 @@ __device__ __forceinline__ void reduce_to_partials(double acc[kAcc], const Batch
 __device__ __noinline__ double grad_max_norm(const double x[7], const double g[6]) {
     // ||x - Plus(x, -g)||_inf  (TrustRegionMinimizer::EvaluateGradientAndJacobian)
     double neg[6], xp[7];
-    for (int j = 0; j < 6; ++j) neg[j] = -g[j];
+    _Pragma("unroll") for (int j = 0; j < 6; ++j) neg[j] = -g[j];
     pose_plus(x, neg, xp);
     double m = 0.0;
-    for (int i = 0; i < 7; ++i) m = fmax(m, fabs(x[i] - xp[i]));
+    _Pragma("unroll") for (int i = 0; i < 7; ++i) m = fmax(m, fabs(x[i] - xp[i]));
     return m;
 }
 
@@ -79,23 +79,23 @@ __device__ __noinline__ void covariance_and_errors(IcpState& st) {
     // ceres::Covariance{apply_loss_function, DENSE_SVD, null_space_rank=-1} in tangent space (LidarSlam.cpp:854-871):
     // pseudo-inverse of J^T J dropping singular directions with s_i/s_max < sqrt(1e-14) (covariance_impl.cc).
     double A[36], V[36], w[6];
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) A[i * 6 + j] = st.H[i <= j ? tri(i, j) : tri(j, i)];
+    _Pragma("unroll") for (int i = 0; i < 6; ++i) _Pragma("unroll") for (int j = 0; j < 6; ++j) A[i * 6 + j] = st.H[i <= j ? tri(i, j) : tri(j, i)];
     jacobi_eig<6, 30>(A, V, w);
     const double lmax = w[5];
     double inv[6];
     bool cut = false;
-    for (int k = 5; k >= 0; --k) {          // descending singular values = descending eigenvalues
+    _Pragma("unroll") for (int k = 5; k >= 0; --k) {          // descending singular values = descending eigenvalues
         const double ratio = (w[k] > 0.0 && lmax > 0.0) ? sqrt(w[k] / lmax) : 0.0;
         if (cut || ratio < 1e-7) { cut = true; inv[k] = 0.0; } else inv[k] = 1.0 / w[k];
     }
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
+    _Pragma("unroll") for (int i = 0; i < 6; ++i) _Pragma("unroll") for (int j = 0; j < 6; ++j) {
         double t = 0.0;
-        for (int k = 0; k < 6; ++k) t += V[i * 6 + k] * inv[k] * V[j * 6 + k];
+        _Pragma("unroll") for (int k = 0; k < 6; ++k) t += V[i * 6 + k] * inv[k] * V[j * 6 + k];
         st.cov[i * 6 + j] = t;
     }
     // EstimateRegistrationError (LidarSlam.cpp:873-884): 3x3 eigen of the position / orientation blocks
     double P[9], O[9], E[9], e[3];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { P[i * 3 + j] = st.cov[i * 6 + j]; O[i * 3 + j] = st.cov[(i + 3) * 6 + (j + 3)]; }
+    _Pragma("unroll") for (int i = 0; i < 3; ++i) _Pragma("unroll") for (int j = 0; j < 3; ++j) { P[i * 3 + j] = st.cov[i * 6 + j]; O[i * 3 + j] = st.cov[(i + 3) * 6 + (j + 3)]; }
     jacobi_eig<3, 20>(P, E, e);
     st.pos_err = sqrt(e[2]); st.pos_dir[0] = E[2]; st.pos_dir[1] = E[5]; st.pos_dir[2] = E[8];
     st.pos_inv_cond = sqrt(e[0]) / sqrt(e[2]);
@@ -138,23 +138,23 @@ __device__ __noinline__ void lm_continue(IcpState& st, bool step_successful) {
         step_successful = false;
         // LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system
         double Hs[36], gs[6];
-        for (int i = 0; i < 6; ++i) {
+        _Pragma("unroll") for (int i = 0; i < 6; ++i) {
             gs[i] = st.g[i] * st.scale[i];
-            for (int j = 0; j < 6; ++j) Hs[i * 6 + j] = st.H[i <= j ? tri(i, j) : tri(j, i)] * st.scale[i] * st.scale[j];
+            _Pragma("unroll") for (int j = 0; j < 6; ++j) Hs[i * 6 + j] = st.H[i <= j ? tri(i, j) : tri(j, i)] * st.scale[i] * st.scale[j];
         }
         if (!st.reuse_diagonal)
-            for (int j = 0; j < 6; ++j) st.diag[j] = fmin(fmax(Hs[j * 6 + j], 1e-6), 1e32);
+            _Pragma("unroll") for (int j = 0; j < 6; ++j) st.diag[j] = fmin(fmax(Hs[j * 6 + j], 1e-6), 1e32);
         st.reuse_diagonal = 1;
         double M[36], y[6];
-        for (int i = 0; i < 36; ++i) M[i] = Hs[i];
-        for (int j = 0; j < 6; ++j) M[j * 6 + j] += st.diag[j] / st.radius;       // lm_diagonal^2 = diagonal / radius
+        _Pragma("unroll") for (int i = 0; i < 36; ++i) M[i] = Hs[i];
+        _Pragma("unroll") for (int j = 0; j < 6; ++j) M[j * 6 + j] += st.diag[j] / st.radius;       // lm_diagonal^2 = diagonal / radius
         bool valid = chol6_solve(M, gs, y);
         double step[6], mcc = 0.0;
         if (valid) {
-            for (int j = 0; j < 6; ++j) { step[j] = -y[j]; valid = valid && isfinite(step[j]); }
+            _Pragma("unroll") for (int j = 0; j < 6; ++j) { step[j] = -y[j]; valid = valid && isfinite(step[j]); }
             // model_cost_change = -(J step)'(f + J step / 2) = -step'gs - step'Hs step / 2
             double sg = 0.0, sHs = 0.0;
-            for (int i = 0; i < 6; ++i) { sg += step[i] * gs[i]; double t = 0.0; for (int j = 0; j < 6; ++j) t += Hs[i * 6 + j] * step[j]; sHs += step[i] * t; }
+            _Pragma("unroll") for (int i = 0; i < 6; ++i) { sg += step[i] * gs[i]; double t = 0.0; _Pragma("unroll") for (int j = 0; j < 6; ++j) t += Hs[i * 6 + j] * step[j]; sHs += step[i] * t; }
             mcc = -sg - 0.5 * sHs;
         }
         if (!valid || !(mcc > 0.0)) {           // HandleInvalidStep
@@ -165,7 +165,7 @@ __device__ __noinline__ void lm_continue(IcpState& st, bool step_successful) {
         st.consecutive_invalid = 0;
         st.model_cost_change = mcc;
         double delta[6];
-        for (int j = 0; j < 6; ++j) delta[j] = step[j] * st.scale[j];
+        _Pragma("unroll") for (int j = 0; j < 6; ++j) delta[j] = step[j] * st.scale[j];
         pose_plus(st.x, delta, st.cand);
         st.phase = PH_EVAL;
         return;
@@ -182,47 +182,47 @@ __device__ __noinline__ void add_pose_prior(const IcpState& st, const double x[7
     qmul(qm, x + 3, e);
     double r[6] = {x[0] - st.x0[0], x[1] - st.x0[1], x[2] - st.x0[2], 2.0 * e[0], 2.0 * e[1], 2.0 * e[2]};
     double J[36];
-    for (int i = 0; i < 36; ++i) J[i] = 0.0;
+    _Pragma("unroll") for (int i = 0; i < 36; ++i) J[i] = 0.0;
     J[0] = J[7] = J[14] = 1.0;
     J[3 * 6 + 3] = e[3];  J[3 * 6 + 4] = -e[2]; J[3 * 6 + 5] = e[1];
     J[4 * 6 + 3] = e[2];  J[4 * 6 + 4] = e[3];  J[4 * 6 + 5] = -e[0];
     J[5 * 6 + 3] = -e[1]; J[5 * 6 + 4] = e[0];  J[5 * 6 + 5] = e[3];
-    for (int i = 0; i < 6; ++i) { r[i] *= st.prior_sqrt_info[i]; for (int j = 0; j < 6; ++j) J[i * 6 + j] *= st.prior_sqrt_info[i]; }
-    for (int i = 0; i < 6; ++i) {
-        for (int j = i; j < 6; ++j) { double t = 0.0; for (int k = 0; k < 6; ++k) t += J[k * 6 + i] * J[k * 6 + j]; a[tri(i, j)] += t; }
-        double t = 0.0; for (int k = 0; k < 6; ++k) t += J[k * 6 + i] * r[k];
+    _Pragma("unroll") for (int i = 0; i < 6; ++i) { r[i] *= st.prior_sqrt_info[i]; _Pragma("unroll") for (int j = 0; j < 6; ++j) J[i * 6 + j] *= st.prior_sqrt_info[i]; }
+    _Pragma("unroll") for (int i = 0; i < 6; ++i) {
+        _Pragma("unroll") for (int j = i; j < 6; ++j) { double t = 0.0; _Pragma("unroll") for (int k = 0; k < 6; ++k) t += J[k * 6 + i] * J[k * 6 + j]; a[tri(i, j)] += t; }
+        double t = 0.0; _Pragma("unroll") for (int k = 0; k < 6; ++k) t += J[k * 6 + i] * r[k];
         a[21 + i] += t;
     }
-    double sq = 0.0; for (int k = 0; k < 6; ++k) sq += r[k] * r[k];
+    double sq = 0.0; _Pragma("unroll") for (int k = 0; k < 6; ++k) sq += r[k] * r[k];
     a[27] += 0.5 * sq;
 }
 
 // IterationZero of a new solve, fed by k_fit's reduction.
 __device__ __noinline__ void lm_begin_solve(IcpState& st, const double* acc_in, int n_ok) {
     double acc[kAcc];
-    for (int k = 0; k < kAcc; ++k) acc[k] = acc_in[k];
+    _Pragma("unroll") for (int k = 0; k < kAcc; ++k) acc[k] = acc_in[k];
     if (st.use_prior) {
         // information diagonal (LidarSlam.cpp:287-294); sqrt by Eigen's unblocked LLT: the first non-positive pivot and
         // everything after it stay un-square-rooted
         const double vcf = double(st.prior_vcf);
         double info[6];
         const int m1 = max(50, int(n_ok * 0.1)), m2 = max(10, int(n_ok * 0.01));
-        for (int a = 0; a < 3; ++a) info[a] = (1 - double(st.prior_unc[a])) * m1 * vcf;
+        _Pragma("unroll") for (int a = 0; a < 3; ++a) info[a] = (1 - double(st.prior_unc[a])) * m1 * vcf;
         info[3] = info[4] = m2 * vcf;
         info[5] = max(5, int(n_ok * 0.001)) * 0;
         bool failed = false;
-        for (int k = 0; k < 6; ++k) { if (!failed && info[k] <= 0.0) failed = true; st.prior_sqrt_info[k] = failed ? info[k] : sqrt(info[k]); }
+        _Pragma("unroll") for (int k = 0; k < 6; ++k) { if (!failed && info[k] <= 0.0) failed = true; st.prior_sqrt_info[k] = failed ? info[k] : sqrt(info[k]); }
         add_pose_prior(st, st.x, acc);
     }
-    for (int k = 0; k < 21; ++k) st.H[k] = acc[k];
-    for (int k = 0; k < 6; ++k) st.g[k] = acc[21 + k];
+    _Pragma("unroll") for (int k = 0; k < 21; ++k) st.H[k] = acc[k];
+    _Pragma("unroll") for (int k = 0; k < 6; ++k) st.g[k] = acc[21 + k];
     st.cost = acc[27];
     st.n_ok = n_ok;
-    for (int i = 0; i < 7; ++i) st.x_iter_start[i] = st.x[i];
+    _Pragma("unroll") for (int i = 0; i < 7; ++i) st.x_iter_start[i] = st.x[i];
     st.lm_iter = 0; st.num_successful = 0; st.num_unsuccessful = 0; st.consecutive_invalid = 0; st.termination = 0;
     if (n_ok == 0 && !st.use_prior) { st.termination = 6; end_solve(st); return; }
-    for (int j = 0; j < 6; ++j) st.scale[j] = 1.0 / (1.0 + sqrt(st.H[tri(j, j)]));      // jacobi_scaling at iteration 0
-    double xn = 0.0; for (int i = 0; i < 7; ++i) xn += st.x[i] * st.x[i];
+    _Pragma("unroll") for (int j = 0; j < 6; ++j) st.scale[j] = 1.0 / (1.0 + sqrt(st.H[tri(j, j)]));      // jacobi_scaling at iteration 0
+    double xn = 0.0; _Pragma("unroll") for (int i = 0; i < 7; ++i) xn += st.x[i] * st.x[i];
     st.x_norm = sqrt(xn);
     st.gmax = grad_max_norm(st.x, st.g);
     st.radius = 1e4; st.decrease_factor = 2.0; st.reuse_diagonal = 0;
@@ -232,11 +232,11 @@ __device__ __noinline__ void lm_begin_solve(IcpState& st, const double* acc_in, 
 // After the cost (and H, g) at the candidate are known.
 __device__ __noinline__ void lm_after_eval(IcpState& st, const double* acc_in) {
     double acc[kAcc];
-    for (int k = 0; k < kAcc; ++k) acc[k] = acc_in[k];
+    _Pragma("unroll") for (int k = 0; k < kAcc; ++k) acc[k] = acc_in[k];
     if (st.use_prior) add_pose_prior(st, st.cand, acc);
     const double cand_cost = acc[27];
     // ParameterToleranceReached
-    double sn = 0.0; for (int i = 0; i < 7; ++i) { const double d = st.x[i] - st.cand[i]; sn += d * d; }
+    double sn = 0.0; _Pragma("unroll") for (int i = 0; i < 7; ++i) { const double d = st.x[i] - st.cand[i]; sn += d * d; }
     sn = sqrt(sn);
     if (sn <= 1e-8 * (st.x_norm + 1e-8)) { st.termination = 2; end_solve(st); return; }
     // FunctionToleranceReached
@@ -244,11 +244,11 @@ __device__ __noinline__ void lm_after_eval(IcpState& st, const double* acc_in) {
     if (fabs(cost_change) <= 1e-6 * st.cost) { st.termination = 3; end_solve(st); return; }
     const double rd = cost_change / st.model_cost_change;
     if (rd > 1e-3) {        // HandleSuccessfulStep
-        for (int i = 0; i < 7; ++i) st.x[i] = st.cand[i];
-        double xn = 0.0; for (int i = 0; i < 7; ++i) xn += st.x[i] * st.x[i];
+        _Pragma("unroll") for (int i = 0; i < 7; ++i) st.x[i] = st.cand[i];
+        double xn = 0.0; _Pragma("unroll") for (int i = 0; i < 7; ++i) xn += st.x[i] * st.x[i];
         st.x_norm = sqrt(xn);
-        for (int k = 0; k < 21; ++k) st.H[k] = acc[k];
-        for (int k = 0; k < 6; ++k) st.g[k] = acc[21 + k];
+        _Pragma("unroll") for (int k = 0; k < 21; ++k) st.H[k] = acc[k];
+        _Pragma("unroll") for (int k = 0; k < 6; ++k) st.g[k] = acc[21 + k];
         st.cost = cand_cost;
         st.gmax = grad_max_norm(st.x, st.g);
         const double t = 2.0 * rd - 1.0;

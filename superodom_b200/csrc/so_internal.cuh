@@ -347,22 +347,45 @@ __host__ __device__ inline void colpiv_qr_solve_5x3(double A[5][3], double b[5],
 }
 
 // Solve the SPD 6x6 system M y = r by Cholesky (M full row-major, destroyed).  Returns false on a non-positive pivot.
+// Fully unrolled: every index is a compile-time constant, so on the device the 36 + 18 values live in registers instead of a
+// dynamically indexed local-memory array (the optimiser step is ONE thread's dependent FP64 chain; local-memory round trips
+// were most of its 10-20 us).
 __host__ __device__ inline bool chol6_solve(double* M, const double* r, double* y) {
+    bool ok = true;
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
         double s = M[j * 6 + j];
+#pragma unroll
         for (int k = 0; k < j; ++k) s -= M[j * 6 + k] * M[j * 6 + k];
-        if (!(s > 0.0)) return false;
+        if (!(s > 0.0)) ok = false;
         const double l = sqrt(s);
         M[j * 6 + j] = l;
+        const double il = 1.0 / l;
+#pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double t = M[i * 6 + j];
+#pragma unroll
             for (int k = 0; k < j; ++k) t -= M[i * 6 + k] * M[j * 6 + k];
             M[i * 6 + j] = t / l;
         }
+        (void)il;
     }
+    if (!ok) return false;
     double z[6];
-    for (int i = 0; i < 6; ++i) { double t = r[i]; for (int k = 0; k < i; ++k) t -= M[i * 6 + k] * z[k]; z[i] = t / M[i * 6 + i]; }
-    for (int i = 5; i >= 0; --i) { double t = z[i]; for (int k = i + 1; k < 6; ++k) t -= M[k * 6 + i] * y[k]; y[i] = t / M[i * 6 + i]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double t = r[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) t -= M[i * 6 + k] * z[k];
+        z[i] = t / M[i * 6 + i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double t = z[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) t -= M[k * 6 + i] * y[k];
+        y[i] = t / M[i * 6 + i];
+    }
     return true;
 }
 

@@ -427,15 +427,18 @@ __global__ void k_mark_touched_new(const float4* __restrict__ pts, uint32_t n_ne
         touched[gx + kW * gy + kW * kH * gz] = 1;
 }
 
-// insert key of every point (old cloud followed by the new points), the block recomputed from the coordinates
+// insert key of every point (old cloud followed by the new points), the block recomputed from the coordinates:
+// [class: 0 untouched block, 1 touched, 2 dropped][block 13 bits][vk][vj][vi], vb bits per block-local voxel index (50 m / leaf + 5
+// values: 8 bits at leaf 0.2) -- 39 key bits = 5 radix passes instead of the 8 of a full 64-bit key
 __global__ void k_insert_keys(const float4* __restrict__ raw, uint32_t n, float inv_leaf, int3 origin, const uint8_t* __restrict__ touched,
-                              uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                              int vb, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = raw[i];
     const int gx = block_coord(double(p.x) + kHalfBlock, origin.x), gy = block_coord(double(p.y) + kHalfBlock, origin.y),
               gz = block_coord(double(p.z) + kHalfBlock, origin.z);
-    uint64_t key = ~uint64_t(0);                                          // off-grid / non-finite: dropped
+    const int cls_shift = 13 + 3 * vb;
+    uint64_t key = uint64_t(2) << cls_shift;                              // off-grid / non-finite: dropped
     if (gx >= 0 && gx < kW && gy >= 0 && gy < kH && gz >= 0 && gz < kD && isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
         const int b = gx + kW * gy + kW * kH * gz;
         if (!touched[b]) key = 0;                                         // untouched block: kept in place (stable sort)
@@ -444,11 +447,12 @@ __global__ void k_insert_keys(const float4* __restrict__ raw, uint32_t n, float 
             const int64_t bx = int64_t(floor((double(gx - origin.x) * kBlock - kHalfBlock) * il)) - 2;
             const int64_t by = int64_t(floor((double(gy - origin.y) * kBlock - kHalfBlock) * il)) - 2;
             const int64_t bz = int64_t(floor((double(gz - origin.z) * kBlock - kHalfBlock) * il)) - 2;
-            auto local = [](int64_t v) { return uint64_t(v < 0 ? 0 : (v > 65535 ? 65535 : v)); };
+            const int64_t vmax = (int64_t(1) << vb) - 1;
+            auto local = [vmax](int64_t v) { return uint64_t(v < 0 ? 0 : (v > vmax ? vmax : v)); };
             const uint64_t vi = local(int64_t(floorf(__fmul_rn(p.x, inv_leaf))) - bx);      // pcl::VoxelGrid: floor(coord * inverse_leaf_size) in float
             const uint64_t vj = local(int64_t(floorf(__fmul_rn(p.y, inv_leaf))) - by);
             const uint64_t vk = local(int64_t(floorf(__fmul_rn(p.z, inv_leaf))) - bz);
-            key = (uint64_t(1) << 63) | (uint64_t(b) << 48) | (vk << 32) | (vj << 16) | vi;
+            key = (uint64_t(1) << cls_shift) | (uint64_t(b) << (3 * vb)) | (vk << (2 * vb)) | (vj << vb) | vi;
         }
     }
     keys[i] = key;
@@ -456,13 +460,13 @@ __global__ void k_insert_keys(const float4* __restrict__ raw, uint32_t n, float 
 }
 
 // boundaries of the three key classes in the sorted keys, by binary search (one thread)
-__global__ void k_insert_bounds(const uint64_t* __restrict__ keys, uint32_t total, InsertInfo* __restrict__ info) {
+__global__ void k_insert_bounds(const uint64_t* __restrict__ keys, uint32_t total, int cls_shift, InsertInfo* __restrict__ info) {
     if (threadIdx.x || blockIdx.x) return;
     uint32_t lo = 0, hi = total;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[mid] >> 63) hi = mid; else lo = mid + 1; }      // first key with the touched flag
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((keys[mid] >> cls_shift) >= 1) hi = mid; else lo = mid + 1; }      // first touched key
     info->begin = lo;
     hi = total;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[mid] == ~uint64_t(0)) hi = mid; else lo = mid + 1; }
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((keys[mid] >> cls_shift) >= 2) hi = mid; else lo = mid + 1; }      // first dropped key
     info->end = lo;
     info->error = 0;
 }
@@ -496,13 +500,19 @@ __global__ void k_voxel_centroid_dev(const float4* __restrict__ raw, const uint6
 }
 
 // ---- index of a cloud whose size lives on the device (every point on-grid): block counts, slots, cell keys, cell table ------------
+// One atomic per (warp, block) instead of one per point: the cloud is ordered block by block, so a warp almost always holds a
+// single block (1.1 M same-address atomics took 660 us; aggregated they take a few).
 __global__ void k_block_count_dev(const float4* __restrict__ raw, const InsertInfo* __restrict__ info, int3 origin, int32_t* __restrict__ block_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= info->n_out) return;
-    const float4 p = raw[i];
-    const int gx = block_coord(double(p.x) + kHalfBlock, origin.x), gy = block_coord(double(p.y) + kHalfBlock, origin.y),
-              gz = block_coord(double(p.z) + kHalfBlock, origin.z);
-    if (gx >= 0 && gx < kW && gy >= 0 && gy < kH && gz >= 0 && gz < kD) atomicAdd(&block_count[gx + kW * gy + kW * kH * gz], 1);
+    int lin = -1;
+    if (i < info->n_out) {
+        const float4 p = raw[i];
+        const int gx = block_coord(double(p.x) + kHalfBlock, origin.x), gy = block_coord(double(p.y) + kHalfBlock, origin.y),
+                  gz = block_coord(double(p.z) + kHalfBlock, origin.z);
+        if (gx >= 0 && gx < kW && gy >= 0 && gy < kH && gz >= 0 && gz < kD) lin = gx + kW * gy + kW * kH * gz;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, lin);
+    if (lin >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&block_count[lin], __popc(peers));
 }
 
 // slots of the non-empty blocks in block order (what the host loop of map_rebuild does), one CTA
@@ -527,12 +537,6 @@ __global__ void __launch_bounds__(1024) k_assign_slots(const int32_t* __restrict
         if (b < kNumBlocks) block_slot[b] = block_count[b] > 0 ? int32_t(slot++) : -1;
     }
     if (threadIdx.x == 1023) { info->n_slots = s_part[1023]; if (s_part[1023] > slot_cap) info->error = 1; }
-}
-
-__global__ void k_cell_clear_dev(uint32_t* __restrict__ cell_start, const InsertInfo* __restrict__ info, uint32_t cells_per_slot, size_t cap) {
-    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const size_t cells = size_t(info->n_slots) * cells_per_slot + 1;
-    if (i < cap && (i < cells || info->error)) cell_start[i] = 0;
 }
 
 // cell key + histogram; positions >= n_out get the largest key so that they sort behind every real point
@@ -584,10 +588,10 @@ int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new) {
     const uint32_t cells_per_slot = uint32_t(nb) * uint32_t(nb) * uint32_t(nb);
     // cell table capacity for the slots this insert can need: the current ones plus every block a new point may open
     {
-        const size_t want_slots = size_t(ms.n_slots) + 8;
+        const size_t want_slots = size_t(ms.n_slots) + 4;
         const size_t want = want_slots * cells_per_slot + 1;
         if (want > ms.cell_cap || ms.nb != nb) {
-            size_t slots = std::max<size_t>(want_slots, size_t(ms.n_slots) * 2);
+            size_t slots = want_slots + 4;
             while (slots > want_slots && slots * cells_per_slot + 1 >= (size_t(1) << 31)) --slots;
             if (slots * cells_per_slot + 1 >= (size_t(1) << 31)) return map_add_points_sync(c, ms, n_new);
             SO_CUDA_TRY(cudaStreamSynchronize(st));
@@ -604,17 +608,22 @@ int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new) {
             }
         }
     }
-    const uint32_t slot_cap = uint32_t((ms.cell_cap - 1) / cells_per_slot);
+    // this insert indexes at most the current slots + 4 new ones (more: error flag -> synchronous rebuild); table work is sized for that
+    const uint32_t slot_cap = uint32_t(std::min<size_t>((ms.cell_cap - 1) / cells_per_slot, size_t(ms.n_slots) + 4));
+    const size_t cells_used = size_t(slot_cap) * cells_per_slot + 1;
     ms.nb = nb;
     InsertInfo* d_info = reinterpret_cast<InsertInfo*>(c->d_insert_info);
     uint8_t* d_touched = reinterpret_cast<uint8_t*>(c->d_insert_info) + 64;         // 4851 bytes behind the info struct
     SO_CUDA_TRY(cudaMemsetAsync(d_touched, 0, kNumBlocks, st));
     k_mark_touched_new<<<(n_new + 255) / 256, 256, 0, st>>>(ms.d_xyzi + ms.n, n_new, origin, d_touched);
     const float inv_leaf = 1.0f / ms.res;                               // Eigen::Array4f::Ones() / leaf_size_
-    k_insert_keys<<<grid, 256, 0, st>>>(ms.d_xyzi, total, inv_leaf, origin, d_touched, c->d_keys, c->d_vals);
+    int vb = 1;                                                         // bits of a block-local voxel index: 50 m / leaf + 5 values
+    while (vb < 16 && double(1 << vb) < kBlock * double(inv_leaf) + 5.0) ++vb;
+    const int cls_shift = 13 + 3 * vb;
+    k_insert_keys<<<grid, 256, 0, st>>>(ms.d_xyzi, total, inv_leaf, origin, d_touched, vb, c->d_keys, c->d_vals);
     size_t tmp = c->cub_tmp_bytes;
-    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, tmp, c->d_keys, c->d_keys_out, c->d_vals, c->d_vals_out, int(total), 0, 64, st));
-    k_insert_bounds<<<1, 32, 0, st>>>(c->d_keys_out, total, d_info);
+    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, tmp, c->d_keys, c->d_keys_out, c->d_vals, c->d_vals_out, int(total), 0, cls_shift + 2, st));
+    k_insert_bounds<<<1, 32, 0, st>>>(c->d_keys_out, total, cls_shift, d_info);
     uint32_t* d_head = reinterpret_cast<uint32_t*>(c->d_keys);          // keys_in is free after the sort: [heads total][ranks total]
     uint32_t* d_rank = d_head + total;
     k_voxel_heads_dev<<<grid, 256, 0, st>>>(c->d_keys_out, total, d_info, d_head);
@@ -626,7 +635,7 @@ int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new) {
     SO_CUDA_TRY(cudaMemsetAsync(ms.d_block_count, 0, kNumBlocks * sizeof(int32_t), st));
     k_block_count_dev<<<grid, 256, 0, st>>>(ms.d_xyzi, d_info, origin, ms.d_block_count);
     k_assign_slots<<<1, 1024, 0, st>>>(ms.d_block_count, ms.d_block_slot, d_info, slot_cap);
-    k_cell_clear_dev<<<uint32_t((ms.cell_cap + 255) / 256), 256, 0, st>>>(ms.d_cell_start, d_info, cells_per_slot, ms.cell_cap);
+    SO_CUDA_TRY(cudaMemsetAsync(ms.d_cell_start, 0, cells_used * sizeof(uint32_t), st));
     uint32_t* keys32 = reinterpret_cast<uint32_t*>(c->d_keys);          // heads / ranks are dead now
     uint32_t* keys32_out = reinterpret_cast<uint32_t*>(c->d_keys_out);
     k_keys_dev<<<grid, 256, 0, st>>>(ms.d_xyzi, total, d_info, origin, ms.d_block_slot, nb, double(nb) / kBlock, keys32, c->d_vals, ms.d_cell_start);
@@ -637,7 +646,7 @@ int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new) {
     (void)bits;
     k_gather_dev<<<grid, 256, 0, st>>>(ms.d_xyzi, c->d_vals_out, total, d_info, ms.d_sorted);
     tmp = c->cub_tmp_bytes;
-    SO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, tmp, ms.d_cell_start, ms.d_cell_start, int(ms.cell_cap), st));
+    SO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, tmp, ms.d_cell_start, ms.d_cell_start, int(cells_used), st));
     // ---- the one read-back
     InsertInfo* h_info = reinterpret_cast<InsertInfo*>(c->h_insert_info);
     SO_CUDA_TRY(cudaMemcpyAsync(h_info, d_info, sizeof(InsertInfo), cudaMemcpyDeviceToHost, st));
