@@ -435,6 +435,8 @@ __device__ __forceinline__ void knn_select(const Grid& g, const MapView& m, cons
             for (int j = K - 1; j > 0; --j) a[j] = fminf(a[j], fmaxf(a[j - 1], d));
             a[0] = fminf(a[0], d);
         };
+        // (measured and not kept for dense query sets: the bound from the query's own cell alone -- cfg5 2.83 ms against 2.72 ms; a
+        // tight bound saves more in round 2 than a short round 1 saves)
         if (OCT) walk_octant(g, m.nb, m.cs, qc, net);
         else walk_cube(g, m.nb, m.cs, qc, bound, 1, net);
         U = a[K - 1] * 1.000004f;
