@@ -211,25 +211,38 @@ static void timed_launch_end(Ctx* c, int cls) {
 }
 
 // A contiguous run of scans of the batch that is uploaded, ordered and registered together.
-struct Chunk { uint32_t first, count, pt_first, pt_count, grid_x, grid_e = 0; };
+// grid_in: CTAs covering the longest scan as uploaded (scan ordering); grid_x: CTAs covering the longest scan once it is reduced to the
+// points shouldProcessPoint keeps (the ICP kernels); small: every scan's survivors fit k_prepare_small
+struct Chunk { uint32_t first, count, pt_first, pt_count, grid_x, grid_e = 0, grid_in = 0; bool small = false; };
 
-// Once per registration: order every scan by map cell at its prior pose (k_scan_keys -> radix sort -> k_scan_gather).
-static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch, cudaStream_t st) {
+// Once per registration: order every scan by map cell at its prior pose (k_scan_keys -> radix sort -> k_scan_gather, or the one-CTA
+// k_prepare_small for small registrations).  compact: drop the points the decimation skips here, once, instead of in every kernel.
+static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch, cudaStream_t st, bool compact) {
     const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, d_scan_in, ch.first);
     timed_launch_begin(c);
-    // key layout: [scan inside the chunk | cell]; 32-bit keys whenever both fit
-    const uint64_t n_cells = scan_key_space(c->surf.n_slots, mv.nb);       // brick-order keys (so_knn.cuh)
+    // key layout: [scan inside the chunk | dropped (compact only) | cell]; 32-bit keys whenever everything fits
+    const uint64_t n_cells = scan_key_space(c->surf.n_slots, mv.nb);       // cell / brick-order keys (so_knn.cuh)
     int cell_bits = 1, scan_bits = 0;
     while (cell_bits < 32 && (uint64_t(1) << cell_bits) <= n_cells) ++cell_bits;       // cells 0..n_cells-1 < mask = 2^cell_bits - 1
+    if (compact && ch.small && !c->no_small_prepare) {
+        launch_prepare_small(mv, bv, c->d_scan_sorted, ch.count, cell_bits, st);
+        c->launches++;
+        timed_launch_end(c, 3);
+        SO_CUDA_TRY(cudaGetLastError());
+        return SO_OK;
+    }
     while ((1u << scan_bits) < ch.count) ++scan_bits;
-    const bool key32 = !c->force_key64 && cell_bits < 32 && cell_bits + scan_bits <= 32;
+    const int extra = compact ? 1 : 0;
+    const bool key32 = !c->force_key64 && cell_bits < 32 && cell_bits + extra + scan_bits <= 32;
     if (!key32) cell_bits = 32;
-    launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, ch.grid_x, ch.count, cell_bits, key32, st);
-    int rc = scan_sort(c, ch.pt_first, ch.pt_count, int(ch.count), cell_bits, key32, st);
+    const uint32_t grid_in = ch.grid_in ? ch.grid_in : ch.grid_x;
+    launch_scan_keys(mv, bv, c->d_skeys, c->d_svals, grid_in, ch.count, cell_bits, key32, compact, st);
+    int rc = scan_sort(c, ch.pt_first, ch.pt_count, int(ch.count), cell_bits + extra, key32, st);
     if (rc) return rc;
     launch_scan_gather(d_scan_in, c->d_svals_out, c->d_skeys_out, ch.pt_first, c->d_offset + ch.first, ch.pt_count,
-                       c->d_scan_sorted + ch.pt_first, cell_bits, key32, st);
+                       c->d_scan_sorted + ch.pt_first, cell_bits + extra, key32, st);
+    if (compact) { launch_scan_finish(bv, c->d_skeys_out, ch.pt_first, ch.pt_first, cell_bits, key32, ch.count, st); c->launches++; }
     c->launches++;
     timed_launch_end(c, 3);
     SO_CUDA_TRY(cudaGetLastError());
@@ -353,6 +366,7 @@ static void init_state(IcpState& s, const double pose[7], uint32_t n, const so_i
     std::memcpy(s.x, pose, 7 * sizeof(double));
     std::memcpy(s.cand, pose, 7 * sizeof(double));
     s.n_points = int32_t(n);
+    s.n_input = int32_t(n);
     s.n_edge = int32_t(n_edge);
     s.max_icp_iters = o.max_icp_iters;
     s.lm_max_iterations = o.lm_max_iterations;
@@ -457,8 +471,15 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             const uint32_t f = bounds[k], e = bounds[k + 1];
             if (e == f) continue;
             Chunk ch{f, e - f, c->h_offset[f], (e < n_scans ? c->h_offset[e] : off) - c->h_offset[f], 0};
-            uint32_t mx = 0;
-            for (uint32_t s = f; s < e; ++s) if (c->h_state[s].phase == PH_CORR) mx = std::max(mx, n_points[s]);
+            uint32_t mx = 0, mx_in = 0;
+            for (uint32_t s = f; s < e; ++s) if (c->h_state[s].phase == PH_CORR) {
+                mx_in = std::max(mx_in, n_points[s]);
+                // shouldProcessPoint keeps at most max_surface_features + 1 points of a decimated scan (one per wrap of i * rate)
+                const uint32_t kept = c->h_state[s].sampling_rate < 0.0 ? n_points[s] : std::min<uint32_t>(n_points[s], uint32_t(o.max_surface_features) + 1);
+                mx = std::max(mx, kept);
+            }
+            ch.grid_in = (mx_in + kThreads - 1) / kThreads;
+            ch.small = mx <= kPrepareSmallCap && mx_in > 0;
             ch.grid_x = (mx + kThreads - 1) / kThreads;
             // rounded up to a bucket of 16 CTAs so that scans of slightly different sizes (live SLAM: every scan differs) share one
             // captured graph; the kernels guard i < n_points and k_lm_step sums only the partial rows n_points implies
@@ -490,7 +511,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             cudaStream_t st = (two_streams && (k & 1)) ? c->aux_stream : c->stream;
             if (host_src) SO_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copy[k], 0));
             if (ch.grid_x == 0) continue;
-            int rc = prepare_scans(c, d_scan, ch, st);
+            int rc = prepare_scans(c, d_scan, ch, st, true);
             bool was_loop = false;
             if (!rc) rc = run_schedule(c, ch, o.max_icp_iters, o.lm_max_iterations, false, &was_loop, st, d_inject, inject_iters);
             if (rc) {                                       // leave no work behind on the side streams before reporting the error
@@ -566,6 +587,7 @@ so_ctx* so_create(const so_config* cfg_in) {
     if (std::getenv("SO_NO_COND_GRAPH")) c->no_cond_graph = true;
     if (std::getenv("SO_SINGLE_STREAM")) c->single_stream = true;
     if (std::getenv("SO_NO_FUSED_LM")) c->no_fused_lm = true;
+    if (std::getenv("SO_NO_SMALL_PREPARE")) c->no_small_prepare = true;
     if (std::getenv("SO_FORCE_KEY64")) c->force_key64 = true;
     if (const char* e = std::getenv("SO_CHUNKS")) c->chunk_override = std::max(0, std::min(16, std::atoi(e)));      // profiling aid: ncu cannot see inside conditional-node bodies
     if (ctx_alloc(c) != SO_OK) { ctx_free(c); return nullptr; }
@@ -1058,7 +1080,7 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     const uint32_t grid_x = (uint32_t(n) + kThreads - 1) / kThreads;
     const Chunk ch{0, 1, 0, uint32_t(n), grid_x};
-    rc = prepare_scans(c, c->d_scan, ch, c->stream);
+    rc = prepare_scans(c, c->d_scan, ch, c->stream, false);              // stage API reports every point: decimation stays inside the kernels
     if (rc) return rc;
     const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, c->d_scan_sorted);

@@ -17,6 +17,9 @@
 //   k_knn        : stand-alone k-NN (so_knn*), radius-bounded or exact with ring expansion.
 //
 // Reference citations are relative to /root/reference/super_odometry/.
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
+
 #include "so_icp.cuh"
 #include "so_knn.cuh"
 
@@ -331,7 +334,10 @@ __device__ __forceinline__ bool should_process(uint32_t i, double rate) {
 // ------------------------------------------------------------------------------------------------------------------
 // Key = (scan index inside the chunk) << cell_bits | cell; cells beyond the mask and off-map points sort last inside their scan.
 // KeyT = uint32_t when cell_bits + scan bits fit (the usual case: 4 radix passes over 8-byte pairs instead of 5 over 12-byte ones).
-template <class KeyT>
+// COMPACT: points that shouldProcessPoint (LidarSlam.cpp:353-359) drops get one more key bit above the cell and sort behind every
+// survivor of their scan; k_scan_finish then shrinks the scan to its survivors (the decimation depends on the original index only,
+// so it is decided once per registration and the ICP kernels run over max_surface_features points instead of the whole scan).
+template <class KeyT, bool COMPACT>
 __global__ void __launch_bounds__(kThreads) k_scan_keys(MapView m, BatchView bv, KeyT* __restrict__ keys, uint32_t* __restrict__ vals, int cell_bits) {
     const int s = blockIdx.y;
     const IcpState* st = bv.st + s;
@@ -339,6 +345,11 @@ __global__ void __launch_bounds__(kThreads) k_scan_keys(MapView m, BatchView bv,
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     const size_t gi = size_t(bv.offset[s]) + i;
+    if (COMPACT && !should_process(i, st->sampling_rate)) {
+        keys[gi] = KeyT((KeyT(s) << (cell_bits + 1)) | (KeyT(1) << cell_bits));
+        vals[gi] = uint32_t(gi);
+        return;
+    }
     const float4 sp = __ldg(&bv.scan[gi]);
     const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
     double pf[3];
@@ -347,8 +358,23 @@ __global__ void __launch_bounds__(kThreads) k_scan_keys(MapView m, BatchView bv,
     locate(m, float(pf[0] + st->x[0]), float(pf[1] + st->x[1]), float(pf[2] + st->x[2]), qc);
     const uint32_t cell = qc.slot >= 0 ? scan_order_key(m, qc) : 0xFFFFFFFFu;      // brick order (so_knn.cuh)
     const uint32_t mask = cell_bits >= 32 ? 0xFFFFFFFFu : ((1u << cell_bits) - 1u);
-    keys[gi] = KeyT((KeyT(s) << cell_bits) | KeyT(cell < mask ? cell : mask));
+    keys[gi] = KeyT((KeyT(s) << (cell_bits + (COMPACT ? 1 : 0))) | KeyT(cell < mask ? cell : mask));
     vals[gi] = uint32_t(gi);
+}
+
+// After the sort of a COMPACT chunk: survivors of scan s = sorted keys of its range without the dropped bit (binary search);
+// the scan shrinks to them and its decimation is switched off.
+template <class KeyT>
+__global__ void k_scan_finish(BatchView bv, const KeyT* __restrict__ sorted_keys, uint32_t pt_first, int cell_bits, uint32_t n_scans) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    IcpState* st = bv.st + s;
+    if (st->phase != PH_CORR) return;
+    const KeyT* k = sorted_keys + (bv.offset[s] - pt_first);
+    uint32_t lo = 0, hi = uint32_t(st->n_points);
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((k[mid] >> cell_bits) & 1) hi = mid; else lo = mid + 1; }
+    st->n_points = int32_t(lo);
+    st->sampling_rate = -1.0;
 }
 
 template <class KeyT>
@@ -357,9 +383,79 @@ __global__ void __launch_bounds__(kThreads) k_scan_gather(const float4* __restri
     const size_t j = size_t(blockIdx.x) * kThreads + threadIdx.x;
     if (j >= total) return;
     const uint32_t g = vals[j];
-    const uint32_t s = uint32_t(keys[j] >> cell_bits);
+    const uint32_t s = uint32_t(keys[j] >> cell_bits);                 // cell_bits here = all key bits below the scan index
     const float4 p = __ldg(&in[g]);
     out[j] = make_float4(p.x, p.y, p.z, __uint_as_float(g - offset[s]));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_prepare_small: the whole scan preparation of a SMALL registration in one CTA per scan -- what k_scan_keys + a device-wide
+// radix sort (4-5 launches whose fixed cost, ~35 us, is most of a latency-bound so_register) + k_scan_gather do for batches.
+// Points that shouldProcessPoint (LidarSlam.cpp:353-359) drops are removed HERE, once (the decimation is a function of the
+// original index only): the ICP kernels then run over the <= max_surface_features + 1 surviving points with sampling off.
+// Deterministic: the survivors are compacted in index order (block scans), sorted by cell key with a stable block radix sort.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 1024, kSmallItems = 4, kSmallCap = kSmallThreads * kSmallItems;
+__global__ void __launch_bounds__(kSmallThreads) k_prepare_small(MapView m, BatchView bv, float4* __restrict__ out, int key_bits) {
+    using Sort = cub::BlockRadixSort<uint32_t, kSmallThreads, kSmallItems, uint32_t>;
+    using Scan = cub::BlockScan<uint32_t, kSmallThreads>;
+    struct Compact { typename Scan::TempStorage scan; uint32_t idx[kSmallCap]; };
+    __shared__ union { typename Sort::TempStorage sort; Compact c; } s_tmp;      // the index list is consumed (into registers) before the sort starts
+    uint32_t* s_idx = s_tmp.c.idx;
+    __shared__ double s_pose[7];
+    __shared__ uint32_t s_count;
+    const int s = blockIdx.x;
+    IcpState* st = bv.st + s;
+    if (st->phase != PH_CORR) return;
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const uint32_t n = uint32_t(st->n_points);
+    const double rate = st->sampling_rate;
+    const size_t base = size_t(bv.offset[s]);
+    // survivors, in index order
+    for (uint32_t i0 = 0; i0 < n; i0 += kSmallThreads) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t keep = (i < n && should_process(i, rate)) ? 1u : 0u;
+        uint32_t pos, total;
+        Scan(s_tmp.c.scan).ExclusiveSum(keep, pos, total);
+        const uint32_t before = s_count;
+        if (keep && before + pos < uint32_t(kSmallCap)) s_idx[before + pos] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) s_count = before + total;
+        __syncthreads();
+    }
+    const uint32_t n_act = min(s_count, uint32_t(kSmallCap));           // the host chose this path only when the survivors fit
+    uint32_t key[kSmallItems], val[kSmallItems];
+#pragma unroll
+    for (int k = 0; k < kSmallItems; ++k) {
+        const uint32_t j = threadIdx.x * kSmallItems + k;               // blocked arrangement
+        key[k] = 0xFFFFFFFFu; val[k] = 0xFFFFFFFFu;
+        if (j < n_act) {
+            const uint32_t i = s_idx[j];
+            const float4 sp = __ldg(&bv.scan[base + i]);
+            const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+            double pf[3];
+            qrot(s_pose + 3, pin, pf);
+            QueryCell qc;
+            locate(m, float(pf[0] + s_pose[0]), float(pf[1] + s_pose[1]), float(pf[2] + s_pose[2]), qc);
+            const uint32_t mask = key_bits >= 32 ? 0xFFFFFFFFu : ((1u << key_bits) - 1u);
+            const uint32_t cell = qc.slot >= 0 ? scan_order_key(m, qc) : 0xFFFFFFFFu;
+            key[k] = cell < mask ? cell : mask;                          // off-map points sort last among the survivors, as in the batch path
+            val[k] = i;
+        }
+    }
+    __syncthreads();
+    Sort(s_tmp.sort).Sort(key, val, 0, key_bits < 32 ? key_bits + 1 : 32);      // + 1: the padding keys (all ones) sort behind the mask
+#pragma unroll
+    for (int k = 0; k < kSmallItems; ++k) {
+        const uint32_t j = threadIdx.x * kSmallItems + k;
+        if (j < n_act) {
+            const float4 p = __ldg(&bv.scan[base + val[k]]);
+            out[base + j] = make_float4(p.x, p.y, p.z, __uint_as_float(val[k]));
+        }
+    }
+    if (threadIdx.x == 0) { st->n_points = int32_t(n_act); st->sampling_rate = -1.0; }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -468,7 +564,7 @@ __global__ void __launch_bounds__(kThreads) k_knn_inject(MapView m, const float4
         pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
         const int it = st->icp_iter;
         if (it < n_trace_iters) {
-            const uint32_t* p = ids + (size_t(it) * n + orig) * 5;
+            const uint32_t* p = ids + (size_t(it) * uint32_t(st->n_input) + orig) * 5;      // the trace is laid out over the scan as uploaded
             bool ok = true;
 #pragma unroll
             for (int j = 0; j < 5; ++j) ok = ok && p[j] < n_map;
@@ -1176,9 +1272,18 @@ __global__ void k_pack_poses(const IcpState* __restrict__ st, uint32_t n_scans, 
 // ------------------------------------------------------------------------------------------------------------------
 // keys: the 64-bit key buffer; with key32 it is used as an array of uint32_t (same point indexing)
 void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, int cell_bits, bool key32,
-                      cudaStream_t st) {
-    if (key32) k_scan_keys<uint32_t><<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, reinterpret_cast<uint32_t*>(keys), vals, cell_bits);
-    else k_scan_keys<uint64_t><<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, keys, vals, cell_bits);
+                      bool compact, cudaStream_t st) {
+    const dim3 g(grid_x, n_scans);
+    uint32_t* k32 = reinterpret_cast<uint32_t*>(keys);
+    if (key32) { if (compact) k_scan_keys<uint32_t, true><<<g, kThreads, 0, st>>>(m, bv, k32, vals, cell_bits); else k_scan_keys<uint32_t, false><<<g, kThreads, 0, st>>>(m, bv, k32, vals, cell_bits); }
+    else { if (compact) k_scan_keys<uint64_t, true><<<g, kThreads, 0, st>>>(m, bv, keys, vals, cell_bits); else k_scan_keys<uint64_t, false><<<g, kThreads, 0, st>>>(m, bv, keys, vals, cell_bits); }
+}
+void launch_scan_finish(const BatchView& bv, const uint64_t* sorted_keys, size_t first, uint32_t pt_first, int cell_bits, bool key32, uint32_t n_scans, cudaStream_t st) {
+    if (key32) k_scan_finish<uint32_t><<<(n_scans + 63) / 64, 64, 0, st>>>(bv, reinterpret_cast<const uint32_t*>(sorted_keys) + first, pt_first, cell_bits, n_scans);
+    else k_scan_finish<uint64_t><<<(n_scans + 63) / 64, 64, 0, st>>>(bv, sorted_keys + first, pt_first, cell_bits, n_scans);
+}
+void launch_prepare_small(const MapView& m, const BatchView& bv, float4* out, uint32_t n_scans, int key_bits, cudaStream_t st) {
+    k_prepare_small<<<n_scans, kSmallThreads, 0, st>>>(m, bv, out, key_bits);
 }
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, size_t first, const uint32_t* offset, size_t total, float4* out,
                         int cell_bits, bool key32, cudaStream_t st) {

@@ -78,7 +78,10 @@ constexpr int kFitThreads = SO_FIT_THREADS;
 constexpr int kCorrLaunches = SO_FUSE_KNN_FIT ? 1 : 2;      // launches of the correspondence stage before the first evaluation
 
 void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t n_scans, int cell_bits, bool key32,
-                      cudaStream_t st);
+                      bool compact, cudaStream_t st);
+void launch_scan_finish(const BatchView& bv, const uint64_t* sorted_keys, size_t first, uint32_t pt_first, int cell_bits, bool key32, uint32_t n_scans, cudaStream_t st);
+constexpr uint32_t kPrepareSmallCap = 4096;    // survivors k_prepare_small can order (one CTA per scan)
+void launch_prepare_small(const MapView& m, const BatchView& bv, float4* out, uint32_t n_scans, int key_bits, cudaStream_t st);
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, size_t first, const uint32_t* offset, size_t total, float4* out,
                         int cell_bits, bool key32, cudaStream_t st);
 // part: 0 = the whole stage; split build only: 1 = k_knn_scan alone, 2 = k_fit alone (profiling)

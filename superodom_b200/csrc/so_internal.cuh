@@ -40,7 +40,8 @@ struct MapView {
 struct IcpState {
     // --- inputs
     double x0[7];          // T_w_initial_guess
-    int32_t n_points;
+    int32_t n_points;      // points the ICP kernels run over (after scan preparation: those shouldProcessPoint keeps)
+    int32_t n_input;       // points of the scan as uploaded
     int32_t n_edge;        // edge points of this scan (0: edge branch idle, as upstream)
     int32_t max_icp_iters, lm_max_iterations;
     double sampling_rate;  // calculateSamplingRate(): <0 = keep all

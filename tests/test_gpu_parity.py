@@ -626,7 +626,16 @@ def test_scan_order_key_paths_and_stream_modes_agree(gpu_api, monkeypatch):
         ctx.close()
         return out
     base = run()
-    for env in ("SO_FORCE_KEY64", "SO_SINGLE_STREAM", "SO_NO_COND_GRAPH"):
+    # ... and so are the one-CTA scan preparation of small registrations (these capped scans keep <= 2001 points each) against the
+    # device-wide ordering, and the optimiser step folded into the evaluation kernel against the two-kernel form
+    for env in ("SO_FORCE_KEY64", "SO_SINGLE_STREAM", "SO_NO_COND_GRAPH", "SO_NO_SMALL_PREPARE", "SO_NO_FUSED_LM"):
         monkeypatch.setenv(env, "1")
         assert np.array_equal(run(), base), env
         monkeypatch.delenv(env)
+    # the batch equals its scans registered one by one (small path, fused optimiser step), bit for bit
+    ctx = gpu_api.Context(max_map_points=1 << 20, max_scan_points=int(n_points.max()), max_batch=1, plane_res=0.2)
+    ctx.map_set_points(case["map_xyzi"])
+    for i in (0, 7, 15):
+        r = ctx.register(scans[i], priors[i], 5, 2000, skip_map_checks=True)
+        assert np.array_equal(np.array(list(r.pose) + [r.n_iterations] + list(r.hist_obs)), base[i]), i
+    ctx.close()
