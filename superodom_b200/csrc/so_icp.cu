@@ -861,7 +861,9 @@ __device__ __forceinline__ void evaluate_body(const BatchView& bv, const CorrBuf
     for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
     // Software-pipelined: the three loads of point r+1 are issued (unconditionally, so they do not chain behind the weight)
     // before the FP64 work of point r, which keeps two points' worth of the 56 B/pt stream in flight per thread.
-    const uint32_t i0 = blockIdx.x * kEvalPts * kThreads + threadIdx.x;
+    const int pts = eval_pts(n);
+    if (blockIdx.x >= eval_ctas(n)) return;                // the grid covers the largest scan of the chunk
+    const uint32_t i0 = blockIdx.x * uint32_t(pts) * kThreads + threadIdx.x;
     double w_n = 0.0;
     double4 nd_n = make_double4(0.0, 0.0, 0.0, 0.0);
     float4 sp_n = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -871,13 +873,13 @@ __device__ __forceinline__ void evaluate_body(const BatchView& bv, const CorrBuf
         sp_n = __ldg(&bv.scan[base + i0]);
     }
 #pragma unroll 1
-    for (int r = 0; r < kEvalPts; ++r) {
+    for (int r = 0; r < pts; ++r) {
         const double w = w_n;
         const double4 nd = nd_n;
         const float4 sp = sp_n;
         const uint32_t inext = i0 + (r + 1) * kThreads;
         w_n = 0.0;
-        if (r + 1 < kEvalPts && inext < n) {
+        if (r + 1 < pts && inext < n) {
             w_n = cb.w[base + inext];
             nd_n = cb.nd[base + inext];
             sp_n = __ldg(&bv.scan[base + inext]);
@@ -1110,7 +1112,7 @@ __device__ __forceinline__ void lm_step_body(const BatchView& bv, int s, uint32_
     double v = 0.0;
     if (comp < kAcc && sub < 4) {
         const double* base = bv.partials + size_t(s) * bv.partial_stride * kAcc;
-        const uint32_t np = (uint32_t(st->n_points) + kThreads * kEvalPts - 1) / (kThreads * kEvalPts);
+        const uint32_t np = eval_ctas(uint32_t(st->n_points));
         // __ldcg: straight from L2 -- in k_evaluate_lm the rows were written by other CTAs of the same launch
         for (uint32_t b = sub; b < np && b < n_partials; b += 4) v += __ldcg(&base[size_t(b) * kAcc + comp]);
         const uint32_t ne = (uint32_t(st->n_edge) + kThreads - 1) / kThreads;          // edge branch partials (0 when no edge cloud)
@@ -1311,7 +1313,7 @@ void launch_inject(const MapView& m, const float4* by_id, uint32_t n_map, const 
 }
 void launch_first_eval(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const MapView* medge, const EdgeBuf* eb,
                        uint32_t grid_e) {
-    const uint32_t gp = (grid_x + kEvalPts - 1) / kEvalPts;
+    const uint32_t gp = grid_x ? eval_grid(grid_x * kThreads) : 0;
     if (bv.counters && gp && !grid_e) { k_evaluate_lm<PH_CORR><<<dim3(gp, n_scans), kThreads, 0, st>>>(bv, cb, bv.counters); return; }
     if (gp) k_evaluate<PH_CORR><<<dim3(gp, n_scans), kThreads, 0, st>>>(bv, cb);
     if (grid_e) k_edge_fit<<<dim3(grid_e, n_scans), kThreads, 0, st>>>(*medge, bv, *eb, bv.edge_partial_offset);
@@ -1323,7 +1325,7 @@ void launch_correspond(const MapView& m, const BatchView& bv, const CorrBuf& cb,
     launch_first_eval(bv, cb, grid_x, n_scans, st, medge, eb, grid_e);
 }
 void launch_evaluate(const BatchView& bv, const CorrBuf& cb, uint32_t grid_x, uint32_t n_scans, cudaStream_t st, const EdgeBuf* eb, uint32_t grid_e) {
-    const uint32_t gx = (grid_x + kEvalPts - 1) / kEvalPts;
+    const uint32_t gx = grid_x ? eval_grid(grid_x * kThreads) : 0;
     if (bv.counters && gx && !grid_e) { k_evaluate_lm<PH_EVAL><<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb, bv.counters); return; }
     if (gx) k_evaluate<PH_EVAL><<<dim3(gx, n_scans), kThreads, 0, st>>>(bv, cb);
     if (grid_e) k_edge_evaluate<<<dim3(grid_e, n_scans), kThreads, 0, st>>>(bv, *eb, bv.edge_partial_offset);

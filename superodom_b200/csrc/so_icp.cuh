@@ -50,7 +50,19 @@ struct NnBuf {
 #ifndef SO_EVAL_PTS
 #define SO_EVAL_PTS 16
 #endif
-constexpr int kEvalPts = SO_EVAL_PTS;     // points per thread in k_evaluate
+constexpr int kEvalPts = SO_EVAL_PTS;     // points per thread in k_evaluate (large scans)
+// Points per thread of the evaluation kernels as a function of the scan's own size (never of the batch it is in, so that a scan's
+// partial sums -- and with them its result, bit for bit -- do not depend on its neighbours): small scans spread over more CTAs,
+// because ONE CTA looping over 16 points per thread was most of a latency-bound optimiser step.
+__host__ __device__ inline int eval_pts(uint32_t n) { return n <= 4096u ? 1 : (n <= 65536u ? 4 : kEvalPts); }
+__host__ __device__ inline uint32_t eval_ctas(uint32_t n) { const uint32_t per = uint32_t(eval_pts(n)) * 256u; return (n + per - 1) / per; }
+// CTAs that cover every scan of up to n_max points (a smaller scan with fewer points per thread may need more CTAs than the largest)
+__host__ inline uint32_t eval_grid(uint32_t n_max) {
+    if (n_max <= 4096u) return (n_max + 255u) / 256u;
+    if (n_max <= 65536u) { const uint32_t g = (n_max + 1023u) / 1024u; return g > 16u ? g : 16u; }
+    const uint32_t g = (n_max + 4095u) / 4096u;
+    return g > 64u ? g : 64u;
+}
 #ifndef SO_FIT_PTS
 #define SO_FIT_PTS 2
 #endif

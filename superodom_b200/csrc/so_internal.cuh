@@ -353,23 +353,29 @@ __host__ __device__ inline void colpiv_qr_solve_5x3(double A[5][3], double b[5],
 // were most of its 10-20 us).
 __host__ __device__ inline bool chol6_solve(double* M, const double* r, double* y) {
     bool ok = true;
+    double inv[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         double s = M[j * 6 + j];
 #pragma unroll
         for (int k = 0; k < j; ++k) s -= M[j * 6 + k] * M[j * 6 + k];
         if (!(s > 0.0)) ok = false;
-        const double l = sqrt(s);
-        M[j * 6 + j] = l;
-        const double il = 1.0 / l;
+        // one reciprocal square root per column; every division by the pivot becomes a multiplication (the step this solves is
+        // compared with Ceres' QR-based one to ~1e-12 in any case: another algorithm, not another rounding)
+#ifdef __CUDA_ARCH__
+        const double il = rsqrt(s);
+#else
+        const double il = 1.0 / sqrt(s);
+#endif
+        inv[j] = il;
+        M[j * 6 + j] = s * il;
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double t = M[i * 6 + j];
 #pragma unroll
             for (int k = 0; k < j; ++k) t -= M[i * 6 + k] * M[j * 6 + k];
-            M[i * 6 + j] = t / l;
+            M[i * 6 + j] = t * il;
         }
-        (void)il;
     }
     if (!ok) return false;
     double z[6];
@@ -378,14 +384,14 @@ __host__ __device__ inline bool chol6_solve(double* M, const double* r, double* 
         double t = r[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) t -= M[i * 6 + k] * z[k];
-        z[i] = t / M[i * 6 + i];
+        z[i] = t * inv[i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double t = z[i];
 #pragma unroll
         for (int k = i + 1; k < 6; ++k) t -= M[k * 6 + i] * y[k];
-        y[i] = t / M[i * 6 + i];
+        y[i] = t * inv[i];
     }
     return true;
 }
