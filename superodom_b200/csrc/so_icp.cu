@@ -83,7 +83,7 @@ __device__ __noinline__ void covariance_and_errors(IcpState& st) {
     // pseudo-inverse of J^T J dropping singular directions with s_i/s_max < sqrt(1e-14) (covariance_impl.cc).
     double A[36], V[36], w[6];
     _Pragma("unroll") for (int i = 0; i < 6; ++i) _Pragma("unroll") for (int j = 0; j < 6; ++j) A[i * 6 + j] = st.H[i <= j ? tri(i, j) : tri(j, i)];
-    jacobi_eig<6, 30>(A, V, w);
+    jacobi_eig6_rr<30>(A, V, w);
     const double lmax = w[5];
     double inv[6];
     bool cut = false;

@@ -194,6 +194,80 @@ __device__ inline void jacobi_eig(double* a, double* v, double* w) {
     }
 }
 
+// Cyclic Jacobi for the symmetric 6x6 of the covariance step, rotations taken in ROUND-ROBIN order: five rounds of three pairs
+// with disjoint indices -- (0,5)(1,4)(2,3) / (0,4)(3,5)(1,2) / (0,3)(2,4)(1,5) / (0,2)(1,3)(4,5) / (0,1)(2,5)(3,4).  The angle of a
+// pair depends only on its own 2x2 block, which the other two rotations of the round do not touch, so the three angle
+// computations (the latency-bound part: reciprocal, square roots) are independent instruction streams for the one thread that
+// runs them; the row-cyclic order chained all fifteen.  Same convergence test and ascending output as jacobi_eig<6>.
+template <int SWEEPS>
+__device__ inline void jacobi_eig6_rr(double* a, double* v, double* w) {
+    constexpr int N = 6;
+    constexpr int PP[15] = {0, 1, 2, 0, 3, 1, 0, 2, 1, 0, 1, 4, 0, 2, 3};
+    constexpr int QQ[15] = {5, 4, 3, 4, 5, 2, 3, 4, 5, 2, 3, 5, 1, 5, 4};
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[i * N + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int sweep = 0; sweep < SWEEPS; ++sweep) {
+        double off = 0.0, dia = 0.0;
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+            dia += a[p * N + p] * a[p * N + p];
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) off += a[p * N + q] * a[p * N + q];
+        }
+        if (off <= SO_JACOBI_OFF_TOL * dia || off == 0.0) break;
+#pragma unroll
+        for (int round = 0; round < 5; ++round) {
+            double tt[3], cc[3], ss[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {                    // three independent angles
+                const int p = PP[round * 3 + k], q = QQ[round * 3 + k];
+                const double apq = a[p * N + q];
+                const float dlt = float(a[q * N + q] - a[p * N + p]), b2 = float(2.0 * apq);
+                float tf = __fdividef(b2, fabsf(dlt) + sqrtf(fmaf(dlt, dlt, b2 * b2)));
+                if (!(fabsf(tf) <= 1.0f)) tf = 0.0f;         // apq == 0 after the cast (or inf / nan): no rotation
+                const double t = apq != 0.0 ? double(dlt < 0.0f ? -tf : tf) : 0.0;
+                const double c = rsqrt(t * t + 1.0);
+                tt[k] = t; cc[k] = c; ss[k] = t * c;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int p = PP[round * 3 + k], q = QQ[round * 3 + k];
+                const double t = tt[k], c = cc[k], sn = ss[k], apq = a[p * N + q];
+                if (t != 0.0) {
+                    a[p * N + p] -= t * apq; a[q * N + q] += t * apq; a[p * N + q] = 0.0; a[q * N + p] = 0.0;
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        if (r != p && r != q) {
+                            const double arp = a[r * N + p], arq = a[r * N + q];
+                            a[r * N + p] = a[p * N + r] = c * arp - sn * arq;
+                            a[r * N + q] = a[q * N + r] = sn * arp + c * arq;
+                        }
+                        const double vrp = v[r * N + p], vrq = v[r * N + q];
+                        v[r * N + p] = c * vrp - sn * vrq;
+                        v[r * N + q] = sn * vrp + c * vrq;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) w[i] = a[i * N + i];
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i) {
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) {
+            if (w[j] < w[i]) {
+                const double t = w[i]; w[i] = w[j]; w[j] = t;
+#pragma unroll
+                for (int r = 0; r < N; ++r) { const double u = v[r * N + i]; v[r * N + i] = v[r * N + j]; v[r * N + j] = u; }
+            }
+        }
+    }
+}
+
 // Eigenvalues (ascending) of the symmetric 3x3 [a00 a01 a02; . a11 a12; . . a22] by the trigonometric solution of its
 // characteristic cubic: with q = tr/3, p^2 = |A - qI|_F^2 / 6 and r = det((A - qI)/p)/2 in [-1, 1], the roots are
 // q + 2p cos(phi + 2k pi/3), phi = acos(r)/3 in [0, pi/3] -- one FP64 acos and one sincos instead of the ~12 Jacobi rotations an
