@@ -669,24 +669,31 @@ int map_add_points(Ctx* c, MapStore& ms, uint32_t n_new) {
 // cloud before Localization (laserMapping.cpp:639-645).  Same voxel/centroid semantics as the map insert, one grid
 // for the whole cloud.  In: d_scan[0..n); out: d_scan_sorted[0..*n_out) ordered by voxel index (k, j, i).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void k_voxel_keys_cloud(const float4* __restrict__ raw, uint32_t n, float inv_leaf, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// VB bits per voxel index (offset 2^(VB-1)); the key of a skipped point has bit 3*VB set and sorts last.  VB = 13 covers +-4096
+// voxels around the sensor (819 m at leaf 0.2) in 40 key bits = 5 radix passes; a point beyond that raises *overflow and the caller
+// repeats the filter with VB = 17 (the layout every cloud fits).
+template <int VB>
+__global__ void k_voxel_keys_cloud(const float4* __restrict__ raw, uint32_t n, float inv_leaf, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                   uint32_t* __restrict__ overflow) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = raw[i];
-    uint64_t key = ~uint64_t(0);                                     // non-finite points are skipped, as PCL does
+    constexpr int64_t kOff = int64_t(1) << (VB - 1), kMask = (int64_t(1) << VB) - 1;
+    uint64_t key = uint64_t(1) << (3 * VB);                          // non-finite points are skipped, as PCL does
     if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-        const int64_t vi = int64_t(floorf(__fmul_rn(p.x, inv_leaf))) + 65536;
-        const int64_t vj = int64_t(floorf(__fmul_rn(p.y, inv_leaf))) + 65536;
-        const int64_t vk = int64_t(floorf(__fmul_rn(p.z, inv_leaf))) + 65536;
-        key = (uint64_t(vk & 0x1FFFF) << 34) | (uint64_t(vj & 0x1FFFF) << 17) | uint64_t(vi & 0x1FFFF);
+        const int64_t vi = int64_t(floorf(__fmul_rn(p.x, inv_leaf))) + kOff;
+        const int64_t vj = int64_t(floorf(__fmul_rn(p.y, inv_leaf))) + kOff;
+        const int64_t vk = int64_t(floorf(__fmul_rn(p.z, inv_leaf))) + kOff;
+        if (((vi | vj | vk) & ~kMask) != 0) *overflow = 1;           // outside the VB-bit range (negative values have high bits set)
+        key = (uint64_t(vk & kMask) << (2 * VB)) | (uint64_t(vj & kMask) << VB) | uint64_t(vi & kMask);
     }
     keys[i] = key;
     vals[i] = i;
 }
 
-__global__ void k_count_valid(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ count) {
+__global__ void k_count_valid(const uint64_t* __restrict__ keys, uint32_t n, uint64_t skipped_key, uint32_t* __restrict__ count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && keys[i] != ~uint64_t(0) && (i + 1 == n || keys[i + 1] == ~uint64_t(0))) *count = i + 1;   // sorted: last valid key
+    if (i < n && keys[i] != skipped_key && (i + 1 == n || keys[i + 1] == skipped_key)) *count = i + 1;   // sorted: last valid key
 }
 
 int scan_voxel_filter(Ctx* c, uint32_t n, float leaf, uint32_t* n_out) {
@@ -695,20 +702,30 @@ int scan_voxel_filter(Ctx* c, uint32_t n, float leaf, uint32_t* n_out) {
     if (n == 0) return SO_OK;
     const uint32_t grid = (n + 255) / 256;
     const float inv_leaf = 1.0f / leaf;
-    k_voxel_keys_cloud<<<grid, 256, 0, st>>>(c->d_scan, n, inv_leaf, c->d_skeys, c->d_svals);
-    size_t tmp = c->sort_tmp_bytes;
-    SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_skeys, c->d_skeys_out, c->d_svals, c->d_svals_out, int(n), 0, 64, st));
+    uint32_t* d_flag = reinterpret_cast<uint32_t*>(c->d_insert_info) + 2000;     // scratch word behind the insert bookkeeping
     uint32_t* d_cnt = reinterpret_cast<uint32_t*>(c->d_skeys);      // keys_in is free after the sort: [count][heads...][ranks...]
-    SO_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, st));
-    k_count_valid<<<grid, 256, 0, st>>>(c->d_skeys_out, n, d_cnt);
     uint32_t n_valid = 0;
-    SO_CUDA_TRY(cudaMemcpyAsync(&n_valid, d_cnt, 4, cudaMemcpyDeviceToHost, st));
-    SO_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int wide = 0; wide < 2; ++wide) {
+        const int vb = wide ? 17 : 13;
+        SO_CUDA_TRY(cudaMemsetAsync(d_flag, 0, 4, st));
+        if (wide) k_voxel_keys_cloud<17><<<grid, 256, 0, st>>>(c->d_scan, n, inv_leaf, c->d_skeys, c->d_svals, d_flag);
+        else k_voxel_keys_cloud<13><<<grid, 256, 0, st>>>(c->d_scan, n, inv_leaf, c->d_skeys, c->d_svals, d_flag);
+        size_t tmp = c->sort_tmp_bytes;
+        SO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_skeys, c->d_skeys_out, c->d_svals, c->d_svals_out, int(n), 0, 3 * vb + 1, st));
+        SO_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, st));
+        k_count_valid<<<grid, 256, 0, st>>>(c->d_skeys_out, n, uint64_t(1) << (3 * vb), d_cnt);
+        uint32_t h[2] = {0, 0};
+        SO_CUDA_TRY(cudaMemcpyAsync(&h[0], d_cnt, 4, cudaMemcpyDeviceToHost, st));
+        SO_CUDA_TRY(cudaMemcpyAsync(&h[1], d_flag, 4, cudaMemcpyDeviceToHost, st));
+        SO_CUDA_TRY(cudaStreamSynchronize(st));
+        n_valid = h[0];
+        if (!h[1]) break;                                           // every voxel index fitted the narrow key
+    }
     if (n_valid == 0) return SO_OK;
     uint32_t* d_head = d_cnt + 4;
     uint32_t* d_rank = d_head + n_valid;
     k_voxel_heads<<<(n_valid + 255) / 256, 256, 0, st>>>(c->d_skeys_out, 0, n_valid, d_head);
-    tmp = c->sort_tmp_bytes;
+    size_t tmp = c->sort_tmp_bytes;
     SO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp, tmp, d_head, d_rank, int(n_valid), st));
     uint32_t last_flag = 0, last_rank = 0;
     SO_CUDA_TRY(cudaMemcpyAsync(&last_flag, d_head + n_valid - 1, 4, cudaMemcpyDeviceToHost, st));

@@ -428,6 +428,12 @@ def test_scan_prefilter_adjust_voxel_size(gpu_api, oracle_mod):
     # the filtered scan registers
     r = ctx.register(out, case["pose_prior"], 5, 2000)
     assert r.status == 0 and np.linalg.norm(np.array(r.pose)[:3] - case["pose_true"][:3]) < 0.05
+    # returns beyond the 13-bit voxel range of the narrow sort key (+-4096 voxels) take the wide-key path: same result as numpy
+    far = s.copy()
+    far[5::997, :3] *= np.float32(400.0)
+    out2, _, _, _ = ctx.scan_prefilter(far, 0.2, 0.2, False)
+    ref2, _, _, _ = oracle_mod.adjust_voxel_size_numpy(far, 0.2, 0.2, False)
+    assert np.abs(far[np.isfinite(far).all(1), :3]).max() > 4096 * 0.2 and np.array_equal(out2, ref2)
     ctx.close()
 
 
