@@ -232,6 +232,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL's version banner does, whatever
+    # NCCL_DEBUG_FILE says) are sent to stderr at the file-descriptor level; the line goes out through the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     t_phase = [time.perf_counter()]
 
     def phase(label):                                  # wall-clock of the untimed set-up phases, to stderr
@@ -491,7 +496,7 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "roofline": roofline, "knn_cfg5": knn5, "cfg4": cfg4, "wide_prior": wide, "latency": latency, "live": live,
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
