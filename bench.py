@@ -43,8 +43,8 @@ DISTINCT = 256                                   # distinct scans per GPU behind
 # algorithmic bytes of the k-NN = 16 B query read + k * 8 B result (u32 id + f32 d2) per query, + the map once.
 KNN_BYTES_PER_QUERY = 16 + 5 * 8
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of ONE k_knn_scan launch / its queries (profiles/README.md says
-# which capture; None until a capture of the current kernel is committed)
-NCU_DRAM_BYTES_PER_QUERY = {"k_knn_scan": 75.1, "k_knn_fit": 63.4}
+# which capture; None where no capture of the current kernel is committed)
+NCU_DRAM_BYTES_PER_QUERY = {"k_knn_scan": 75.4, "k_knn_fit": None}      # profiles/ncu_prof_r2h_metrics.csv: (26.82 MB read + 52.31 MB written) / 1 048 576 queries
 
 
 def _peaks():
