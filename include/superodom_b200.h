@@ -107,6 +107,8 @@ typedef struct {
     int32_t prediction_source;    /* stats.prediction_source: 1 when the pose prior rows were added (LidarSlam.cpp:278,297) */
     double time_ms;               /* stats.time_elapsed: the ICP loop, device time measured with CUDA events */
     double time_total_ms;         /* whole so_register call incl. H2D / D2H (host clock) */
+    int32_t knn_searched;         /* telemetry, summed over the ICP iterations: queries that ran the neighbour search ... */
+    int32_t knn_verified;         /* ... and queries whose previous five neighbours were proven to still be their 5-NN (no search) */
 } so_icp_result;
 
 /* One accepted/rejected plane correspondence, for stage-level parity tests

@@ -50,7 +50,7 @@ class IcpResult(C.Structure):
                 ("translation_from_last", C.c_double), ("rotation_from_last", C.c_double),
                 ("map_surf_5x5", C.c_int32), ("map_edge_5x5", C.c_int32), ("scan_surf_num", C.c_int32), ("scan_edge_num", C.c_int32),
                 ("pos_in_localmap", C.c_int32 * 3), ("prediction_source", C.c_int32),
-                ("time_ms", C.c_double), ("time_total_ms", C.c_double)]
+                ("time_ms", C.c_double), ("time_total_ms", C.c_double), ("knn_searched", C.c_int32), ("knn_verified", C.c_int32)]
 
 
 CORR_DTYPE = np.dtype([("n", "<f8", 3), ("d", "<f8"), ("w", "<f8"), ("nn", "<u4", 5), ("nn_d2", "<f4", 5),

@@ -91,6 +91,7 @@ static int ctx_alloc(Ctx* c) {
     SO_CUDA_TRY(cudaMalloc(&c->nn.pts, c->scan_cap * 5 * sizeof(float4)));
     SO_CUDA_TRY(cudaMalloc(&c->nn.d5, c->scan_cap * sizeof(float)));
     SO_CUDA_TRY(cudaMalloc(&c->nn.pre, c->scan_cap));
+    SO_CUDA_TRY(cudaMalloc(&c->nn.vq, c->scan_cap * sizeof(float4)));
     c->nn.cap = c->scan_cap;
     { int rc2 = scan_sort_alloc(c); if (rc2) return rc2; }
     SO_CUDA_TRY(cudaMalloc(&c->d_offset, c->max_batch * sizeof(uint32_t)));
@@ -133,7 +134,7 @@ static void ctx_free(Ctx* c) {
     for (auto& e : c->ev_copy) if (e) cudaEventDestroy(e);
     map_free(c);
     cudaFree(c->d_scan_sorted); cudaFree(c->d_skeys); cudaFree(c->d_skeys_out); cudaFree(c->d_svals); cudaFree(c->d_svals_out);
-    cudaFree(c->d_sort_tmp); cudaFree(c->d_sort_tmp2); cudaFree(c->nn.pos); cudaFree(c->nn.pts); cudaFree(c->nn.d5); cudaFree(c->nn.pre);
+    cudaFree(c->d_sort_tmp); cudaFree(c->d_sort_tmp2); cudaFree(c->nn.pos); cudaFree(c->nn.pts); cudaFree(c->nn.d5); cudaFree(c->nn.pre); cudaFree(c->nn.vq);
     cudaFree(c->d_scan); cudaFree(c->d_offset); cudaFree(c->d_state); cudaFreeHost(c->h_state); cudaFreeHost(c->h_offset);
     cudaFree(c->d_partials); cudaFree(c->d_counters); cudaFree(c->d_hist);
     cudaFree(c->d_escan); cudaFree(c->d_eoffset); cudaFree(c->ebuf.a); cudaFree(c->ebuf.b); cudaFree(c->ebuf.flags); cudaFree(c->ebuf.nn); cudaFree(c->ebuf.selmask);
@@ -392,6 +393,7 @@ static void fill_result(const Ctx* c, const IcpState& s, const double pose_in[7]
     r->pos_err = s.pos_err; r->pos_inv_cond = s.pos_inv_cond; r->ori_err_deg = s.ori_err_deg; r->ori_inv_cond = s.ori_inv_cond;
     for (int i = 0; i < 3; ++i) { r->pos_dir[i] = s.pos_dir[i]; r->ori_dir[i] = s.ori_dir[i]; }
     if (s.status) r->status = s.status;
+    r->knn_searched = s.knn_searched; r->knn_verified = s.knn_verified;
     r->prediction_source = s.use_prior ? 1 : 0;
     double T[7];
     std::memcpy(T, s.x, sizeof(T));

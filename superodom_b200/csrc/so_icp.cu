@@ -296,6 +296,47 @@ __device__ __forceinline__ void accumulate(double acc[kAcc], const double n[3], 
     acc[27] += 0.5 * rho0;
 }
 
+#ifndef SO_KNN_VERIFY
+#define SO_KNN_VERIFY 0           // 1: try to PROVE the previous five neighbours still exact before searching again.  Off: measured slower
+                                  // on every BASELINE workload (3.6 % of the queries verify on cfg2; DESIGN.md section 4, tried-and-measured)
+#endif
+// ICP iterations after the first, before any walk: the record of the query's last FULL search (nb.vq: where the query was, q0, and a
+// lower bound D on the squared distance from q0 to every point of the block outside the five found) proves the five still ARE the
+// 5-NN at the new position q1 whenever   max_i |q1 - s_i| < sqrt(D) - |q1 - q0|   -- any other point x has
+// |q1 - x| >= |q0 - x| - |q1 - q0| >= sqrt(D) - |q1 - q0| (triangle inequality), strictly beyond all five, so neither membership nor
+// ties with outsiders can differ from what a fresh search returns.  Then only their distances (the reference's rounding) and their
+// (d2, id) order are renewed -- ~150 instructions instead of the ~3 700 of a walk.  Margins cover the float evaluation of the norms.
+// Requires the five to lie in the block the query is in NOW (the search is block-local, LocalMap.h:488-507).  On success tk holds
+// the five in order (tk.pos = positions in the sorted map) and true is returned.
+__device__ __forceinline__ bool verify_neighbours(const MapView& m, const QueryCell& qc, const NnBuf& nb, size_t gi, float qx, float qy, float qz,
+                                                  TopK<5>& tk) {
+    const float4 rec = nb.vq[gi];
+    if (!(rec.w > 0.f)) return false;
+    const uint32_t cells = uint32_t(m.nb) * uint32_t(m.nb) * uint32_t(m.nb);
+    const uint32_t lo = __ldg(&m.cell_start[uint32_t(qc.slot) * cells]), hi = __ldg(&m.cell_start[uint32_t(qc.slot) * cells + cells]);
+    const float mx = qx - rec.x, my = qy - rec.y, mz = qz - rec.z;
+    const float moved = sqrtf(fmaf(mx, mx, fmaf(my, my, mz * mz))) * 1.000002f + 1e-6f;
+    const float reach = sqrtf(rec.w) * 0.999998f - moved - 1e-6f;           // every outsider is at least this far from q1
+    if (!(reach > 0.f)) return false;
+    bool ok = true;
+    float4 c[5]; uint32_t pos[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        pos[j] = nb.pos[size_t(j) * nb.cap + gi];
+        ok = ok && pos[j] >= lo && pos[j] < hi;
+        c[j] = __ldg(&m.pts[ok ? pos[j] : lo]);
+    }
+    if (!ok) return false;
+    float far2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) far2 = fmaxf(far2, exact_d2(c[j], qx, qy, qz));
+    if (!(sqrtf(far2) * 1.000002f < reach)) return false;
+    tk.init(FLT_MAX);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) tk.offer(exact_d2(c[j], qx, qy, qz), __float_as_uint(c[j].w), pos[j]);
+    return true;
+}
+
 // ICP iterations after the first: the previous iteration's five neighbours still exist, so the largest of their (exact)
 // distances to the moved query bounds the new 5th-neighbour distance -- provided they lie in the block the query is in NOW
 // (the search is block-local, LocalMap.h:488-507: after a pose update that carries the point across a 50 m block face the old
@@ -471,7 +512,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_prepare_small(MapView m, Batc
 #endif
 __global__ void __launch_bounds__(kTileThreads, SO_KNN_MINB) k_knn_scan(MapView m, BatchView bv, NnBuf nb) {
     const int s = blockIdx.y;
-    const IcpState* st = bv.st + s;
+    IcpState* st = bv.st + s;
     if (st->phase != PH_CORR) return;
     __shared__ double s_pose[7];
     __shared__ uint32_t s_buf[kBufCap * kTileThreads];
@@ -489,7 +530,7 @@ __global__ void __launch_bounds__(kTileThreads, SO_KNN_MINB) k_knn_scan(MapView 
     int pre = SO_MATCH_SKIPPED;
     TopK<5> tk;
     tk.init(m.bound_d2);
-    bool searchable = false;
+    bool searchable = false, verified = false;
     float qx = 0.f, qy = 0.f, qz = 0.f, u_seed = -1.f;
     QueryCell qc;
     qc.slot = -1; qc.nblock = 0; qc.c[0] = qc.c[1] = qc.c[2] = 0; qc.f[0] = qc.f[1] = qc.f[2] = 0.f;
@@ -502,8 +543,19 @@ __global__ void __launch_bounds__(kTileThreads, SO_KNN_MINB) k_knn_scan(MapView 
         if (qc.slot < 0 || qc.nblock < 5) pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
         else {
             searchable = true;
-            if (st->icp_iter > 0 && nb.pre[gi] == SO_MATCH_SUCCESS) u_seed = seed_bound(m, qc, nb, gi, qx, qy, qz);
+            if (st->icp_iter > 0) {
+                verified = SO_KNN_VERIFY && verify_neighbours(m, qc, nb, gi, qx, qy, qz, tk);
+                if (!verified && nb.pre[gi] == SO_MATCH_SUCCESS) u_seed = seed_bound(m, qc, nb, gi, qx, qy, qz);
+            }
         }
+    }
+    if (verified) {                                       // the stored five are still the 5-NN: distances and order renewed, no walk
+        searchable = false;
+        pre = tk.d2[4] > m.bound_d2 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
+    }
+    if (SO_KNN_VERIFY) {                                  // telemetry: one atomic pair per warp
+        const unsigned ms = __ballot_sync(0xffffffffu, searchable), mv = __ballot_sync(0xffffffffu, verified);
+        if ((threadIdx.x & 31) == 0) { if (ms) atomicAdd(&st->knn_searched, __popc(ms)); if (mv) atomicAdd(&st->knn_verified, __popc(mv)); }
     }
 #if SO_KNN_TILE
     TileGrid tg;
@@ -511,21 +563,29 @@ __global__ void __launch_bounds__(kTileThreads, SO_KNN_MINB) k_knn_scan(MapView 
 #else
     const bool tiled = false;
 #endif
+    float next_lb = -1.f;
     if (searchable) {
 #if SO_KNN_TILE
         if (tiled) {
-            knn_select<5, SO_R1_OCTANT != 0>(tg, m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
+            knn_select<5, SO_R1_OCTANT != 0>(tg, m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk, SO_KNN_VERIFY ? &next_lb : nullptr);
 #pragma unroll
             for (int j = 0; j < 5; ++j) if (tk.id[j] != 0xFFFFFFFFu) tk.pos[j] = tg.pos_of(tk.pos[j]);
         } else
 #endif
         {
             const GlobalGrid gg(m, qc.slot);
-            knn_select<5, SO_R1_OCTANT != 0>(gg, m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk);
+            knn_select<5, SO_R1_OCTANT != 0>(gg, m, qc, qx, qy, qz, u_seed, m.bound_d2, s_buf, tk, SO_KNN_VERIFY ? &next_lb : nullptr);
         }
         pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
+        if (pre != SO_MATCH_SUCCESS) next_lb = -1.f;
     }
     if (!in_range) return;
+    if (SO_KNN_VERIFY && !verified) nb.vq[gi] = make_float4(qx, qy, qz, next_lb);       // a verified query keeps the record of its last full search
+    if (verified && pre != SO_MATCH_SUCCESS) {             // the fifth of the stored neighbours moved beyond the gate: the set stays on record
+        nb.pre[gi] = (unsigned char)pre;
+        nb.d5[gi] = m.bound_d2;
+        return;
+    }
     nb.pre[gi] = (unsigned char)pre;
     nb.d5[gi] = tk.d2[4];
 #pragma unroll

@@ -44,6 +44,9 @@ struct NnBuf {
     float4* pts;         // [5][cap] the neighbours themselves {x,y,z,bitcast(id)}: k_fit streams them instead of gathering
     float* d5;           // [cap] exact 5th-neighbour d2 of the last search (decides whether its neighbours seed the next one)
     unsigned char* pre;  // [cap] SO_MATCH_SKIPPED / NOT_ENOUGH_NEIGHBORS / NEIGHBORS_TOO_FAR / SUCCESS (= has 5 neighbours)
+    float4* vq;          // [cap] record of the last FULL search that found 5 neighbours: the query position {x,y,z} and, in w, a lower
+                         //       bound on the squared distance to every other point of the block (w < 0: no record).  While the query
+                         //       stays close enough to that position the stored five provably remain its 5-NN (k_knn_scan).
     size_t cap;
 };
 

@@ -58,6 +58,13 @@ struct TopK {
             pos[0] = lt[0] ? p : pos[0];
         }
     }
+    // offer() that also tracks `next`: the smallest d2 among everything offered that did NOT end up in the list (candidates that
+    // lose, and entries a better candidate pushes out) -- a lower bound on the (K+1)-th neighbour distance among the offered
+    __device__ __forceinline__ void offer_track(float d, uint32_t i, uint32_t p, float& next) {
+        const bool enters = d < d2[K - 1] || (d == d2[K - 1] && i < id[K - 1]);
+        next = fminf(next, enters ? d2[K - 1] : d);
+        offer(d, i, p);
+    }
     __device__ __forceinline__ int count() const {
         int c = 0;
 #pragma unroll
@@ -420,9 +427,11 @@ constexpr int kBufCap = SO_BUF_CAP;          // recorded candidates per query be
 // of the grid policy (g.pos_of() turns them into positions of the sorted map).
 // OCT: round 1 over the 2x2x2 nearest cells (measured: -7 % on scans, whose lanes sit in different cells anyway) or over the 27
 // cells of ring 1 (dense query sets such as cfg5: lanes that share a cell then read the same rows; the octant splits them, +10 %).
+// *next_lb (optional): receives a lower bound on the squared distance from the query to every point of its block that is NOT in
+// the returned list (the best loser among the examined candidates, or the bound U beyond which nothing was examined).
 template <int K, bool OCT, class Grid>
 __device__ __forceinline__ void knn_select(const Grid& g, const MapView& m, const QueryCell& qc, float qx, float qy, float qz, float u_seed, float bound,
-                                           uint32_t* s_buf, TopK<K>& tk) {
+                                           uint32_t* s_buf, TopK<K>& tk, float* next_lb = nullptr) {
     float U;
     if (u_seed >= 0.f) U = u_seed * 1.000004f;
     else {
@@ -443,18 +452,21 @@ __device__ __forceinline__ void knn_select(const Grid& g, const MapView& m, cons
     }
     U = fminf(U, bound * 1.000004f);
     int cnt = 0;
+    float next = FLT_MAX;
     const int stride = blockDim.x;
     walk_cube(g, m.nb, m.cs, qc, U, m.R, [&](const float4 c, uint32_t e) {
         if (approx_d2(c, qx, qy, qz) <= U) {
             if (cnt < kBufCap) { s_buf[cnt * stride + threadIdx.x] = e; ++cnt; }
-            else tk.offer(exact_d2(c, qx, qy, qz), __float_as_uint(c.w), e);    // overflow (dense cluster inside U): insert directly
+            else tk.offer_track(exact_d2(c, qx, qy, qz), __float_as_uint(c.w), e, next);    // overflow (dense cluster inside U): insert directly
         }
     });
     for (int k = 0; k < cnt; ++k) {
         const uint32_t e = s_buf[k * stride + threadIdx.x];
         const float4 c = g.load_entry(e);
-        tk.offer(exact_d2(c, qx, qy, qz), __float_as_uint(c.w), e);
+        tk.offer_track(exact_d2(c, qx, qy, qz), __float_as_uint(c.w), e, next);
     }
+    // every block point with FP32 d2 <= U was offered; one that was not has true d2 > U (1 - 4e-7)
+    if (next_lb) *next_lb = fminf(next, U) * (1.f - 2e-6f);
 }
 
 // Unpruned cube [c-R, c+R]^3 clipped to the block (fallback rings of the exact, unbounded search), global memory.
