@@ -228,6 +228,12 @@ int so_register(so_ctx* ctx,
 int so_register_batch(so_ctx* ctx, const void* surf_xyzi, const uint32_t* n_points, size_t n_scans,
                       size_t stride_bytes, size_t intensity_offset,
                       const double* poses_in, const so_icp_opts* opts, so_icp_result* results);
+/* Same with an edge cloud per scan (the line branch of so_register, per scan): edge_xyzi holds the n_scans edge clouds back to
+ * back, n_edge[s] points each (0 allowed); their total must fit so_config.max_scan_points.  Upstream the edge cloud is empty
+ * (featureExtraction.cpp:429-436), so this is the batched form of a dormant branch -- complete, not tuned. */
+int so_register_batch_edges(so_ctx* ctx, const void* surf_xyzi, const uint32_t* n_points, const void* edge_xyzi, const uint32_t* n_edge,
+                            size_t n_scans, size_t stride_bytes, size_t intensity_offset,
+                            const double* poses_in, const so_icp_opts* opts, so_icp_result* results);
 /* Same, inputs already resident in device memory: packed float4 points (d_scans_xyzi), host n_points / poses.
  * Used for the device-resident throughput figure; results are still copied back to host structs. */
 int so_register_batch_device(so_ctx* ctx, const void* d_scans_xyzi, const uint32_t* n_points, size_t n_scans,

@@ -20,7 +20,7 @@ EXPORTS = [
     "so_create", "so_destroy", "so_last_error", "so_device_available", "so_set_stream",
     "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
     "so_map_set_edge_points", "so_map_add_surf", "so_map_add_edge", "so_map_add_scan", "so_map_add_registered_scan", "so_map_add_scan_edge", "so_map_counts_5x5", "so_map_download", "so_map_size",
-    "so_scan_prefilter", "so_scan_deskew", "so_scan_extract_uniform", "so_register", "so_register_injected", "so_set_pose_sink", "so_register_batch", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
+    "so_scan_prefilter", "so_scan_deskew", "so_scan_extract_uniform", "so_register", "so_register_injected", "so_set_pose_sink", "so_register_batch", "so_register_batch_edges", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
     "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_build_flags", "so_profile_enable", "so_profile_get",
 ]
 
@@ -103,6 +103,8 @@ def load_library():
     L.so_set_pose_sink.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
     L.so_register_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_register_batch_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_register_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_correspond.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p]
@@ -363,6 +365,22 @@ class Context:
         stride = scans_xyzi.shape[1] * 4
         self._chk(self.L.so_register_batch(self.h, _p(scans_xyzi), _p(n_points), ns, stride, 12, _p(poses), C.byref(o), res),
                   "so_register_batch")
+        return res
+
+    def register_batch_edges(self, scans_xyzi: np.ndarray, n_points, edges_xyzi: np.ndarray, n_edge, poses, max_icp_iters: int,
+                             max_surface_features: int = 0, **kw):
+        """register_batch with one edge cloud per scan: edges_xyzi float32 [sum(n_edge), 4], clouds back to back."""
+        n_points = np.ascontiguousarray(n_points, dtype=np.uint32)
+        n_edge = np.ascontiguousarray(n_edge, dtype=np.uint32)
+        poses = np.ascontiguousarray(poses, dtype=np.float64)
+        ns = len(n_points)
+        assert len(n_edge) == ns
+        o = self._opts(max_icp_iters, max_surface_features, **kw)
+        res = (IcpResult * ns)()
+        scans_xyzi = np.ascontiguousarray(scans_xyzi, dtype=np.float32)
+        edges_xyzi = np.ascontiguousarray(edges_xyzi, dtype=np.float32).reshape(-1, 4)
+        self._chk(self.L.so_register_batch_edges(self.h, _p(scans_xyzi), _p(n_points), _p(edges_xyzi) if len(edges_xyzi) else None, _p(n_edge), ns,
+                                                 16, 12, _p(poses), C.byref(o), res), "so_register_batch_edges")
         return res
 
     def register_batch_device(self, d_scans_ptr: int, n_points, poses, max_icp_iters: int, max_surface_features: int = 0, **kw):

@@ -97,7 +97,8 @@ static int ctx_alloc(Ctx* c) {
     SO_CUDA_TRY(cudaMalloc(&c->d_offset, c->max_batch * sizeof(uint32_t)));
     SO_CUDA_TRY(cudaMalloc(&c->d_state, c->max_batch * sizeof(IcpState)));
     SO_CUDA_TRY(cudaMallocHost(&c->h_state, c->max_batch * sizeof(IcpState)));
-    SO_CUDA_TRY(cudaMallocHost(&c->h_offset, c->max_batch * sizeof(uint32_t)));
+    SO_CUDA_TRY(cudaMallocHost(&c->h_offset, 2 * c->max_batch * sizeof(uint32_t)));      // [0, max_batch): scan offsets; then the edge clouds' offsets
+    c->h_eoffset = c->h_offset + c->max_batch;
     c->edge_cap = c->cfg.max_scan_points;
     c->edge_grid_cap = uint32_t((c->edge_cap + kThreads - 1) / kThreads);
     SO_CUDA_TRY(cudaMalloc(&c->d_partials, size_t(c->max_batch) * (c->grid_x_cap + c->edge_grid_cap) * kAcc * sizeof(double)));
@@ -267,6 +268,7 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
     if (n_scans <= 2 && !c->profiling && !c->no_fused_lm) bv.counters = c->d_counters + ch.first;
     const MapView me = map_view(c, c->edge);
     EdgeBuf eb = c->ebuf;
+    eb.offset = c->d_eoffset + ch.first;                  // like bv.offset: indexed by the scan's position inside the chunk
     if (!with_nn) { eb.nn = nullptr; eb.selmask = nullptr; }
     *was_loop = false;
     if (d_inject && kCorrLaunches != 2) return fail(SO_ERR_ARG, "so_register_injected needs the split k_knn_scan / k_fit build");
@@ -411,14 +413,14 @@ static void fill_result(const Ctx* c, const IcpState& s, const double pose_in[7]
 // function uploads them into d_scan chunk by chunk on the copy stream.
 static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points, size_t n_scans, const double* poses,
                          const so_icp_opts* opts_in, so_icp_result* results, bool allow_shift, const void* host_src = nullptr,
-                         uint32_t n_edge0 = 0, const uint32_t* d_inject = nullptr, int inject_iters = 0) {
+                         const uint32_t* n_edge = nullptr, const uint32_t* d_inject = nullptr, int inject_iters = 0) {
     so_icp_opts o = *opts_in;
     if (o.lm_max_iterations <= 0) o.lm_max_iterations = 4;
     if (o.max_icp_iters <= 0 || o.max_icp_iters > SO_MAX_ICP_ITERS) return fail(SO_ERR_ARG, "max_icp_iters must be in [1,32]");
     if (o.lm_max_iterations > 16) return fail(SO_ERR_ARG, "lm_max_iterations must be <= 16");
     { int rc = ensure_maps(c); if (rc) return rc; }
-    uint32_t max_n = 0, off = 0;
-    bool any = false;
+    uint32_t max_n = 0, off = 0, eoff = 0;
+    bool any = false, any_edge = false;
     for (size_t s = 0; s < n_scans; ++s) {
         so_icp_result* r = results + s;
         std::memset(r, 0, sizeof(*r));
@@ -433,9 +435,11 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         for (int a = 0; a < 3; ++a) r->pos_in_localmap[a] = ijk[a];
         r->map_surf_5x5 = counts_5x5(c, c->surf, ijk);
         r->map_edge_5x5 = counts_5x5(c, c->edge, ijk);
-        init_state(c->h_state[s], pose, n_points[s], o, s == 0 ? n_edge0 : 0);
+        init_state(c->h_state[s], pose, n_points[s], o, n_edge ? n_edge[s] : 0);
         c->h_offset[s] = off;
         off += n_points[s];
+        c->h_eoffset[s] = eoff;                                    // edge clouds: packed back to back in d_escan like the scans in d_scan
+        if (n_edge) { eoff += n_edge[s]; any_edge |= n_edge[s] != 0; r->scan_edge_num = int32_t(n_edge[s]); }
         if (!o.skip_map_checks && !(r->map_surf_5x5 > 50)) {       // hasEnoughFeatures (:379-381): pose stays the prior
             r->status = SO_STATUS_NOT_ENOUGH_FEATURES;
             c->h_state[s].phase = PH_DONE; c->h_state[s].status = r->status;
@@ -453,6 +457,10 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
     if (any) {
         SO_CUDA_TRY(cudaMemcpyAsync(c->d_state, c->h_state, n_scans * sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
         SO_CUDA_TRY(cudaMemcpyAsync(c->d_offset, c->h_offset, n_scans * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        if (any_edge || c->eoffset_dirty) {                        // the all-zero table of the edge-less case is already there
+            SO_CUDA_TRY(cudaMemcpyAsync(c->d_eoffset, c->h_eoffset, n_scans * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+            c->eoffset_dirty = any_edge;
+        }
         count_h2d(c, n_scans * (sizeof(IcpState) + sizeof(uint32_t)));
         // Chunk the batch.  Even chunks run on `stream`, odd ones on aux_stream, so that one chunk's serial stretches (the
         // one-CTA optimiser steps, kernel tails, the loop condition) sit under the other's wide kernels; with host input
@@ -486,7 +494,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             // rounded up to a bucket of 16 CTAs so that scans of slightly different sizes (live SLAM: every scan differs) share one
             // captured graph; the kernels guard i < n_points and k_lm_step sums only the partial rows n_points implies
             if (ch.grid_x) ch.grid_x = std::min<uint32_t>(c->grid_x_cap, (ch.grid_x + 15u) & ~15u);
-            if (f == 0 && n_edge0 && c->h_state[0].phase == PH_CORR) ch.grid_e = (n_edge0 + kThreads - 1) / kThreads;
+            if (n_edge) for (uint32_t s = f; s < e; ++s) if (c->h_state[s].phase == PH_CORR) ch.grid_e = std::max(ch.grid_e, (n_edge[s] + kThreads - 1) / kThreads);
             chunks.push_back(ch);
         }
         SO_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
@@ -991,7 +999,8 @@ int so_register(so_ctx* ctx, const void* surf, size_t n_surf, const void* edge, 
     c->last_scan_n = n;                                                 // so_map_add_registered_scan inserts it without a second upload
     rc = upload_cloud(c, edge, n_edge, stride, ioff, c->d_escan);       // edge branch input (empty upstream: featureExtraction.cpp:429-436)
     if (rc) return rc;
-    rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true, nullptr, uint32_t(n_edge));
+    const uint32_t ne = uint32_t(n_edge);
+    rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true, nullptr, &ne);
     if (rc) return rc;
     out->scan_edge_num = int32_t(n_edge);
     out->time_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1014,7 +1023,7 @@ int so_register_injected(so_ctx* ctx, const void* surf, size_t n_surf, size_t st
     int rc = upload_cloud(c, surf, n_surf, stride, ioff, c->d_scan);
     if (rc) return rc;
     const uint32_t n = uint32_t(n_surf);
-    rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true, nullptr, 0, c->d_inject, int(n_trace_iters));
+    rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true, nullptr, nullptr, c->d_inject, int(n_trace_iters));
     if (rc) return rc;
     return out->status;
 }
@@ -1036,6 +1045,31 @@ int so_register_batch(so_ctx* ctx, const void* surf, const uint32_t* n_points, s
         if (rc) return rc;
         rc = register_core(c, c->d_scan, n_points, n_scans, poses_in, opts, results, false);
     }
+    if (rc) return rc;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (size_t s = 0; s < n_scans; ++s) results[s].time_total_ms = ms;
+    return SO_OK;
+}
+
+int so_register_batch_edges(so_ctx* ctx, const void* surf, const uint32_t* n_points, const void* edge, const uint32_t* n_edge, size_t n_scans,
+                            size_t stride, size_t ioff, const double* poses_in, const so_icp_opts* opts, so_icp_result* results) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !surf || !n_points || !n_edge || !poses_in || !opts || !results || stride < 12) return fail(SO_ERR_ARG, "bad args");
+    if (n_scans == 0 || n_scans > c->max_batch) return fail(SO_ERR_CAPACITY, "n_scans exceeds so_config.max_batch");
+    size_t total = 0, total_e = 0;
+    for (size_t s = 0; s < n_scans; ++s) {
+        if (n_points[s] > c->cfg.max_scan_points) return fail(SO_ERR_CAPACITY, "scan too large");
+        total += n_points[s]; total_e += n_edge[s];
+    }
+    if (total_e > c->edge_cap) return fail(SO_ERR_CAPACITY, "edge clouds of the batch exceed so_config.max_scan_points points in total");
+    if (total_e && !edge) return fail(SO_ERR_ARG, "bad args");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = upload_cloud(c, edge, total_e, stride, ioff, c->d_escan);
+    if (rc) return rc;
+    rc = upload_cloud(c, surf, total, stride, ioff, c->d_scan);
+    if (rc) return rc;
+    rc = register_core(c, c->d_scan, n_points, n_scans, poses_in, opts, results, false, nullptr, n_edge);
     if (rc) return rc;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     for (size_t s = 0; s < n_scans; ++s) results[s].time_total_ms = ms;

@@ -71,6 +71,8 @@ struct Ctx {
     IcpState* d_state = nullptr;
     IcpState* h_state = nullptr;                   // pinned
     uint32_t* h_offset = nullptr;                  // pinned
+    uint32_t* h_eoffset = nullptr;                 // second half of the same allocation
+    bool eoffset_dirty = false;                    // d_eoffset holds non-zero entries from the last batch
     double* d_partials = nullptr;
     uint32_t* d_counters = nullptr;
     int32_t* d_hist = nullptr;

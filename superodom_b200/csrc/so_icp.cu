@@ -956,11 +956,101 @@ __device__ __forceinline__ void evaluate_body(const BatchView& bv, const CorrBuf
     reduce_to_partials(acc, bv, s);
 }
 
+#ifndef SO_EVAL_TMA
+#define SO_EVAL_TMA 1             // 0: k_evaluate streams its correspondences with per-thread loads (evaluate_body)
+#endif
+// The same evaluation with the 56 B/point stream staged by the TMA engine.  A CTA's points are eval_pts(n) consecutive tiles of
+// kThreads points, and a tile is three contiguous spans (normals+offset 32 B/pt, scan point 16 B/pt, weight 8 B/pt): one elected
+// thread enqueues three cp.async.bulk copies per tile into a kEvalStages-deep shared-memory ring, each stage completing on its
+// own mbarrier; every thread then takes its own point from the stage (thread -> point mapping, arithmetic and reduction are
+// those of evaluate_body: results are bit-identical).  kEvalStages tiles (42 KB) are in flight per CTA whatever the threads are
+// doing, instead of the one software-prefetched point per thread that 124 registers x 2 CTAs per SM leave room for.
+// Falls back to generic loads for the ragged last tile of a scan and for scans whose first point is at an odd offset (the 8 B
+// weights of a tile must start 16 B-aligned for the bulk copy).
+constexpr int kEvalStages = 3;
+struct __align__(128) EvalStage { double4 nd[kThreads]; float4 sp[kThreads]; double w[kThreads]; };
+constexpr uint32_t kEvalStageBytes = uint32_t(sizeof(double4) + sizeof(float4) + sizeof(double)) * kThreads;
+
+template <int PHASE>
+__device__ __forceinline__ void evaluate_body_tma(const BatchView& bv, const CorrBuf& cb, int s) {
+    IcpState* st = bv.st + s;
+    __shared__ double s_pose[7];
+    __shared__ double s_R[9];
+    __shared__ EvalStage s_stage[kEvalStages];
+    __shared__ unsigned long long s_bar[kEvalStages];
+    const uint32_t n = uint32_t(st->n_points);
+    const int pts = eval_pts(n);
+    if (blockIdx.x >= eval_ctas(n)) return;                // the grid covers the largest scan of the chunk
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = PHASE == PH_EVAL ? st->cand[threadIdx.x] : st->x[threadIdx.x];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < kEvalStages; ++k) mbar_init(&s_bar[k], 1);
+    }
+    __syncthreads();
+    const size_t base = size_t(bv.offset[s]);
+    const uint32_t cta0 = blockIdx.x * uint32_t(pts) * kThreads;
+    // tiles [0, full) of this CTA are complete (kThreads points each); tile `full` may be ragged, later ones are empty
+    const int full = (base & 1) ? 0 : int(min(uint32_t(pts), (n - min(n, cta0)) / kThreads));
+    auto issue = [&](int r) {                              // thread 0 only
+        EvalStage& sg = s_stage[r % kEvalStages];
+        unsigned long long* bar = &s_bar[r % kEvalStages];
+        const size_t g = base + cta0 + size_t(r) * kThreads;
+        mbar_arrive_expect_tx(bar, kEvalStageBytes);
+        bulk_copy_g2s(sg.nd, cb.nd + g, uint32_t(sizeof(double4)) * kThreads, bar);
+        bulk_copy_g2s(sg.sp, bv.scan + g, uint32_t(sizeof(float4)) * kThreads, bar);
+        bulk_copy_g2s(sg.w, cb.w + g, uint32_t(sizeof(double)) * kThreads, bar);
+    };
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < kEvalStages && r < full; ++r) issue(r);
+        qtoR(s_pose + 3, s_R);
+    }
+    __syncthreads();
+    double acc[kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < pts; ++r) {
+        const uint32_t i = cta0 + uint32_t(r) * kThreads + threadIdx.x;
+        double w = 0.0;
+        double4 nd = make_double4(0.0, 0.0, 0.0, 0.0);
+        float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < full) {                                    // CTA-uniform
+            const EvalStage& sg = s_stage[r % kEvalStages];
+            mbar_wait(&s_bar[r % kEvalStages], uint32_t(r / kEvalStages) & 1u);
+            w = sg.w[threadIdx.x];
+            nd = sg.nd[threadIdx.x];
+            sp = sg.sp[threadIdx.x];
+            __syncthreads();                               // every thread holds its point: the stage may be refilled
+            if (threadIdx.x == 0 && r + kEvalStages < full) issue(r + kEvalStages);
+        } else {
+            if (cta0 + uint32_t(r) * kThreads >= n) break;
+            if (i < n) {
+                w = cb.w[base + i];
+                nd = cb.nd[base + i];
+                sp = __ldg(&bv.scan[base + i]);
+            }
+        }
+        if (w != 0.0) {
+            const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+            double pw[3];
+            qrot(s_pose + 3, pin, pw);
+            pw[0] += s_pose[0]; pw[1] += s_pose[1]; pw[2] += s_pose[2];
+            const double nn[3] = {nd.x, nd.y, nd.z};
+            accumulate(acc, nn, nd.w, w, pin, pw, s_R, bv.tukey_a2);
+        }
+    }
+    reduce_to_partials(acc, bv, s);
+}
+
 template <int PHASE>
 __global__ void __launch_bounds__(kThreads, 2) k_evaluate(BatchView bv, CorrBuf cb) {
     const int s = blockIdx.y;
     if (bv.st[s].phase != PHASE) return;
+#if SO_EVAL_TMA
+    evaluate_body_tma<PHASE>(bv, cb, s);
+#else
     evaluate_body<PHASE>(bv, cb, s);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -63,7 +63,7 @@ __host__ __device__ inline uint32_t eval_ctas(uint32_t n) { const uint32_t per =
 __host__ inline uint32_t eval_grid(uint32_t n_max) {
     if (n_max <= 4096u) return (n_max + 255u) / 256u;
     if (n_max <= 65536u) { const uint32_t g = (n_max + 1023u) / 1024u; return g > 16u ? g : 16u; }
-    const uint32_t g = (n_max + 4095u) / 4096u;
+    const uint32_t per = uint32_t(kEvalPts) * 256u, g = (n_max + per - 1u) / per;
     return g > 64u ? g : 64u;
 }
 #ifndef SO_FIT_PTS

@@ -508,6 +508,36 @@ def test_edge_line_branch_registration(gpu_api, oracle_mod, cap):
     ctx.close()
 
 
+def test_edge_clouds_in_batched_replay(gpu_api):
+    """so_register_batch_edges: every scan of a batch carries its own edge cloud (a19 in replay).  Each scan's result must be
+    BIT-equal to the single-scan so_register of the same (scan, edge cloud, prior) -- whose parity against the oracle is the test
+    above -- including a scan with no edge points and scans of different sizes in one batch (spread over both chunk streams)."""
+    from superodom_b200 import synth
+    case, em, es = _edge_case()
+    ctx = _ctx(gpu_api, case, max_batch=16)
+    ctx.map_set_resolution(0.1, 0.2)
+    ctx.map_set_edge_points(em)
+    B = 16
+    scans, edges, priors = [], [], []
+    for i in range(B):
+        T = synth.perturb_pose(case["pose_true"], 7100 + i, dt=0.3, dth_deg=2.0)
+        scans.append(synth.make_scan(case["scene"], "vlp16", T, 7200 + i))
+        edges.append(np.zeros((0, 4), np.float32) if i == 3 else synth.make_edge_scan(em, T, 3000 + i, keep_every=2 + i % 3))
+        priors.append(synth.perturb_pose(T, 7300 + i, dt=0.05, dth_deg=0.5))
+    singles = [ctx.register(scans[i], priors[i], 5, 0, edge_xyzi=edges[i] if len(edges[i]) else None) for i in range(B)]
+    res = ctx.register_batch_edges(np.concatenate(scans), [len(x) for x in scans], np.concatenate(edges), [len(e) for e in edges], np.array(priors), 5, 0)
+    for i in range(B):
+        a, b = singles[i], res[i]
+        assert a.status == b.status == 0 and np.array_equal(np.array(a.pose), np.array(b.pose)), i
+        assert a.n_iterations == b.n_iterations and list(a.iter_n_edge) == list(b.iter_n_edge) and list(a.hist_reject_line) == list(b.hist_reject_line), i
+        assert np.array_equal(np.array(a.cov), np.array(b.cov)) and b.scan_edge_num == len(edges[i]), i
+        assert (b.iter_n_edge[0] > 500) == (i != 3), (i, b.iter_n_edge[0])
+    # an edge-less batch afterwards runs with the branch idle
+    r0 = ctx.register_batch(np.concatenate(scans), [len(x) for x in scans], np.array(priors), 5, 0)
+    assert all(r.iter_n_edge[0] == 0 and r.status == 0 for r in r0)
+    ctx.close()
+
+
 def test_edge_map_insert_and_download_order(gpu_api, oracle_mod):
     """addEdgePointCloud (LocalMap.h:529-589) = the surf insert at leaf lineRes; getAllLocalMap returns each cube's edge cloud
     followed by its surf cloud, cubes in index order (LocalMap.h:647-658)."""
