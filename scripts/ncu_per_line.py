@@ -17,7 +17,7 @@ import tempfile
 
 
 def ncu_counts(rep, kernel):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kernel}"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kernel}"] + os.environ.get("NCU_EXTRA", "").split(), capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
     H = rows[hdr]

@@ -215,7 +215,7 @@ static void timed_launch_end(Ctx* c, int cls) {
 // A contiguous run of scans of the batch that is uploaded, ordered and registered together.
 // grid_in: CTAs covering the longest scan as uploaded (scan ordering); grid_x: CTAs covering the longest scan once it is reduced to the
 // points shouldProcessPoint keeps (the ICP kernels); small: every scan's survivors fit k_prepare_small
-struct Chunk { uint32_t first, count, pt_first, pt_count, grid_x, grid_e = 0, grid_in = 0; bool small = false; };
+struct Chunk { uint32_t first, count, pt_first, pt_count, grid_x, grid_e = 0, grid_in = 0; bool small = false; uint32_t max_kept = 0; };
 
 // Once per registration: order every scan by map cell at its prior pose (k_scan_keys -> radix sort -> k_scan_gather, or the one-CTA
 // k_prepare_small for small registrations).  compact: drop the points the decimation skips here, once, instead of in every kernel.
@@ -228,7 +228,7 @@ static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch, cudaS
     int cell_bits = 1, scan_bits = 0;
     while (cell_bits < 32 && (uint64_t(1) << cell_bits) <= n_cells) ++cell_bits;       // cells 0..n_cells-1 < mask = 2^cell_bits - 1
     if (compact && ch.small && !c->no_small_prepare) {
-        launch_prepare_small(mv, bv, c->d_scan_sorted, ch.count, cell_bits, st);
+        launch_prepare_small(mv, bv, c->d_scan_sorted, ch.count, cell_bits, ch.max_kept, st);
         c->launches++;
         timed_launch_end(c, 3);
         SO_CUDA_TRY(cudaGetLastError());
@@ -266,6 +266,7 @@ static int run_schedule(Ctx* c, const Chunk& ch, int iters, int lm, bool with_nn
     const uint32_t grid_x = ch.grid_x, n_scans = ch.count, grid_e = ch.grid_e;
     // one or two scans in flight: launch-latency bound -> optimiser step folded into the evaluation kernels (k_evaluate_lm)
     if (n_scans <= 2 && !c->profiling && !c->no_fused_lm) bv.counters = c->d_counters + ch.first;
+    bv.coop_knn = n_scans <= 2 && grid_x <= kCoopMaxGrid && !c->no_coop_knn;      // latency-bound search: a warp per query
     const MapView me = map_view(c, c->edge);
     EdgeBuf eb = c->ebuf;
     eb.offset = c->d_eoffset + ch.first;                  // like bv.offset: indexed by the scan's position inside the chunk
@@ -490,6 +491,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             }
             ch.grid_in = (mx_in + kThreads - 1) / kThreads;
             ch.small = mx <= kPrepareSmallCap && mx_in > 0;
+            ch.max_kept = mx;
             ch.grid_x = (mx + kThreads - 1) / kThreads;
             // rounded up to a bucket of 16 CTAs so that scans of slightly different sizes (live SLAM: every scan differs) share one
             // captured graph; the kernels guard i < n_points and k_lm_step sums only the partial rows n_points implies
@@ -598,6 +600,7 @@ so_ctx* so_create(const so_config* cfg_in) {
     if (std::getenv("SO_SINGLE_STREAM")) c->single_stream = true;
     if (std::getenv("SO_NO_FUSED_LM")) c->no_fused_lm = true;
     if (std::getenv("SO_NO_SMALL_PREPARE")) c->no_small_prepare = true;
+    if (std::getenv("SO_NO_COOP_KNN")) c->no_coop_knn = true;
     if (std::getenv("SO_FORCE_KEY64")) c->force_key64 = true;
     if (const char* e = std::getenv("SO_CHUNKS")) c->chunk_override = std::max(0, std::min(16, std::atoi(e)));      // profiling aid: ncu cannot see inside conditional-node bodies
     if (ctx_alloc(c) != SO_OK) { ctx_free(c); return nullptr; }
@@ -1119,7 +1122,8 @@ int so_correspond(so_ctx* ctx, const void* surf, size_t n, size_t stride, size_t
     rc = prepare_scans(c, c->d_scan, ch, c->stream, false);              // stage API reports every point: decimation stays inside the kernels
     if (rc) return rc;
     const MapView mv = map_view(c, c->surf);
-    const BatchView bv = batch_view(c, c->d_scan_sorted);
+    BatchView bv = batch_view(c, c->d_scan_sorted);
+    bv.coop_knn = grid_x <= kCoopMaxGrid && !c->no_coop_knn;            // as a single small registration would search
     timed_launch_begin(c); launch_correspond(mv, bv, c->corr, c->nn, grid_x, 1, c->stream); c->launches += kCorrLaunches + 2; timed_launch_end(c, 0);
     SO_CUDA_TRY(cudaGetLastError());
     std::vector<double4> nd(n); std::vector<double> w(n); std::vector<uchar4> fl(n); std::vector<uint32_t> nn(n * 5); std::vector<float> d2(n * 5);

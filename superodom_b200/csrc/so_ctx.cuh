@@ -107,6 +107,7 @@ struct Ctx {
     uint64_t graph_clock = 0;
     uint64_t map_epoch = 1;
     bool force_key64 = false;                      // SO_FORCE_KEY64: test aid, take the 64-bit scan-order key path even when 32 bits suffice
+    bool no_coop_knn = false;                      // SO_NO_COOP_KNN: A/B aid, always one query per thread
     bool no_small_prepare = false;                 // SO_NO_SMALL_PREPARE: A/B aid, always the device-wide scan ordering
     bool no_fused_lm = false;                      // SO_NO_FUSED_LM: A/B aid, always the two-kernel evaluation + optimiser step
     bool single_stream = false;                    // SO_SINGLE_STREAM: tuning aid, all chunks on `stream`

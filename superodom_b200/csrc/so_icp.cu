@@ -107,6 +107,132 @@ __device__ __noinline__ void covariance_and_errors(IcpState& st) {
     st.ori_inv_cond = sqrt(e[0]) / sqrt(e[2]);
 }
 
+#ifndef SO_COV_SERIAL
+#define SO_COV_SERIAL 0           // 1: the covariance step on the one thread that runs the optimiser (A/B aid)
+#endif
+// The same computation spread over the 32 lanes of one warp (S and sc in shared memory).  The 6x6 Jacobi takes its rotations in the
+// round-robin order of jacobi_eig6_rr: the three angles of a round are computed by three lanes at once, and each rotation updates
+// its 8 off-diagonal entries, 12 eigenvector entries and 2x2 block on 15 lanes in one step instead of ~110 dependent FP64
+// instructions on one thread (the covariance was 38 of the ~50 us the last optimiser step of a registration took).  Per element
+// the arithmetic and its order are those of the serial routine.
+__constant__ int c_rr_p[15] = {0, 1, 2, 0, 3, 1, 0, 2, 1, 0, 1, 4, 0, 2, 3};
+__constant__ int c_rr_q[15] = {5, 4, 3, 4, 5, 2, 3, 4, 5, 2, 3, 5, 1, 5, 4};
+struct CovScratch { double a[36], v[36], w[6], inv[6], t[3], c[3], s[3]; int perm[6]; };
+
+__device__ __noinline__ void covariance_and_errors_warp(IcpState& S, CovScratch& sc) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < 36; e += 32) {
+        const int i = e / 6, j = e % 6;
+        sc.a[e] = S.H[i <= j ? tri(i, j) : tri(j, i)];
+        sc.v[e] = i == j ? 1.0 : 0.0;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        int stop = 0;
+        if (lane == 0) {
+            double off = 0.0, dia = 0.0;
+#pragma unroll
+            for (int p = 0; p < 6; ++p) {
+                dia += sc.a[p * 6 + p] * sc.a[p * 6 + p];
+#pragma unroll
+                for (int q = p + 1; q < 6; ++q) off += sc.a[p * 6 + q] * sc.a[p * 6 + q];
+            }
+            stop = (off <= SO_JACOBI_OFF_TOL * dia || off == 0.0) ? 1 : 0;
+        }
+        if (__shfl_sync(full, stop, 0)) break;
+#pragma unroll 1
+        for (int round = 0; round < 5; ++round) {
+            if (lane < 3) {                                  // the three angles of the round (disjoint 2x2 blocks)
+                const int p = c_rr_p[round * 3 + lane], q = c_rr_q[round * 3 + lane];
+                const double apq = sc.a[p * 6 + q];
+                const float dlt = float(sc.a[q * 6 + q] - sc.a[p * 6 + p]), b2 = float(2.0 * apq);
+                float tf = __fdividef(b2, fabsf(dlt) + sqrtf(fmaf(dlt, dlt, b2 * b2)));
+                if (!(fabsf(tf) <= 1.0f)) tf = 0.0f;         // apq == 0 after the cast (or inf / nan): no rotation
+                const double t = apq != 0.0 ? double(dlt < 0.0f ? -tf : tf) : 0.0;
+                const double c = rsqrt(t * t + 1.0);
+                sc.t[lane] = t; sc.c[lane] = c; sc.s[lane] = t * c;
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {
+                const int p = c_rr_p[round * 3 + k], q = c_rr_q[round * 3 + k];
+                const double t = sc.t[k], c = sc.c[k], sn = sc.s[k];
+                if (t != 0.0) {                              // warp-uniform
+                    // lanes 0..5: row r of a (r outside the pair); lanes 8..13: row r of v; lane 16: the 2x2 block
+                    const int r = lane < 8 ? lane : lane - 8;
+                    const bool do_a = lane < 6 && r != p && r != q, do_v = lane >= 8 && lane < 14, do_d = lane == 16;
+                    double n0 = 0.0, n1 = 0.0;
+                    if (do_a) { const double arp = sc.a[r * 6 + p], arq = sc.a[r * 6 + q]; n0 = c * arp - sn * arq; n1 = sn * arp + c * arq; }
+                    if (do_v) { const double vrp = sc.v[r * 6 + p], vrq = sc.v[r * 6 + q]; n0 = c * vrp - sn * vrq; n1 = sn * vrp + c * vrq; }
+                    if (do_d) { const double apq = sc.a[p * 6 + q]; n0 = sc.a[p * 6 + p] - t * apq; n1 = sc.a[q * 6 + q] + t * apq; }
+                    __syncwarp();
+                    if (do_a) { sc.a[r * 6 + p] = sc.a[p * 6 + r] = n0; sc.a[r * 6 + q] = sc.a[q * 6 + r] = n1; }
+                    if (do_v) { sc.v[r * 6 + p] = n0; sc.v[r * 6 + q] = n1; }
+                    if (do_d) { sc.a[p * 6 + p] = n0; sc.a[q * 6 + q] = n1; sc.a[p * 6 + q] = 0.0; sc.a[q * 6 + p] = 0.0; }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    if (lane == 0) {                                         // ascending order, as a column permutation
+        double w[6];
+        int pm[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { w[i] = sc.a[i * 6 + i]; pm[i] = i; }
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = i + 1; j < 6; ++j)
+                if (w[j] < w[i]) { const double tw = w[i]; w[i] = w[j]; w[j] = tw; const int tp = pm[i]; pm[i] = pm[j]; pm[j] = tp; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { sc.w[i] = w[i]; sc.perm[i] = pm[i]; }
+    }
+    __syncwarp();
+    {
+        const int e0 = lane, e1 = lane + 32;
+        const double v0 = sc.v[(e0 / 6) * 6 + sc.perm[e0 % 6]];
+        const double v1 = e1 < 36 ? sc.v[(e1 / 6) * 6 + sc.perm[e1 % 6]] : 0.0;
+        __syncwarp();
+        sc.v[e0] = v0;
+        if (e1 < 36) sc.v[e1] = v1;
+    }
+    __syncwarp();
+    // ceres::Covariance{apply_loss_function, DENSE_SVD, null_space_rank=-1} in tangent space (LidarSlam.cpp:854-871):
+    // pseudo-inverse of J^T J dropping singular directions with s_i/s_max < sqrt(1e-14) (covariance_impl.cc).
+    {
+        const double lmax = sc.w[5];
+        const double wk = lane < 6 ? sc.w[lane] : 1.0;
+        const double ratio = (wk > 0.0 && lmax > 0.0) ? sqrt(wk / lmax) : 0.0;
+        const unsigned bad = __ballot_sync(full, lane < 6 && ratio < 1e-7);
+        if (lane < 6) sc.inv[lane] = (bad >> lane) ? 0.0 : 1.0 / wk;     // a cut direction cuts every smaller one (descending singular values)
+    }
+    __syncwarp();
+    for (int e = lane; e < 36; e += 32) {
+        const int i = e / 6, j = e % 6;
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) t += sc.v[i * 6 + k] * sc.inv[k] * sc.v[j * 6 + k];
+        S.cov[e] = t;
+    }
+    __syncwarp();
+    // EstimateRegistrationError (LidarSlam.cpp:873-884): 3x3 eigen of the position (lane 0) / orientation (lane 1) blocks
+    if (lane < 2) {
+        double M[9], E[9], e[3];
+        const int o = lane * 3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) M[i * 3 + j] = S.cov[(i + o) * 6 + (j + o)];
+        jacobi_eig<3, 20>(M, E, e);
+        const double err = sqrt(e[2]), inv_cond = sqrt(e[0]) / sqrt(e[2]);
+        if (lane == 0) { S.pos_err = err; S.pos_dir[0] = E[2]; S.pos_dir[1] = E[5]; S.pos_dir[2] = E[8]; S.pos_inv_cond = inv_cond; }
+        else { S.ori_err_deg = err / M_PI * 180.0; S.ori_dir[0] = E[2]; S.ori_dir[1] = E[5]; S.ori_dir[2] = E[8]; S.ori_inv_cond = inv_cond; }
+    }
+    __syncwarp();
+}
+
 // End of one ceres::Solve == end of one ICP iteration (LidarSlam.cpp:134-146).
 __device__ __noinline__ void end_solve(IcpState& st) {
     const int it = st.icp_iter;
@@ -122,7 +248,11 @@ __device__ __noinline__ void end_solve(IcpState& st) {
         st.status = SO_STATUS_NO_CORRESPONDENCES; st.phase = PH_DONE; return;
     }
     if (st.num_successful == 1 || it == st.max_icp_iters - 1) {      // (:141)
+#if SO_COV_SERIAL
         covariance_and_errors(st);
+#else
+        st.need_cov = 1;                          // lm_step_body: first warp of the CTA, right after this serial step
+#endif
         st.phase = PH_DONE;
     } else {
         st.icp_iter = it + 1;
@@ -362,7 +492,8 @@ __device__ __forceinline__ float seed_bound(const MapView& m, const QueryCell& q
 // shouldProcessPoint (LidarSlam.cpp:353-359)
 __device__ __forceinline__ bool should_process(uint32_t i, double rate) {
     if (rate < 0.0) return true;
-    const double rem = fmod(double(i) * rate, 1.0);
+    const double x = double(i) * rate;
+    const double rem = x - floor(x);                      // == std::fmod(x, 1.0) for x >= 0: both are exact
     return !(rem + 0.001 > rate);
 }
 
@@ -436,41 +567,38 @@ __global__ void __launch_bounds__(kThreads) k_scan_gather(const float4* __restri
 // original index only): the ICP kernels then run over the <= max_surface_features + 1 surviving points with sampling off.
 // Deterministic: the survivors are compacted in index order (block scans), sorted by cell key with a stable block radix sort.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kSmallThreads = 1024, kSmallItems = 4, kSmallCap = kSmallThreads * kSmallItems;
+constexpr int kSmallThreads = 1024, kSmallCap = kPrepareSmallCap;
+static_assert(kSmallCap == kSmallThreads * 4, "k_prepare_small<4> covers kPrepareSmallCap survivors");
+// ITEMS: survivors per thread in the sort (2 when they fit 2048 -- the shipped max_surface_features of 2000 -- else 4)
+template <int ITEMS>
 __global__ void __launch_bounds__(kSmallThreads) k_prepare_small(MapView m, BatchView bv, float4* __restrict__ out, int key_bits) {
-    using Sort = cub::BlockRadixSort<uint32_t, kSmallThreads, kSmallItems, uint32_t>;
+    constexpr int kCap = kSmallThreads * ITEMS;
+    using Sort = cub::BlockRadixSort<uint32_t, kSmallThreads, ITEMS, uint32_t>;
     using Scan = cub::BlockScan<uint32_t, kSmallThreads>;
-    struct Compact { typename Scan::TempStorage scan; uint32_t idx[kSmallCap]; };
+    struct Compact { typename Scan::TempStorage scan; uint32_t idx[kCap]; };
     __shared__ union { typename Sort::TempStorage sort; Compact c; } s_tmp;      // the index list is consumed (into registers) before the sort starts
     uint32_t* s_idx = s_tmp.c.idx;
     __shared__ double s_pose[7];
-    __shared__ uint32_t s_count;
     const int s = blockIdx.x;
     IcpState* st = bv.st + s;
     if (st->phase != PH_CORR) return;
     if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
     const uint32_t n = uint32_t(st->n_points);
     const double rate = st->sampling_rate;
     const size_t base = size_t(bv.offset[s]);
-    // survivors, in index order
-    for (uint32_t i0 = 0; i0 < n; i0 += kSmallThreads) {
-        const uint32_t i = i0 + threadIdx.x;
-        const uint32_t keep = (i < n && should_process(i, rate)) ? 1u : 0u;
-        uint32_t pos, total;
-        Scan(s_tmp.c.scan).ExclusiveSum(keep, pos, total);
-        const uint32_t before = s_count;
-        if (keep && before + pos < uint32_t(kSmallCap)) s_idx[before + pos] = i;
-        __syncthreads();
-        if (threadIdx.x == 0) s_count = before + total;
-        __syncthreads();
-    }
-    const uint32_t n_act = min(s_count, uint32_t(kSmallCap));           // the host chose this path only when the survivors fit
-    uint32_t key[kSmallItems], val[kSmallItems];
+    // survivors, in index order: every thread owns a contiguous run of indices, ONE block scan places the runs
+    const uint32_t per = (n + kSmallThreads - 1) / kSmallThreads, lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+    uint32_t mine = 0;
+    for (uint32_t i = lo; i < hi; ++i) mine += should_process(i, rate) ? 1u : 0u;
+    uint32_t pos, total;
+    Scan(s_tmp.c.scan).ExclusiveSum(mine, pos, total);
+    for (uint32_t i = lo; i < hi && pos < uint32_t(kCap); ++i) if (should_process(i, rate)) s_idx[pos++] = i;
+    __syncthreads();
+    const uint32_t n_act = min(total, uint32_t(kCap));                  // the host chose this path only when the survivors fit
+    uint32_t key[ITEMS], val[ITEMS];
 #pragma unroll
-    for (int k = 0; k < kSmallItems; ++k) {
-        const uint32_t j = threadIdx.x * kSmallItems + k;               // blocked arrangement
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t j = threadIdx.x * ITEMS + k;                     // blocked arrangement
         key[k] = 0xFFFFFFFFu; val[k] = 0xFFFFFFFFu;
         if (j < n_act) {
             const uint32_t i = s_idx[j];
@@ -489,8 +617,8 @@ __global__ void __launch_bounds__(kSmallThreads) k_prepare_small(MapView m, Batc
     __syncthreads();
     Sort(s_tmp.sort).Sort(key, val, 0, key_bits < 32 ? key_bits + 1 : 32);      // + 1: the padding keys (all ones) sort behind the mask
 #pragma unroll
-    for (int k = 0; k < kSmallItems; ++k) {
-        const uint32_t j = threadIdx.x * kSmallItems + k;
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t j = threadIdx.x * ITEMS + k;
         if (j < n_act) {
             const float4 p = __ldg(&bv.scan[base + val[k]]);
             out[base + j] = make_float4(p.x, p.y, p.z, __uint_as_float(val[k]));
@@ -594,6 +722,116 @@ __global__ void __launch_bounds__(kTileThreads, SO_KNN_MINB) k_knn_scan(MapView 
         nb.pos[size_t(j) * nb.cap + gi] = ok ? tk.pos[j] : 0xFFFFFFFFu;
         // the five points are L1-hot here; handing them on as coalesced 16-byte stores saves k_fit five scattered gathers
         if (pre == SO_MATCH_SUCCESS) nb.pts[size_t(j) * nb.cap + gi] = __ldg(&m.pts[tk.pos[j]]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_knn_scan_coop: the same search for SMALL registrations (a live scan after the shouldProcessPoint decimation: ~2 000 queries),
+// one WARP per query.  With one query per thread such a launch is eight CTAs whose threads each walk ~3 800 dependent instructions
+// (~20 us); here lane l < 25 takes row l of the 5 x 5 rows of the two-ring cube (the same pruning against the gate 3 * planeRes_
+// as walk_cube), a warp scan flattens the rows' candidate spans, the lanes take the candidates 32 at a time -- FP32 filter, the
+// reference's exact d2, a private top-5 -- and five warp arg-min rounds over (d2, id) merge the private lists.  The result is
+// the exact block-local 5-NN in (d2, id) order with the same distances, i.e. bit-identical to k_knn_scan's, in ~700 instructions
+// per warp spread over every SM.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kCoopWarps = kThreads / 32;
+__global__ void __launch_bounds__(kThreads) k_knn_scan_coop(MapView m, BatchView bv, NnBuf nb) {
+    const int s = blockIdx.y;
+    const IcpState* st = bv.st + s;
+    if (st->phase != PH_CORR) return;
+    __shared__ double s_pose[7];
+    __shared__ uint32_t s_scan[kCoopWarps][33], s_t[kCoopWarps][32];
+    if (threadIdx.x < 7) s_pose[threadIdx.x] = st->x[threadIdx.x];
+    __syncthreads();
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n = uint32_t(st->n_points);
+    const uint32_t i = blockIdx.x * kCoopWarps + warp;     // the warp's query
+    if (i >= n) return;
+    const size_t gi = size_t(bv.offset[s]) + i;
+    const float4 sp = __ldg(&bv.scan[gi]);
+    int pre = SO_MATCH_SKIPPED;
+    TopK<5> tk;
+    tk.init(m.bound_d2);
+    if (should_process(__float_as_uint(sp.w), st->sampling_rate)) {
+        const double pin[3] = {double(sp.x), double(sp.y), double(sp.z)};
+        double pf[3];
+        qrot(s_pose + 3, pin, pf);
+        const float qx = float(pf[0] + s_pose[0]), qy = float(pf[1] + s_pose[1]), qz = float(pf[2] + s_pose[2]);
+        QueryCell qc;
+        locate(m, qx, qy, qz, qc);
+        if (qc.slot < 0 || qc.nblock < 5) pre = SO_MATCH_NOT_ENOUGH_NEIGHBORS;
+        else {
+            const GlobalGrid g(m, qc.slot);
+            const int nbc = m.nb, R = m.R;
+            const float cs = m.cs, U = m.bound_d2 * 1.000004f, Um = U * 1.0001f;
+            // ---- lane l: row (oz, oy) of the cube, its candidate span
+            uint32_t t = 0, len = 0;
+            const int side = 2 * R + 1;
+            if (lane < side * side) {                      // R <= 2 by construction of the grid (cells >= half the search radius)
+                const int oz = lane / side - R, oy = lane % side - R;
+                const int zz = qc.c[2] + oz, yy = qc.c[1] + oy, cx = qc.c[0];
+                const float fx = qc.f[0], gx = cs - fx;
+                const float lz = axis_gap(oz, qc.f[2], cs - qc.f[2], cs), ly = axis_gap(oy, qc.f[1], cs - qc.f[1], cs);
+                const float lb = fmaf(ly, ly, lz * lz);
+                if (zz >= 0 && zz < nbc && yy >= 0 && yy < nbc && lb <= Um) {
+                    const bool l1 = cx >= 1 && fmaf(fx, fx, lb) <= Um;
+                    const bool l2 = l1 && R >= 2 && cx >= 2 && fmaf(fx + cs, fx + cs, lb) <= Um;
+                    const bool r1 = cx + 1 < nbc && fmaf(gx, gx, lb) <= Um;
+                    const bool r2 = r1 && R >= 2 && cx + 2 < nbc && fmaf(gx + cs, gx + cs, lb) <= Um;
+                    uint32_t end, tag;
+                    g.row(zz, yy, cx - int(l1) - int(l2), cx + int(r1) + int(r2), t, end, tag);
+                    len = end - t;
+                }
+            }
+            // ---- exclusive scan of the span lengths: candidate c of the flattened list sits in the row whose prefix interval holds c
+            uint32_t incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(full, incl, o); if (lane >= o) incl += v; }
+            const uint32_t total = __shfl_sync(full, incl, 31);
+            s_scan[warp][lane] = incl - len;
+            s_t[warp][lane] = t;
+            if (lane == 0) s_scan[warp][32] = total;
+            __syncwarp();
+            for (uint32_t c = lane; c < total; c += 32) {
+                int lo = 0;                                // largest row with prefix <= c (empty rows share a prefix: the search lands past them)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) if (s_scan[warp][lo + o] <= c) lo += o;
+                const uint32_t e = s_t[warp][lo] + (c - s_scan[warp][lo]);
+                const float4 cand = g.load(e);
+                if (approx_d2(cand, qx, qy, qz) <= U) tk.offer(exact_d2(cand, qx, qy, qz), __float_as_uint(cand.w), e);
+            }
+            // ---- merge: five rounds of warp arg-min over the heads of the private lists
+            TopK<5> out;
+            out.init(m.bound_d2);
+            int head = 0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                float hd = m.bound_d2; uint32_t hi = 0xFFFFFFFFu, hp = 0;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) if (k == head) { hd = tk.d2[k]; hi = tk.id[k]; hp = tk.pos[k]; }
+                if (head >= 5) { hd = FLT_MAX; hi = 0xFFFFFFFFu; }
+                const uint32_t dbits = hi != 0xFFFFFFFFu ? __float_as_uint(hd) : 0xFFFFFFFFu;      // d2 >= 0: the bit pattern orders like the value
+                const uint32_t dmin = __reduce_min_sync(full, dbits);
+                if (dmin == 0xFFFFFFFFu) break;            // fewer than five within the gate (warp-uniform)
+                const uint32_t imin = __reduce_min_sync(full, dbits == dmin ? hi : 0xFFFFFFFFu);
+                const bool win = dbits == dmin && hi == imin;      // ids are unique: exactly one lane
+                const int src = __ffs(__ballot_sync(full, win)) - 1;
+                out.d2[j] = __uint_as_float(dmin); out.id[j] = imin; out.pos[j] = __shfl_sync(full, hp, src);
+                if (win) ++head;
+            }
+            tk = out;
+            pre = tk.count() < 5 ? SO_MATCH_NEIGHBORS_TOO_FAR : SO_MATCH_SUCCESS;       // d2[4] > 3*planeRes_ (:741-744)
+        }
+    }
+    if (lane == 0) { nb.pre[gi] = (unsigned char)pre; nb.d5[gi] = tk.d2[4]; }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        if (lane == j) {
+            const bool ok = tk.id[j] != 0xFFFFFFFFu;
+            nb.pos[size_t(j) * nb.cap + gi] = ok ? tk.pos[j] : 0xFFFFFFFFu;
+            if (pre == SO_MATCH_SUCCESS) nb.pts[size_t(j) * nb.cap + gi] = __ldg(&m.pts[tk.pos[j]]);
+        }
     }
 }
 
@@ -1306,6 +1544,11 @@ __device__ __forceinline__ void lm_step_body(const BatchView& bv, int s, uint32_
         }
     }
     __syncthreads();
+    if (s_st.need_cov) {                                   // the registration just ended (CTA-uniform)
+        __shared__ CovScratch s_cov;
+        if (threadIdx.x < 32) covariance_and_errors_warp(s_st, s_cov);      // need_cov stays set: the state is re-initialised per registration
+        __syncthreads();
+    }
     {
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_st);
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(st);
@@ -1434,8 +1677,9 @@ void launch_scan_finish(const BatchView& bv, const uint64_t* sorted_keys, size_t
     if (key32) k_scan_finish<uint32_t><<<(n_scans + 63) / 64, 64, 0, st>>>(bv, reinterpret_cast<const uint32_t*>(sorted_keys) + first, pt_first, cell_bits, n_scans);
     else k_scan_finish<uint64_t><<<(n_scans + 63) / 64, 64, 0, st>>>(bv, sorted_keys + first, pt_first, cell_bits, n_scans);
 }
-void launch_prepare_small(const MapView& m, const BatchView& bv, float4* out, uint32_t n_scans, int key_bits, cudaStream_t st) {
-    k_prepare_small<<<n_scans, kSmallThreads, 0, st>>>(m, bv, out, key_bits);
+void launch_prepare_small(const MapView& m, const BatchView& bv, float4* out, uint32_t n_scans, int key_bits, uint32_t max_kept, cudaStream_t st) {
+    if (max_kept <= 2u * kSmallThreads) k_prepare_small<2><<<n_scans, kSmallThreads, 0, st>>>(m, bv, out, key_bits);
+    else k_prepare_small<4><<<n_scans, kSmallThreads, 0, st>>>(m, bv, out, key_bits);
 }
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, size_t first, const uint32_t* offset, size_t total, float4* out,
                         int cell_bits, bool key32, cudaStream_t st) {
@@ -1452,7 +1696,10 @@ void launch_match(const MapView& m, const BatchView& bv, const CorrBuf& cb, cons
     (void)part;
     k_knn_fit<<<dim3(grid_x, n_scans), kThreads, 0, st>>>(m, bv, cb, nb);
 #else
-    if (part != 2) k_knn_scan<<<dim3(grid_x * (kThreads / kTileThreads), n_scans), kTileThreads, 0, st>>>(m, bv, nb);
+    if (part != 2) {
+        if (bv.coop_knn) k_knn_scan_coop<<<dim3(grid_x * (kThreads / kCoopWarps), n_scans), kThreads, 0, st>>>(m, bv, nb);
+        else k_knn_scan<<<dim3(grid_x * (kThreads / kTileThreads), n_scans), kTileThreads, 0, st>>>(m, bv, nb);
+    }
     const uint32_t gf = (grid_x * kThreads + kFitPts * kFitThreads - 1) / (kFitPts * kFitThreads);
     if (part != 1) k_fit<<<dim3(gf, n_scans), kFitThreads, 0, st>>>(m, bv, cb, nb);
 #endif

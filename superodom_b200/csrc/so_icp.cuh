@@ -36,6 +36,7 @@ struct BatchView {
     double tukey_a2_line;     // a^2 for edges, a = double(sqrtf(3*lineRes_))  (LidarSlam.cpp:263)
     double tukey_a2;          // a^2, a = double(sqrtf(3*planeRes_))  (LidarSlam.cpp:271)
     uint32_t* counters;       // [n_scans] CTA tickets of k_evaluate_lm; nullptr = two-kernel form (k_evaluate + k_lm_step)
+    bool coop_knn = false;    // small registration: one warp per query (k_knn_scan_coop)
 };
 
 // neighbour hand-off between k_knn_scan and k_fit
@@ -53,6 +54,7 @@ struct NnBuf {
 #ifndef SO_EVAL_PTS
 #define SO_EVAL_PTS 16
 #endif
+constexpr uint32_t kCoopMaxGrid = 32;     // k_knn_scan_coop serves scans of up to 32 x 256 queries (a decimated live scan is ~2 000)
 constexpr int kEvalPts = SO_EVAL_PTS;     // points per thread in k_evaluate (large scans)
 // Points per thread of the evaluation kernels as a function of the scan's own size (never of the batch it is in, so that a scan's
 // partial sums -- and with them its result, bit for bit -- do not depend on its neighbours): small scans spread over more CTAs,
@@ -96,7 +98,7 @@ void launch_scan_keys(const MapView& m, const BatchView& bv, uint64_t* keys, uin
                       bool compact, cudaStream_t st);
 void launch_scan_finish(const BatchView& bv, const uint64_t* sorted_keys, size_t first, uint32_t pt_first, int cell_bits, bool key32, uint32_t n_scans, cudaStream_t st);
 constexpr uint32_t kPrepareSmallCap = 4096;    // survivors k_prepare_small can order (one CTA per scan)
-void launch_prepare_small(const MapView& m, const BatchView& bv, float4* out, uint32_t n_scans, int key_bits, cudaStream_t st);
+void launch_prepare_small(const MapView& m, const BatchView& bv, float4* out, uint32_t n_scans, int key_bits, uint32_t max_kept, cudaStream_t st);
 void launch_scan_gather(const float4* in, const uint32_t* vals, const uint64_t* keys, size_t first, const uint32_t* offset, size_t total, float4* out,
                         int cell_bits, bool key32, cudaStream_t st);
 // part: 0 = the whole stage; split build only: 1 = k_knn_scan alone, 2 = k_fit alone (profiling)

@@ -67,6 +67,7 @@ struct IcpState {
     int32_t iter_lm_steps[SO_MAX_ICP_ITERS], iter_lm_successful[SO_MAX_ICP_ITERS], iter_lm_termination[SO_MAX_ICP_ITERS];
     int32_t hist_obs[9], hist_rej[7], hist_rej_line[7];
     int32_t knn_searched, knn_verified;      // over the whole registration: queries that ran the grid walk / whose stored neighbours were proven still exact
+    int32_t need_cov;                        // set by the serial step that ends the registration: the CTA's first warp then runs the covariance
     double cov[36];
     double pos_err, pos_dir[3], pos_inv_cond, ori_err_deg, ori_dir[3], ori_inv_cond;
 };

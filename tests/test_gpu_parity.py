@@ -675,3 +675,22 @@ def test_scan_order_key_paths_and_stream_modes_agree(gpu_api, monkeypatch):
         r = ctx.register(scans[i], priors[i], 5, 2000, skip_map_checks=True)
         assert np.array_equal(np.array(list(r.pose) + [r.n_iterations] + list(r.hist_obs)), base[i]), i
     ctx.close()
+    # a single small registration searches with one WARP per query (k_knn_scan_coop); the batch above used one thread per query:
+    # equal results already say the two searches agree -- here also against the single registration with the warp search off,
+    # and on the neighbour ids themselves (stage call, decimated scan)
+    ctx = gpu_api.Context(max_map_points=1 << 20, max_scan_points=int(n_points.max()), max_batch=1, plane_res=0.2)
+    ctx.map_set_points(case["map_xyzi"])
+    corr_coop = ctx.correspond(scans[3][::4], priors[3], 2000)[0]          # 7 200 points: small enough for the warp search
+    ctx.close()
+    monkeypatch.setenv("SO_NO_COOP_KNN", "1")
+    ctx = gpu_api.Context(max_map_points=1 << 20, max_scan_points=int(n_points.max()), max_batch=1, plane_res=0.2)
+    ctx.map_set_points(case["map_xyzi"])
+    for i in (0, 7, 15):
+        r = ctx.register(scans[i], priors[i], 5, 2000, skip_map_checks=True)
+        assert np.array_equal(np.array(list(r.pose) + [r.n_iterations] + list(r.hist_obs)), base[i]), i
+    corr_lane = ctx.correspond(scans[3][::4], priors[3], 2000)[0]
+    ctx.close()
+    monkeypatch.delenv("SO_NO_COOP_KNN")
+    assert (corr_coop["status"] == 0).sum() > 1000
+    for f in ("status", "nn", "nn_d2", "n", "d", "w"):
+        assert np.array_equal(corr_coop[f], corr_lane[f]), f
