@@ -637,7 +637,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="scans per registration call (sub-batch)")
-    ap.add_argument("--sub-batches", type=int, default=8, help="registration calls per step per GPU")
+    ap.add_argument("--sub-batches", type=int, default=10, help="registration calls per step per GPU")
     ap.add_argument("--ref-scans", type=int, default=2, help="scans per step for --impl reference")
     ap.add_argument("--cfg5-queries", type=int, default=10_000_000)
     ap.add_argument("--live-scans", type=int, default=60)

@@ -222,6 +222,12 @@ int so_register(so_ctx* ctx,
                 size_t stride_bytes, size_t intensity_offset,
                 const double pose_in[7], const so_icp_opts* opts, so_icp_result* out);
 
+/* so_register of the cloud the LAST so_scan_prefilter call produced, which is still on the device (laserMapping.cpp:639-649 filters
+ * the scan, :713-714 registers the filtered cloud): no download + second upload between the two steps.  The caller may pass
+ * out_xyzi = NULL / cap = 0 to so_scan_prefilter when it does not need the filtered cloud on the host.  Fails with SO_ERR_ARG when
+ * anything that reuses the scan buffers ran in between.  so_map_add_registered_scan afterwards inserts that same cloud. */
+int so_register_prefiltered(so_ctx* ctx, const double pose_in[7], const so_icp_opts* opts, so_icp_result* out);
+
 /* Batched replay against the frozen map (BASELINE cfg4): n_scans independent Localization() calls.
  * scans: n_scans consecutive clouds, scan s has n_points[s] points starting at point offset sum(n_points[0..s)).
  * poses_in: n_scans x 7.  results: n_scans structs.  n_scans <= so_config.max_batch. */

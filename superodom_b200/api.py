@@ -20,7 +20,7 @@ EXPORTS = [
     "so_create", "so_destroy", "so_last_error", "so_device_available", "so_set_stream",
     "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
     "so_map_set_edge_points", "so_map_add_surf", "so_map_add_edge", "so_map_add_scan", "so_map_add_registered_scan", "so_map_add_scan_edge", "so_map_counts_5x5", "so_map_download", "so_map_size",
-    "so_scan_prefilter", "so_scan_deskew", "so_scan_extract_uniform", "so_register", "so_register_injected", "so_set_pose_sink", "so_register_batch", "so_register_batch_edges", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
+    "so_scan_prefilter", "so_scan_deskew", "so_scan_extract_uniform", "so_register", "so_register_prefiltered", "so_register_injected", "so_set_pose_sink", "so_register_batch", "so_register_batch_edges", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
     "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_build_flags", "so_profile_enable", "so_profile_get",
 ]
 
@@ -99,6 +99,7 @@ def load_library():
                                           C.c_void_p, C.c_size_t, C.c_void_p]
     L.so_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                               C.c_void_p, C.c_void_p, C.c_void_p]
+    L.so_register_prefiltered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_register_injected.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.so_set_pose_sink.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
     L.so_register_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
@@ -264,17 +265,19 @@ class Context:
         return out[: n.value]
 
     # ---- scan pre-filter
-    def scan_prefilter(self, scan_xyzi: np.ndarray, line_res: float, plane_res: float, auto_voxel_size: bool = True):
-        """-> (filtered float32 [m,4], line_res, plane_res, average_distance)"""
+    def scan_prefilter(self, scan_xyzi: np.ndarray, line_res: float, plane_res: float, auto_voxel_size: bool = True, download: bool = True):
+        """-> (filtered float32 [m,4], line_res, plane_res, average_distance); download=False leaves the filtered cloud on the device
+        (for register_prefiltered) and returns its point count in place of the array."""
         a = np.ascontiguousarray(scan_xyzi, dtype=np.float32)
         lr, pr = C.c_float(line_res), C.c_float(plane_res)
-        out = np.zeros((max(len(a), 1), 4), np.float32)
+        out = np.empty((max(len(a), 1), 4), np.float32) if download else None
         n = C.c_size_t()
         avg = C.c_double(0.0)
         stride = a.shape[1] * 4
         self._chk(self.L.so_scan_prefilter(self.h, _p(a), a.shape[0], stride, 12 if a.shape[1] >= 4 else stride, int(auto_voxel_size),
-                                           C.byref(lr), C.byref(pr), _p(out), len(out), C.byref(n), C.byref(avg)), "so_scan_prefilter")
-        return out[: n.value], lr.value, pr.value, avg.value
+                                           C.byref(lr), C.byref(pr), _p(out) if download else None, len(out) if download else 0, C.byref(n), C.byref(avg)),
+                  "so_scan_prefilter")
+        return (out[: n.value] if download else int(n.value)), lr.value, pr.value, avg.value
 
     def scan_deskew(self, points: np.ndarray, time_col: int, lidar_start_time: float, sample_times, sample_poses, imu_only: bool = False, T_i_l=None):
         """points: float32 [n, C] with x,y,z first and the per-point time in column time_col; rewritten IN PLACE.
@@ -353,6 +356,16 @@ class Context:
         self._chk(self.L.so_correspond_edge(self.h, _p(e), e.shape[0], stride, 12 if e.shape[1] >= 4 else stride, _p(pose), _p(corr), _p(hr)),
                   "so_correspond_edge")
         return corr, hr
+
+    def register_prefiltered(self, pose7, max_icp_iters: int, max_surface_features: int = 0, **kw) -> IcpResult:
+        """so_register of the cloud the last scan_prefilter call left on the device."""
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        o = self._opts(max_icp_iters, max_surface_features, **kw)
+        res = IcpResult()
+        rc = self.L.so_register_prefiltered(self.h, _p(pose), C.byref(o), C.byref(res))
+        if rc < 0:
+            self._chk(rc, "so_register_prefiltered")
+        return res
 
     def register_batch(self, scans_xyzi: np.ndarray, n_points, poses, max_icp_iters: int, max_surface_features: int = 0, **kw):
         """scans_xyzi: float32 [sum(n_points), 4] host array (pinned or pageable)."""

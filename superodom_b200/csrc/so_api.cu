@@ -220,6 +220,7 @@ struct Chunk { uint32_t first, count, pt_first, pt_count, grid_x, grid_e = 0, gr
 // Once per registration: order every scan by map cell at its prior pose (k_scan_keys -> radix sort -> k_scan_gather, or the one-CTA
 // k_prepare_small for small registrations).  compact: drop the points the decimation skips here, once, instead of in every kernel.
 static int prepare_scans(Ctx* c, const float4* d_scan_in, const Chunk& ch, cudaStream_t st, bool compact) {
+    c->prefiltered_n = SIZE_MAX;                                   // d_scan_sorted is about to be overwritten
     const MapView mv = map_view(c, c->surf);
     const BatchView bv = batch_view(c, d_scan_in, ch.first);
     timed_launch_begin(c);
@@ -831,6 +832,7 @@ int so_scan_prefilter(so_ctx* ctx, const void* xyzi, size_t n, size_t stride, si
     timed_launch_end(c, 3);
     if (rc) return rc;
     *n_out = m;
+    c->prefiltered_n = m;                                          // so_register_prefiltered: the filtered cloud stays in d_scan_sorted
     const size_t ncopy = std::min<size_t>(m, cap);
     if (ncopy) {
         SO_CUDA_TRY(cudaMemcpyAsync(out_xyzi, c->d_scan_sorted, ncopy * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
@@ -1006,6 +1008,23 @@ int so_register(so_ctx* ctx, const void* surf, size_t n_surf, const void* edge, 
     rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true, nullptr, &ne);
     if (rc) return rc;
     out->scan_edge_num = int32_t(n_edge);
+    out->time_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return out->status;
+}
+
+int so_register_prefiltered(so_ctx* ctx, const double pose_in[7], const so_icp_opts* opts, so_icp_result* out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !pose_in || !opts || !out) return fail(SO_ERR_ARG, "bad args");
+    if (c->prefiltered_n == SIZE_MAX) return fail(SO_ERR_ARG, "so_register_prefiltered needs a preceding so_scan_prefilter (and nothing that reuses the scan buffers in between)");
+    SO_CUDA_TRY(cudaSetDevice(c->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    const uint32_t n = uint32_t(c->prefiltered_n);
+    c->prefiltered_n = SIZE_MAX;
+    if (n) SO_CUDA_TRY(cudaMemcpyAsync(c->d_scan, c->d_scan_sorted, size_t(n) * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    c->last_scan_n = n;
+    int rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true);
+    if (rc) return rc;
+    out->scan_edge_num = 0;
     out->time_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return out->status;
 }

@@ -59,6 +59,7 @@ struct Ctx {
     // ---- scans / correspondences / optimiser state -------------------------------------------------------------
     uint32_t max_batch = 1;
     size_t scan_cap = 0;                           // points over the whole batch
+    size_t prefiltered_n = SIZE_MAX;               // points so_scan_prefilter left in d_scan_sorted (SIZE_MAX: none / overwritten since)
     uint32_t last_scan_n = 0;                      // points of the scan so_register uploaded last (d_scan[0..n), original order)
     float4* d_scan = nullptr;                      // upload target for host scans (original order)
     float4* d_scan_sorted = nullptr;               // cell-ordered copy the kernels read; w = original index

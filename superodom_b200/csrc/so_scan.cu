@@ -140,6 +140,7 @@ int scan_extract_uniform(Ctx* c, uint32_t n, uint32_t skip, float block_range, i
     uint32_t last_flag = 0, last_rank = 0;
     SO_CUDA_TRY(cudaMemcpyAsync(&last_flag, c->d_svals + n_cand - 1, 4, cudaMemcpyDeviceToHost, st));
     SO_CUDA_TRY(cudaMemcpyAsync(&last_rank, c->d_svals_out + n_cand - 1, 4, cudaMemcpyDeviceToHost, st));
+    c->prefiltered_n = SIZE_MAX;
     k_uniform_scatter<<<grid, 256, 0, st>>>(c->d_scan, n_cand, skip, c->d_svals, c->d_svals_out, c->d_scan_sorted);
     SO_CUDA_TRY(cudaStreamSynchronize(st));
     *n_out = last_rank + last_flag;

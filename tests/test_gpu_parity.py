@@ -428,6 +428,21 @@ def test_scan_prefilter_adjust_voxel_size(gpu_api, oracle_mod):
     # the filtered scan registers
     r = ctx.register(out, case["pose_prior"], 5, 2000)
     assert r.status == 0 and np.linalg.norm(np.array(r.pose)[:3] - case["pose_true"][:3]) < 0.05
+    # ... and registering it straight from the device (no download + second upload) is the same registration, bit for bit; the
+    # registered-scan insert that follows puts that cloud into the map
+    m, _, _, _ = ctx.scan_prefilter(s, 0.2, 0.4, False, download=False)
+    assert m == len(out)
+    r2 = ctx.register_prefiltered(case["pose_prior"], 5, 2000)
+    assert np.array_equal(np.array(r2.pose), np.array(r.pose)) and r2.n_iterations == r.n_iterations and np.array_equal(np.array(r2.cov), np.array(r.cov))
+    with pytest.raises(gpu_api.SuperOdomError):
+        ctx.register_prefiltered(case["pose_prior"], 5, 2000)                                  # consumed: needs a new so_scan_prefilter
+    ref = gpu_api.Context(max_map_points=max(1 << 20, len(case["map_xyzi"]) + 1024), max_scan_points=262144, plane_res=case["cfg"]["plane_res"])
+    ref.map_set_points(case["map_xyzi"])
+    ref.map_set_resolution(0.2, 0.4)                                                           # what the prefilter call set (laserMapping.cpp:648-649)
+    ref.map_add_scan(out, np.array(r2.pose))
+    ctx.map_add_registered_scan(np.array(r2.pose))
+    assert np.array_equal(ctx.map_download(0), ref.map_download(0))
+    ref.close()
     # returns beyond the 13-bit voxel range of the narrow sort key (+-4096 voxels) take the wide-key path: same result as numpy
     far = s.copy()
     far[5::997, :3] *= np.float32(400.0)
