@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one process per GPU)
     python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port + verbatim octree)
 
-A "step" registers SUB x B independent OS1-128 scans per GPU (default 8 x 64 = 512; 131 072 points each, drawn from 256
+A "step" registers SUB x B independent OS1-128 scans per GPU (default 6 x 128 = 768; 131 072 points each, drawn from 256
 distinct scans per GPU, consecutive sub-batches never repeat an input) against the 1 M-point warehouse map with up to 20 ICP
 iterations each -- exactly what LidarSLAM::Localization does per scan -- and ends with ONE all-gather of the per-scan result
 rows, enqueued on the compute stream from device memory (so_set_pose_sink; no host hop before the collective).
@@ -488,7 +488,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "scans_per_step_per_gpu": per_step, "scans_per_step": n_total, "sub_batches": SUB, "batch": B,
                            "distinct_scans_per_gpu": n_distinct, "parallelism": f"replay-shard x{world}",
-                           "l2": "inputs larger than L2 (every sub-batch reads 134 MB of scans it did not touch in the previous sub-batch)",
+                           "l2": f"inputs larger than L2 (every sub-batch reads {B * 2.1:.0f} MB of scans it did not touch in the previous sub-batch)",
                            "collective": "one all-gather of the per-scan rows per step, from device memory on the compute stream",
                            "timed_region_s": ms * 1e-3, "icp_iterations_executed_mean": icp_mean, "cpu_affinity": numa},
                 "clocks": clocks,
@@ -636,8 +636,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="scans per registration call (sub-batch)")
-    ap.add_argument("--sub-batches", type=int, default=10, help="registration calls per step per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="scans per registration call (sub-batch)")
+    ap.add_argument("--sub-batches", type=int, default=6, help="registration calls per step per GPU")
     ap.add_argument("--ref-scans", type=int, default=2, help="scans per step for --impl reference")
     ap.add_argument("--cfg5-queries", type=int, default=10_000_000)
     ap.add_argument("--live-scans", type=int, default=60)

@@ -469,14 +469,16 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         // the H2D of chunk k+1 (copy stream) also overlaps the kernels of chunk k.
         // Device-resident scans: two chunks (one per stream).  Host scans: four, the first one small so that the only upload
         // nothing can hide (chunk 0's) is short.  Chunks stay >= 8 scans: below that the wide kernels stop filling the GPU.
+        // Host scans: ~16 per chunk (at most 16 chunks), so that a LARGE call pays the one upload nothing can hide -- chunk 0's,
+        // kept to 8 scans -- once, and every later chunk's upload runs under the kernels of the chunk before it.
         const size_t n_chunks = c->profiling ? 1 : (c->chunk_override ? size_t(c->chunk_override)
-                                                   : (host_src ? (n_scans >= 32 ? 4 : (n_scans >= 16 ? 2 : 1)) : (n_scans >= 16 ? 2 : 1)));
+                                                   : (host_src ? (n_scans >= 32 ? std::min<size_t>(16, std::max<size_t>(4, n_scans / 16)) : (n_scans >= 16 ? 2 : 1))
+                                                               : (n_scans >= 16 ? 2 : 1)));
         std::vector<uint32_t> bounds(n_chunks + 1);
         for (size_t k = 0; k <= n_chunks; ++k) bounds[k] = uint32_t(k * n_scans / n_chunks);
-        if (host_src && n_chunks == 4 && n_scans >= 64 && !c->chunk_override) {
-            bounds[1] = uint32_t(n_scans / 8);
-            bounds[2] = bounds[1] + uint32_t((n_scans - bounds[1]) / 3);
-            bounds[3] = bounds[2] + uint32_t((n_scans - bounds[2]) / 2);
+        if (host_src && n_chunks >= 4 && n_scans >= 64 && !c->chunk_override) {
+            const size_t first = 8, rest = n_scans - first;
+            for (size_t k = 1; k < n_chunks; ++k) bounds[k] = uint32_t(first + (k - 1) * rest / (n_chunks - 1));
         }
         std::vector<Chunk> chunks;
         for (size_t k = 0; k < n_chunks; ++k) {
