@@ -283,6 +283,13 @@ int so_evaluate(so_ctx* ctx, const double pose[7], double H[36], double g[6], do
 int so_knn(so_ctx* ctx, const float* q_xyz, size_t nq, size_t stride_bytes, int k, float max_d2, uint32_t* idx, float* d2);
 int so_knn_device(so_ctx* ctx, const void* d_q_xyzw, size_t nq, int k, float max_d2, uint32_t* d_idx, float* d_d2);
 
+/* ---- feature sampling (calculateSamplingRate + shouldProcessPoint, LidarSlam.cpp:346-359) ---------- */
+/* The indices of an n-point scan that a registration capped at max_surface_features processes (ascending; all of 0..n-1 when
+ * the cap is <= 0 or >= n).  Host-only (needs no device): this is the list so_register uses to upload the processed points of a
+ * capped scan ahead of the rest of the cloud.  Writes min(count, cap) indices to out (may be NULL with cap 0) and the count to
+ * *n_out.  Returns SO_OK or SO_ERR_ARG. */
+int so_sampling_indices(uint32_t n, int32_t max_surface_features, uint32_t* out, size_t cap, size_t* n_out);
+
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 /* Number of this library's kernels launched since the last reset (bench.py gpu_launches). */
 uint64_t so_kernel_launches(so_ctx* ctx, int reset);

@@ -21,7 +21,7 @@ EXPORTS = [
     "so_map_set_resolution", "so_map_set_origin", "so_map_get_origin", "so_map_shift", "so_map_set_points",
     "so_map_set_edge_points", "so_map_add_surf", "so_map_add_edge", "so_map_add_scan", "so_map_add_registered_scan", "so_map_add_scan_edge", "so_map_counts_5x5", "so_map_download", "so_map_size",
     "so_scan_prefilter", "so_scan_deskew", "so_scan_extract_uniform", "so_register", "so_register_prefiltered", "so_register_injected", "so_set_pose_sink", "so_register_batch", "so_register_batch_edges", "so_register_batch_device", "so_correspond", "so_correspond_edge", "so_evaluate",
-    "so_knn", "so_knn_device", "so_kernel_launches", "so_bytes_copied", "so_build_flags", "so_profile_enable", "so_profile_get",
+    "so_knn", "so_knn_device", "so_sampling_indices", "so_kernel_launches", "so_bytes_copied", "so_build_flags", "so_profile_enable", "so_profile_get",
 ]
 
 
@@ -112,6 +112,7 @@ def load_library():
     L.so_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
     L.so_knn_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    L.so_sampling_indices.argtypes = [C.c_uint32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
     L.so_kernel_launches.restype = C.c_uint64
     L.so_kernel_launches.argtypes = [C.c_void_p, C.c_int]
     L.so_bytes_copied.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -123,6 +124,17 @@ def load_library():
 
 def build_flags() -> int:
     return int(load_library().so_build_flags())
+
+
+def sampling_indices(n: int, max_surface_features: int) -> np.ndarray:
+    """Indices a registration capped at max_surface_features processes (calculateSamplingRate + shouldProcessPoint,
+    LidarSlam.cpp:346-359).  Host-only."""
+    L = load_library()
+    out = np.empty(n, np.uint32)
+    cnt = C.c_size_t(0)
+    if L.so_sampling_indices(n, max_surface_features, out.ctypes.data_as(C.c_void_p), n, C.byref(cnt)) != 0:
+        raise SuperOdomError("so_sampling_indices failed")
+    return out[:cnt.value].copy()
 
 
 def device_available() -> bool:

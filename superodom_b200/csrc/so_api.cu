@@ -82,6 +82,8 @@ static int ctx_alloc(Ctx* c) {
     c->scan_cap = size_t(c->cfg.max_scan_points) * c->max_batch;
     c->grid_x_cap = (c->cfg.max_scan_points + kThreads - 1) / kThreads;
     SO_CUDA_TRY(cudaMalloc(&c->d_scan, c->scan_cap * sizeof(float4)));
+    SO_CUDA_TRY(cudaMalloc(&c->d_dec, size_t(kPrepareSmallCap) * sizeof(float4)));
+    SO_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_dec, cudaEventDisableTiming));
     SO_CUDA_TRY(cudaMalloc(&c->d_scan_sorted, c->scan_cap * sizeof(float4)));
     SO_CUDA_TRY(cudaMalloc(&c->d_skeys, c->scan_cap * sizeof(uint64_t) + 64));      // + slack: scan_voxel_filter lays [count 16 B][heads][ranks] over it
     SO_CUDA_TRY(cudaMalloc(&c->d_skeys_out, c->scan_cap * sizeof(uint64_t)));
@@ -143,6 +145,8 @@ static void ctx_free(Ctx* c) {
     cudaFree(c->d_q); cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2); cudaFree(c->d_inject);
     cudaFree(c->d_qkeys); cudaFree(c->d_qkeys_out); cudaFree(c->d_qvals); cudaFree(c->d_qvals_out); cudaFree(c->d_qsort_tmp);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    cudaFree(c->d_dec);
+    if (c->ev_dec) cudaEventDestroy(c->ev_dec);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evp0) cudaEventDestroy(c->evp0);
@@ -153,7 +157,7 @@ static void ctx_free(Ctx* c) {
 
 static int ensure_stage(Ctx* c, size_t bytes) {
     if (bytes <= c->h_stage_bytes) return SO_OK;
-    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_stage) { cudaDeviceSynchronize(); cudaFreeHost(c->h_stage); }      // no copy out of the old buffer may still be in flight
     c->h_stage = nullptr; c->h_stage_bytes = 0;
     SO_CUDA_TRY(cudaMallocHost(&c->h_stage, bytes));
     c->h_stage_bytes = bytes;
@@ -181,6 +185,51 @@ static int upload_cloud(Ctx* c, const void* src, size_t n, size_t stride, size_t
     }
     SO_CUDA_TRY(cudaMemcpyAsync(dst, h, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     c->bytes_h2d += n * sizeof(float4);
+    return SO_OK;
+}
+
+// shouldProcessPoint (LidarSlam.cpp:353-359) on the host: the same three IEEE operations as so_icp.cu's should_process (no FMA)
+static inline bool should_process_h(uint32_t i, double rate) {
+    const double x = double(i) * rate;
+    const double rem = x - double(int64_t(x));            // x >= 0 and < 2^32: truncation == floor
+    return !(rem + 0.001 > rate);
+}
+
+// Indices shouldProcessPoint keeps of an n-point scan capped at max_features (ascending).  A function of (n, max_features) only,
+// so the list of the last call is kept.
+static const std::vector<uint32_t>& decimation_list(Ctx* c, uint32_t n, int32_t max_features) {
+    if (c->dec_n == n && c->dec_mf == max_features && !c->dec_idx.empty()) return c->dec_idx;
+    const double rate = 1.0 * max_features / double(n);       // calculateSamplingRate (LidarSlam.cpp:346-351)
+    c->dec_idx.clear();
+    for (uint32_t i = 0; i < n; ++i) if (should_process_h(i, rate)) c->dec_idx.push_back(i);
+    c->dec_n = n; c->dec_mf = max_features;
+    return c->dec_idx;
+}
+
+static inline float4 read_point(const unsigned char* p, size_t stride, size_t ioff) {
+    float xyz[3], it = 0.f;
+    std::memcpy(xyz, p, 12);
+    if (ioff + 4 <= stride) std::memcpy(&it, p + ioff, 4);
+    return make_float4(xyz[0], xyz[1], xyz[2], it);
+}
+
+// The pending whole-cloud upload of a decimated so_register (Ctx::defer), on the COPY stream: it only has to land before the scan
+// is inserted, so it runs beside the registration instead of in front of it.  No-op when nothing is pending.
+static int run_deferred_upload(Ctx* c) {
+    if (!c->defer.src) return SO_OK;
+    const void* src = c->defer.src;
+    c->defer.src = nullptr;
+    const size_t n = c->defer.n;
+    if (c->defer.stride == 16 && c->defer.ioff == 12) {
+        SO_CUDA_TRY(cudaMemcpyAsync(c->d_scan, src, n * sizeof(float4), cudaMemcpyHostToDevice, c->copy_stream));
+    } else {
+        float4* h = static_cast<float4*>(c->h_stage) + c->defer.stage_off;
+        const unsigned char* p = static_cast<const unsigned char*>(src);
+        for (size_t i = 0; i < n; ++i, p += c->defer.stride) h[i] = read_point(p, c->defer.stride, c->defer.ioff);
+        SO_CUDA_TRY(cudaMemcpyAsync(c->d_scan, h, n * sizeof(float4), cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    c->bytes_h2d += n * sizeof(float4);
+    SO_CUDA_TRY(cudaEventRecord(c->ev_dec, c->copy_stream));
     return SO_OK;
 }
 
@@ -541,6 +590,7 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
             SO_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         }
         SO_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+        { int rc = run_deferred_upload(c); if (rc) return rc; }      // host-side staging of the whole cloud while the registration runs
         if (c->d_pose_sink) { launch_pack_poses(c->d_state, uint32_t(n_scans), c->d_pose_sink + c->sink_cursor * 8, c->stream); c->launches++; }
         SO_CUDA_TRY(cudaMemcpyAsync(c->h_state, c->d_state, n_scans * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
         count_d2h(c, n_scans * sizeof(IcpState));
@@ -605,6 +655,7 @@ so_ctx* so_create(const so_config* cfg_in) {
     if (std::getenv("SO_NO_SMALL_PREPARE")) c->no_small_prepare = true;
     if (std::getenv("SO_NO_COOP_KNN")) c->no_coop_knn = true;
     if (std::getenv("SO_FORCE_KEY64")) c->force_key64 = true;
+    if (std::getenv("SO_NO_DEC_UPLOAD")) c->no_dec_upload = true;
     if (const char* e = std::getenv("SO_CHUNKS")) c->chunk_override = std::max(0, std::min(16, std::atoi(e)));      // profiling aid: ncu cannot see inside conditional-node bodies
     if (ctx_alloc(c) != SO_OK) { ctx_free(c); return nullptr; }
     return reinterpret_cast<so_ctx*>(c);
@@ -1000,15 +1051,51 @@ int so_register(so_ctx* ctx, const void* surf, size_t n_surf, const void* edge, 
     if (n_surf > c->cfg.max_scan_points) return fail(SO_ERR_CAPACITY, "scan larger than so_config.max_scan_points");
     SO_CUDA_TRY(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
-    int rc = upload_cloud(c, surf, n_surf, stride, ioff, c->d_scan);
-    if (rc) return rc;
     const uint32_t n = uint32_t(n_surf);
-    c->last_scan_n = n;                                                 // so_map_add_registered_scan inserts it without a second upload
-    rc = upload_cloud(c, edge, n_edge, stride, ioff, c->d_escan);       // edge branch input (empty upstream: featureExtraction.cpp:429-436)
-    if (rc) return rc;
     const uint32_t ne = uint32_t(n_edge);
-    rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true, nullptr, &ne);
-    if (rc) return rc;
+    int rc;
+    // Decimated scan (the shipped configurations cap a 28 800-point scan at 2 000 features): the registration reads only the points
+    // shouldProcessPoint keeps, so only those go up in front of it (32 KB instead of 460 KB); the whole cloud -- needed by
+    // so_map_add_registered_scan, not by the registration -- is staged and copied on the copy stream while the registration runs.
+    const bool decimated = !c->no_dec_upload && opts->max_surface_features > 0 && n > uint32_t(opts->max_surface_features) &&
+                           uint32_t(opts->max_surface_features) + 1 <= kPrepareSmallCap;
+    if (decimated) {
+        const std::vector<uint32_t>& keep = decimation_list(c, n, opts->max_surface_features);
+        const uint32_t kept = uint32_t(keep.size());
+        if (kept == 0 || kept > kPrepareSmallCap) return fail(SO_ERR_ARG, "decimation list out of range");
+        const bool packed = stride == 16 && ioff == 12;
+        rc = upload_cloud(c, edge, n_edge, stride, ioff, c->d_escan);   // first: a strided edge cloud goes through the same staging buffer
+        if (rc) return rc;
+        if (n_edge && !packed) SO_CUDA_TRY(cudaStreamSynchronize(c->stream));       // ... and has to have left it
+        SO_CUDA_TRY(cudaEventSynchronize(c->ev_dec));                    // so has the previous call's deferred copy
+        rc = ensure_stage(c, (size_t(kPrepareSmallCap) + (packed ? 0 : n_surf)) * sizeof(float4));
+        if (rc) return rc;
+        float4* h = static_cast<float4*>(c->h_stage);
+        const unsigned char* p = static_cast<const unsigned char*>(surf);
+        for (uint32_t j = 0; j < kept; ++j) h[j] = read_point(p + size_t(keep[j]) * stride, stride, ioff);
+        SO_CUDA_TRY(cudaEventRecord(c->ev_copy[16], c->stream));        // the whole-cloud copy must not overtake earlier readers of d_scan
+        SO_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[16], 0));
+        SO_CUDA_TRY(cudaMemcpyAsync(c->d_dec, h, size_t(kept) * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        c->bytes_h2d += size_t(kept) * sizeof(float4);
+        c->defer.src = surf; c->defer.n = n_surf; c->defer.stride = stride; c->defer.ioff = ioff; c->defer.stage_off = kPrepareSmallCap;
+        c->last_scan_n = n;
+        so_icp_opts o2 = *opts;
+        o2.max_surface_features = 0;                                     // the decimation has been applied
+        rc = register_core(c, c->d_dec, &kept, 1, pose_in, &o2, out, true, nullptr, &ne);
+        const int rc2 = run_deferred_upload(c);                          // not yet run when nothing was launched (soft statuses) or on errors
+        SO_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_dec, 0));       // later work on the context stream (the insert) sees the whole cloud
+        if (rc) return rc;
+        if (rc2) return rc2;
+        out->scan_surf_num = int32_t(n_surf);
+    } else {
+        rc = upload_cloud(c, surf, n_surf, stride, ioff, c->d_scan);
+        if (rc) return rc;
+        c->last_scan_n = n;                                             // so_map_add_registered_scan inserts it without a second upload
+        rc = upload_cloud(c, edge, n_edge, stride, ioff, c->d_escan);   // edge branch input (empty upstream: featureExtraction.cpp:429-436)
+        if (rc) return rc;
+        rc = register_core(c, c->d_scan, &n, 1, pose_in, opts, out, true, nullptr, &ne);
+        if (rc) return rc;
+    }
     out->scan_edge_num = int32_t(n_edge);
     out->time_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return out->status;
@@ -1291,6 +1378,19 @@ uint64_t so_kernel_launches(so_ctx* ctx, int reset) {
     const uint64_t v = c->launches;
     if (reset) c->launches = 0;
     return v;
+}
+
+int so_sampling_indices(uint32_t n, int32_t max_surface_features, uint32_t* out, size_t cap, size_t* n_out) {
+    if (!n_out || (!out && cap)) return fail(SO_ERR_ARG, "bad args");
+    const double rate = (max_surface_features > 0 && n > uint32_t(max_surface_features)) ? 1.0 * max_surface_features / double(n) : -1.0;
+    size_t k = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (rate >= 0.0 && !should_process_h(i, rate)) continue;
+        if (k < cap) out[k] = i;
+        ++k;
+    }
+    *n_out = k;
+    return SO_OK;
 }
 
 int so_bytes_copied(so_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset) {

@@ -86,6 +86,14 @@ struct Ctx {
     uint32_t* d_inject = nullptr; size_t inject_cap = 0;   // so_register_injected: caller-supplied neighbour ids [iters][n][5]
     void* h_stage = nullptr;                       // pinned staging for strided host clouds
     size_t h_stage_bytes = 0;
+    // so_register of a DECIMATED scan (max_surface_features < n): only the points shouldProcessPoint keeps go up before the
+    // registration is launched; the whole cloud (what so_map_add_registered_scan inserts) follows on the copy stream while it runs
+    float4* d_dec = nullptr;                       // [kPrepareSmallCap] the kept points, index order, w = intensity
+    std::vector<uint32_t> dec_idx;                 // kept indices for (dec_n, dec_mf): the list depends on nothing else
+    uint32_t dec_n = 0; int32_t dec_mf = 0;
+    cudaEvent_t ev_dec = nullptr;                  // the deferred upload of the whole cloud has landed in d_scan
+    struct { const void* src = nullptr; size_t n = 0, stride = 0, ioff = 0, stage_off = 0; } defer;      // pending whole-cloud upload (src == nullptr: none)
+    bool no_dec_upload = false;                    // SO_NO_DEC_UPLOAD: A/B aid, always upload the whole cloud first
 
     // ---- k-NN scratch -------------------------------------------------------------------------------------------
     float4* d_q = nullptr; uint32_t* d_knn_idx = nullptr; float* d_knn_d2 = nullptr; size_t knn_cap = 0;

@@ -492,9 +492,11 @@ __device__ __forceinline__ float seed_bound(const MapView& m, const QueryCell& q
 // shouldProcessPoint (LidarSlam.cpp:353-359)
 __device__ __forceinline__ bool should_process(uint32_t i, double rate) {
     if (rate < 0.0) return true;
-    const double x = double(i) * rate;
-    const double rem = x - floor(x);                      // == std::fmod(x, 1.0) for x >= 0: both are exact
-    return !(rem + 0.001 > rate);
+    // explicit round-to-nearest operations: no FMA contraction, so that the host twin (so_api.cu: should_process_h, the decimated
+    // upload of so_register) and the reference's x86 arithmetic select exactly the same points
+    const double x = __dmul_rn(double(i), rate);
+    const double rem = __dsub_rn(x, floor(x));            // == std::fmod(x, 1.0) for x >= 0: both are exact
+    return !(__dadd_rn(rem, 0.001) > rate);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

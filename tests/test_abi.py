@@ -85,3 +85,22 @@ def test_library_holds_only_sm_100a_images():
     assert elfs and all("sm_100a" in ln for ln in elfs), elfs
     ptx = [ln for ln in subprocess.run([tool, "-lptx", lib], capture_output=True, text=True).stdout.splitlines() if "PTX file" in ln]
     assert not ptx, ptx
+
+
+def test_sampling_indices_match_should_process_point():
+    """so_sampling_indices (host-only) == calculateSamplingRate + shouldProcessPoint (LidarSlam.cpp:346-359) restated in numpy:
+    rate = max/n, keep i unless fmod(i * rate, 1) + 0.001 > rate.  This list decides which points so_register uploads first."""
+    from superodom_b200 import api
+    rng = np.random.default_rng(5)
+    cases = [(28800, 2000), (131072, 2000), (2001, 2000), (2000, 2000), (10, 0), (50000, 4095), (1, 1), (7, 3), (240000, 2000)]
+    cases += [(int(n), int(m)) for n, m in zip(rng.integers(1, 60000, 40), rng.integers(1, 4096, 40))]
+    for n, mf in cases:
+        got = api.sampling_indices(n, mf)
+        i = np.arange(n, dtype=np.float64)
+        if mf > 0 and n > mf:
+            rate = np.float64(mf) / np.float64(n)
+            want = np.nonzero(~(np.fmod(i * rate, 1.0) + 0.001 > rate))[0]
+            assert len(want) <= mf + 1
+        else:
+            want = np.arange(n)
+        assert np.array_equal(got, want.astype(np.uint32)), (n, mf)

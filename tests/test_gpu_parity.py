@@ -709,3 +709,43 @@ def test_scan_order_key_paths_and_stream_modes_agree(gpu_api, monkeypatch):
     assert (corr_coop["status"] == 0).sum() > 1000
     for f in ("status", "nn", "nn_d2", "n", "d", "w"):
         assert np.array_equal(corr_coop[f], corr_lane[f]), f
+
+
+@pytest.mark.gpu
+def test_decimated_upload_equals_whole_upload(gpu_api, monkeypatch):
+    """so_register of a capped scan uploads only the points shouldProcessPoint keeps ahead of the registration and the whole
+    cloud beside it: the result must equal the whole-cloud-first path bit for bit (packed and pcl::PointXYZI layouts), and the
+    cloud so_map_add_registered_scan inserts afterwards must be the whole scan, not the kept points."""
+    case = get_case("cfg1")
+    s, prior = case["scan_xyzi"], np.ascontiguousarray(case["pose_prior"])
+    pcl = np.zeros((len(s), 8), np.float32)
+    pcl[:, :3] = s[:, :3]
+    pcl[:, 4] = s[:, 3]
+
+    def run(strided):
+        ctx = gpu_api.Context(max_map_points=1 << 20, max_scan_points=len(s), max_batch=1, plane_res=0.2)
+        ctx.map_set_points(case["map_xyzi"])
+        outs = []
+        for _ in range(2):                                    # second call: cached index list, staging buffer reuse
+            if strided:
+                o, r = ctx._opts(5, 2000), gpu_api.IcpResult()
+                rc = ctx.L.so_register(ctx.h, pcl.ctypes.data_as(C.c_void_p), len(s), None, 0, 32, 16, prior.ctypes.data_as(C.c_void_p), C.byref(o), C.byref(r))
+                assert rc == 0
+            else:
+                r = ctx.register(s, prior, 5, 2000)
+            assert r.status == 0 and r.scan_surf_num == len(s)
+            outs.append(list(r.pose) + list(r.pose_opt) + list(r.cov) + [r.n_iterations] + list(r.hist_obs) + list(r.hist_reject_plane) + list(r.iter_n_surf))
+        assert outs[0] == outs[1]
+        n0 = ctx.map_size()
+        ctx.map_add_registered_scan(np.array(r.pose))
+        m = ctx.map_download(0)
+        ctx.close()
+        return np.array(outs[0]), n0, m
+    base, n0, m_base = run(False)
+    pcl_out, _, m_pcl = run(True)
+    assert np.array_equal(base, pcl_out) and np.array_equal(m_base, m_pcl)
+    monkeypatch.setenv("SO_NO_DEC_UPLOAD", "1")
+    whole, _, m_whole = run(False)
+    monkeypatch.delenv("SO_NO_DEC_UPLOAD")
+    assert np.array_equal(base, whole)
+    assert np.array_equal(m_base, m_whole) and len(m_base) > n0 + 2001       # the insert saw the whole 28 800-point scan
