@@ -44,7 +44,7 @@ DISTINCT = 256                                   # distinct scans per GPU behind
 KNN_BYTES_PER_QUERY = 16 + 5 * 8
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of ONE k_knn_scan launch / its queries (profiles/README.md says
 # which capture; None where no capture of the current kernel is committed)
-NCU_DRAM_BYTES_PER_QUERY = {"k_knn_scan": 75.4, "k_knn_fit": None}      # profiles/ncu_prof_r2h_metrics.csv: (26.82 MB read + 52.31 MB written) / 1 048 576 queries
+NCU_DRAM_BYTES_PER_QUERY = {"k_knn_scan": 76.8, "k_knn_fit": None}      # profiles/ncu_prof_r2t_metrics.csv: (26.78 MB read + 53.74 MB written) / 1 048 576 queries
 
 
 def _peaks():

@@ -67,7 +67,8 @@ def line_table(lib, kernel):
 
 def main():
     rep, kernel, lib = sys.argv[1:4]
-    cnt, m = ncu_counts(rep, kernel), line_table(lib, kernel)
+    # SO_LIB_KERNEL: regex for the (mangled) section name in the library when the plain kernel name also matches another kernel
+    cnt, m = ncu_counts(rep, kernel), line_table(lib, os.environ.get("SO_LIB_KERNEL", kernel))
     op = lambda t: (t.split()[1] if t.startswith("@") else t.split()[0]).split(".")[0]
     bad = sum(1 for off, (_, _, t) in cnt.items() if off not in m or op(t) != op(m[off][1]))
     if bad:

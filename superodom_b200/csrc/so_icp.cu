@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_prepare_small(MapView m, Batc
 // fit search global memory.  Measured slower than the global search (so_knn.cuh), so it is not the default.
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef SO_KNN_MINB
-#define SO_KNN_MINB (SO_KNN_TILE ? 6 : 4)
+#define SO_KNN_MINB (SO_KNN_TILE ? 6 : 1024 / SO_KNN_THREADS)      // 64 registers per thread either way
 #endif
 __global__ void __launch_bounds__(kTileThreads, SO_KNN_MINB) k_knn_scan(MapView m, BatchView bv, NnBuf nb) {
     const int s = blockIdx.y;
@@ -1092,7 +1092,7 @@ __global__ void __launch_bounds__(kFitThreads, SO_FIT_MINB) k_fit(MapView m, Bat
 // that are in the FP64-heavy fit share an SM, so both pipes stay busy.  The fit reads its neighbours straight from the
 // search-ordered map at the positions the search just visited (L1/L2 hits).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, SO_KNN_MINB) k_knn_fit(MapView m, BatchView bv, CorrBuf cb, NnBuf nb) {
+__global__ void __launch_bounds__(kThreads, 4) k_knn_fit(MapView m, BatchView bv, CorrBuf cb, NnBuf nb) {
     const int s = blockIdx.y;
     const IcpState* st = bv.st + s;
     if (st->phase != PH_CORR) return;

@@ -167,7 +167,10 @@ struct GlobalGrid {
 #ifndef SO_KNN_TILE
 #define SO_KNN_TILE 0
 #endif
-constexpr int kTileThreads = SO_KNN_TILE ? 128 : 256;      // queries per CTA of the search kernels
+#ifndef SO_KNN_THREADS
+#define SO_KNN_THREADS 64          // measured on B200: 256 -> 0.2825, 128 -> 0.2749, 64 -> 0.2729, 32 -> 0.2758 ms per 2.1 M scan queries; cfg5 2.718 / 2.587 / 2.585 / 2.650 ms
+#endif
+constexpr int kTileThreads = SO_KNN_TILE ? 128 : SO_KNN_THREADS;      // queries per CTA of the search kernels
 #ifndef SO_TILE_PTS
 #define SO_TILE_PTS 1024
 #endif
