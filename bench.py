@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one process per GPU)
     python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port + verbatim octree)
 
-A "step" registers SUB x B independent OS1-128 scans per GPU (default 6 x 128 = 768; 131 072 points each, drawn from 256
+A "step" registers SUB x B independent OS1-128 scans per GPU (default 4 x 256 = 1024; 131 072 points each, drawn from 512
 distinct scans per GPU, consecutive sub-batches never repeat an input) against the 1 M-point warehouse map with up to 20 ICP
 iterations each -- exactly what LidarSLAM::Localization does per scan -- and ends with ONE all-gather of the per-scan result
 rows, enqueued on the compute stream from device memory (so_set_pose_sink; no host hop before the collective).
@@ -39,7 +39,7 @@ METRIC = "ICP scans/sec (128-beam, 1M-pt map)"
 UNIT = "scans/s"
 WORKLOAD = "cfg2: OS1-128 synthetic scans (131072 pts) vs 1M-pt local map, 20 ICP iters, planeRes 0.2, all points active"
 CFG4_TOTAL = 1024
-DISTINCT = 256                                   # distinct scans per GPU behind the weak-scaling step
+DISTINCT = 512                                   # distinct scans per GPU behind the weak-scaling step (two calls' worth: consecutive calls never repeat an input)
 # algorithmic bytes of the k-NN = 16 B query read + k * 8 B result (u32 id + f32 d2) per query, + the map once.
 KNN_BYTES_PER_QUERY = 16 + 5 * 8
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of ONE k_knn_scan launch / its queries (profiles/README.md says
@@ -364,6 +364,20 @@ def run_ours(args):
     h2d, d2h = ctx.bytes_copied()
     d2h += gathered.numel() * 8
     e2e = n_total * args.steps / (ms_e2e * 1e-3)
+    # what the host link gives a plain pinned copy on this box (after the timed regions): the denominator the e2e / value gap is read against
+    nb_link = min(int(offs[n_distinct]) * 16, 512 << 20)
+    link_dst = torch.empty(nb_link, dtype=torch.uint8, device=dev)
+    link_src = h_pinned.view(-1).view(torch.uint8)[:nb_link]
+    link_dst.copy_(link_src, non_blocking=True)
+    torch.cuda.synchronize()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    for _ in range(3):
+        link_dst.copy_(link_src, non_blocking=True)
+    l1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * nb_link / (l0.elapsed_time(l1) * 1e-3) / 1e9
+    del link_dst
     phase("timed regions (device-resident + e2e)")
 
     # ---- cfg4 as BASELINE.json states it: 1024 distinct scans, fixed total, sharded, one gather (strong scaling) -------------------
@@ -493,7 +507,8 @@ def run_ours(args):
                            "timed_region_s": ms * 1e-3, "icp_iterations_executed_mean": icp_mean, "cpu_affinity": numa},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d // args.steps), "d2h_bytes_per_step": int(d2h // args.steps),
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps, "h2d_link_GBps_measured": h2d_gbs,
+                        "h2d_GBps_needed_at_value": value / world * 131072 * 16 / 1e9},
                 "gpu_launches": int(launches), "roofline": roofline, "knn_cfg5": knn5, "cfg4": cfg4, "wide_prior": wide, "latency": latency, "live": live,
                 "cpu_baseline": cpu}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -640,8 +655,8 @@ def main():
     ap.add_argument("--steps", type=int, default=15)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="scans per registration call (sub-batch)")
-    ap.add_argument("--sub-batches", type=int, default=6, help="registration calls per step per GPU")
+    ap.add_argument("--batch", type=int, default=256, help="scans per registration call (sub-batch)")
+    ap.add_argument("--sub-batches", type=int, default=4, help="registration calls per step per GPU")
     ap.add_argument("--ref-scans", type=int, default=2, help="scans per step for --impl reference")
     ap.add_argument("--cfg5-queries", type=int, default=10_000_000)
     ap.add_argument("--live-scans", type=int, default=60)
