@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "so_ctx.cuh"
+#include "so_chunks.h"
 #include "so_knn.cuh"
 
 namespace so {
@@ -517,21 +518,8 @@ static int register_core(Ctx* c, const float4* d_scan, const uint32_t* n_points,
         // one-CTA optimiser steps, kernel tails, the loop condition) sit under the other's wide kernels; with host input
         // the H2D of chunk k+1 (copy stream) also overlaps the kernels of chunk k.
         // Device-resident scans: two chunks (one per stream).  Chunks stay >= 8 scans: below that the wide kernels stop filling the GPU.
-        // Host scans: chunks that GROW -- 8, 16, 40, 64, then doubling (cumulative bounds 8, 24, 64, 128, 256, ...).  The one upload
-        // nothing can hide is chunk 0's, so it is short; every later chunk is uploaded (copy stream, back to back) while the chunks
-        // before it compute, and it can be large because that computing takes longer than its copy (a scan costs ~90 us of kernels and
-        // ~40 us of PCIe).  Large chunks matter: the wide kernels of an 8- or 16-scan chunk leave the GPU launch-bound (measured:
-        // 128 scans in 16 / 8 / 4 / 2 equal chunks run at 9 476 / ~10 400 / 10 775 / 11 027 scans/s device-resident).
-        std::vector<uint32_t> bounds;
-        if (c->profiling) bounds = {0u, uint32_t(n_scans)};
-        else if (c->chunk_override) { for (int k = 0; k <= c->chunk_override; ++k) bounds.push_back(uint32_t(size_t(k) * n_scans / size_t(c->chunk_override))); }
-        else if (host_src && n_scans >= 32) {
-            bounds = {0u, 8u, 24u};
-            for (size_t b = 64; b < n_scans && bounds.size() < 16; b *= 2) bounds.push_back(uint32_t(b));
-            if (n_scans - bounds.back() < 8) bounds.pop_back();           // no sliver at the end
-            bounds.push_back(uint32_t(n_scans));
-        } else if (n_scans >= 16) bounds = {0u, uint32_t(n_scans / 2), uint32_t(n_scans)};
-        else bounds = {0u, uint32_t(n_scans)};
+        // (the rule -- growing chunks for host input -- lives in so_chunks.h, where a CPU test can reach it)
+        const std::vector<uint32_t> bounds = chunk_bounds(n_scans, host_src != nullptr, c->profiling, c->chunk_override);
         const size_t n_chunks = bounds.size() - 1;
         std::vector<Chunk> chunks;
         for (size_t k = 0; k < n_chunks; ++k) {

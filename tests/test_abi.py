@@ -104,3 +104,13 @@ def test_sampling_indices_match_should_process_point():
         else:
             want = np.arange(n)
         assert np.array_equal(got, want.astype(np.uint32)), (n, mf)
+
+
+def test_batch_chunking_rule(tmp_path):
+    """Host logic of so_register_batch*: the chunk bounds (superodom_b200/csrc/so_chunks.h, plain C++) cover the batch in order
+    in at most 16 chunks; host batches expose one 8-scan upload and then grow (8, 16, 40, 64, 128, ...) with no sliver at the end."""
+    exe = tmp_path / "chunks_test"
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-O1", "-I", os.path.join(ROOT, "superodom_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "cpp", "chunks_test.cpp"), "-o", str(exe)])
+    out = subprocess.check_output([str(exe), "64", "256", "65"], text=True).splitlines()
+    assert out == ["64: 0 8 24 64", "256: 0 8 24 64 128 256", "65: 0 8 24 65", "ok"]
